@@ -1,0 +1,215 @@
+#!/usr/bin/env python3
+"""Mint the golden fixtures under tests/golden/ by RUNNING THE REFERENCE (build container only).
+
+    SA_JIT_TWEAK=true PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Imports /root/reference/satools (read-only; nothing is written there), executes the reference's
+own PyTorch generator (satools/satools/hifigan/archi.py) and records its outputs.  The reference
+ships no golden vectors for this path, so these are the pins for
+oracle/hifigan_numpy.py, oracle/hifigan_torch_cpu.py and the CUDA path.
+
+Weights are NOT stored (58 MB): they are the reference's random init for a seed, which
+satools_b200.CoreHifiGan reproduces bit for bit (same construction order, same RNG draws);
+the fixture stores a SHA-256 of the state dict so every consumer proves it regenerated the
+same weights.  Inputs come from satools_b200.conditioning (numpy PCG64, host independent).
+"""
+import hashlib
+import importlib.util
+import json
+import os
+import sys
+import types
+
+os.environ.setdefault("SA_JIT_TWEAK", "true")
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, "/root/reference/satools")
+sys.path.insert(0, os.path.join(ROOT, "sa-toolkit_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import satools  # noqa: E402  (the reference; sets torch threads to 1, yaapt.py:27)
+from satools.hifigan.archi import CoreHifiGan as RefGen  # noqa: E402
+
+torch.set_num_threads(8)
+from satools_b200 import conditioning  # noqa: E402
+from satools_b200.archi import CoreHifiGan as OurGen  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def state_sha256(state) -> str:
+    h = hashlib.sha256()
+    for k in sorted(state):
+        h.update(k.encode())
+        h.update(state[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def ref_stages(g, x):
+    """forward_resnet (archi.py:77-91) with the stage outputs exposed."""
+    outs = []
+    h = g.conv_pre(x)
+    outs.append(h)
+    for i, up in enumerate(g.ups):
+        h = up(F.leaky_relu(h, 0.1))
+        xs = torch.zeros_like(h)
+        for j in range(g.num_kernels):
+            xs += g.resblocks[i * g.num_kernels + j](h)
+        h = xs / g.num_kernels
+        outs.append(h)
+    return outs
+
+
+def slices(t):
+    """A small, position-diverse sample of an activation [B,C,L]: first/last 48 steps of 4 channels."""
+    C = t.shape[1]
+    ch = [0, 1, C // 2, C - 1]
+    return torch.cat([t[:, ch, :48], t[:, ch, -48:]], dim=2).contiguous().numpy()
+
+
+def generator_cases():
+    meta = {}
+    cases = [  # (seed, frames per item)
+        (0, [20]),
+        (0, [41]),
+        (1, [7, 5, 2]),
+        (2, [33, 12]),
+    ]
+    shas = {}
+    for seed in sorted({c[0] for c in cases}):
+        torch.manual_seed(seed)
+        ref = RefGen(imput_dim=504).eval()
+        torch.manual_seed(seed)
+        ours = OurGen(imput_dim=504)
+        sref, sours = ref.state_dict(), ours.state_dict()
+        assert list(sref.keys()) == list(sours.keys()), "state-dict keys differ"
+        for k in sref:
+            assert torch.equal(sref[k], sours[k]), f"RNG mirror broke at {k}"
+        shas[seed] = state_sha256(sref)
+        for ci, (s, frames) in enumerate(cases):
+            if s != seed:
+                continue
+            x = torch.from_numpy(conditioning.batch(1000 + ci, frames))
+            with torch.no_grad():
+                y32, _ = ref(x)
+                ref64 = __import__("copy").deepcopy(ref).double()
+                y64, _ = ref64(x.double())
+                st64 = ref_stages(ref64, x.double())
+            name = f"gen_seed{seed}_case{ci}"
+            np.savez_compressed(
+                os.path.join(OUT, name + ".npz"),
+                y_ref_fp32=y32.numpy(), y_ref_fp64=y64.numpy(),
+                x_sha256=np.frombuffer(hashlib.sha256(x.numpy().tobytes()).digest(), dtype=np.uint8),
+                **{f"stage{i}": slices(t) for i, t in enumerate(st64)})
+            meta[name] = {"seed": seed, "frames": frames, "cond_seed": 1000 + ci,
+                          "state_sha256": shas[seed], "y_shape": list(y64.shape)}
+            print(name, y64.shape, "fp32-vs-fp64 maxabs", float((y32.double() - y64).abs().max()))
+    return meta
+
+
+def layer_kats():
+    """Per-op known answers straight from the ATen ops the reference calls."""
+    g = torch.Generator().manual_seed(7)
+    out = {}
+
+    def rn(*s):
+        return torch.randn(*s, generator=g, dtype=torch.float64)
+
+    for k, d in [(3, 1), (3, 5), (7, 3), (11, 5), (7, 1)]:
+        x, w, b = rn(2, 16, 70), rn(16, 16, k) * 0.2, rn(16)
+        y = F.conv1d(x, w, b, dilation=d, padding=(k * d - d) // 2)
+        out[f"conv_k{k}_d{d}"] = dict(x=x, w=w, b=b, y=y)
+    for k, u in [(11, 5), (8, 4), (4, 2)]:
+        x, w, b = rn(2, 12, 9), rn(12, 6, k) * 0.2, rn(6)
+        y = F.conv_transpose1d(x, w, b, stride=u, padding=(k - u) // 2)
+        out[f"convt_k{k}_u{u}"] = dict(x=x, w=w, b=b, y=y)
+    # ReflectionPad1d((1,0)) + leaky_relu(0.01) + conv_post + tanh  (archi.py:87-90)
+    x, w, b = rn(2, 16, 33), rn(1, 16, 7) * 0.2, rn(1)
+    y = torch.tanh(F.conv1d(torch.nn.ReflectionPad1d((1, 0))(F.leaky_relu(x)), w, b, padding=3))
+    out["tail"] = dict(x=x, w=w, b=b, y=y)
+    # old-style weight_norm fold, both conv kinds
+    from torch.nn.utils import weight_norm
+    c = weight_norm(torch.nn.Conv1d(6, 4, 3).double())
+    c(rn(1, 6, 8))
+    out["wn_conv"] = dict(g=c.weight_g.detach(), v=c.weight_v.detach(), w=c.weight.detach())
+    c = weight_norm(torch.nn.ConvTranspose1d(6, 4, 4, 2).double())
+    c(rn(1, 6, 8))
+    out["wn_convt"] = dict(g=c.weight_g.detach(), v=c.weight_v.detach(), w=c.weight.detach())
+    # one reference ResBlock1 (nn.py:93-175)
+    from satools.hifigan.nn import ResBlock1
+    torch.manual_seed(11)
+    rb = ResBlock1(8, 7, (1, 3, 5)).double().eval()
+    x = rn(2, 8, 90)
+    with torch.no_grad():
+        y = rb(x)
+    sd = {k: v.detach() for k, v in rb.state_dict().items()}
+    out["resblock_k7"] = dict(x=x, y=y, **{"p_" + k: v for k, v in sd.items()})
+    flat = {}
+    for name, d in out.items():
+        for k, v in d.items():
+            flat[f"{name}/{k}"] = v.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "layer_kats.npz"), **flat)
+    print("layer_kats:", len(flat), "arrays")
+
+
+def net_forward_case():
+    """G4: the reference's own conditioning assembly (Net._forward, hifigan.py:83-102) on fixed
+    (f0, bn, spk_id), with and without f0_transformation=quant_16_awgn_2, captured at the
+    hifigan(x) boundary."""
+    ref_root = "/root/reference"
+
+    def load(path, name):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    tdnnf = load(f"{ref_root}/egs/asr/librispeech/local/chain/tuning/tdnnf_vq.py", "tdnnf_vq_cfg")
+    import satools.infer_helper
+    satools.infer_helper.load_model = lambda *a, **k: tdnnf.build(
+        types.SimpleNamespace(freeze_encoder="False", codebook_size=48))(output_dim=3280)
+    hf = load(f"{ref_root}/egs/vc/libritts/local/tuning/hifigan.py", "hifigan_cfg")
+    res = {}
+    for tag, f0t in [("plain", ""), ("quant_16_awgn_2", "quant_16_awgn_2")]:
+        torch.manual_seed(3)
+        Net = hf.build(types.SimpleNamespace(asrbn_model="x", f0_transformation=f0t))
+        net = Net(utt2spk={f"u{i}": str(1000 + i) for i in range(247)})
+        net.eval()
+        captured = {}
+        orig = net.hifigan.forward
+        net.hifigan.forward = lambda x: (captured.__setitem__("x", x.detach().clone()), orig(x))[1]
+        rng = np.random.default_rng(5)
+        T = 16
+        bn = torch.from_numpy(conditioning.codebook()[rng.integers(48, size=(2, T))]).permute(0, 2, 1).contiguous()
+        f0 = torch.from_numpy((rng.random((2, T)) * 120 + 80).astype(np.float32))
+        f0[:, 3:6] = 0.0
+        spk = net.get_spk_id(None, target=["1003", "1100"])
+        torch.manual_seed(17)  # awgn draws from the global CPU RNG (nn.py:53-57)
+        with torch.no_grad():
+            y = net._forward(f0.clone(), bn, spk)
+        res[f"{tag}/x"] = captured["x"].numpy()
+        res[f"{tag}/y"] = y.numpy()
+        res[f"{tag}/f0"] = f0.numpy()
+        res[f"{tag}/bn"] = bn.numpy()
+        res[f"{tag}/spk"] = spk.numpy()
+        res[f"{tag}/state_sha256"] = np.frombuffer(bytes.fromhex(state_sha256(net.hifigan.state_dict())), dtype=np.uint8)
+        # the generator weights of this Net are not seed-reproducible through our ctor alone
+        # (the BN extractor consumes RNG first), so ship them for the *tiny* check only as a
+        # fp64 output of the reference on the captured x; weights stay unshipped.
+        print("net_forward", tag, captured["x"].shape, y.shape)
+    np.savez_compressed(os.path.join(OUT, "net_forward.npz"), **res)
+
+
+if __name__ == "__main__":
+    meta = generator_cases()
+    layer_kats()
+    net_forward_case()
+    with open(os.path.join(OUT, "manifest.json"), "w") as f:
+        json.dump({"generator": meta, "torch": torch.__version__,
+                   "made_by": "oracle/make_golden.py (runs /root/reference)"}, f, indent=1, sort_keys=True)
+    print("wrote", OUT)

@@ -1,0 +1,559 @@
+// libsatools_hifigan.so -- C ABI + host orchestration of the B200 HiFi-GAN generator.
+// See include/sa_hifigan.h for the contract and the reference entry points each call replaces.
+//
+// Graph executed (reference: satools/satools/hifigan/archi.py:77-91, nn.py:168-175):
+//   h = conv_pre(x)
+//   for stage i: h = convT_i(lrelu(h)); h = mean_j ResBlock1_{k_j}(h)
+//   y = tanh(conv_post(reflect_pad(lrelu(h, 0.01))))
+#include "../../include/sa_hifigan.h"
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels_f32.cuh"
+#include "tc_path.cuh"
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define SA_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(SA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// One conv layer: raw state-dict tensors on the host, packed weights on the device.
+struct sa_conv {
+  std::string name;
+  bool transposed = false;   // ConvTranspose1d: weight [Cin,Cout,k]; Conv1d: [Cout,Cin,k]
+  int cin = 0, cout = 0, k = 0, dil = 1, pad = 0, stride = 1;
+  std::vector<float> g, v, w, bias;  // g/v raw; w folded, in the torch layout
+  bool has_g = false, has_v = false, has_w = false, has_bias = false;
+  float* d_w32 = nullptr;    // fp32 path: [Cin][k][Cout]
+  float* d_bias = nullptr;   // [Cout]
+  sa::tc_weights tc;         // tensor-core path packing
+};
+
+struct sa_hifigan {
+  sa_hifigan_cfg cfg;
+  int device = 0;
+  std::vector<sa_conv> convs;
+  std::map<std::string, int> index;
+  int precision = -1;
+  bool finalized = false;
+  int64_t launches = 0;
+  int debug_tap = -1;
+  float* debug_out = nullptr;
+  int n_sm = 148;
+  sa::tc_context tc;
+
+  int conv_pre() const { return 0; }
+  int up(int i) const { return 1 + i; }
+  int rb(int i, int j, int which, int m) const {   // which: 0 convs1, 1 convs2
+    const int nrb = cfg.n_resblocks, nd = cfg.n_dilations;
+    return 1 + cfg.n_stages + ((i * nrb + j) * 2 + which) * nd + m;
+  }
+  int conv_post() const { return 1 + cfg.n_stages + cfg.n_stages * cfg.n_resblocks * 2 * cfg.n_dilations; }
+  int stage_channels(int i) const { return cfg.initial_channels >> (i + 1); }
+  int64_t stage_rate(int i) const {
+    int64_t r = 1;
+    for (int s = 0; s <= i; ++s) r *= cfg.upsample_rates[s];
+    return r;
+  }
+  // largest C*L of any activation, per frame
+  int64_t max_elems_per_frame() const {
+    int64_t m = cfg.initial_channels;
+    for (int i = 0; i < cfg.n_stages; ++i) m = std::max<int64_t>(m, stage_channels(i) * stage_rate(i));
+    return m;
+  }
+};
+
+extern "C" {
+
+int sa_hifigan_abi_version(void) { return SA_HIFIGAN_ABI_VERSION; }
+const char* sa_hifigan_last_error(void) { return g_err; }
+
+int sa_hifigan_default_cfg(sa_hifigan_cfg* cfg) {
+  if (!cfg) return fail(SA_ERR_INVALID_ARG, "cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->input_dim = 256 + 1 + 247;   // hifigan.py:45-46 with the 247 LibriTTS speakers
+  cfg->initial_channels = 512;
+  cfg->n_stages = 5;
+  const int rates[5] = {5, 4, 4, 2, 2}, kernels[5] = {11, 8, 8, 4, 4};
+  for (int i = 0; i < 5; ++i) { cfg->upsample_rates[i] = rates[i]; cfg->upsample_kernels[i] = kernels[i]; }
+  cfg->n_resblocks = 3;
+  const int rk[3] = {3, 7, 11}, rd[3] = {1, 3, 5};
+  cfg->n_dilations = 3;
+  for (int j = 0; j < 3; ++j) {
+    cfg->resblock_kernels[j] = rk[j];
+    for (int m = 0; m < 3; ++m) cfg->resblock_dilations[j][m] = rd[m];
+  }
+  cfg->device = -1;
+  return SA_OK;
+}
+
+int sa_hifigan_create(const sa_hifigan_cfg* cfg, sa_hifigan** out) {
+  if (!cfg || !out) return fail(SA_ERR_INVALID_ARG, "cfg/out is NULL");
+  *out = nullptr;
+  if (cfg->n_stages < 1 || cfg->n_stages > SA_HIFIGAN_MAX_STAGES || cfg->n_resblocks < 1 ||
+      cfg->n_resblocks > SA_HIFIGAN_MAX_RB || cfg->n_dilations < 1 || cfg->n_dilations > SA_HIFIGAN_MAX_RB ||
+      cfg->input_dim < 1 || cfg->initial_channels < (1 << cfg->n_stages))
+    return fail(SA_ERR_INVALID_ARG, "bad generator configuration");
+  if (cfg->initial_channels % (1 << cfg->n_stages) != 0)
+    return fail(SA_ERR_INVALID_ARG, "initial_channels must be divisible by 2^n_stages");
+  for (int i = 0; i < cfg->n_stages; ++i) {
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernels[i];
+    if (u < 1 || k < u || ((k - u) & 1))
+      return fail(SA_ERR_UNSUPPORTED, "upsample stage %d: need kernel >= rate and (kernel - rate) even", i);
+  }
+  for (int j = 0; j < cfg->n_resblocks; ++j)
+    if (cfg->resblock_kernels[j] < 1 || !(cfg->resblock_kernels[j] & 1))
+      return fail(SA_ERR_UNSUPPORTED, "resblock kernel sizes must be odd");
+
+  int dev = cfg->device;
+  if (dev < 0) SA_CUDA(cudaGetDevice(&dev));
+  int n_dev = 0;
+  SA_CUDA(cudaGetDeviceCount(&n_dev));
+  if (dev >= n_dev) return fail(SA_ERR_INVALID_ARG, "device %d out of range (%d devices)", dev, n_dev);
+  cudaDeviceProp prop;
+  SA_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(SA_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                dev, prop.major, prop.minor);
+
+  sa_hifigan* h = new sa_hifigan();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->n_sm = prop.multiProcessorCount;
+
+  auto add = [&](const std::string& name, bool tr, int cin, int cout, int k, int dil, int pad, int stride) {
+    sa_conv c;
+    c.name = name; c.transposed = tr; c.cin = cin; c.cout = cout; c.k = k; c.dil = dil; c.pad = pad; c.stride = stride;
+    h->index[name] = (int)h->convs.size();
+    h->convs.push_back(std::move(c));
+  };
+  add("conv_pre", false, cfg->input_dim, cfg->initial_channels, 7, 1, 3, 1);                  // archi.py:40-42
+  for (int i = 0; i < cfg->n_stages; ++i) {                                                    // archi.py:47-59
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernels[i];
+    add("ups." + std::to_string(i), true, cfg->initial_channels >> i, cfg->initial_channels >> (i + 1), k, 1, (k - u) / 2, u);
+  }
+  for (int i = 0; i < cfg->n_stages; ++i)                                                      // archi.py:61-67
+    for (int j = 0; j < cfg->n_resblocks; ++j) {
+      const int ch = h->stage_channels(i), k = cfg->resblock_kernels[j];
+      const std::string base = "resblocks." + std::to_string(i * cfg->n_resblocks + j);
+      for (int m = 0; m < cfg->n_dilations; ++m) {                                             // nn.py:96-131
+        const int d = cfg->resblock_dilations[j][m];
+        add(base + ".convs1." + std::to_string(m), false, ch, ch, k, d, (k * d - d) / 2, 1);
+      }
+      for (int m = 0; m < cfg->n_dilations; ++m)                                               // nn.py:133-166
+        add(base + ".convs2." + std::to_string(m), false, ch, ch, k, 1, (k - 1) / 2, 1);
+    }
+  add("conv_post", false, h->stage_channels(cfg->n_stages - 1), 1, 7, 1, 3, 1);                // archi.py:72
+  *out = h;
+  return SA_OK;
+}
+
+static void free_device_weights(sa_hifigan* h) {
+  for (auto& c : h->convs) {
+    if (c.d_w32) cudaFree(c.d_w32);
+    if (c.d_bias) cudaFree(c.d_bias);
+    c.d_w32 = nullptr; c.d_bias = nullptr;
+    sa::tc_free_weights(c.tc);
+  }
+}
+
+void sa_hifigan_destroy(sa_hifigan* h) {
+  if (!h) return;
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess) {
+    cudaSetDevice(h->device);
+    free_device_weights(h);
+    cudaSetDevice(cur);
+  }
+  delete h;
+}
+
+int sa_hifigan_set_weight(sa_hifigan* h, const char* key, const void* data, const int64_t* shape,
+                          int32_t ndim, int32_t dtype) {
+  if (!h || !key || !data || !shape) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  const std::string k(key);
+  const size_t dot = k.rfind('.');
+  if (dot == std::string::npos) return fail(SA_ERR_BAD_KEY, "unknown key '%s'", key);
+  const std::string layer = k.substr(0, dot), leaf = k.substr(dot + 1);
+  auto it = h->index.find(layer);
+  if (it == h->index.end()) return fail(SA_ERR_BAD_KEY, "unknown layer in key '%s'", key);
+  sa_conv& c = h->convs[it->second];
+  const int64_t d0 = c.transposed ? c.cin : c.cout, d1 = c.transposed ? c.cout : c.cin;
+
+  std::vector<float>* dst = nullptr;
+  bool* flag = nullptr;
+  int64_t expect[3] = {0, 0, 0};
+  int expect_nd = 0;
+  if (leaf == "weight_v" || leaf == "weight") {
+    expect[0] = d0; expect[1] = d1; expect[2] = c.k; expect_nd = 3;
+    dst = (leaf == "weight") ? &c.w : &c.v;
+    flag = (leaf == "weight") ? &c.has_w : &c.has_v;
+  } else if (leaf == "weight_g") {
+    expect[0] = d0; expect[1] = 1; expect[2] = 1; expect_nd = 3;   // weight_norm dim=0
+    dst = &c.g; flag = &c.has_g;
+  } else if (leaf == "bias") {
+    expect[0] = c.cout; expect_nd = 1;
+    dst = &c.bias; flag = &c.has_bias;
+  } else {
+    return fail(SA_ERR_BAD_KEY, "unknown parameter '%s' in key '%s'", leaf.c_str(), key);
+  }
+  if (ndim != expect_nd) return fail(SA_ERR_BAD_SHAPE, "%s: expected %d dims, got %d", key, expect_nd, ndim);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] != expect[i])
+      return fail(SA_ERR_BAD_SHAPE, "%s: dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)expect[i]);
+    n *= (size_t)shape[i];
+  }
+  size_t esz = 0;
+  switch (dtype) {
+    case SA_DTYPE_F32: esz = 4; break;
+    case SA_DTYPE_F16: case SA_DTYPE_BF16: esz = 2; break;
+    case SA_DTYPE_F64: esz = 8; break;
+    default: return fail(SA_ERR_INVALID_ARG, "%s: unsupported dtype %d", key, dtype);
+  }
+  std::vector<unsigned char> raw(n * esz);
+  SA_CUDA(cudaMemcpy(raw.data(), data, n * esz, cudaMemcpyDefault));   // host or device source
+  dst->resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    float f;
+    switch (dtype) {
+      case SA_DTYPE_F32: f = reinterpret_cast<const float*>(raw.data())[i]; break;
+      case SA_DTYPE_F64: f = (float)reinterpret_cast<const double*>(raw.data())[i]; break;
+      case SA_DTYPE_F16: f = __half2float(reinterpret_cast<const __half*>(raw.data())[i]); break;
+      default: f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(raw.data())[i]); break;
+    }
+    (*dst)[i] = f;
+  }
+  *flag = true;
+  if (leaf == "weight") { c.has_g = c.has_v = false; }
+  else if (leaf == "weight_g" || leaf == "weight_v") c.has_w = false;
+  h->finalized = false;
+  return SA_OK;
+}
+
+int sa_hifigan_finalize(sa_hifigan* h, int32_t precision) {
+  if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
+  if (precision != SA_PRECISION_FP32 && precision != SA_PRECISION_FP16 && precision != SA_PRECISION_BF16)
+    return fail(SA_ERR_INVALID_ARG, "unknown precision %d", precision);
+  SA_CUDA(cudaSetDevice(h->device));
+  // 1. fold weight-norm on the host: w = g * v / ||v||_2, norm over all dims but 0.
+  for (auto& c : h->convs) {
+    if (!c.has_bias) return fail(SA_ERR_MISSING_WEIGHT, "%s.bias was never set", c.name.c_str());
+    if (c.has_g && c.has_v) {
+      const int64_t d0 = c.transposed ? c.cin : c.cout;
+      const size_t inner = c.v.size() / (size_t)d0;
+      c.w.resize(c.v.size());
+      for (int64_t r = 0; r < d0; ++r) {
+        double ss = 0.0;
+        const float* vr = c.v.data() + r * inner;
+        for (size_t i = 0; i < inner; ++i) ss += (double)vr[i] * vr[i];
+        const float scale = (float)((double)c.g[r] / std::sqrt(ss));
+        for (size_t i = 0; i < inner; ++i) c.w[r * inner + i] = vr[i] * scale;
+      }
+    } else if (!c.has_w) {
+      return fail(SA_ERR_MISSING_WEIGHT, "%s: need weight_g + weight_v, or weight", c.name.c_str());
+    }
+  }
+  free_device_weights(h);
+  // 2. pack + upload.
+  for (auto& c : h->convs) {
+    SA_CUDA(cudaMalloc(&c.d_bias, c.cout * sizeof(float)));
+    SA_CUDA(cudaMemcpy(c.d_bias, c.bias.data(), c.cout * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  const bool is_post = true;
+  (void)is_post;
+  for (size_t li = 0; li < h->convs.size(); ++li) {
+    sa_conv& c = h->convs[li];
+    const bool need_f32 = precision == SA_PRECISION_FP32 || (int)li == h->conv_post() ||
+                          !sa::tc_layer_supported(c.transposed, c.cin, c.cout, c.k);
+    if (need_f32) {
+      // [Cin][k][Cout] from [Cout][Cin][k] (Conv1d) or [Cin][Cout][k] (ConvTranspose1d)
+      std::vector<float> p((size_t)c.cin * c.k * c.cout);
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int j = 0; j < c.k; ++j)
+          for (int co = 0; co < c.cout; ++co) {
+            const size_t src = c.transposed ? ((size_t)ci * c.cout + co) * c.k + j
+                                            : ((size_t)co * c.cin + ci) * c.k + j;
+            p[((size_t)ci * c.k + j) * c.cout + co] = c.w[src];
+          }
+      SA_CUDA(cudaMalloc(&c.d_w32, p.size() * sizeof(float)));
+      SA_CUDA(cudaMemcpy(c.d_w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (precision != SA_PRECISION_FP32 && !need_f32) {
+      const char* err = sa::tc_pack_weights(c.tc, c.w.data(), c.transposed, c.cin, c.cout, c.k, c.stride, c.pad,
+                                            precision == SA_PRECISION_BF16);
+      if (err) return fail(SA_ERR_CUDA, "%s: %s", c.name.c_str(), err);
+    }
+  }
+  if (precision != SA_PRECISION_FP32) {
+    const char* err = sa::tc_init(h->tc, h->device);
+    if (err) return fail(SA_ERR_CUDA, "tensor-core path init: %s", err);
+  }
+  h->precision = precision;
+  h->finalized = true;
+  return SA_OK;
+}
+
+int64_t sa_hifigan_output_length(const sa_hifigan* h, int64_t T) {
+  if (!h) return -1;
+  return h->stage_rate(h->cfg.n_stages - 1) * T + 1;
+}
+
+// Workspace: five fp32 activation buffers of the largest activation (fp32 path), or the
+// tensor-core path's own arena.
+static size_t buf_bytes(const sa_hifigan* h, int B, int T) {
+  return align_up((size_t)B * (size_t)T * (size_t)h->max_elems_per_frame() * sizeof(float), 256);
+}
+
+size_t sa_hifigan_workspace_bytes(const sa_hifigan* h, int32_t B, int32_t T) {
+  if (!h || B < 1 || T < 1) return 0;
+  if (h->finalized && h->precision != SA_PRECISION_FP32) return sa::tc_workspace_bytes(h->cfg, B, T);
+  return 5 * buf_bytes(h, B, T);
+}
+
+int sa_hifigan_set_debug_tap(sa_hifigan* h, int32_t tap, float* out) {
+  if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
+  if (out && (tap < 0 || tap > h->cfg.n_stages)) return fail(SA_ERR_INVALID_ARG, "tap %d out of range", tap);
+  h->debug_tap = out ? tap : -1;
+  h->debug_out = out;
+  return SA_OK;
+}
+
+int64_t sa_hifigan_last_launch_count(const sa_hifigan* h) { return h ? h->launches : -1; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// fp32 path
+// ---------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kTT = 128;
+constexpr int kCIB = 8;
+
+int launch_conv_f32(sa_hifigan* h, const sa_conv& c, const float* x, const float* res, float* y, int B, int64_t L,
+                    float slope_in, cudaStream_t st) {
+  const int halo = (c.k - 1) * c.dil;
+  dim3 grid((unsigned)((L + kTT - 1) / kTT), 1, (unsigned)B);
+  if (c.cout % 32 == 0) {
+    grid.y = c.cout / 32;
+    const size_t smem = (size_t)(kCIB * (kTT + halo) + kCIB * c.k * 32) * sizeof(float);
+    sa::conv1d_f32_kernel<32, kTT, kCIB><<<grid, kTT, smem, st>>>(x, c.d_w32, c.d_bias, res, y, c.cin, c.cout, (int)L,
+                                                                  c.k, c.dil, c.pad, slope_in);
+  } else if (c.cout % 16 == 0) {
+    grid.y = c.cout / 16;
+    const size_t smem = (size_t)(kCIB * (kTT + halo) + kCIB * c.k * 16) * sizeof(float);
+    sa::conv1d_f32_kernel<16, kTT, kCIB><<<grid, kTT, smem, st>>>(x, c.d_w32, c.d_bias, res, y, c.cin, c.cout, (int)L,
+                                                                  c.k, c.dil, c.pad, slope_in);
+  } else if (c.cout % 4 == 0) {
+    grid.y = c.cout / 4;
+    const size_t smem = (size_t)(kCIB * (kTT + halo) + kCIB * c.k * 4) * sizeof(float);
+    sa::conv1d_f32_kernel<4, kTT, kCIB><<<grid, kTT, smem, st>>>(x, c.d_w32, c.d_bias, res, y, c.cin, c.cout, (int)L,
+                                                                 c.k, c.dil, c.pad, slope_in);
+  } else {
+    return fail(SA_ERR_UNSUPPORTED, "%s: Cout=%d must be a multiple of 4", c.name.c_str(), c.cout);
+  }
+  h->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int launch_convt_f32(sa_hifigan* h, const sa_conv& c, const float* x, float* y, int B, int64_t Lin, float slope_in,
+                     cudaStream_t st) {
+  const int u = c.stride, taps = (c.k + u - 1) / u;
+  const int64_t Lout = Lin * u;
+  dim3 grid((unsigned)((Lout + kTT - 1) / kTT), 1, (unsigned)B);
+  const int xw_max = kTT / u + taps + 2;
+  if (c.cout % 16 == 0) {
+    grid.y = c.cout / 16;
+    const size_t smem = (size_t)(kCIB * xw_max + kCIB * c.k * 16) * sizeof(float);
+    sa::convt1d_f32_kernel<16, kTT, kCIB><<<grid, kTT, smem, st>>>(x, c.d_w32, c.d_bias, y, c.cin, c.cout, (int)Lin,
+                                                                   c.k, u, c.pad, slope_in);
+  } else if (c.cout % 4 == 0) {
+    grid.y = c.cout / 4;
+    const size_t smem = (size_t)(kCIB * xw_max + kCIB * c.k * 4) * sizeof(float);
+    sa::convt1d_f32_kernel<4, kTT, kCIB><<<grid, kTT, smem, st>>>(x, c.d_w32, c.d_bias, y, c.cin, c.cout, (int)Lin,
+                                                                  c.k, u, c.pad, slope_in);
+  } else {
+    return fail(SA_ERR_UNSUPPORTED, "%s: Cout=%d must be a multiple of 4", c.name.c_str(), c.cout);
+  }
+  h->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int launch_mrf(sa_hifigan* h, float* s, const float* r, float* out, size_t n, int mode, int nrb, cudaStream_t st) {
+  const int threads = 256;
+  const unsigned blocks = (unsigned)std::min<size_t>((n + threads - 1) / threads, (size_t)h->n_sm * 16);
+  sa::mrf_combine_f32_kernel<<<blocks, threads, 0, st>>>(s, r, out, n, mode, (float)nrb);
+  h->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int copy_tap(sa_hifigan* h, int tap, const float* src, size_t n, cudaStream_t st) {
+  if (h->debug_out && h->debug_tap == tap)
+    SA_CUDA(cudaMemcpyAsync(h->debug_out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SA_OK;
+}
+
+int forward_f32(sa_hifigan* h, const float* x, int B, int T, void* y, int y_dtype, void* ws, cudaStream_t st) {
+  const sa_hifigan_cfg& cfg = h->cfg;
+  const size_t bb = buf_bytes(h, B, T);
+  float* buf[5];
+  for (int i = 0; i < 5; ++i) buf[i] = reinterpret_cast<float*>(static_cast<char*>(ws) + i * bb);
+  float *P = buf[0], *X = buf[1], *R = buf[2], *Tm = buf[3], *S = buf[4];
+  int rc;
+
+  if ((rc = launch_conv_f32(h, h->convs[h->conv_pre()], x, nullptr, P, B, T, 1.0f, st))) return rc;       // archi.py:78
+  if ((rc = copy_tap(h, SA_TAP_CONV_PRE, P, (size_t)B * cfg.initial_channels * T, st))) return rc;
+  int64_t L = T;
+  for (int i = 0; i < cfg.n_stages; ++i) {
+    const sa_conv& up = h->convs[h->up(i)];
+    if ((rc = launch_convt_f32(h, up, P, X, B, L, 0.1f, st))) return rc;                                   // archi.py:80-81
+    L *= up.stride;
+    const size_t n = (size_t)B * up.cout * L;
+    for (int j = 0; j < cfg.n_resblocks; ++j) {
+      const float* src = X;
+      for (int m = 0; m < cfg.n_dilations; ++m) {                                                          // nn.py:169-174
+        if ((rc = launch_conv_f32(h, h->convs[h->rb(i, j, 0, m)], src, nullptr, Tm, B, L, 0.1f, st))) return rc;
+        if ((rc = launch_conv_f32(h, h->convs[h->rb(i, j, 1, m)], Tm, src, R, B, L, 0.1f, st))) return rc;
+        src = R;
+      }
+      const int mode = (j == cfg.n_resblocks - 1) ? 2 : (j == 0 ? 0 : 1);                                  // archi.py:82-86
+      if (cfg.n_resblocks == 1) {
+        SA_CUDA(cudaMemcpyAsync(P, R, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      } else if ((rc = launch_mrf(h, S, R, P, n, mode, cfg.n_resblocks, st))) return rc;
+    }
+    if ((rc = copy_tap(h, SA_TAP_STAGE0 + i, P, n, st))) return rc;
+  }
+  const sa_conv& post = h->convs[h->conv_post()];
+  {
+    const int threads = 256;
+    dim3 grid((unsigned)((L + 1 + threads - 1) / threads), (unsigned)B);
+    sa::conv_post_f32_kernel<<<grid, threads, 0, st>>>(P, post.d_w32, post.d_bias, y, post.cin, (int)L, post.k, 0.01f,
+                                                       y_dtype);                                          // archi.py:87-90
+    h->launches++;
+    SA_CUDA(cudaGetLastError());
+  }
+  return SA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, const int32_t* frames_per_item, void* y,
+                       int32_t y_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x || !y || !workspace) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
+  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2 frames (got B=%d T=%d)", B, T);
+  if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
+    return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(SA_ERR_INVALID_ARG, "x must be 16-byte and workspace 256-byte aligned");
+  const size_t need = sa_hifigan_workspace_bytes(h, B, T);
+  if (workspace_bytes < need)
+    return fail(SA_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if ((int64_t)T * h->stage_rate(h->cfg.n_stages - 1) + 1 > 0x7fffff00LL)
+    return fail(SA_ERR_INVALID_ARG, "T=%d too long: chunk the utterance", T);
+  if (frames_per_item)
+    for (int b = 0; b < B; ++b)
+      if (frames_per_item[b] < 1 || frames_per_item[b] > T)
+        return fail(SA_ERR_INVALID_ARG, "frames_per_item[%d]=%d outside [1,%d]", b, frames_per_item[b], T);
+  int cur = -1;
+  SA_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->launches = 0;
+  int rc;
+  if (h->precision == SA_PRECISION_FP32) {
+    rc = forward_f32(h, x, B, T, y, y_dtype, workspace, st);
+  } else {
+    sa::tc_forward_args a;
+    a.cfg = &h->cfg; a.x = x; a.B = B; a.T = T; a.frames_per_item = frames_per_item; a.y = y; a.y_dtype = y_dtype;
+    a.workspace = workspace; a.stream = st; a.debug_tap = h->debug_tap; a.debug_out = h->debug_out;
+    a.bf16 = h->precision == SA_PRECISION_BF16; a.n_sm = h->n_sm;
+    std::vector<sa::tc_layer> layers(h->convs.size());
+    for (size_t i = 0; i < h->convs.size(); ++i) {
+      const sa_conv& c = h->convs[i];
+      layers[i] = sa::tc_layer{&c.tc, c.d_w32, c.d_bias, c.cin, c.cout, c.k, c.dil, c.pad, c.stride, c.transposed};
+    }
+    a.layers = layers.data();
+    a.n_layers = (int)layers.size();
+    const char* err = sa::tc_forward(h->tc, a, &h->launches);
+    rc = err ? fail(SA_ERR_CUDA, "%s", err) : SA_OK;
+  }
+  if (cur != h->device) cudaSetDevice(cur);
+  return rc;
+}
+
+size_t sa_hifigan_host_scratch_bytes(const sa_hifigan* h, int32_t B, int32_t T, int32_t y_dtype) {
+  if (!h || B < 1 || T < 1) return 0;
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  const size_t xb = align_up((size_t)B * h->cfg.input_dim * T * sizeof(float), 256);
+  const size_t yb = align_up((size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz, 256);
+  return xb + yb + sa_hifigan_workspace_bytes(h, B, T);
+}
+
+int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
+                               const int32_t* frames_per_item, void* y_host, int32_t y_dtype, void* dev_scratch,
+                               size_t dev_scratch_bytes, void* stream) {
+  if (!h || !x_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
+  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2");
+  const size_t need = sa_hifigan_host_scratch_bytes(h, B, T, y_dtype);
+  if (dev_scratch_bytes < need) return fail(SA_ERR_WORKSPACE, "dev_scratch too small: %zu < %zu", dev_scratch_bytes, need);
+  if (reinterpret_cast<uintptr_t>(dev_scratch) & 255) return fail(SA_ERR_INVALID_ARG, "dev_scratch must be 256-byte aligned");
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  const size_t x_bytes = (size_t)B * h->cfg.input_dim * T * sizeof(float);
+  const size_t y_bytes = (size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz;
+  char* base = static_cast<char*>(dev_scratch);
+  float* xd = reinterpret_cast<float*>(base);
+  void* yd = base + align_up(x_bytes, 256);
+  void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+  const size_t ws_bytes = dev_scratch_bytes - align_up(x_bytes, 256) - align_up(y_bytes, 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cur = -1;
+  SA_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
+  SA_CUDA(cudaMemcpyAsync(xd, x_host, x_bytes, cudaMemcpyHostToDevice, st));
+  int rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, ws_bytes, stream);
+  if (rc == SA_OK) {
+    SA_CUDA(cudaMemcpyAsync(y_host, yd, y_bytes, cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+  }
+  if (cur != h->device) cudaSetDevice(cur);
+  return rc;
+}
+
+}  // extern "C"

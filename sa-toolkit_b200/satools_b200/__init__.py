@@ -1,0 +1,13 @@
+"""satools_b200 -- B200 (sm_100a) implementation of SA-toolkit's HiFi-GAN synthesis hot path.
+
+Public surface:
+  CoreHifiGan          drop-in for satools.hifigan.archi.CoreHifiGan (archi.py)
+  install()            rebind satools.hifigan.archi.CoreHifiGan to it (install.py)
+  scheduler            length-balanced utterance sharding for multi-GPU runs (scheduler.py)
+  synth                host-side batch driver: bucket, pad, convert, trim (synth.py)
+"""
+from .archi import CoreHifiGan, ResBlock1  # noqa: F401
+from .install import install, uninstall  # noqa: F401
+from . import scheduler  # noqa: F401
+
+__all__ = ["CoreHifiGan", "ResBlock1", "install", "uninstall", "scheduler"]

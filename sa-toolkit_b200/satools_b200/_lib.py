@@ -1,0 +1,88 @@
+"""ctypes binding of libsatools_hifigan.so (C ABI in include/sa_hifigan.h).
+
+There is no fallback: if the shared library is missing or fails to load, importing the
+compute path raises.  Build it with ``python __graft_entry__.py build`` (or
+``python -m satools_b200.build``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libsatools_hifigan.so"))
+
+MAX_STAGES = 8
+MAX_RB = 4
+
+DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64, DTYPE_PCM16 = 0, 1, 2, 3, 4
+PRECISION_FP32, PRECISION_FP16, PRECISION_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PRECISION_FP32, "fp16": PRECISION_FP16, "bf16": PRECISION_BF16}
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("input_dim", C.c_int32),
+        ("initial_channels", C.c_int32),
+        ("n_stages", C.c_int32),
+        ("upsample_rates", C.c_int32 * MAX_STAGES),
+        ("upsample_kernels", C.c_int32 * MAX_STAGES),
+        ("n_resblocks", C.c_int32),
+        ("resblock_kernels", C.c_int32 * MAX_RB),
+        ("n_dilations", C.c_int32),
+        ("resblock_dilations", (C.c_int32 * MAX_RB) * MAX_RB),
+        ("device", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes): every symbol include/sa_hifigan.h declares.
+SYMBOLS = {
+    "sa_hifigan_abi_version": (C.c_int, []),
+    "sa_hifigan_last_error": (C.c_char_p, []),
+    "sa_hifigan_default_cfg": (C.c_int, [C.POINTER(Cfg)]),
+    "sa_hifigan_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(C.c_void_p)]),
+    "sa_hifigan_destroy": (None, [C.c_void_p]),
+    "sa_hifigan_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
+    "sa_hifigan_finalize": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sa_hifigan_output_length": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "sa_hifigan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    "sa_hifigan_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_hifigan_host_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "sa_hifigan_synthesize_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                             C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_hifigan_set_debug_tap": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "sa_hifigan_last_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class SaHifiganError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SaHifiganError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python __graft_entry__.py build`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sa_hifigan_abi_version() != 1:
+        raise SaHifiganError("libsatools_hifigan.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().sa_hifigan_last_error()
+        raise SaHifiganError(f"sa_hifigan error {rc}: {msg.decode() if msg else ''}")

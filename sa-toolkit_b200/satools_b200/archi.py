@@ -1,0 +1,301 @@
+"""Drop-in replacement for ``satools.hifigan.archi.CoreHifiGan`` running on the B200 library.
+
+Mirrors the reference interface (/root/reference/satools/satools/hifigan/archi.py:21-116):
+same constructor keywords (incl. the ``imput_dim`` spelling), same sub-module names and hence
+the same 291 state-dict keys ``{conv_pre, ups.N, resblocks.M.convs{1,2}.K, conv_post}.
+{weight_g, weight_v, bias}`` (strict ``load_state_dict`` of a reference checkpoint works,
+infer_helper.py:57-58), ``forward(x) -> (wav, torch.empty(1))`` and ``remove_weight_norm()``.
+
+The parameters live in ordinary torch modules, but no torch op ever computes with them:
+``forward`` hands raw pointers to ``libsatools_hifigan.so`` (include/sa_hifigan.h), which folds
+weight-norm once, packs the weights for the sm_100a kernels and runs the whole generator.
+There is no CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+warnings.filterwarnings("ignore", message=r".*weight_norm is deprecated.*")
+from torch.nn.utils import remove_weight_norm, weight_norm  # noqa: E402  (old-style, as the reference: archi.py:4)
+
+_TORCH_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16,
+                torch.bfloat16: _lib.DTYPE_BF16, torch.float64: _lib.DTYPE_F64}
+_OUT_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.int16: _lib.DTYPE_PCM16}
+
+
+def _redraw(conv: nn.Module) -> None:
+    # The reference calls init_weights (normal(0, 0.01) on `.weight`, nn.py:11-14) after
+    # weight_norm has wrapped the conv.  That write is overwritten by the weight_norm hook on
+    # the next forward, i.e. it changes no effective weight -- but it advances the global RNG.
+    # Drawing the same amount here keeps "same seed -> same random weights as the reference".
+    conv.weight.data.normal_(0.0, 0.01)
+
+
+class ResBlock1(nn.Module):
+    """Parameter container with the layout of satools.hifigan.nn.ResBlock1 (nn.py:93-166)."""
+
+    def __init__(self, channels: int, kernel_size: int, dilation: Sequence[int]):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.dilation = tuple(dilation)
+        self.convs1 = nn.ModuleList(
+            weight_norm(nn.Conv1d(channels, channels, kernel_size, 1, dilation=d,
+                                  padding=(kernel_size * d - d) // 2)) for d in dilation)
+        for c in self.convs1:
+            _redraw(c)
+        self.convs2 = nn.ModuleList(
+            weight_norm(nn.Conv1d(channels, channels, kernel_size, 1, dilation=1,
+                                  padding=(kernel_size - 1) // 2)) for _ in dilation)
+        for c in self.convs2:
+            _redraw(c)
+
+    def remove_weight_norm(self):
+        for c in list(self.convs1) + list(self.convs2):
+            remove_weight_norm(c)
+
+
+class CoreHifiGan(nn.Module):
+    """B200-native HiFi-GAN generator; see module docstring."""
+
+    def __init__(
+        self,
+        upsample_rates=[5, 4, 4, 2, 2],
+        upsample_kernel_sizes=[11, 8, 8, 4, 4],
+        imput_dim=256 + 1,
+        upsample_initial_channel=512,
+        resblock_kernel_sizes=[3, 7, 11],
+        resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+        iSTFTNetout=False,
+        iSTFTNet_n_fft=16,
+        precision: Optional[str] = None,
+    ):
+        super().__init__()
+        if iSTFTNetout:
+            raise NotImplementedError("iSTFTNetout=True is never enabled by any SA-toolkit model file; not supported")
+        self.iSTFTNetout = False
+        self.resblock_kernel_sizes = list(resblock_kernel_sizes)
+        self.resblock_dilation_sizes = [list(d) for d in resblock_dilation_sizes]
+        self.num_kernels = len(resblock_kernel_sizes)
+        self.upsample_rates = list(upsample_rates)
+        self.upsample_kernel_sizes = list(upsample_kernel_sizes)
+        self.imput_dim = imput_dim
+        self.upsample_initial_channel = upsample_initial_channel
+        self.precision = precision or os.environ.get("SATOOLS_B200_PRECISION", "fp16")
+
+        # Same construction order as the reference so the RNG stream is consumed identically.
+        self.conv_pre = weight_norm(nn.Conv1d(imput_dim, upsample_initial_channel, 7, 1, padding=3))
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(upsample_rates, upsample_kernel_sizes)):
+            self.ups.append(weight_norm(nn.ConvTranspose1d(
+                upsample_initial_channel // (2 ** i), upsample_initial_channel // (2 ** (i + 1)),
+                k, u, padding=(k - u) // 2)))
+        self.resblocks = nn.ModuleList()
+        ch = upsample_initial_channel
+        for i in range(len(self.ups)):
+            ch = upsample_initial_channel // (2 ** (i + 1))
+            for k, d in zip(resblock_kernel_sizes, resblock_dilation_sizes):
+                self.resblocks.append(ResBlock1(ch, k, d))
+        self.conv_post = weight_norm(nn.Conv1d(ch, 1, 7, 1, padding=3))
+        for up in self.ups:
+            _redraw(up)
+        _redraw(self.conv_post)
+
+        self._handle: Optional[int] = None
+        self._handle_pid = -1
+        self._handle_device = -1
+        self._weights_sig = None
+        self._finalized_precision = None
+        self._workspace: Optional[torch.Tensor] = None
+        self._host_scratch: Optional[torch.Tensor] = None
+        self._debug_buf: Optional[torch.Tensor] = None
+        self.last_launch_count = 0
+
+    # ---- reference API -----------------------------------------------------------------
+    def remove_weight_norm(self):
+        """archi.py:109-115."""
+        for up in self.ups:
+            remove_weight_norm(up)
+        for rb in self.resblocks:
+            rb.remove_weight_norm()
+        remove_weight_norm(self.conv_pre)
+        remove_weight_norm(self.conv_post)
+
+    def output_length(self, frames: int) -> int:
+        r = 1
+        for u in self.upsample_rates:
+            r *= u
+        return r * frames + 1
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, frames_per_item: Optional[Sequence[int]] = None,
+                out_dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x [B, imput_dim, T] on a CUDA device -> (wav [B, 1, 320*T+1], torch.empty(1)) as
+        archi.py:93-107.  The autocast context the caller holds (hifigan.py:99) is ignored."""
+        if not x.is_cuda:
+            raise RuntimeError("satools_b200.CoreHifiGan runs on CUDA (sm_100a) only; got a CPU tensor. "
+                               "There is no CPU fallback.")
+        if x.dim() != 3 or x.shape[1] != self.imput_dim:
+            raise ValueError(f"expected x [B, {self.imput_dim}, T], got {tuple(x.shape)}")
+        lib = _lib.load()
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, T = x.shape
+        with torch.cuda.device(x.device):
+            self._ensure_ready(x.device)
+            need = lib.sa_hifigan_workspace_bytes(self._handle, B, T)
+            ws = self._get_workspace(need, x.device)
+            y = torch.empty((B, 1, self.output_length(T)), dtype=out_dtype, device=x.device)
+            fpi = None
+            if frames_per_item is not None:
+                fpi = (C.c_int32 * B)(*[int(v) for v in frames_per_item])
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.sa_hifigan_forward(self._handle, x.data_ptr(), B, T, fpi, y.data_ptr(),
+                                              _OUT_DTYPE[out_dtype], ws.data_ptr(), ws.numel(), stream))
+            self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
+        return (y, torch.empty((1)))
+
+    # ---- host-buffer entry (anonymize pipeline: H2D, convert, D2H; pipeline.py:104-149) ----
+    @torch.no_grad()
+    def synthesize_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None,
+                        out_dtype: torch.dtype = torch.float32, device=None,
+                        frames_per_item: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """x_host: CPU fp32 [B, imput_dim, T] (pinned for full speed).  Returns a CPU tensor
+        [B, 1, 320*T+1]; host<->device copies happen inside the C-ABI call."""
+        if x_host.is_cuda:
+            raise ValueError("synthesize_host takes a CPU tensor")
+        lib = _lib.load()
+        device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        x_host = x_host.to(torch.float32).contiguous()
+        B, _, T = x_host.shape
+        if out is None:
+            out = torch.empty((B, 1, self.output_length(T)), dtype=out_dtype, pin_memory=True)
+        with torch.cuda.device(device):
+            self._ensure_ready(device)
+            need = lib.sa_hifigan_host_scratch_bytes(self._handle, B, T, _OUT_DTYPE[out.dtype])
+            if self._host_scratch is None or self._host_scratch.numel() < need or self._host_scratch.device != device:
+                self._host_scratch = None
+                self._host_scratch = torch.empty(need, dtype=torch.uint8, device=device)
+            fpi = None
+            if frames_per_item is not None:
+                fpi = (C.c_int32 * B)(*[int(v) for v in frames_per_item])
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.sa_hifigan_synthesize_host(self._handle, x_host.data_ptr(), B, T, fpi, out.data_ptr(),
+                                                      _OUT_DTYPE[out.dtype], self._host_scratch.data_ptr(),
+                                                      self._host_scratch.numel(), stream))
+            self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
+        return out
+
+    # ---- test hook: stage activations ------------------------------------------------------
+    @torch.no_grad()
+    def forward_with_tap(self, x: torch.Tensor, tap: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Run forward and also return activation `tap` (0 = conv_pre, 1+i = stage i) as fp32 [B,C,L]."""
+        lib = _lib.load()
+        B, _, T = x.shape
+        with torch.cuda.device(x.device):
+            self._ensure_ready(x.device)
+            if tap == 0:
+                c, length = self.upsample_initial_channel, T
+            else:
+                c, length = self.upsample_initial_channel >> tap, T
+                for u in self.upsample_rates[:tap]:
+                    length *= u
+            buf = torch.zeros((B, c, length), dtype=torch.float32, device=x.device)
+            _lib.check(lib.sa_hifigan_set_debug_tap(self._handle, tap, buf.data_ptr()))
+            try:
+                y, _ = self.forward(x)
+                torch.cuda.synchronize(x.device)
+            finally:
+                lib.sa_hifigan_set_debug_tap(self._handle, 0, None)
+        return y, buf
+
+    # ---- internals ---------------------------------------------------------------------
+    def _cfg(self, device_index: int) -> "_lib.Cfg":
+        cfg = _lib.Cfg()
+        cfg.input_dim = self.imput_dim
+        cfg.initial_channels = self.upsample_initial_channel
+        cfg.n_stages = len(self.upsample_rates)
+        for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
+            cfg.upsample_rates[i] = u
+            cfg.upsample_kernels[i] = k
+        cfg.n_resblocks = len(self.resblock_kernel_sizes)
+        cfg.n_dilations = len(self.resblock_dilation_sizes[0])
+        for j, k in enumerate(self.resblock_kernel_sizes):
+            cfg.resblock_kernels[j] = k
+            if len(self.resblock_dilation_sizes[j]) != cfg.n_dilations:
+                raise ValueError("all ResBlocks must have the same number of dilations")
+            for m, d in enumerate(self.resblock_dilation_sizes[j]):
+                cfg.resblock_dilations[j][m] = d
+        cfg.device = device_index
+        return cfg
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_ready(self, device: torch.device) -> None:
+        lib = _lib.load()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle is not None and (self._handle_pid != os.getpid() or self._handle_device != idx):
+            if self._handle_pid == os.getpid():
+                lib.sa_hifigan_destroy(self._handle)
+            self._handle = None                      # a forked child never touches the parent's handle
+        if self._handle is None:
+            out = C.c_void_p()
+            cfg = self._cfg(idx)
+            _lib.check(lib.sa_hifigan_create(C.byref(cfg), C.byref(out)))
+            self._handle, self._handle_pid, self._handle_device = out.value, os.getpid(), idx
+            self._weights_sig = None
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}")
+        sig = self._signature()
+        if sig != self._weights_sig or self._finalized_precision != self.precision:
+            if sig != self._weights_sig:
+                for name, p in self.named_parameters():
+                    t = p.detach()
+                    if t.dtype not in _TORCH_DTYPE:
+                        t = t.float()
+                    t = t.contiguous()
+                    shape = (C.c_int64 * t.dim())(*t.shape)
+                    _lib.check(lib.sa_hifigan_set_weight(self._handle, name.encode(), t.data_ptr(), shape,
+                                                         t.dim(), _TORCH_DTYPE[t.dtype]))
+            _lib.check(lib.sa_hifigan_finalize(self._handle, _lib.PRECISIONS[self.precision]))
+            self._weights_sig = sig
+            self._finalized_precision = self.precision
+
+    def _get_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            self._workspace = None                   # release before growing
+            self._workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        return self._workspace
+
+    def release(self) -> None:
+        """Free the native handle and cached device buffers."""
+        if self._handle is not None and self._handle_pid == os.getpid():
+            _lib.load().sa_hifigan_destroy(self._handle)
+        self._handle = None
+        self._workspace = None
+        self._host_scratch = None
+        self._weights_sig = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle_pid == os.getpid():
+                _lib.load().sa_hifigan_destroy(self._handle)
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        # Pickling / deepcopy (DataLoader workers capture the model, pipeline.py:175): the native
+        # handle and device scratch stay behind.
+        state = self.__dict__.copy()
+        for k in ("_handle", "_workspace", "_host_scratch", "_weights_sig", "_finalized_precision", "_debug_buf"):
+            state[k] = None
+        state["_handle_pid"] = -1
+        return state

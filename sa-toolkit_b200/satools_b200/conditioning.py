@@ -1,0 +1,59 @@
+"""Synthetic conditioning features with the structure of the real ones.
+
+x[B, 256+1+n_spk, T] as assembled by Net._forward
+(/root/reference/egs/vc/libritts/local/tuning/hifigan.py:83-97): channels 0..255 are the
+ASR bottleneck (rows of a 48-entry VQ codebook, held for geometric run lengths), channel 256
+the CMVN-normalised F0 (0 on unvoiced frames), channels 257.. the one-hot target speaker,
+constant in time.  numpy's PCG64 generator makes it reproducible on any host.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+N_BN = 256
+N_CODEWORDS = 48
+N_SPEAKERS = 247
+
+
+def codebook(seed: int = 1234) -> np.ndarray:
+    return np.random.default_rng(seed).standard_normal((N_CODEWORDS, N_BN)).astype(np.float32)
+
+
+def utterance(rng: np.random.Generator, frames: int, n_spk: int = N_SPEAKERS,
+              cb: Optional[np.ndarray] = None, voiced_fraction: float = 0.6) -> np.ndarray:
+    """One utterance: float32 [256+1+n_spk, frames]."""
+    cb = codebook() if cb is None else cb
+    idx = np.empty(frames, dtype=np.int64)
+    f0 = np.zeros(frames, dtype=np.float32)
+    t = 0
+    while t < frames:                       # VQ index held for a geometric run (mean 4 frames)
+        run = int(rng.geometric(0.25))
+        idx[t:t + run] = rng.integers(N_CODEWORDS)
+        t += run
+    t = 0
+    while t < frames:                       # alternating voiced / unvoiced segments
+        seg = int(rng.integers(5, 40))
+        if rng.random() < voiced_fraction:
+            f0[t:t + seg] = rng.standard_normal(min(seg, frames - t)).astype(np.float32)
+        t += seg
+    x = np.zeros((N_BN + 1 + n_spk, frames), dtype=np.float32)
+    x[:N_BN] = cb[idx].T
+    x[N_BN] = f0
+    x[N_BN + 1 + int(rng.integers(n_spk))] = 1.0
+    return x
+
+
+def batch(seed: int, frames: Sequence[int], n_spk: int = N_SPEAKERS, pad_to: Optional[int] = None) -> np.ndarray:
+    """Batch padded to the longest item the way the pipeline pads (zeros in BN/F0, but the
+    speaker one-hot stays on: it is interpolated over the padded length, hifigan.py:94-97)."""
+    rng = np.random.default_rng(seed)
+    cb = codebook()
+    T = max(frames) if pad_to is None else pad_to
+    out = np.zeros((len(frames), N_BN + 1 + n_spk, T), dtype=np.float32)
+    for b, n in enumerate(frames):
+        u = utterance(rng, n, n_spk, cb)
+        out[b, :, :n] = u
+        out[b, N_BN + 1:, n:] = u[N_BN + 1:, :1]
+    return out
