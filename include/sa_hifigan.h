@@ -19,6 +19,8 @@
  *                           Net._forward, egs/vc/libritts/local/tuning/hifigan.py:99-100)
  *   sa_hifigan_synthesize_host   the H2D / convert / D2H sequence of the anonymize pipeline
  *                           satools/satools/bin/pipeline.py:104-107,148-149
+ *   sa_hifigan_set_profiling / sa_hifigan_get_profile  (no reference counterpart; the reference has
+ *                           no profiler hooks) per-launch CUDA-event timing
  *   sa_hifigan_set_debug_tap  (no reference counterpart; exposes stage activations so the
  *                           parity tests can localise a mismatch)
  *
@@ -139,6 +141,16 @@ int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, in
  * as fp32 [B,C,L] to `out` (device memory, caller sized: conv_pre B*initial_channels*T,
  * stage i B*C_i*L_i floats).  out = NULL switches it off. */
 int sa_hifigan_set_debug_tap(sa_hifigan* h, int32_t tap, float* out);
+
+/* Per-launch device timing (off by default; costs two CUDA events per launch).  While it is
+ * on, every forward records an event before each kernel launch.  sa_hifigan_get_profile waits
+ * for the stream and returns, for each launch of the most recent forward in launch order, its
+ * duration in milliseconds and a tag = 16 * section + kind, where section 0 is conv_pre
+ * (and input packing), 1 + i is stage i, n_stages + 1 is the tail, and kind 0 is the section's
+ * own conv (conv_pre / upsampler / conv_post), 1 + j a conv of ResBlock j, 15 anything else.
+ * Returns the number of launches (<= max_n entries are written). */
+int sa_hifigan_set_profiling(sa_hifigan* h, int32_t enable);
+int sa_hifigan_get_profile(sa_hifigan* h, float* ms, int32_t* tags, int32_t max_n);
 
 /* Kernel launches enqueued by the most recent forward on this handle. */
 int64_t sa_hifigan_last_launch_count(const sa_hifigan* h);

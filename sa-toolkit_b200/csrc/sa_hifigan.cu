@@ -70,6 +70,24 @@ struct sa_hifigan {
   float* debug_out = nullptr;
   int n_sm = 148;
   sa::tc_context tc;
+  // per-launch profiling: one event before every launch + one closing event
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_tag;
+  int prof_n = 0;
+  cudaStream_t prof_stream = nullptr;
+  void mark(int tag, cudaStream_t st) {
+    if (!prof_on) return;
+    if (prof_n == (int)prof_ev.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      prof_ev.push_back(e);
+      prof_tag.push_back(0);
+    }
+    prof_tag[prof_n] = tag;
+    cudaEventRecord(prof_ev[prof_n++], st);
+    prof_stream = st;
+  }
 
   int conv_pre() const { return 0; }
   int up(int i) const { return 1 + i; }
@@ -192,6 +210,7 @@ void sa_hifigan_destroy(sa_hifigan* h) {
   if (cudaGetDevice(&cur) == cudaSuccess) {
     cudaSetDevice(h->device);
     free_device_weights(h);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     cudaSetDevice(cur);
   }
   delete h;
@@ -361,7 +380,8 @@ constexpr int kTT = 128;
 constexpr int kCIB = 8;
 
 int launch_conv_f32(sa_hifigan* h, const sa_conv& c, const float* x, const float* res, float* y, int B, int64_t L,
-                    float slope_in, cudaStream_t st) {
+                    float slope_in, cudaStream_t st, int tag) {
+  h->mark(tag, st);
   const int halo = (c.k - 1) * c.dil;
   dim3 grid((unsigned)((L + kTT - 1) / kTT), 1, (unsigned)B);
   if (c.cout % 32 == 0) {
@@ -388,7 +408,8 @@ int launch_conv_f32(sa_hifigan* h, const sa_conv& c, const float* x, const float
 }
 
 int launch_convt_f32(sa_hifigan* h, const sa_conv& c, const float* x, float* y, int B, int64_t Lin, float slope_in,
-                     cudaStream_t st) {
+                     cudaStream_t st, int tag) {
+  h->mark(tag, st);
   const int u = c.stride, taps = (c.k + u - 1) / u;
   const int64_t Lout = Lin * u;
   dim3 grid((unsigned)((Lout + kTT - 1) / kTT), 1, (unsigned)B);
@@ -411,7 +432,9 @@ int launch_convt_f32(sa_hifigan* h, const sa_conv& c, const float* x, float* y, 
   return SA_OK;
 }
 
-int launch_mrf(sa_hifigan* h, float* s, const float* r, float* out, size_t n, int mode, int nrb, cudaStream_t st) {
+int launch_mrf(sa_hifigan* h, float* s, const float* r, float* out, size_t n, int mode, int nrb, cudaStream_t st,
+               int tag) {
+  h->mark(tag, st);
   const int threads = 256;
   const unsigned blocks = (unsigned)std::min<size_t>((n + threads - 1) / threads, (size_t)h->n_sm * 16);
   sa::mrf_combine_f32_kernel<<<blocks, threads, 0, st>>>(s, r, out, n, mode, (float)nrb);
@@ -434,25 +457,25 @@ int forward_f32(sa_hifigan* h, const float* x, int B, int T, void* y, int y_dtyp
   float *P = buf[0], *X = buf[1], *R = buf[2], *Tm = buf[3], *S = buf[4];
   int rc;
 
-  if ((rc = launch_conv_f32(h, h->convs[h->conv_pre()], x, nullptr, P, B, T, 1.0f, st))) return rc;       // archi.py:78
+  if ((rc = launch_conv_f32(h, h->convs[h->conv_pre()], x, nullptr, P, B, T, 1.0f, st, 0))) return rc;       // archi.py:78
   if ((rc = copy_tap(h, SA_TAP_CONV_PRE, P, (size_t)B * cfg.initial_channels * T, st))) return rc;
   int64_t L = T;
   for (int i = 0; i < cfg.n_stages; ++i) {
     const sa_conv& up = h->convs[h->up(i)];
-    if ((rc = launch_convt_f32(h, up, P, X, B, L, 0.1f, st))) return rc;                                   // archi.py:80-81
+    if ((rc = launch_convt_f32(h, up, P, X, B, L, 0.1f, st, 16 * (1 + i)))) return rc;                                   // archi.py:80-81
     L *= up.stride;
     const size_t n = (size_t)B * up.cout * L;
     for (int j = 0; j < cfg.n_resblocks; ++j) {
       const float* src = X;
       for (int m = 0; m < cfg.n_dilations; ++m) {                                                          // nn.py:169-174
-        if ((rc = launch_conv_f32(h, h->convs[h->rb(i, j, 0, m)], src, nullptr, Tm, B, L, 0.1f, st))) return rc;
-        if ((rc = launch_conv_f32(h, h->convs[h->rb(i, j, 1, m)], Tm, src, R, B, L, 0.1f, st))) return rc;
+        if ((rc = launch_conv_f32(h, h->convs[h->rb(i, j, 0, m)], src, nullptr, Tm, B, L, 0.1f, st, 16 * (1 + i) + 1 + j))) return rc;
+        if ((rc = launch_conv_f32(h, h->convs[h->rb(i, j, 1, m)], Tm, src, R, B, L, 0.1f, st, 16 * (1 + i) + 1 + j))) return rc;
         src = R;
       }
       const int mode = (j == cfg.n_resblocks - 1) ? 2 : (j == 0 ? 0 : 1);                                  // archi.py:82-86
       if (cfg.n_resblocks == 1) {
         SA_CUDA(cudaMemcpyAsync(P, R, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      } else if ((rc = launch_mrf(h, S, R, P, n, mode, cfg.n_resblocks, st))) return rc;
+      } else if ((rc = launch_mrf(h, S, R, P, n, mode, cfg.n_resblocks, st, 16 * (1 + i) + 15))) return rc;
     }
     if ((rc = copy_tap(h, SA_TAP_STAGE0 + i, P, n, st))) return rc;
   }
@@ -460,6 +483,7 @@ int forward_f32(sa_hifigan* h, const float* x, int B, int T, void* y, int y_dtyp
   {
     const int threads = 256;
     dim3 grid((unsigned)((L + 1 + threads - 1) / threads), (unsigned)B);
+    h->mark(16 * (cfg.n_stages + 1), st);
     sa::conv_post_f32_kernel<<<grid, threads, 0, st>>>(P, post.d_w32, post.d_bias, y, post.cin, (int)L, post.k, 0.01f,
                                                        y_dtype);                                          // archi.py:87-90
     h->launches++;
@@ -495,6 +519,7 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, cons
   if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   h->launches = 0;
+  h->prof_n = 0;
   int rc;
   if (h->precision == SA_PRECISION_FP32) {
     rc = forward_f32(h, x, B, T, y, y_dtype, workspace, st);
@@ -510,11 +535,36 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, cons
     }
     a.layers = layers.data();
     a.n_layers = (int)layers.size();
+    a.mark_ctx = h;
+    a.mark = h->prof_on ? +[](void* ctx, int tag, cudaStream_t s) { static_cast<sa_hifigan*>(ctx)->mark(tag, s); }
+                        : nullptr;
     const char* err = sa::tc_forward(h->tc, a, &h->launches);
     rc = err ? fail(SA_ERR_CUDA, "%s", err) : SA_OK;
   }
+  h->mark(-1, st);
   if (cur != h->device) cudaSetDevice(cur);
   return rc;
+}
+
+int sa_hifigan_set_profiling(sa_hifigan* h, int32_t enable) {
+  if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
+  h->prof_on = enable != 0;
+  h->prof_n = 0;
+  return SA_OK;
+}
+
+int sa_hifigan_get_profile(sa_hifigan* h, float* ms, int32_t* tags, int32_t max_n) {
+  if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
+  if (h->prof_n < 2) return 0;
+  SA_CUDA(cudaEventSynchronize(h->prof_ev[h->prof_n - 1]));
+  const int n = h->prof_n - 1;
+  for (int i = 0; i < n && i < max_n; ++i) {
+    float t = 0.f;
+    SA_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+    if (ms) ms[i] = t;
+    if (tags) tags[i] = h->prof_tag[i];
+  }
+  return n;
 }
 
 size_t sa_hifigan_host_scratch_bytes(const sa_hifigan* h, int32_t B, int32_t T, int32_t y_dtype) {

@@ -42,6 +42,8 @@ struct tc_forward_args {
   int n_sm;
   const tc_layer* layers;
   int n_layers;
+  void* mark_ctx = nullptr;                                   // per-launch profiling hook
+  void (*mark)(void* ctx, int tag, cudaStream_t s) = nullptr;
 };
 
 bool tc_layer_supported(bool transposed, int cin, int cout, int k);

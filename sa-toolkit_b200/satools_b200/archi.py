@@ -107,6 +107,12 @@ class CoreHifiGan(nn.Module):
         for up in self.ups:
             _redraw(up)
         _redraw(self.conv_post)
+        # weight_norm() leaves a non-leaf `.weight` attribute behind, which breaks deepcopy /
+        # pickling (the reference works around it with fix_weight_norm_deepcopy, nn.py:177-181).
+        # Nothing here ever reads it, so keep a detached copy.
+        for m in self.modules():
+            if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)) and "weight" in m.__dict__:
+                m.weight = m.weight.detach()
 
         self._handle: Optional[int] = None
         self._handle_pid = -1
@@ -214,6 +220,29 @@ class CoreHifiGan(nn.Module):
             finally:
                 lib.sa_hifigan_set_debug_tap(self._handle, 0, None)
         return y, buf
+
+    @torch.no_grad()
+    def profile(self, x: torch.Tensor, repeats: int = 1):
+        """Per-launch device times of forward(x) (CUDA events on the launching stream).
+        Returns a list of (tag, milliseconds) averaged over `repeats` runs; tag = 16*section + kind
+        (see include/sa_hifigan.h)."""
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            self._ensure_ready(x.device)
+            _lib.check(lib.sa_hifigan_set_profiling(self._handle, 1))
+            try:
+                acc = None
+                for _ in range(repeats):
+                    self.forward(x)
+                    n = lib.sa_hifigan_get_profile(self._handle, None, None, 0)
+                    ms = (C.c_float * n)()
+                    tags = (C.c_int32 * n)()
+                    lib.sa_hifigan_get_profile(self._handle, ms, tags, n)
+                    cur = [float(v) for v in ms]
+                    acc = cur if acc is None else [a + b for a, b in zip(acc, cur)]
+                return [(int(t), v / repeats) for t, v in zip(tags, acc)]
+            finally:
+                lib.sa_hifigan_set_profiling(self._handle, 0)
 
     # ---- internals ---------------------------------------------------------------------
     def _cfg(self, device_index: int) -> "_lib.Cfg":

@@ -1,0 +1,193 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI via the drop-in
+module, against (a) the golden vectors minted from the reference and (b) the CPU oracles on
+the same seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8c), all against the fp64 truth:
+  fp32 mode : SNR >= 100 dB, max-abs <= 1e-5     (fp32 FMA accumulation; the parity mode)
+  fp16 mode : SNR >=  50 dB, max-abs <= 1e-3     (fp16 tensor-core operands, fp32 accumulate)
+  bf16 mode : max-abs <= 1e-3, SNR >= 40 dB      (bf16 operands; 50 dB is seed dependent on
+                                                  random-init weights)
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import hifigan_numpy as onp
+from oracle import hifigan_torch_cpu as otc
+from satools_b200 import conditioning, scheduler
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": (100.0, 1e-5), "fp16": (50.0, 1e-3), "bf16": (40.0, 1e-3)}
+GEN_CASES = sorted(helpers.manifest()["generator"].items())
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+_DEV_GEN = {}
+
+
+def dev_gen(seed, precision):
+    _need_gpu()
+    if seed not in _DEV_GEN:
+        _DEV_GEN[seed] = copy.deepcopy(helpers.seeded_generator(seed)).to("cuda:0")
+    g = _DEV_GEN[seed]
+    g.precision = precision
+    return g
+
+
+def run(gen, x_np, **kw):
+    y, aux = gen(torch.from_numpy(np.ascontiguousarray(x_np)).to("cuda:0"), **kw)
+    torch.cuda.synchronize()
+    assert tuple(aux.shape) == (1,)
+    return y.cpu().numpy()
+
+
+def check(ref, y, precision, what=""):
+    snr, mx = helpers.snr_db(ref, y), helpers.max_abs(ref, y)
+    min_snr, max_err = TOL[precision]
+    print(f"{what} [{precision}] SNR {snr:.1f} dB max-abs {mx:.2e}")
+    assert np.isfinite(y).all()
+    assert mx <= max_err, f"{what} {precision}: max-abs {mx:.3e} > {max_err}"
+    assert snr >= min_snr, f"{what} {precision}: SNR {snr:.1f} dB < {min_snr}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("name,meta", GEN_CASES)
+def test_matches_reference_golden(name, meta, precision):
+    g = np.load(os.path.join(helpers.GOLDEN, name + ".npz"))
+    gen = dev_gen(meta["seed"], precision)
+    x = conditioning.batch(meta["cond_seed"], meta["frames"])
+    y = run(gen, x)
+    assert list(y.shape) == meta["y_shape"]
+    check(g["y_ref_fp64"], y, precision, name)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_stage_activations_match_reference(precision):
+    name, meta = GEN_CASES[1]
+    g = np.load(os.path.join(helpers.GOLDEN, name + ".npz"))
+    gen = dev_gen(meta["seed"], precision)
+    x = torch.from_numpy(conditioning.batch(meta["cond_seed"], meta["frames"])).to("cuda:0")
+    for tap in range(6):
+        _, act = gen.forward_with_tap(x, tap)
+        got = helpers.stage_slices(act.cpu().numpy())
+        ref = g[f"stage{tap}"]
+        snr = helpers.snr_db(ref, got)
+        print(f"tap {tap} [{precision}] SNR {snr:.1f} dB")
+        assert snr >= (100.0 if precision == "fp32" else 45.0), f"stage tap {tap}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("B,T", [(1, 2), (1, 3), (2, 9), (3, 64), (1, 250), (2, 129)])
+def test_matches_cpu_oracle_shapes(B, T, precision):
+    """Edge and ragged shapes: T=2 is the shortest legal input (ReflectionPad1d needs 2 samples);
+    dense random input instead of structured conditioning."""
+    gen = dev_gen(0, precision)
+    rng = np.random.default_rng(100 * B + T)
+    x = rng.standard_normal((B, 504, T)).astype(np.float32)
+    ref = otc.generator_forward(otc.fold(helpers.seeded_generator(0).state_dict(), torch.float64),
+                                torch.from_numpy(x).double()).numpy()
+    y = run(gen, x)
+    assert y.shape == (B, 1, 320 * T + 1)
+    check(ref, y, precision, f"B{B} T{T}")
+
+
+def test_batch_items_are_independent_fp32():
+    """Utterances are independent units: an item synthesized inside a batch equals the
+    same item synthesized alone, bit for bit in the fp32 path."""
+    gen = dev_gen(1, "fp32")
+    x = conditioning.batch(5, [40, 40, 40])
+    yb = run(gen, x)
+    for b in range(3):
+        np.testing.assert_array_equal(yb[b:b + 1], run(gen, x[b:b + 1]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_chunked_equals_unchunked(precision):
+    """Halo-20 windows reproduce the unchunked waveform (the latency path of config 4)."""
+    gen = dev_gen(0, precision)
+    T = 300
+    x = conditioning.batch(9, [T])
+    full = run(gen, x)
+    out = np.zeros_like(full)
+    for rlo, rhi, klo, khi in scheduler.chunks(T, 128):
+        y = run(gen, x[:, :, rlo:rhi])
+        lo, hi = 320 * (klo - rlo), 320 * (khi - rlo)
+        if klo == 0:
+            out[:, :, :1 + 320 * khi] = y[:, :, :1 + hi]
+        else:
+            out[:, :, 1 + 320 * klo:1 + 320 * khi] = y[:, :, 1 + lo:1 + hi]
+    snr = helpers.snr_db(full, out)
+    print(f"chunked vs unchunked [{precision}] SNR {snr:.1f} dB")
+    assert snr >= (120.0 if precision == "fp32" else 50.0)
+
+
+def test_output_dtypes_and_host_entry():
+    gen = dev_gen(0, "fp32")
+    x = conditioning.batch(3, [24, 17])
+    y = run(gen, x)
+    y16 = run(gen, x, out_dtype=torch.float16)
+    pcm = run(gen, x, out_dtype=torch.int16)
+    assert y16.dtype == np.float16 and pcm.dtype == np.int16
+    np.testing.assert_allclose(y16.astype(np.float32), y, atol=1e-3)
+    np.testing.assert_array_equal(pcm, np.clip(np.rint(y * 32767.0), -32768, 32767).astype(np.int16))
+    xh = torch.from_numpy(x).pin_memory()
+    yh = gen.synthesize_host(xh)
+    assert not yh.is_cuda
+    np.testing.assert_array_equal(yh.numpy(), y)
+
+
+def test_weight_update_and_remove_weight_norm():
+    gen = copy.deepcopy(helpers.seeded_generator(2)).to("cuda:0")
+    gen.precision = "fp32"
+    x = conditioning.batch(8, [16])
+    y0 = run(gen, x)
+    with torch.no_grad():
+        gen.conv_post.bias.add_(0.25)                      # in-place update must trigger a re-fold
+    y1 = run(gen, x)
+    assert helpers.max_abs(y0, y1) > 1e-2
+    ref = onp.generator_forward({k: v.cpu().numpy() for k, v in gen.state_dict().items()}, x)
+    check(ref, y1, "fp32", "after update")
+    gen.remove_weight_norm()                               # archi.py:109-115: keys become '.weight'
+    y2 = run(gen, x)
+    assert helpers.max_abs(y1, y2) < 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp16"])
+def test_full_size_batch_properties(precision):
+    """BASELINE config 2 size (64 x up to 15 s): the oracle is too slow here, so check
+    size-independent properties: finite, |y| <= 1, item 0 of the batch equals item 0 run alone,
+    and the first utterance agrees with the fp32 path."""
+    gen = dev_gen(0, precision)
+    rng = np.random.default_rng(42)
+    frames = rng.integers(500, 751, size=64).tolist()
+    x = torch.from_numpy(conditioning.batch(4242, frames, pad_to=750)).to("cuda:0")
+    y, _ = gen(x)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (64, 1, 240001)
+    assert torch.isfinite(y).all() and float(y.abs().max()) <= 1.0
+    y0, _ = gen(x[:1])
+    assert float((y0 - y[:1]).abs().max()) == 0.0
+    g32 = dev_gen(0, "fp32")
+    yr, _ = g32(x[:1])
+    torch.cuda.synchronize()
+    check(yr.cpu().numpy(), y[:1].cpu().numpy(), precision, "full-size item 0 vs fp32 path")
+
+
+def test_errors_are_reported_not_fatal():
+    gen = dev_gen(0, "fp32")
+    with pytest.raises(ValueError):
+        gen(torch.zeros(1, 100, 8, device="cuda:0"))
+    from satools_b200 import _lib
+    with pytest.raises(_lib.SaHifiganError, match="T >= 2"):
+        gen(torch.zeros(1, 504, 1, device="cuda:0"))
+    with pytest.raises(_lib.SaHifiganError, match="frames_per_item"):
+        gen(torch.zeros(2, 504, 8, device="cuda:0"), frames_per_item=[8, 9])
