@@ -19,6 +19,8 @@
  *                           Net._forward, egs/vc/libritts/local/tuning/hifigan.py:99-100)
  *   sa_hifigan_synthesize_host   the H2D / convert / D2H sequence of the anonymize pipeline
  *                           satools/satools/bin/pipeline.py:104-107,148-149
+ *   sa_hifigan_check        torch.cuda.synchronize() + error check (the reference gets CUDA errors
+ *                           as Python exceptions from torch)
  *   sa_hifigan_set_profiling / sa_hifigan_get_profile  (no reference counterpart; the reference has
  *                           no profiler hooks) per-launch CUDA-event timing
  *   sa_hifigan_set_debug_tap  (no reference counterpart; exposes stage activations so the
@@ -151,6 +153,10 @@ int sa_hifigan_set_debug_tap(sa_hifigan* h, int32_t tap, float* out);
  * Returns the number of launches (<= max_n entries are written). */
 int sa_hifigan_set_profiling(sa_hifigan* h, int32_t enable);
 int sa_hifigan_get_profile(sa_hifigan* h, float* ms, int32_t* tags, int32_t max_n);
+
+/* Wait for `stream` and report any device-side failure of the work enqueued so far (a CUDA
+ * error, or a tensor-core kernel that gave up waiting on a barrier).  0 = all good. */
+int sa_hifigan_check(sa_hifigan* h, void* stream);
 
 /* Kernel launches enqueued by the most recent forward on this handle. */
 int64_t sa_hifigan_last_launch_count(const sa_hifigan* h);

@@ -546,6 +546,15 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, cons
   return rc;
 }
 
+int sa_hifigan_check(sa_hifigan* h, void* stream) {
+  if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
+  SA_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  SA_CUDA(cudaGetLastError());
+  if (sa::tc_error_raised(h->tc))
+    return fail(SA_ERR_CUDA, "a tcgen05 kernel timed out waiting on an mbarrier (protocol bug); results are invalid");
+  return SA_OK;
+}
+
 int sa_hifigan_set_profiling(sa_hifigan* h, int32_t enable) {
   if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
   h->prof_on = enable != 0;

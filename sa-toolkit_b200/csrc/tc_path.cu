@@ -1,10 +1,469 @@
-// placeholder until the tcgen05 path lands
+// Host side of the tensor-core path: weight packing, workspace carving, tensor maps and the
+// launch sequence of one generator forward on tcgen05 (kernels in conv_tc.cuh).
+//
+// Activation buffers (all channel-blocked [B][C/8][L][8]; E = largest activation):
+//   XIN16  packed input x                           16-bit  B*T*512
+//   P16    lrelu(previous stage / conv_pre output)  16-bit  E      input of the upsampler
+//   AX16   lrelu(h), h = upsampler output           16-bit  E      shared by the 3 ResBlocks
+//   A16    lrelu(residual stream)                   16-bit  E
+//   T16    lrelu(conv1 output)                      16-bit  E
+//   X32    h (stage input), later the stage output  fp32    E
+//   R32    residual stream of the running ResBlock  fp32    E
+//   S32    multi-receptive-field sum                fp32    E
 #include "tc_path.cuh"
+#include "conv_tc.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
 namespace sa {
-bool tc_layer_supported(bool, int, int, int) { return false; }
-const char* tc_pack_weights(tc_weights&, const float*, bool, int, int, int, int, int, bool) { return "tensor-core path not built"; }
-void tc_free_weights(tc_weights& w) { if (w.d_w) cudaFree(w.d_w); w = tc_weights(); }
-const char* tc_init(tc_context&, int) { return "tensor-core path not built"; }
-size_t tc_workspace_bytes(const sa_hifigan_cfg&, int, int) { return 0; }
-const char* tc_forward(tc_context&, const tc_forward_args&, int64_t*) { return "tensor-core path not built"; }
+
+namespace {
+
+thread_local char g_msg[512];
+const char* msgf(const char* fmt, const char* a, const char* b = "") {
+  snprintf(g_msg, sizeof(g_msg), fmt, a, b);
+  return g_msg;
 }
+#define TC_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t e_ = (expr);                                                 \
+    if (e_ != cudaSuccess) return msgf("%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+uint16_t to16(float f, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+  }
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+
+// ---- small CUDA-core helper kernels ------------------------------------------------------
+
+// x fp32 [B][Cin][T] -> 16-bit blocked [B][Cpad/8][T][8] (channels >= Cin are zero).
+__global__ void pack_input_kernel(const float* __restrict__ x, uint4* __restrict__ out, int Cin, int chunks, int T,
+                                  int bf16) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c8 * 8 + e;
+    v[e] = c < Cin ? __ldg(x + ((size_t)b * Cin + c) * T + t) : 0.f;
+  }
+  out[((size_t)b * chunks + c8) * T + t] = tc::pack8(v, bf16 != 0);
+}
+
+// fp32 blocked [B][C/8][L][8] -> fp32 [B][C][L]  (debug taps only)
+__global__ void unblock_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int L) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  if (t >= L) return;
+  const float4* src = reinterpret_cast<const float4*>(in + (((size_t)b * (C / 8) + c8) * L + t) * 8);
+  const float4 a = src[0], c = src[1];
+  float* o = out + ((size_t)b * C + c8 * 8) * L + t;
+  o[0] = a.x; o[(size_t)L] = a.y; o[(size_t)2 * L] = a.z; o[(size_t)3 * L] = a.w;
+  o[(size_t)4 * L] = c.x; o[(size_t)5 * L] = c.y; o[(size_t)6 * L] = c.z; o[(size_t)7 * L] = c.w;
+}
+
+// Tail on the blocked fp32 stage output (archi.py:87-90): lrelu(0.01) -> reflect pad (1,0) ->
+// Conv1d(C->1, k, pad (k-1)/2) -> tanh.  w: [C][k] (the fp32 packing [Cin][k][1]).
+__global__ void conv_post_blocked_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                         const float* __restrict__ bias, void* y, int C, int L, int k, float slope,
+                                         int y_dtype) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < C * k; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Lout = L + 1;
+  if (n >= Lout) return;
+  const int pad = (k - 1) / 2;
+  float acc = __ldg(bias);
+  for (int j = 0; j < k; ++j) {
+    const int i = n + j - pad;
+    if (i < 0 || i >= Lout) continue;
+    const int src = (i == 0) ? 1 : i - 1;
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+      const float4* p = reinterpret_cast<const float4*>(h + (((size_t)b * (C / 8) + c8) * L + src) * 8);
+      const float4 a = __ldg(p), c = __ldg(p + 1);
+      const float* wr = ws + (c8 * 8) * k + j;
+      acc = fmaf(wr[0], tc::lrelu_f(a.x, slope), acc);
+      acc = fmaf(wr[k], tc::lrelu_f(a.y, slope), acc);
+      acc = fmaf(wr[2 * k], tc::lrelu_f(a.z, slope), acc);
+      acc = fmaf(wr[3 * k], tc::lrelu_f(a.w, slope), acc);
+      acc = fmaf(wr[4 * k], tc::lrelu_f(c.x, slope), acc);
+      acc = fmaf(wr[5 * k], tc::lrelu_f(c.y, slope), acc);
+      acc = fmaf(wr[6 * k], tc::lrelu_f(c.z, slope), acc);
+      acc = fmaf(wr[7 * k], tc::lrelu_f(c.w, slope), acc);
+    }
+  }
+  const float v = tanhf(acc);
+  const size_t o = (size_t)b * Lout + n;
+  if (y_dtype == SA_DTYPE_F32) reinterpret_cast<float*>(y)[o] = v;
+  else if (y_dtype == SA_DTYPE_F16) reinterpret_cast<__half*>(y)[o] = __float2half_rn(v);
+  else {
+    float s = rintf(v * 32767.f);
+    s = fminf(fmaxf(s, -32768.f), 32767.f);
+    reinterpret_cast<int16_t*>(y)[o] = (int16_t)s;
+  }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Plan {          // launch geometry of one conv on the tensor cores
+  int msub, rows_alloc, box_rows, nseg, box_chunks, k16_per_stage;
+  size_t smem;
+};
+
+size_t smem_need(int cin_pad, int rows_alloc, int n, int k16_per_stage) {
+  return (size_t)(cin_pad / 8) * rows_alloc * 16 + (size_t)tc::kStages * k16_per_stage * n * 32 + (size_t)n * 4 +
+         (2 + 2 * tc::kStages) * 8 + 16;
+}
+
+bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int max_smem) {
+  for (int msub = (m_rows > 128 ? 2 : 1); msub >= 1; --msub) {
+    const int rows = 128 * msub + span;
+    const int nseg = (rows + 255) / 256;
+    const int box_rows = (int)align_up((size_t)(rows + nseg - 1) / nseg, 8);
+    if (box_rows > 256) continue;
+    const int rows_alloc = nseg * box_rows;
+    // ring stage ~16 KB, at least one K=16 step
+    for (int stage_kb = 16; stage_kb >= 4; stage_kb /= 2) {
+      const int k16 = std::max(1, stage_kb * 1024 / (n * 32));
+      const size_t need = smem_need(cin_pad, rows_alloc, n, k16);
+      if (need <= (size_t)max_smem) {
+        pl.msub = msub; pl.rows_alloc = rows_alloc; pl.box_rows = box_rows; pl.nseg = nseg;
+        pl.box_chunks = (nseg == 1) ? std::min(cin_pad / 8, 256) : 1;
+        pl.k16_per_stage = k16; pl.smem = need;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+template <int N, int MSUB>
+cudaError_t launch_one(const tc::ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<N, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  tc::conv_tc_kernel<N, MSUB><<<grid, tc::kThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t dispatch(int n, int msub, const tc::ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+#define SA_CASE(NN)                                                                       \
+  case NN: return msub == 2 ? launch_one<NN, 2>(p, grid, smem, st) : launch_one<NN, 1>(p, grid, smem, st);
+  switch (n) {
+    SA_CASE(16) SA_CASE(32) SA_CASE(64) SA_CASE(128) SA_CASE(256)
+    default: return cudaErrorInvalidValue;
+  }
+#undef SA_CASE
+}
+
+struct Epi {
+  uint32_t flags = 0;
+  const float* res32 = nullptr;
+  float* out32 = nullptr;
+  float* sum32 = nullptr;
+  void* out16 = nullptr;
+  float slope_out = 0.1f;
+  float n_blocks = 3.f;
+};
+
+struct Runner {
+  tc_context& ctx;
+  const tc_forward_args& a;
+  int64_t* launches;
+  void mark(int tag) { if (a.mark) a.mark(a.mark_ctx, tag, a.stream); }
+
+  // One conv layer (all phases / n-tiles) on the tensor cores.  in16: blocked input with
+  // cin_pad channels and l_in rows per item.
+  const char* conv(const tc_layer& ly, const void* in16, int l_in, const Epi& e, int tag) {
+    const tc_weights& w = *ly.w;
+    tc::ConvParams p;
+    memset(&p, 0, sizeof(p));
+    int span = 0;
+    p.tap_step = ly.transposed ? -1 : ly.dil;
+    for (int ph = 0; ph < w.n_phases; ++ph) {
+      p.n_taps[ph] = w.n_taps[ph];
+      p.tap_base[ph] = ly.transposed ? w.tap_base[ph] : -ly.pad;
+      const int last = p.tap_base[ph] + (w.n_taps[ph] - 1) * p.tap_step;
+      p.row_lo[ph] = std::min(p.tap_base[ph], last);
+      span = std::max(span, std::max(p.tap_base[ph], last) - p.row_lo[ph]);
+    }
+    Plan pl;
+    if (!make_plan(pl, w.cin_pad, w.n, span, l_in, ctx.max_smem)) return "conv does not fit in shared memory";
+    // tensor map over the input activation [B][cin_pad/8][l_in][8]
+    const cuuint64_t gdim[4] = {8, (cuuint64_t)l_in, (cuuint64_t)(w.cin_pad / 8), (cuuint64_t)a.B};
+    const cuuint64_t gstr[3] = {16, (cuuint64_t)l_in * 16, (cuuint64_t)(w.cin_pad / 8) * l_in * 16};
+    const cuuint32_t box[4] = {8, (cuuint32_t)pl.box_rows, (cuuint32_t)pl.box_chunks, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = reinterpret_cast<encode_tiled_fn>(ctx.encode_fn)(
+        &p.tmap, a.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in16),
+        gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for L=%d chunks=%d box_rows=%d", (int)r, l_in,
+               w.cin_pad / 8, pl.box_rows);
+      return g_msg;
+    }
+    p.w = w.d_w;
+    p.bias = ly.d_bias;
+    p.res32 = e.res32; p.out32 = e.out32; p.sum32 = e.sum32; p.out16 = e.out16;
+    p.error_flag = ctx.d_error;
+    p.cin = w.cin_pad;
+    p.cout_total = ly.cout;
+    p.m_rows = l_in;
+    p.out_stride = ly.transposed ? ly.stride : 1;
+    p.l_out = l_in * p.out_stride;
+    p.n_phases = w.n_phases;
+    p.n_tiles = w.n_tiles;
+    p.rows_alloc = pl.rows_alloc; p.box_rows = pl.box_rows; p.nseg = pl.nseg; p.box_chunks = pl.box_chunks;
+    p.k16_per_stage = pl.k16_per_stage;
+    p.w_tile_bytes = (uint32_t)w.tile_bytes;
+    p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+    p.slope_out = e.slope_out;
+    p.inv_blocks = e.n_blocks;
+    dim3 grid((unsigned)((l_in + 128 * pl.msub - 1) / (128 * pl.msub)), (unsigned)(w.n_phases * w.n_tiles), (unsigned)a.B);
+    mark(tag);
+    cudaError_t ce = dispatch(w.n, pl.msub, p, grid, pl.smem, a.stream);
+    if (ce != cudaSuccess) return msgf("conv_tc launch: %s", cudaGetErrorString(ce));
+    ++*launches;
+    return nullptr;
+  }
+};
+
+}  // namespace
+
+bool tc_layer_supported(bool transposed, int cin, int cout, int k) {
+  (void)cin; (void)k;
+  if (cout % 16 != 0) return false;
+  if (cout > 256 && cout % 256 != 0) return false;
+  if (transposed && cout > 256) return false;
+  return true;
+}
+
+const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed, int cin, int cout, int k, int stride,
+                            int pad, bool bf16) {
+  tc_free_weights(w);
+  w.cin_pad = (int)align_up(cin, 16);
+  w.n = cout > 256 ? 256 : cout;
+  w.n_tiles = cout / w.n;
+  const int k16_per_tap = w.cin_pad / 16;
+  int max_taps = 0;
+  if (!transposed) {
+    w.n_phases = 1;
+    w.n_taps[0] = k;
+    w.tap_base[0] = 0;       // -pad applied per launch
+    w.tap_step = 1;
+    max_taps = k;
+  } else {
+    if (stride > kTcMaxPhases) return "upsample rate too large for the tensor-core path";
+    w.n_phases = stride;
+    w.tap_step = -1;
+    for (int ph = 0; ph < stride; ++ph) {
+      const int j0 = (ph + pad) % stride;
+      w.n_taps[ph] = j0 < k ? (k - j0 + stride - 1) / stride : 0;
+      w.tap_base[ph] = (ph + pad) / stride;       // tap m reads input row q + tap_base - m
+      if (w.n_taps[ph] < 1) return "transposed conv phase without taps";
+      max_taps = std::max(max_taps, w.n_taps[ph]);
+    }
+  }
+  w.tile_bytes = (size_t)max_taps * k16_per_tap * w.n * 32;
+  w.bytes = w.tile_bytes * w.n_phases * w.n_tiles;
+  std::vector<uint16_t> host(w.bytes / 2, 0);
+  for (int ph = 0; ph < w.n_phases; ++ph)
+    for (int t = 0; t < w.n_tiles; ++t) {
+      uint16_t* tile = host.data() + ((size_t)(ph * w.n_tiles + t) * w.tile_bytes) / 2;
+      for (int tap = 0; tap < w.n_taps[ph]; ++tap) {
+        const int j = transposed ? ((ph + pad) % stride + stride * tap) : tap;
+        for (int cb = 0; cb < k16_per_tap; ++cb) {
+          uint16_t* step = tile + (size_t)(tap * k16_per_tap + cb) * w.n * 16;
+          for (int h = 0; h < 2; ++h)
+            for (int r = 0; r < w.n; ++r)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = cb * 16 + h * 8 + e, co = t * w.n + r;
+                float v = 0.f;
+                if (ci < cin)
+                  v = transposed ? folded[((size_t)ci * cout + co) * k + j] : folded[((size_t)co * cin + ci) * k + j];
+                step[((size_t)h * w.n + r) * 8 + e] = to16(v, bf16);
+              }
+        }
+      }
+    }
+  TC_CUDA(cudaMalloc(&w.d_w, w.bytes));
+  TC_CUDA(cudaMemcpy(w.d_w, host.data(), w.bytes, cudaMemcpyHostToDevice));
+  return nullptr;
+}
+
+void tc_free_weights(tc_weights& w) {
+  if (w.d_w) cudaFree(w.d_w);
+  w = tc_weights();
+}
+
+const char* tc_init(tc_context& ctx, int device) {
+  if (ctx.ready) return nullptr;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  TC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return "cuTensorMapEncodeTiled not available from the driver";
+  ctx.encode_fn = fn;
+  TC_CUDA(cudaDeviceGetAttribute(&ctx.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  // error flag in mapped pinned host memory: kernels can raise it, the host reads it without a sync
+  TC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx.h_error), sizeof(int), cudaHostAllocMapped));
+  *ctx.h_error = 0;
+  TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
+  ctx.ready = true;
+  return nullptr;
+}
+
+bool tc_error_raised(const tc_context& ctx) {
+  return ctx.h_error && *static_cast<volatile int*>(ctx.h_error) != 0;
+}
+
+namespace {
+struct Sizes { size_t e16, e32, xin; };
+Sizes sizes(const sa_hifigan_cfg& cfg, int B, int T) {
+  int64_t per_frame = cfg.initial_channels, rate = 1;
+  for (int i = 0; i < cfg.n_stages; ++i) {
+    rate *= cfg.upsample_rates[i];
+    per_frame = std::max<int64_t>(per_frame, (int64_t)(cfg.initial_channels >> (i + 1)) * rate);
+  }
+  const size_t E = (size_t)B * T * per_frame;
+  Sizes s;
+  s.e16 = align_up(E * 2, 256);
+  s.e32 = align_up(E * 4, 256);
+  s.xin = align_up((size_t)B * T * align_up(cfg.input_dim, 16) * 2, 256);
+  return s;
+}
+}  // namespace
+
+size_t tc_workspace_bytes(const sa_hifigan_cfg& cfg, int B, int T) {
+  const Sizes s = sizes(cfg, B, T);
+  return s.xin + 4 * s.e16 + 3 * s.e32;
+}
+
+const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launches) {
+  if (!ctx.ready) return "tensor-core context not initialised";
+  if (tc_error_raised(ctx)) return "a tcgen05 kernel of an earlier forward timed out on an mbarrier (protocol bug)";
+  const sa_hifigan_cfg& cfg = *a.cfg;
+  const Sizes s = sizes(cfg, a.B, a.T);
+  char* base = static_cast<char*>(a.workspace);
+  void* XIN16 = base; base += s.xin;
+  void* P16 = base; base += s.e16;
+  void* AX16 = base; base += s.e16;
+  void* A16 = base; base += s.e16;
+  void* T16 = base; base += s.e16;
+  float* X32 = reinterpret_cast<float*>(base); base += s.e32;
+  float* R32 = reinterpret_cast<float*>(base); base += s.e32;
+  float* S32 = reinterpret_cast<float*>(base);
+  cudaStream_t st = a.stream;
+  Runner run{ctx, a, launches};
+  const int nst = cfg.n_stages, nrb = cfg.n_resblocks, nd = cfg.n_dilations;
+  auto L_up = [&](int i) { return 1 + i; };
+  auto L_rb = [&](int i, int j, int which, int m) { return 1 + nst + ((i * nrb + j) * 2 + which) * nd + m; };
+  const int L_post = 1 + nst + nst * nrb * 2 * nd;
+  const char* err;
+
+  auto unblock_tap = [&](int tap, int C, int L) -> const char* {
+    if (!a.debug_out || a.debug_tap != tap) return nullptr;
+    dim3 g((unsigned)((L + 255) / 256), (unsigned)(C / 8), (unsigned)a.B);
+    run.mark(15);
+    unblock_kernel<<<g, 256, 0, st>>>(X32, a.debug_out, C, L);
+    ++*launches;
+    TC_CUDA(cudaGetLastError());
+    return nullptr;
+  };
+
+  // pack x -> 16-bit blocked
+  {
+    const int cpad = (int)align_up(cfg.input_dim, 16);
+    dim3 g((unsigned)((a.T + 127) / 128), (unsigned)(cpad / 8), (unsigned)a.B);
+    run.mark(15);
+    pack_input_kernel<<<g, 128, 0, st>>>(a.x, reinterpret_cast<uint4*>(XIN16), cfg.input_dim, cpad / 8, a.T, a.bf16 ? 1 : 0);
+    ++*launches;
+    TC_CUDA(cudaGetLastError());
+  }
+  // conv_pre (archi.py:78); its consumer applies lrelu(0.1) (archi.py:80)
+  {
+    Epi e;
+    e.flags = tc::EPI_OUT16 | ((a.debug_out && a.debug_tap == SA_TAP_CONV_PRE) ? tc::EPI_OUT32 : 0u);
+    e.out16 = P16; e.out32 = X32; e.slope_out = 0.1f;
+    if ((err = run.conv(a.layers[0], XIN16, a.T, e, 0))) return err;
+    if ((err = unblock_tap(SA_TAP_CONV_PRE, cfg.initial_channels, a.T))) return err;
+  }
+  int L = a.T;
+  for (int i = 0; i < nst; ++i) {
+    const tc_layer& up = a.layers[L_up(i)];
+    {                                               // archi.py:80-81
+      Epi e;
+      e.flags = tc::EPI_OUT32 | tc::EPI_OUT16;
+      e.out32 = X32; e.out16 = AX16; e.slope_out = 0.1f;
+      if ((err = run.conv(up, P16, L, e, 16 * (1 + i)))) return err;
+    }
+    L *= up.stride;
+    const bool last_stage = (i == nst - 1);
+    const bool tap_here = a.debug_out && a.debug_tap == SA_TAP_STAGE0 + i;
+    for (int j = 0; j < nrb; ++j) {
+      const int tag = 16 * (1 + i) + 1 + j;
+      for (int m = 0; m < nd; ++m) {               // nn.py:169-174
+        Epi e1;
+        e1.flags = tc::EPI_OUT16; e1.out16 = T16; e1.slope_out = 0.1f;
+        if ((err = run.conv(a.layers[L_rb(i, j, 0, m)], m == 0 ? AX16 : A16, L, e1, tag))) return err;
+        Epi e2;
+        e2.flags = tc::EPI_RES;
+        e2.res32 = (m == 0) ? X32 : R32;
+        if (m < nd - 1) {
+          e2.flags |= tc::EPI_OUT32 | tc::EPI_OUT16;
+          e2.out32 = R32; e2.out16 = A16; e2.slope_out = 0.1f;
+        } else {                                    // archi.py:82-86
+          e2.sum32 = S32; e2.n_blocks = (float)nrb;
+          if (nrb > 1) e2.flags |= (j == 0) ? tc::EPI_SUM_SET : (j == nrb - 1 ? tc::EPI_SUM_FIN : tc::EPI_SUM_ADD);
+          if (j == nrb - 1) {
+            if (last_stage || tap_here) { e2.flags |= tc::EPI_OUT32; e2.out32 = X32; }
+            if (!last_stage) { e2.flags |= tc::EPI_OUT16; e2.out16 = P16; e2.slope_out = 0.1f; }
+          }
+        }
+        if ((err = run.conv(a.layers[L_rb(i, j, 1, m)], T16, L, e2, tag))) return err;
+      }
+    }
+    if ((err = unblock_tap(SA_TAP_STAGE0 + i, up.cout, L))) return err;
+  }
+  {                                                 // archi.py:87-90
+    const tc_layer& post = a.layers[L_post];
+    const int threads = 256;
+    dim3 g((unsigned)((L + 1 + threads - 1) / threads), (unsigned)a.B);
+    run.mark(16 * (nst + 1));
+    conv_post_blocked_kernel<<<g, threads, post.cin * post.k * sizeof(float), st>>>(X32, post.d_w32, post.d_bias, a.y,
+                                                                                    post.cin, L, post.k, 0.01f, a.y_dtype);
+    ++*launches;
+    TC_CUDA(cudaGetLastError());
+  }
+  return nullptr;
+}
+
+}  // namespace sa

@@ -6,17 +6,29 @@
 
 namespace sa {
 
-// Packed 16-bit weights of one conv for the implicit-GEMM kernels (see conv_tc.cuh).
+constexpr int kTcMaxPhases = 8;
+
+// Packed 16-bit weights of one conv for the implicit-GEMM kernel (conv_tc.cuh):
+// [phase][n_tile][k16 step = tap * cin_pad/16 + cb][2][N][8].
 struct tc_weights {
-  void* d_w = nullptr;       // device, 16-bit, [n_k16][2][N][8] K-major core-matrix order
-  int n_k16 = 0;             // number of K=16 MMA steps
-  int n_rows = 0;            // N rows per step (Cout, or phases*Cout for the upsamplers)
+  void* d_w = nullptr;
+  int n = 0;                 // N per MMA (Cout tile)
+  int n_tiles = 0;           // Cout / N
+  int n_phases = 0;          // 1 for Conv1d, stride for ConvTranspose1d
+  int cin_pad = 0;           // Cin rounded up to 16
+  int n_taps[kTcMaxPhases] = {0};
+  int tap_base[kTcMaxPhases] = {0};
+  int tap_step = 1;          // informational for transposed convs (-1); convs use the layer dilation
+  size_t tile_bytes = 0;     // bytes of one (phase, n_tile) block
   size_t bytes = 0;
 };
 
 struct tc_context {
   bool ready = false;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
+  int* h_error = nullptr;     // mapped pinned flag raised by a kernel whose barrier wait timed out
+  int* d_error = nullptr;     // device alias of h_error
+  int max_smem = 0;
 };
 
 struct tc_layer {
@@ -51,6 +63,7 @@ const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed,
                             int stride, int pad, bool bf16);
 void tc_free_weights(tc_weights& w);
 const char* tc_init(tc_context& ctx, int device);
+bool tc_error_raised(const tc_context& ctx);
 size_t tc_workspace_bytes(const sa_hifigan_cfg& cfg, int B, int T);
 const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launches);
 

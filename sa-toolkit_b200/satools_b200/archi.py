@@ -177,7 +177,7 @@ class CoreHifiGan(nn.Module):
         if x_host.is_cuda:
             raise ValueError("synthesize_host takes a CPU tensor")
         lib = _lib.load()
-        device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         x_host = x_host.to(torch.float32).contiguous()
         B, _, T = x_host.shape
         if out is None:
@@ -220,6 +220,14 @@ class CoreHifiGan(nn.Module):
             finally:
                 lib.sa_hifigan_set_debug_tap(self._handle, 0, None)
         return y, buf
+
+    def check(self, device=None) -> None:
+        """Synchronize the current stream and raise if any enqueued generator work failed."""
+        if self._handle is None:
+            return
+        dev = torch.device("cuda", self._handle_device)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().sa_hifigan_check(self._handle, torch.cuda.current_stream(dev).cuda_stream))
 
     @torch.no_grad()
     def profile(self, x: torch.Tensor, repeats: int = 1):

@@ -45,7 +45,7 @@ def dev_gen(seed, precision):
 
 def run(gen, x_np, **kw):
     y, aux = gen(torch.from_numpy(np.ascontiguousarray(x_np)).to("cuda:0"), **kw)
-    torch.cuda.synchronize()
+    gen.check()
     assert tuple(aux.shape) == (1,)
     return y.cpu().numpy()
 
