@@ -2,10 +2,10 @@
 // path (every conv of the generator except the 16->1 tail runs through it).
 //
 // Formulation ("time on M"):   D[t, co] = sum_j sum_ci  A[t + off_j, ci] * W_j[co, ci]
-//   M = 128 output time steps per MMA (MSUB sub-tiles per CTA), N = Cout tile, K = Cin per tap.
+//   M = 128 output time steps per MMA (MSUB sub-tiles per CTA tile), N = Cout tile, K = Cin per tap.
 //   A  activations, 16-bit, channel-blocked  [B][C/8][L][8]   (one time step of 8 channels = 16 B)
 //   W  weights, 16-bit, pre-packed on the host in MMA order [k16 step][2][N][8]
-//   D  fp32 accumulators in TMEM (MSUB * N columns)
+//   D  fp32 accumulators in TMEM (MSUB * N columns, double buffered when they fit twice)
 //
 // Why this layout: in the no-swizzle K-major canonical layout of the UMMA shared-memory
 // descriptor a core matrix is 8 rows x 16 bytes with rows 16 B apart, 8-row groups SBO apart
@@ -15,11 +15,18 @@
 // no im2col; the +-(k-1)d/2 halo lives in shared memory.  TMA (cp.async.bulk.tensor) loads the
 // tile and zero-fills rows outside [0, L), which is exactly the per-layer zero padding of
 // the reference convs (nn.py:98-166).  Weights stream through an mbarrier ring with 1-D bulk
-// copies.  The polyphase transposed convs (archi.py:47-59) are the same kernel: phase phi is
-// a conv with taps at rows (off_phi - m) whose output row is u*q + phi.
+// copies (or stay resident when the whole filter bank is small).  The polyphase transposed
+// convs (archi.py:47-59) are the same kernel: phase phi is a conv with taps at rows
+// (off_phi - m) whose output row is u*q + phi.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias / residual / MRF / leaky-ReLU -> global).
+// Persistent CTAs: grid.x CTAs walk the (item, time-tile) list with stride grid.x, so barrier
+// setup, TMEM allocation and (resident) weights are paid once and the three pipelines overlap
+// across tiles:
+//   warp 0      A producer: TMA tile loads into a 1- or 2-deep ring            (a_full / a_empty)
+//   warp 1      W producer: bulk copies of weight stages                       (w_full / w_empty)
+//   warp 2      MMA issuer (one thread) + TMEM owner                           (acc_full / acc_empty)
+//   warps 3..10 epilogue: TMEM -> registers -> bias / residual / MRF sum / leaky-ReLU -> global,
+//               two warps per TMEM lane group, each taking half of the N columns
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,9 +37,10 @@
 namespace sa {
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 352;           // 11 warps
+constexpr int kEpiWarps = 8;
 constexpr int kMaxPhases = 8;
-constexpr int kStages = 4;              // weight ring depth
+constexpr int kMaxStages = 8;           // weight ring depth (runtime n_wstages <= this)
 
 // epilogue flags
 enum : uint32_t {
@@ -53,7 +61,7 @@ struct ConvParams {
   float* out32;
   float* sum32;
   void* out16;              // 16-bit blocked
-  int* error_flag;          // set when a barrier wait times out
+  int* error_flag;          // raised when a barrier wait times out
   int cin;                  // multiple of 16
   int cout_total;           // channels of the output tensor
   int m_rows;               // valid output rows per item on the M axis (L for conv, L_in for convT)
@@ -67,11 +75,16 @@ struct ConvParams {
   int row_lo[kMaxPhases];   // min tap offset of the phase (first staged row = m0 + row_lo)
   int rows_alloc;           // staged rows per chunk (nseg * box_rows)
   int box_rows, nseg, box_chunks;
-  int k16_per_stage;        // K=16 steps per weight-ring stage
+  int k16_per_stage;        // K=16 steps per weight stage
+  int n_wstages;            // weight ring depth
+  int w_resident;           // 1: all weight stages stay in smem (loaded once per CTA)
+  int n_abuf;               // A-tile ring depth (1 or 2)
+  int m_tiles;              // time tiles per item
+  int total_tiles;          // m_tiles * B
   uint32_t w_tile_bytes;
   uint32_t flags;
   float slope_out;
-  float inv_blocks;         // 1 / n_resblocks is NOT used (true division below); kept = n_blocks
+  float n_blocks;           // divisor of EPI_SUM_FIN (true division, as xs / num_kernels)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -84,6 +97,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -98,6 +114,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {          // ~2 s at 2 GHz
@@ -108,7 +125,6 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   return true;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -148,17 +164,17 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 32 lanes x 8 columns of 32-bit: thread i of the warp gets columns [c, c+8) of TMEM lane base+i.
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+// TMEM -> registers, 32 lanes x 16 columns of 32-bit (thread i gets 16 columns of lane base+i).
+// Asynchronous until tmem_ld_wait().
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, no swizzle (layout_type 0), version 1 (sm_100).
 //   bits [0,14) start >> 4 | [16,30) LBO >> 4 (between the two 16-byte K halves)
@@ -195,48 +211,62 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], bool bf16) {
   return o;
 }
 
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
 // ---------------------------------------------------------------------------------------
-// The kernel.  grid = (m_tiles, n_phases * n_tiles, B).  Dynamic smem:
-//   [A tile: (cin/8) * rows_alloc * 16][W ring: kStages * k16_per_stage * N * 32][bias N*4][barriers]
+// The kernel.  grid = (persistent CTAs, n_phases * n_tiles).  Dynamic smem:
+//   [A ring: n_abuf * (cin/8) * rows_alloc * 16][W ring: n_wstages * k16_per_stage * N * 32]
+//   [bias N*4][barriers][tmem holder]
 // ---------------------------------------------------------------------------------------
 template <int N, int MSUB>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int phase = blockIdx.y / p.n_tiles, ntile = blockIdx.y % p.n_tiles;
-  const int b = blockIdx.z;
-  const int m0 = blockIdx.x * (128 * MSUB);
+
+  constexpr int kAccCols = N * MSUB;                              // columns of one accumulator buffer
+  constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;
+  constexpr uint32_t kTmemCols = (kNumAcc * kAccCols <= 32) ? 32 : (kNumAcc * kAccCols <= 64) ? 64
+                                 : (kNumAcc * kAccCols <= 128) ? 128 : (kNumAcc * kAccCols <= 256) ? 256 : 512;
 
   const int chunks = p.cin >> 3;
   const uint32_t chunk_stride = (uint32_t)p.rows_alloc * 16u;
   const uint32_t a_bytes = (uint32_t)chunks * chunk_stride;
   const uint32_t stage_bytes = (uint32_t)p.k16_per_stage * N * 32u;
   uint8_t* a_smem = smem;
-  uint8_t* w_smem = smem + a_bytes;
-  float* bias_s = reinterpret_cast<float*>(w_smem + kStages * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + N);       // 8-byte aligned: all sizes are multiples of 16
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages);
-  const uint32_t bar_a_full = smem_u32(&bars[0]);
-  const uint32_t bar_acc_full = smem_u32(&bars[1]);
-  auto bar_w_full = [&](int s) { return smem_u32(&bars[2 + s]); };
-  auto bar_w_empty = [&](int s) { return smem_u32(&bars[2 + kStages + s]); };
+  uint8_t* w_smem = smem + (size_t)p.n_abuf * a_bytes;
+  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)p.n_wstages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + N);
+  // barrier slots: a_full[2] a_empty[2] acc_full[2] acc_empty[2] w_full[8] w_empty[8]
+  auto bar_a_full = [&](int i) { return smem_u32(&bars[0 + i]); };
+  auto bar_a_empty = [&](int i) { return smem_u32(&bars[2 + i]); };
+  auto bar_acc_full = [&](int i) { return smem_u32(&bars[4 + i]); };
+  auto bar_acc_empty = [&](int i) { return smem_u32(&bars[6 + i]); };
+  auto bar_w_full = [&](int s) { return smem_u32(&bars[8 + s]); };
+  auto bar_w_empty = [&](int s) { return smem_u32(&bars[8 + kMaxStages + s]); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxStages);
 
-  constexpr uint32_t kTmemCols = (N * MSUB <= 32) ? 32 : (N * MSUB <= 64) ? 64 : (N * MSUB <= 128) ? 128
-                                 : (N * MSUB <= 256) ? 256 : 512;
   const int n_taps = p.n_taps[phase];
   const int k16_per_tap = p.cin >> 4;
   const int n_k16 = n_taps * k16_per_tap;
-  const int n_iters = (n_k16 + p.k16_per_stage - 1) / p.k16_per_stage;
+  const int n_iters = (n_k16 + p.k16_per_stage - 1) / p.k16_per_stage;   // weight stages per tile
   const uint8_t* w_tile = static_cast<const uint8_t*>(p.w) + (size_t)(phase * p.n_tiles + ntile) * p.w_tile_bytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmap);
-    mbar_init(bar_a_full, 1);
-    mbar_init(bar_acc_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_a_full(i), 1);
+      mbar_init(bar_a_empty(i), 1);
+      mbar_init(bar_acc_full(i), 1);
+      mbar_init(bar_acc_empty(i), kEpiWarps);
+    }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = p.bias[ntile * N + i];
   tc_fence_before();
   __syncthreads();
@@ -244,112 +274,173 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== A producer: one TMA tile per work item =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_a_full, a_bytes);
-      const int row0 = m0 + p.row_lo[phase];
-      for (int c = 0; c < chunks; c += p.box_chunks)
-        for (int s = 0; s < p.nseg; ++s)
-          tma_load_4d(smem_u32(a_smem) + (uint32_t)c * chunk_stride + (uint32_t)(s * p.box_rows) * 16u, &p.tmap,
-                      bar_a_full, 0, row0 + s * p.box_rows, c, b);
-      for (int it = 0; it < n_iters; ++it) {
-        const int slot = it % kStages;
-        if (it >= kStages && !mbar_wait(bar_w_empty(slot), ((it / kStages) - 1) & 1, p.error_flag)) break;
-        const int k16 = min(p.k16_per_stage, n_k16 - it * p.k16_per_stage);
-        const uint32_t bytes = (uint32_t)k16 * N * 32u;
-        mbar_arrive_expect_tx(bar_w_full(slot), bytes);
-        bulk_load(smem_u32(w_smem) + slot * stage_bytes, w_tile + (size_t)it * stage_bytes, bytes, bar_w_full(slot));
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it % p.n_abuf, use = it / p.n_abuf;
+        if (use > 0 && !mbar_wait(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
+        const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+        mbar_arrive_expect_tx(bar_a_full(buf), a_bytes);
+        const int row0 = m0 + p.row_lo[phase];
+        const uint32_t dst = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
+        for (int c = 0; c < chunks; c += p.box_chunks)
+          for (int s = 0; s < p.nseg; ++s)
+            tma_load_4d(dst + (uint32_t)c * chunk_stride + (uint32_t)(s * p.box_rows) * 16u, &p.tmap, bar_a_full(buf), 0,
+                        row0 + s * p.box_rows, c, b);
       }
     }
   } else if (warp == 1) {
+    // ===== W producer: weight stages through the ring (once, when resident) =====
+    if (lane == 0) {
+      int wit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        if (p.w_resident && tile != (int)blockIdx.x) break;
+        bool ok = true;
+        for (int i = 0; i < n_iters && ok; ++i, ++wit) {
+          const int slot = wit % p.n_wstages, use = wit / p.n_wstages;
+          if (use > 0) ok = mbar_wait(bar_w_empty(slot), (use - 1) & 1, p.error_flag);
+          if (!ok) break;
+          const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
+          const uint32_t bytes = (uint32_t)k16 * N * 32u;
+          mbar_arrive_expect_tx(bar_w_full(slot), bytes);
+          bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
+                    bar_w_full(slot));
+        }
+        if (!ok) break;
+      }
+    }
+  } else if (warp == 2) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N, (p.flags & EPI_BF16) != 0);
       const int row_lo = p.row_lo[phase];
-      bool ok = mbar_wait(bar_a_full, 0, p.error_flag);
-      tc_fence_after();
-      int step = 0;
-      for (int it = 0; it < n_iters && ok; ++it) {
-        const int slot = it % kStages;
-        ok = mbar_wait(bar_w_full(slot), (it / kStages) & 1, p.error_flag);
+      int it = 0, wit = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+        const int buf = it % p.n_abuf, use = it / p.n_abuf;
+        const int acc = it % kNumAcc, acc_use = it / kNumAcc;
+        if (acc_use > 0) ok = mbar_wait(bar_acc_empty(acc), (acc_use - 1) & 1, p.error_flag);
+        if (ok) ok = mbar_wait(bar_a_full(buf), use & 1, p.error_flag);
         if (!ok) break;
         tc_fence_after();
-        const int k16 = min(p.k16_per_stage, n_k16 - it * p.k16_per_stage);
-        for (int kk = 0; kk < k16; ++kk, ++step) {
-          const int tap = step / k16_per_tap, cb = step - tap * k16_per_tap;
-          const int off = p.tap_base[phase] + tap * p.tap_step - row_lo;          // staged row of output row m0
-          const uint32_t a_addr = smem_u32(a_smem) + (uint32_t)(2 * cb) * chunk_stride + (uint32_t)off * 16u;
-          const uint64_t bdesc = make_smem_desc(smem_u32(w_smem) + slot * stage_bytes + (uint32_t)kk * N * 32u,
-                                                (uint32_t)N * 16u, 128u);
+        const uint32_t a_base = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * kAccCols);
+        int step = 0;
+        for (int i = 0; i < n_iters; ++i) {
+          int slot, wuse;
+          if (p.w_resident) { slot = i; wuse = 0; } else { slot = wit % p.n_wstages; wuse = wit / p.n_wstages; ++wit; }
+          ok = mbar_wait(bar_w_full(slot), wuse & 1, p.error_flag);
+          if (!ok) break;
+          tc_fence_after();
+          const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
+          for (int kk = 0; kk < k16; ++kk, ++step) {
+            const int tap = step / k16_per_tap, cb = step - tap * k16_per_tap;
+            const int off = p.tap_base[phase] + tap * p.tap_step - row_lo;        // staged row of output row m0
+            const uint32_t a_addr = a_base + (uint32_t)(2 * cb) * chunk_stride + (uint32_t)off * 16u;
+            const uint64_t bdesc = make_smem_desc(smem_u32(w_smem) + (uint32_t)slot * stage_bytes + (uint32_t)kk * N * 32u,
+                                                  (uint32_t)N * 16u, 128u);
 #pragma unroll
-          for (int ms = 0; ms < MSUB; ++ms) {
-            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)ms * 128u * 16u, chunk_stride, 128u);
-            umma_f16(tmem_base + (uint32_t)ms * N, adesc, bdesc, idesc, step > 0 ? 1u : 0u);
+            for (int ms = 0; ms < MSUB; ++ms) {
+              const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)ms * 128u * 16u, chunk_stride, 128u);
+              umma_f16(d_base + (uint32_t)ms * N, adesc, bdesc, idesc, step > 0 ? 1u : 0u);
+            }
           }
+          if (!p.w_resident) umma_commit(bar_w_empty(slot));     // slot free once these MMAs have read it
         }
-        umma_commit(bar_w_empty(slot));           // frees the ring slot once these MMAs have read it
+        if (!ok) break;
+        umma_commit(bar_a_empty(buf));                            // A tile consumed
+        umma_commit(bar_acc_full(acc));                           // accumulators complete
       }
-      umma_commit(bar_acc_full);                  // accumulators complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    // ===== epilogue: warps 3..10; TMEM lane group = warp % 4; column half = (warp - 3) / 4 =====
     const int lg = warp & 3;
-    const bool ok = mbar_wait(bar_acc_full, 0, p.error_flag);
-    tc_fence_after();
+    const int half = (warp - 3) >> 2;
+    constexpr int kColsPerWarp = (N >= 32) ? N / 2 : N;            // N = 16: only half 0 has columns
+    const bool has_cols = (N >= 32) || half == 0;
+    const int col0 = (N >= 32) ? half * kColsPerWarp : 0;
     const bool bf16 = (p.flags & EPI_BF16) != 0;
     const int cchunks_total = p.cout_total >> 3;
-    if (ok) {
+    const uint32_t flags = p.flags;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it % kNumAcc, acc_use = it / kNumAcc;
+      if (!mbar_wait(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
+      tc_fence_after();
+      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+      if (has_cols) {
 #pragma unroll
-      for (int ms = 0; ms < MSUB; ++ms) {
-        const int t = m0 + ms * 128 + lg * 32 + lane;            // output row on the M axis
-        const bool valid = t < p.m_rows;
-        const long long orow = (long long)t * p.out_stride + phase;
+        for (int ms = 0; ms < MSUB; ++ms) {
+          const int t = m0 + ms * 128 + lg * 32 + lane;            // output row on the M axis
+          const bool valid = t < p.m_rows;
+          const size_t orow = (size_t)t * p.out_stride + phase;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0);
 #pragma unroll 1
-        for (int c8 = 0; c8 < N / 8; ++c8) {
-          float v[8];
-          __syncwarp();                                          // tcgen05.ld is .sync.aligned
-          tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ms * N + c8 * 8), v);   // warp-collective
-          if (valid) {
-          const size_t idx = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + (size_t)orow) * 8;
+          for (int g = 0; g < kColsPerWarp / 16; ++g) {            // 16 columns = 2 channel chunks per step
+            uint32_t r[16];
+            __syncwarp();                                          // tcgen05.ld is .sync.aligned
+            tmem_ld16(t_addr + (uint32_t)(g * 16), r);
+            const int c8 = (col0 >> 3) + g * 2;                    // first channel chunk inside this n-tile
+            const size_t idx0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
+            const size_t idx1 = idx0 + (size_t)p.l_out * 8;
+            float4 qr[4], qs[4];
+            if (valid) {                                           // issue every global load before waiting on TMEM
+              if (flags & EPI_RES) {
+                qr[0] = ldg_f4(p.res32 + idx0); qr[1] = ldg_f4(p.res32 + idx0 + 4);
+                qr[2] = ldg_f4(p.res32 + idx1); qr[3] = ldg_f4(p.res32 + idx1 + 4);
+              }
+              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
+                qs[0] = ldg_f4(p.sum32 + idx0); qs[1] = ldg_f4(p.sum32 + idx0 + 4);
+                qs[2] = ldg_f4(p.sum32 + idx1); qs[3] = ldg_f4(p.sum32 + idx1 + 4);
+              }
+            }
+            tmem_ld_wait();
+            if (valid) {
+              float v[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += bias_s[c8 * 8 + e];
-          if (p.flags & EPI_RES) {
-            const float4 r0 = *reinterpret_cast<const float4*>(p.res32 + idx);
-            const float4 r1 = *reinterpret_cast<const float4*>(p.res32 + idx + 4);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-          }
-          if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
-            const float4 s0 = *reinterpret_cast<const float4*>(p.sum32 + idx);
-            const float4 s1 = *reinterpret_cast<const float4*>(p.sum32 + idx + 4);
-            v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
-            v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-          }
-          if (p.flags & EPI_SUM_FIN) {
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
+              if (flags & EPI_RES) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = v[e] / p.inv_blocks;     // xs / num_kernels (true division)
-          }
-          if (p.flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-            *reinterpret_cast<float4*>(p.sum32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(p.sum32 + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-          if (p.flags & EPI_OUT32) {
-            *reinterpret_cast<float4*>(p.out32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(p.out32 + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-          if (p.flags & EPI_OUT16) {
+                for (int h = 0; h < 4; ++h) { v[4 * h] += qr[h].x; v[4 * h + 1] += qr[h].y; v[4 * h + 2] += qr[h].z; v[4 * h + 3] += qr[h].w; }
+              }
+              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = lrelu_f(v[e], p.slope_out);
-            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx * 2) = pack8(v, bf16);
-          }
+                for (int h = 0; h < 4; ++h) {
+                  v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
+                }
+              }
+              if (flags & EPI_SUM_FIN) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;            // xs / num_kernels
+              }
+              if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
+                stg_f4(p.sum32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx0 + 4, v[4], v[5], v[6], v[7]);
+                stg_f4(p.sum32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + idx1 + 4, v[12], v[13], v[14], v[15]);
+              }
+              if (flags & EPI_OUT32) {
+                stg_f4(p.out32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx0 + 4, v[4], v[5], v[6], v[7]);
+                stg_f4(p.out32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + idx1 + 4, v[12], v[13], v[14], v[15]);
+              }
+              if (flags & EPI_OUT16) {
+                float lo[8], hi[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { lo[e] = lrelu_f(v[e], p.slope_out); hi[e] = lrelu_f(v[8 + e], p.slope_out); }
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx0 * 2) = pack8(lo, bf16);
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx1 * 2) = pack8(hi, bf16);
+              }
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty(acc));              // this warp is done with the accumulator buffer
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

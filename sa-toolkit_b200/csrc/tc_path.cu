@@ -129,54 +129,80 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct Plan {          // launch geometry of one conv on the tensor cores
-  int msub, rows_alloc, box_rows, nseg, box_chunks, k16_per_stage;
+  int msub, rows_alloc, box_rows, nseg, box_chunks, k16_per_stage, n_wstages, w_resident, n_abuf;
   size_t smem;
 };
 
-size_t smem_need(int cin_pad, int rows_alloc, int n, int k16_per_stage) {
-  return (size_t)(cin_pad / 8) * rows_alloc * 16 + (size_t)tc::kStages * k16_per_stage * n * 32 + (size_t)n * 4 +
-         (2 + 2 * tc::kStages) * 8 + 16;
-}
+constexpr size_t kResidentWeightBytes = 48 * 1024;   // keep the whole filter bank in smem below this
 
-bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int max_smem) {
+bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int n_k16_max, int max_smem) {
+  const size_t fixed = (size_t)n * 4 + (8 + 2 * tc::kMaxStages) * 8 + 16;
   for (int msub = (m_rows > 128 ? 2 : 1); msub >= 1; --msub) {
     const int rows = 128 * msub + span;
     const int nseg = (rows + 255) / 256;
     const int box_rows = (int)align_up((size_t)(rows + nseg - 1) / nseg, 8);
     if (box_rows > 256) continue;
     const int rows_alloc = nseg * box_rows;
-    // ring stage ~16 KB, at least one K=16 step
-    for (int stage_kb = 16; stage_kb >= 4; stage_kb /= 2) {
-      const int k16 = std::max(1, stage_kb * 1024 / (n * 32));
-      const size_t need = smem_need(cin_pad, rows_alloc, n, k16);
-      if (need <= (size_t)max_smem) {
+    const size_t a_bytes = (size_t)(cin_pad / 8) * rows_alloc * 16;
+    for (int n_abuf = 2; n_abuf >= 1; --n_abuf) {
+      auto accept = [&](int k16, int stages, int resident) {
         pl.msub = msub; pl.rows_alloc = rows_alloc; pl.box_rows = box_rows; pl.nseg = nseg;
         pl.box_chunks = (nseg == 1) ? std::min(cin_pad / 8, 256) : 1;
-        pl.k16_per_stage = k16; pl.smem = need;
-        return true;
+        pl.k16_per_stage = k16; pl.n_wstages = stages; pl.w_resident = resident; pl.n_abuf = n_abuf;
+        pl.smem = n_abuf * a_bytes + (size_t)stages * k16 * n * 32 + fixed;
+      };
+      const size_t w_all = (size_t)n_k16_max * n * 32;
+      if (w_all <= kResidentWeightBytes) {
+        const int k16 = std::max((n_k16_max + tc::kMaxStages - 1) / tc::kMaxStages, std::max(1, 8 * 1024 / (n * 32)));
+        const int stages = (n_k16_max + k16 - 1) / k16;
+        if (n_abuf * a_bytes + (size_t)stages * k16 * n * 32 + fixed <= (size_t)max_smem) {
+          accept(k16, stages, 1);
+          return true;
+        }
       }
+      const int k16 = std::max(1, 16 * 1024 / (n * 32));
+      for (int stages = 4; stages >= 2; --stages)
+        if (n_abuf * a_bytes + (size_t)stages * k16 * n * 32 + fixed <= (size_t)max_smem) {
+          accept(k16, stages, 0);
+          return true;
+        }
     }
   }
   return false;
 }
 
 template <int N, int MSUB>
-cudaError_t launch_one(const tc::ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
+  static int occ_cache[16] = {0};
+  static size_t occ_smem[16] = {0};
   static bool attr_set[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 16 && !attr_set[dev]) {
+  dev &= 15;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<N, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
+  if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
+    int occ = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::conv_tc_kernel<N, MSUB>, tc::kThreads, smem);
+    if (e != cudaSuccess) return e;
+    constexpr int acc_cols = N * MSUB * ((2 * N * MSUB <= 512) ? 2 : 1);
+    constexpr int tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+    occ_cache[dev] = std::max(1, std::min(occ, 512 / tmem_cols));
+    occ_smem[dev] = smem;
+  }
+  tc::ConvParams p = p_in;
+  const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev] / grid_y));
+  dim3 grid((unsigned)ctas, (unsigned)grid_y, 1);
   tc::conv_tc_kernel<N, MSUB><<<grid, tc::kThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t dispatch(int n, int msub, const tc::ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+cudaError_t dispatch(int n, int msub, const tc::ConvParams& p, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
 #define SA_CASE(NN)                                                                       \
-  case NN: return msub == 2 ? launch_one<NN, 2>(p, grid, smem, st) : launch_one<NN, 1>(p, grid, smem, st);
+  case NN: return msub == 2 ? launch_one<NN, 2>(p, grid_y, smem, n_sm, st) : launch_one<NN, 1>(p, grid_y, smem, n_sm, st);
   switch (n) {
     SA_CASE(16) SA_CASE(32) SA_CASE(64) SA_CASE(128) SA_CASE(256)
     default: return cudaErrorInvalidValue;
@@ -216,7 +242,9 @@ struct Runner {
       span = std::max(span, std::max(p.tap_base[ph], last) - p.row_lo[ph]);
     }
     Plan pl;
-    if (!make_plan(pl, w.cin_pad, w.n, span, l_in, ctx.max_smem)) return "conv does not fit in shared memory";
+    int n_k16_max = 0;
+    for (int ph = 0; ph < w.n_phases; ++ph) n_k16_max = std::max(n_k16_max, w.n_taps[ph] * (w.cin_pad / 16));
+    if (!make_plan(pl, w.cin_pad, w.n, span, l_in, n_k16_max, ctx.max_smem)) return "conv does not fit in shared memory";
     // tensor map over the input activation [B][cin_pad/8][l_in][8]
     const cuuint64_t gdim[4] = {8, (cuuint64_t)l_in, (cuuint64_t)(w.cin_pad / 8), (cuuint64_t)a.B};
     const cuuint64_t gstr[3] = {16, (cuuint64_t)l_in * 16, (cuuint64_t)(w.cin_pad / 8) * l_in * 16};
@@ -244,13 +272,15 @@ struct Runner {
     p.n_tiles = w.n_tiles;
     p.rows_alloc = pl.rows_alloc; p.box_rows = pl.box_rows; p.nseg = pl.nseg; p.box_chunks = pl.box_chunks;
     p.k16_per_stage = pl.k16_per_stage;
+    p.n_wstages = pl.n_wstages; p.w_resident = pl.w_resident; p.n_abuf = pl.n_abuf;
+    p.m_tiles = (l_in + 128 * pl.msub - 1) / (128 * pl.msub);
+    p.total_tiles = p.m_tiles * a.B;
     p.w_tile_bytes = (uint32_t)w.tile_bytes;
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
     p.slope_out = e.slope_out;
-    p.inv_blocks = e.n_blocks;
-    dim3 grid((unsigned)((l_in + 128 * pl.msub - 1) / (128 * pl.msub)), (unsigned)(w.n_phases * w.n_tiles), (unsigned)a.B);
+    p.n_blocks = e.n_blocks;
     mark(tag);
-    cudaError_t ce = dispatch(w.n, pl.msub, p, grid, pl.smem, a.stream);
+    cudaError_t ce = dispatch(w.n, pl.msub, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream);
     if (ce != cudaSuccess) return msgf("conv_tc launch: %s", cudaGetErrorString(ce));
     ++*launches;
     return nullptr;
