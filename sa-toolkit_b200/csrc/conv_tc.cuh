@@ -222,7 +222,7 @@ __device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, floa
 //   [bias N*4][barriers][tmem holder]
 // ---------------------------------------------------------------------------------------
 template <int N, int MSUB>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int phase = blockIdx.y / p.n_tiles, ntile = blockIdx.y % p.n_tiles;
