@@ -1,0 +1,297 @@
+// Fused ResBlock1 kernel for the narrow stages (C = 64, 32, 16) on tcgen05.
+//
+// One CTA keeps a time tile of MS*128 rows (halo included) in shared memory and runs all six
+// convs of a ResBlock1 (nn.py:168-175) on it without touching HBM in between:
+//     x -> [ lrelu -> conv1(k, d) -> lrelu -> conv2(k, 1) -> + x ] for d in (1, 3, 5)
+// and folds the multi-receptive-field combine (archi.py:82-86) into the last epilogue.
+//
+//   bufA  [C/8][PAD + MS*128 + PAD][8] 16-bit   lrelu(x)            operand of conv1
+//   bufT  same shape                            lrelu(conv1 + b)    operand of conv2
+//   x     fp32 residual stream, in REGISTERS of the epilogue threads (one thread owns a row
+//         of a sub-tile and half of the channels for the whole ResBlock)
+//   D     fp32 accumulators in TMEM, two buffers per sub-tile (conv parity)
+//
+// Same implicit-GEMM formulation as conv_tc.cuh: time on M, Cout on N, the staged tile is the
+// A operand and tap j is the tile with the descriptor start advanced by (j*d - pad) rows.
+// Rows computed from data beyond the tile are garbage by construction; the halo
+// H = sum of all conv reaches (12 / 36 / 60 rows for k = 3 / 7 / 11) is discarded at the end,
+// so a tile yields MS*128 - 2H valid rows.  Rows outside the utterance [0, L) are forced to
+// zero in every staged activation: that is the per-layer zero padding of the reference.
+//
+// Schedule inside a CTA (sub-tile major): MMA(c, s) needs the activations of sub-tiles s-1..s+1
+// written by the epilogue of conv c-1, so the tensor pipe works on sub-tile s+1.. while the
+// eight epilogue warps drain sub-tile s.  Weights of one conv sit in a ring (slot = stage) and
+// are released on the last sub-tile, which lets the next conv's weights stream in behind.
+//
+// Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (TMEM lane group = warp % 4, channel half = (warp - 2) / 4).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace sa {
+namespace tc {
+
+constexpr int kChainThreads = 320;
+constexpr int kChainPad = 32;            // slack rows on both sides of the staged tile (>= max tap reach 25)
+constexpr int kChainMaxConvs = 8;
+constexpr int kChainMaxSlots = 16;
+
+struct ChainParams {
+  const float* x32;         // stage input h, fp32 blocked [B][C/8][L][8]
+  float* sum32;             // MRF running sum, fp32 blocked
+  float* out32;             // stage output (EPI_OUT32)
+  void* out16;              // lrelu(stage output), 16-bit blocked (EPI_OUT16)
+  const void* w;            // weights of the n_convs convs, conv-major, each [k16 step][2][C][8]
+  const float* bias;        // [n_convs][C]
+  int* error_flag;
+  int L;                    // rows per item
+  int n_convs;              // 2 * n_dilations
+  int ktaps;
+  int dil[kChainMaxConvs];
+  int pad[kChainMaxConvs];
+  int halo;                 // H
+  int tiles_per_item, total_tiles;
+  int k16_per_stage, stages_per_conv, n_slots;
+  uint32_t flags;           // EPI_* of the final epilogue (SUM_SET / SUM_ADD / SUM_FIN / OUT32 / OUT16 / BF16)
+  float slope_out;
+  float n_blocks;
+};
+
+template <int C, int MS>
+__global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int N = C;
+  constexpr int R = MS * 128;
+  constexpr int ROWS = R + 2 * kChainPad;
+  constexpr int CHUNKS = C / 8;
+  constexpr uint32_t kChunkStride = ROWS * 16u;
+  constexpr uint32_t kBufBytes = CHUNKS * kChunkStride;
+  constexpr int kCPT = C / 16;                                   // 8-channel chunks per epilogue thread
+  constexpr uint32_t kTmemNeed = 2u * MS * N;
+  constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = (uint32_t)p.k16_per_stage * N * 32u;
+  uint8_t* bufA = smem;
+  uint8_t* bufT = smem + kBufBytes;
+  uint8_t* w_smem = smem + 2 * kBufBytes;
+  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)p.n_slots * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kChainMaxConvs * C);
+  // barrier slots: ready[2][8] acc_full[2][8] w_full[16] w_empty[16]
+  auto bar_ready = [&](int buf, int s) { return smem_u32(&bars[buf * 8 + s]); };
+  auto bar_acc_full = [&](int par, int s) { return smem_u32(&bars[16 + par * 8 + s]); };
+  auto bar_w_full = [&](int i) { return smem_u32(&bars[32 + i]); };
+  auto bar_w_empty = [&](int i) { return smem_u32(&bars[32 + kChainMaxSlots + i]); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32 + 2 * kChainMaxSlots);
+
+  const int valid_rows = R - 2 * p.halo;
+  const int k16_per_tap = C / 16;
+  const bool bf16 = (p.flags & EPI_BF16) != 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(bar_ready(0, s), 8); mbar_init(bar_ready(1, s), 8);
+      mbar_init(bar_acc_full(0, s), 1); mbar_init(bar_acc_full(1, s), 1);
+    }
+    for (int i = 0; i < kChainMaxSlots; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  for (int i = threadIdx.x; i < p.n_convs * C; i += kChainThreads) bias_s[i] = p.bias[i];
+  // zero the slack rows of both staged tiles (never written afterwards)
+  for (int i = threadIdx.x; i < 2 * CHUNKS * 2 * kChainPad; i += kChainThreads) {
+    const int buf = i / (CHUNKS * 2 * kChainPad), rem = i % (CHUNKS * 2 * kChainPad);
+    const int ch = rem / (2 * kChainPad), r = rem % (2 * kChainPad);
+    const int row = r < kChainPad ? r : R + r;                   // [0,PAD) and [PAD+R, PAD+R+PAD)
+    *reinterpret_cast<uint4*>(smem + buf * kBufBytes + ch * kChunkStride + row * 16) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== weight producer: stage g = (conv counter, stage in conv); slot = g % n_slots =====
+    if (lane == 0) {
+      int g = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x)
+        for (int c = 0; c < p.n_convs && ok; ++c)
+          for (int i = 0; i < p.stages_per_conv; ++i, ++g) {
+            const int slot = g % p.n_slots, use = g / p.n_slots;
+            if (use > 0) ok = mbar_wait(bar_w_empty(slot), (use - 1) & 1, p.error_flag);
+            if (!ok) break;
+            mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
+            bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes,
+                      static_cast<const uint8_t*>(p.w) + (size_t)(c * p.stages_per_conv + i) * stage_bytes, stage_bytes,
+                      bar_w_full(slot));
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(N, bf16);
+      int it = 0, g0 = 0;                                        // g0: first weight stage of the running conv
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+        for (int c = 0; c < p.n_convs && ok; ++c, g0 += p.stages_per_conv) {
+          const uint32_t in_base = smem_u32((c & 1) ? bufT : bufA);
+          const uint32_t rdy_parity = (uint32_t)(it * (p.n_convs / 2) + c / 2) & 1u;
+          const int dil = p.dil[c], pad = p.pad[c];
+          for (int s = 0; s < MS && ok; ++s) {
+            // inputs of sub-tiles s-1..s+1 are staged once ready[.][min(s+1, MS-1)] has completed
+            ok = mbar_wait(bar_ready(c & 1, min(s + 1, MS - 1)), rdy_parity, p.error_flag);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
+            int step = 0;
+            for (int i = 0; i < p.stages_per_conv && ok; ++i) {
+              const int g = g0 + i, slot = g % p.n_slots, use = g / p.n_slots;
+              if (s == 0) {                                      // later sub-tiles reuse the landed stage
+                ok = mbar_wait(bar_w_full(slot), use & 1, p.error_flag);
+                if (!ok) break;
+                tc_fence_after();
+              }
+              for (int kk = 0; kk < p.k16_per_stage; ++kk, ++step) {
+                const int tap = step / k16_per_tap, cb = step - tap * k16_per_tap;
+                const int row = kChainPad + s * 128 + tap * dil - pad;
+                const uint64_t adesc = make_smem_desc(in_base + (uint32_t)(2 * cb) * kChunkStride + (uint32_t)row * 16u,
+                                                      kChunkStride, 128u);
+                const uint64_t bdesc = make_smem_desc(smem_u32(w_smem) + (uint32_t)slot * stage_bytes + (uint32_t)kk * N * 32u,
+                                                      (uint32_t)N * 16u, 128u);
+                umma_f16(d_tmem, adesc, bdesc, idesc, step > 0 ? 1u : 0u);
+              }
+              if (s == MS - 1) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
+            }
+            if (ok) umma_commit(bar_acc_full(c & 1, s));
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ch0 = half * kCPT;                                 // first 8-channel chunk of this thread
+    const int cchunks = C / 8;
+    float xr[MS][kCPT * 8];                                      // fp32 residual stream of this thread
+    int it = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_item, mt = tile - b * p.tiles_per_item;
+      const int t_start = mt * valid_rows - p.halo;              // global row of tile row 0
+      // ---- P0: load x, keep it in registers, stage lrelu(x) ----
+#pragma unroll
+      for (int s = 0; s < MS; ++s) {
+        const int r = s * 128 + lg * 32 + lane;
+        const int t = t_start + r;
+        const bool inside = t >= 0 && t < p.L;
+#pragma unroll
+        for (int q = 0; q < kCPT; ++q) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
+          if (inside) {
+            const float* src = p.x32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
+            a = ldg_f4(src); c4 = ldg_f4(src + 4);
+          }
+          xr[s][q * 8 + 0] = a.x; xr[s][q * 8 + 1] = a.y; xr[s][q * 8 + 2] = a.z; xr[s][q * 8 + 3] = a.w;
+          xr[s][q * 8 + 4] = c4.x; xr[s][q * 8 + 5] = c4.y; xr[s][q * 8 + 6] = c4.z; xr[s][q * 8 + 7] = c4.w;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < MS; ++s) {
+        const int r = s * 128 + lg * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < kCPT; ++q) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[s][q * 8 + e], 0.1f);
+          *reinterpret_cast<uint4*>(bufA + (ch0 + q) * kChunkStride + (kChainPad + r) * 16) = pack8(v, bf16);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready(0, s));
+      }
+      // ---- the convs ----
+      for (int c = 0; c < p.n_convs && ok; ++c) {
+        const uint32_t acc_parity = (uint32_t)(it * (p.n_convs / 2) + c / 2) & 1u;
+        const bool second = (c & 1) != 0;                        // conv2 of a pair: x += ..
+        const bool last = (c == p.n_convs - 1);
+        const float* bias_c = bias_s + c * C + ch0 * 8;
+        uint8_t* out_buf = second ? bufA : bufT;
+#pragma unroll
+        for (int s = 0; s < MS; ++s) {
+          if (!ok) break;
+          ok = mbar_wait(bar_acc_full(c & 1, s), acc_parity, p.error_flag);
+          if (!ok) break;
+          tc_fence_after();
+          const int r = s * 128 + lg * 32 + lane;
+          const int t = t_start + r;
+          const bool inside = t >= 0 && t < p.L;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N + ch0 * 8);
+#pragma unroll
+          for (int q = 0; q < kCPT; ++q) {
+            uint32_t rr[8];
+            __syncwarp();
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                         : "r"(t_addr + (uint32_t)(q * 8))
+                         : "memory");
+            tmem_ld_wait();
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[e]) + bias_c[q * 8 + e];
+            if (second) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { xr[s][q * 8 + e] += v[e]; v[e] = xr[s][q * 8 + e]; }
+            }
+            if (!last) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = inside ? lrelu_f(v[e], 0.1f) : 0.f;
+              *reinterpret_cast<uint4*>(out_buf + (ch0 + q) * kChunkStride + (kChainPad + r) * 16) = pack8(v, bf16);
+            } else if (inside && r >= p.halo && r < R - p.halo) {
+              // final epilogue: multi-receptive-field combine + stores (v = x_final)
+              const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
+              if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
+                const float4 s0 = ldg_f4(p.sum32 + idx), s1 = ldg_f4(p.sum32 + idx + 4);
+                v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+                v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+              }
+              if (p.flags & EPI_SUM_FIN) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = v[e] / p.n_blocks;
+              }
+              if (p.flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
+                stg_f4(p.sum32 + idx, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx + 4, v[4], v[5], v[6], v[7]);
+              }
+              if (p.flags & EPI_OUT32) {
+                stg_f4(p.out32 + idx, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx + 4, v[4], v[5], v[6], v[7]);
+              }
+              if (p.flags & EPI_OUT16) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = lrelu_f(v[e], p.slope_out);
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx * 2) = pack8(v, bf16);
+              }
+            }
+          }
+          if (!last) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready(second ? 0 : 1, s));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace tc
+}  // namespace sa

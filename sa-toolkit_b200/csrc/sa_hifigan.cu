@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -66,10 +67,12 @@ struct sa_hifigan {
   int precision = -1;
   bool finalized = false;
   int64_t launches = 0;
+  bool use_fused = true;                // SATOOLS_B200_FUSED=0 forces the per-layer tensor-core path
   int debug_tap = -1;
   float* debug_out = nullptr;
   int n_sm = 148;
   sa::tc_context tc;
+  std::vector<sa::tc_chain> chains;     // [n_stages * n_resblocks], fused narrow-stage ResBlocks
   // per-launch profiling: one event before every launch + one closing event
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -166,6 +169,7 @@ int sa_hifigan_create(const sa_hifigan_cfg* cfg, sa_hifigan** out) {
   sa_hifigan* h = new sa_hifigan();
   h->cfg = *cfg;
   h->device = dev;
+  if (const char* env = getenv("SATOOLS_B200_FUSED")) h->use_fused = atoi(env) != 0;
   h->n_sm = prop.multiProcessorCount;
 
   auto add = [&](const std::string& name, bool tr, int cin, int cout, int k, int dil, int pad, int stride) {
@@ -202,6 +206,8 @@ static void free_device_weights(sa_hifigan* h) {
     c.d_w32 = nullptr; c.d_bias = nullptr;
     sa::tc_free_weights(c.tc);
   }
+  for (auto& ch : h->chains) sa::tc_free_chain(ch);
+  h->chains.clear();
 }
 
 void sa_hifigan_destroy(sa_hifigan* h) {
@@ -334,6 +340,24 @@ int sa_hifigan_finalize(sa_hifigan* h, int32_t precision) {
     }
   }
   if (precision != SA_PRECISION_FP32) {
+    // fused ResBlock packing for the narrow stages (C <= 64)
+    const sa_hifigan_cfg& cfg = h->cfg;
+    h->chains.assign((size_t)cfg.n_stages * cfg.n_resblocks, sa::tc_chain());
+    for (int i = 0; i < cfg.n_stages; ++i)
+      for (int j = 0; j < cfg.n_resblocks; ++j) {
+        const int C = h->stage_channels(i), k = cfg.resblock_kernels[j], nc = 2 * cfg.n_dilations;
+        if (!sa::tc_chain_supported(C, k, nc)) continue;
+        const float* wp[8]; const float* bp[8]; int dil[8], pad[8];
+        for (int m = 0; m < cfg.n_dilations; ++m)
+          for (int which = 0; which < 2; ++which) {
+            const sa_conv& c = h->convs[h->rb(i, j, which, m)];
+            wp[2 * m + which] = c.w.data(); bp[2 * m + which] = c.bias.data();
+            dil[2 * m + which] = c.dil; pad[2 * m + which] = c.pad;
+          }
+        const char* err = sa::tc_pack_chain(h->chains[(size_t)i * cfg.n_resblocks + j], C, k, nc, wp, bp, dil, pad,
+                                            precision == SA_PRECISION_BF16);
+        if (err) return fail(SA_ERR_CUDA, "resblocks.%d: %s", i * cfg.n_resblocks + j, err);
+      }
     const char* err = sa::tc_init(h->tc, h->device);
     if (err) return fail(SA_ERR_CUDA, "tensor-core path init: %s", err);
   }
@@ -535,6 +559,7 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, cons
     }
     a.layers = layers.data();
     a.n_layers = (int)layers.size();
+    a.chains = (h->use_fused && !h->chains.empty()) ? h->chains.data() : nullptr;
     a.mark_ctx = h;
     a.mark = h->prof_on ? +[](void* ctx, int tag, cudaStream_t s) { static_cast<sa_hifigan*>(ctx)->mark(tag, s); }
                         : nullptr;

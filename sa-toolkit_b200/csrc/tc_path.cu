@@ -12,6 +12,7 @@
 //   S32    multi-receptive-field sum                fp32    E
 #include "tc_path.cuh"
 #include "conv_tc.cuh"
+#include "chain_tc.cuh"
 
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -210,6 +211,56 @@ cudaError_t dispatch(int n, int msub, const tc::ConvParams& p, int grid_y, size_
 #undef SA_CASE
 }
 
+// ---- fused ResBlock (chain) launch -------------------------------------------------------
+struct ChainPlan { int ms, n_slots; size_t smem; };
+
+bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
+  const int C = ch.c;
+  const size_t stage = (size_t)ch.k16_per_stage * C * 32;
+  auto need = [&](int ms, int slots) {
+    const size_t rows = (size_t)ms * 128 + 2 * tc::kChainPad;
+    return 2 * (size_t)(C / 8) * rows * 16 + slots * stage + (size_t)tc::kChainMaxConvs * C * 4 +
+           (32 + 2 * tc::kChainMaxSlots) * 8 + 16;
+  };
+  const int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
+  if (slots > tc::kChainMaxSlots) return false;
+  int ms;
+  if (C == 64) ms = need(4, slots) <= (size_t)max_smem ? 4 : 3;
+  else if (C == 32) ms = 4;
+  else ms = 8;
+  if (need(ms, slots) > (size_t)max_smem) return false;
+  if (ms * 128 - 2 * ch.halo < 64) return false;
+  pl.ms = ms; pl.n_slots = slots; pl.smem = need(ms, slots);
+  return true;
+}
+
+template <int C, int MS>
+cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  static int occ_cache[16] = {0};
+  static size_t occ_smem[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
+    int occ = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS>, tc::kChainThreads, smem);
+    if (e != cudaSuccess) return e;
+    constexpr int need = 2 * MS * C;
+    constexpr int cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    occ_cache[dev] = std::max(1, std::min(occ, 512 / cols));
+    occ_smem[dev] = smem;
+  }
+  const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev]));
+  tc::resblock_chain_kernel<C, MS><<<ctas, tc::kChainThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 struct Epi {
   uint32_t flags = 0;
   const float* res32 = nullptr;
@@ -285,6 +336,43 @@ struct Runner {
     ++*launches;
     return nullptr;
   }
+
+  // One whole ResBlock1 on a narrow stage, fused (chain_tc.cuh).  Returns "" (empty, not an
+  // error) when this block must run layer by layer instead.
+  bool chain_usable(const tc_chain& ch, int L) const {
+    ChainPlan pl;
+    if (!ch.d_w || !chain_plan(pl, ch, ctx.max_smem)) return false;
+    return L >= 2 * (pl.ms * 128 - 2 * ch.halo);                // short sequences: the per-layer path wastes less
+  }
+
+  const char* chain(const tc_chain& ch, const float* x32, int L, const Epi& e, int tag, bool* done) {
+    *done = false;
+    ChainPlan pl;
+    if (!chain_usable(ch, L) || !chain_plan(pl, ch, ctx.max_smem)) return nullptr;
+    const int valid = pl.ms * 128 - 2 * ch.halo;
+    tc::ChainParams p;
+    memset(&p, 0, sizeof(p));
+    p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
+    p.w = ch.d_w; p.bias = ch.d_bias; p.error_flag = ctx.d_error;
+    p.L = L; p.n_convs = ch.n_convs; p.ktaps = ch.k;
+    for (int c = 0; c < ch.n_convs; ++c) { p.dil[c] = ch.dil[c]; p.pad[c] = ch.pad[c]; }
+    p.halo = ch.halo;
+    p.tiles_per_item = (L + valid - 1) / valid;
+    p.total_tiles = p.tiles_per_item * a.B;
+    p.k16_per_stage = ch.k16_per_stage; p.stages_per_conv = ch.stages_per_conv; p.n_slots = pl.n_slots;
+    p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+    p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
+    mark(tag);
+    cudaError_t ce = cudaErrorInvalidValue;
+    if (ch.c == 64 && pl.ms == 4) ce = launch_chain<64, 4>(p, pl.smem, a.n_sm, a.stream);
+    else if (ch.c == 64 && pl.ms == 3) ce = launch_chain<64, 3>(p, pl.smem, a.n_sm, a.stream);
+    else if (ch.c == 32 && pl.ms == 4) ce = launch_chain<32, 4>(p, pl.smem, a.n_sm, a.stream);
+    else if (ch.c == 16 && pl.ms == 8) ce = launch_chain<16, 8>(p, pl.smem, a.n_sm, a.stream);
+    if (ce != cudaSuccess) return msgf("resblock_chain launch: %s", cudaGetErrorString(ce));
+    ++*launches;
+    *done = true;
+    return nullptr;
+  }
 };
 
 }  // namespace
@@ -348,6 +436,52 @@ const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed,
   TC_CUDA(cudaMalloc(&w.d_w, w.bytes));
   TC_CUDA(cudaMemcpy(w.d_w, host.data(), w.bytes, cudaMemcpyHostToDevice));
   return nullptr;
+}
+
+bool tc_chain_supported(int c, int k, int n_convs) {
+  if (c != 16 && c != 32 && c != 64) return false;
+  if (n_convs < 2 || n_convs > tc::kChainMaxConvs || (n_convs & 1)) return false;
+  const int spc = (c == 64) ? k : 1;
+  return spc <= tc::kChainMaxSlots && k >= 1;
+}
+
+const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* const* folded, const float* const* bias,
+                          const int* dil, const int* pad, bool bf16) {
+  tc_free_chain(ch);
+  if (!tc_chain_supported(c, k, n_convs)) return nullptr;
+  ch.c = c; ch.k = k; ch.n_convs = n_convs;
+  ch.halo = 0;
+  for (int i = 0; i < n_convs; ++i) { ch.dil[i] = dil[i]; ch.pad[i] = pad[i]; ch.halo += pad[i]; }
+  for (int i = 0; i < n_convs; ++i) if (pad[i] > 25 || (k - 1) * dil[i] - pad[i] > 25) return nullptr;   // tap reach > slack rows
+  const int k16_per_tap = c / 16;
+  if (c == 64) { ch.k16_per_stage = k16_per_tap; ch.stages_per_conv = k; }     // one tap (8 KB) per stage
+  else { ch.k16_per_stage = k * k16_per_tap; ch.stages_per_conv = 1; }         // the whole conv per stage
+  const size_t conv_elems = (size_t)k * k16_per_tap * c * 16;
+  std::vector<uint16_t> host(conv_elems * n_convs);
+  for (int cv = 0; cv < n_convs; ++cv)
+    for (int tap = 0; tap < k; ++tap)
+      for (int cb = 0; cb < k16_per_tap; ++cb) {
+        uint16_t* step = host.data() + cv * conv_elems + (size_t)(tap * k16_per_tap + cb) * c * 16;
+        for (int h = 0; h < 2; ++h)
+          for (int r = 0; r < c; ++r)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = cb * 16 + h * 8 + e;
+              step[((size_t)h * c + r) * 8 + e] = to16(folded[cv][((size_t)r * c + ci) * k + tap], bf16);
+            }
+      }
+  std::vector<float> hb((size_t)n_convs * c);
+  for (int cv = 0; cv < n_convs; ++cv) memcpy(hb.data() + (size_t)cv * c, bias[cv], c * sizeof(float));
+  TC_CUDA(cudaMalloc(&ch.d_w, host.size() * 2));
+  TC_CUDA(cudaMemcpy(ch.d_w, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
+  TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ch.d_bias), hb.size() * sizeof(float)));
+  TC_CUDA(cudaMemcpy(ch.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return nullptr;
+}
+
+void tc_free_chain(tc_chain& ch) {
+  if (ch.d_w) cudaFree(ch.d_w);
+  if (ch.d_bias) cudaFree(ch.d_bias);
+  ch = tc_chain();
 }
 
 void tc_free_weights(tc_weights& w) {
@@ -419,11 +553,12 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
   const int L_post = 1 + nst + nst * nrb * 2 * nd;
   const char* err;
 
+  float* Hout = X32;                                // where the fp32 output of the running section lives
   auto unblock_tap = [&](int tap, int C, int L) -> const char* {
     if (!a.debug_out || a.debug_tap != tap) return nullptr;
     dim3 g((unsigned)((L + 255) / 256), (unsigned)(C / 8), (unsigned)a.B);
     run.mark(15);
-    unblock_kernel<<<g, 256, 0, st>>>(X32, a.debug_out, C, L);
+    unblock_kernel<<<g, 256, 0, st>>>(Hout, a.debug_out, C, L);
     ++*launches;
     TC_CUDA(cudaGetLastError());
     return nullptr;
@@ -458,25 +593,36 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     L *= up.stride;
     const bool last_stage = (i == nst - 1);
     const bool tap_here = a.debug_out && a.debug_tap == SA_TAP_STAGE0 + i;
+    // The fused kernel reads X32 (with halo) while other CTAs store results, so its fp32 stage
+    // output goes to R32; the per-layer path writes it over the then-dead X32.
+    const bool last_rb_fused = a.chains && run.chain_usable(a.chains[i * nrb + nrb - 1], L);
+    float* H32 = last_rb_fused ? R32 : X32;
+    Hout = H32;
     for (int j = 0; j < nrb; ++j) {
       const int tag = 16 * (1 + i) + 1 + j;
+      // multi-receptive-field epilogue of this block's last conv (archi.py:82-86)
+      Epi fin;
+      fin.sum32 = S32; fin.n_blocks = (float)nrb;
+      if (nrb > 1) fin.flags |= (j == 0) ? tc::EPI_SUM_SET : (j == nrb - 1 ? tc::EPI_SUM_FIN : tc::EPI_SUM_ADD);
+      if (j == nrb - 1) {
+        if (last_stage || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = H32; }
+        if (!last_stage) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = 0.1f; }
+      }
+      if (a.chains) {                               // narrow stages: the whole ResBlock in one kernel
+        bool done = false;
+        if ((err = run.chain(a.chains[i * nrb + j], X32, L, fin, tag, &done))) return err;
+        if (done) continue;
+      }
       for (int m = 0; m < nd; ++m) {               // nn.py:169-174
         Epi e1;
         e1.flags = tc::EPI_OUT16; e1.out16 = T16; e1.slope_out = 0.1f;
         if ((err = run.conv(a.layers[L_rb(i, j, 0, m)], m == 0 ? AX16 : A16, L, e1, tag))) return err;
-        Epi e2;
-        e2.flags = tc::EPI_RES;
+        Epi e2 = (m < nd - 1) ? Epi() : fin;
+        e2.flags |= tc::EPI_RES;
         e2.res32 = (m == 0) ? X32 : R32;
         if (m < nd - 1) {
           e2.flags |= tc::EPI_OUT32 | tc::EPI_OUT16;
           e2.out32 = R32; e2.out16 = A16; e2.slope_out = 0.1f;
-        } else {                                    // archi.py:82-86
-          e2.sum32 = S32; e2.n_blocks = (float)nrb;
-          if (nrb > 1) e2.flags |= (j == 0) ? tc::EPI_SUM_SET : (j == nrb - 1 ? tc::EPI_SUM_FIN : tc::EPI_SUM_ADD);
-          if (j == nrb - 1) {
-            if (last_stage || tap_here) { e2.flags |= tc::EPI_OUT32; e2.out32 = X32; }
-            if (!last_stage) { e2.flags |= tc::EPI_OUT16; e2.out16 = P16; e2.slope_out = 0.1f; }
-          }
         }
         if ((err = run.conv(a.layers[L_rb(i, j, 1, m)], T16, L, e2, tag))) return err;
       }
@@ -488,7 +634,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     const int threads = 256;
     dim3 g((unsigned)((L + 1 + threads - 1) / threads), (unsigned)a.B);
     run.mark(16 * (nst + 1));
-    conv_post_blocked_kernel<<<g, threads, post.cin * post.k * sizeof(float), st>>>(X32, post.d_w32, post.d_bias, a.y,
+    conv_post_blocked_kernel<<<g, threads, post.cin * post.k * sizeof(float), st>>>(Hout, post.d_w32, post.d_bias, a.y,
                                                                                     post.cin, L, post.k, 0.01f, a.y_dtype);
     ++*launches;
     TC_CUDA(cudaGetLastError());

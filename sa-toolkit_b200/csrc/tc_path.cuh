@@ -23,6 +23,17 @@ struct tc_weights {
   size_t bytes = 0;
 };
 
+// One ResBlock1 packed for the fused narrow-stage kernel (chain_tc.cuh): the 2*n_dilations convs in
+// execution order (convs1[0], convs2[0], convs1[1], ...), each [k16 step][2][C][8]; bias [n_convs][C].
+struct tc_chain {
+  void* d_w = nullptr;
+  float* d_bias = nullptr;
+  int c = 0, k = 0, n_convs = 0;
+  int dil[8] = {0}, pad[8] = {0};
+  int halo = 0;
+  int k16_per_stage = 0, stages_per_conv = 0;
+};
+
 struct tc_context {
   bool ready = false;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -54,6 +65,7 @@ struct tc_forward_args {
   int n_sm;
   const tc_layer* layers;
   int n_layers;
+  const tc_chain* chains = nullptr;                           // [n_stages * n_resblocks]; d_w == NULL: not packed
   void* mark_ctx = nullptr;                                   // per-launch profiling hook
   void (*mark)(void* ctx, int tag, cudaStream_t s) = nullptr;
 };
@@ -62,6 +74,10 @@ bool tc_layer_supported(bool transposed, int cin, int cout, int k);
 const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed, int cin, int cout, int k,
                             int stride, int pad, bool bf16);
 void tc_free_weights(tc_weights& w);
+bool tc_chain_supported(int c, int k, int n_convs);
+const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* const* folded, const float* const* bias,
+                          const int* dil, const int* pad, bool bf16);
+void tc_free_chain(tc_chain& ch);
 const char* tc_init(tc_context& ctx, int device);
 bool tc_error_raised(const tc_context& ctx);
 size_t tc_workspace_bytes(const sa_hifigan_cfg& cfg, int B, int T);
