@@ -115,56 +115,62 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   if (warp == 0) {
     // ===== weight producer: stage g = (conv counter, stage in conv); slot = g % n_slots =====
     if (lane == 0) {
-      int g = 0;
-      bool ok = true;
+      int slot = 0;
+      uint32_t par = 1;                                          // parity of the previous use of `slot`
+      bool wrapped = false, ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x)
         for (int c = 0; c < p.n_convs && ok; ++c)
-          for (int i = 0; i < p.stages_per_conv; ++i, ++g) {
-            const int slot = g % p.n_slots, use = g / p.n_slots;
-            if (use > 0) ok = mbar_wait(bar_w_empty(slot), (use - 1) & 1, p.error_flag);
+          for (int i = 0; i < p.stages_per_conv; ++i) {
+            if (wrapped) ok = mbar_wait(bar_w_empty(slot), par, p.error_flag);
             if (!ok) break;
             mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
             bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes,
                       static_cast<const uint8_t*>(p.w) + (size_t)(c * p.stages_per_conv + i) * stage_bytes, stage_bytes,
                       bar_w_full(slot));
+            if (++slot == p.n_slots) { slot = 0; par ^= 1u; wrapped = true; }
           }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N, bf16);
-      int it = 0, g0 = 0;                                        // g0: first weight stage of the running conv
+      const uint32_t hi128 = desc_hi(128u);
+      const uint32_t cs8 = kChunkStride >> 3;
+      const uint32_t b_lo0 = desc_lo(smem_u32(w_smem), (uint32_t)N * 16u);
+      int it = 0, slot0 = 0;                                     // slot0 / par0: first weight stage of the running conv
+      uint32_t par0 = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
-        for (int c = 0; c < p.n_convs && ok; ++c, g0 += p.stages_per_conv) {
-          const uint32_t in_base = smem_u32((c & 1) ? bufT : bufA);
+        for (int c = 0; c < p.n_convs && ok; ++c) {
+          const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA), kChunkStride) + (uint32_t)(kChainPad - p.pad[c]);
           const uint32_t rdy_parity = (uint32_t)(it * (p.n_convs / 2) + c / 2) & 1u;
-          const int dil = p.dil[c], pad = p.pad[c];
+          const uint32_t dil = (uint32_t)p.dil[c];
           for (int s = 0; s < MS && ok; ++s) {
             // inputs of sub-tiles s-1..s+1 are staged once ready[.][min(s+1, MS-1)] has completed
             ok = mbar_wait(bar_ready(c & 1, min(s + 1, MS - 1)), rdy_parity, p.error_flag);
             if (!ok) break;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
-            int step = 0;
+            uint32_t a_tap = in_lo0 + (uint32_t)(s * 128), a_cb = 0, accum = 0;
+            int cb = 0, slot = slot0;
+            uint32_t par = par0;
             for (int i = 0; i < p.stages_per_conv && ok; ++i) {
-              const int g = g0 + i, slot = g % p.n_slots, use = g / p.n_slots;
               if (s == 0) {                                      // later sub-tiles reuse the landed stage
-                ok = mbar_wait(bar_w_full(slot), use & 1, p.error_flag);
+                ok = mbar_wait(bar_w_full(slot), par, p.error_flag);
                 if (!ok) break;
                 tc_fence_after();
               }
-              for (int kk = 0; kk < p.k16_per_stage; ++kk, ++step) {
-                const int tap = step / k16_per_tap, cb = step - tap * k16_per_tap;
-                const int row = kChainPad + s * 128 + tap * dil - pad;
-                const uint64_t adesc = make_smem_desc(in_base + (uint32_t)(2 * cb) * kChunkStride + (uint32_t)row * 16u,
-                                                      kChunkStride, 128u);
-                const uint64_t bdesc = make_smem_desc(smem_u32(w_smem) + (uint32_t)slot * stage_bytes + (uint32_t)kk * N * 32u,
-                                                      (uint32_t)N * 16u, 128u);
-                umma_f16(d_tmem, adesc, bdesc, idesc, step > 0 ? 1u : 0u);
+              uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
+              for (int kk = 0; kk < p.k16_per_stage; ++kk) {
+                umma_f16(d_tmem, desc64(a_tap + a_cb, hi128), desc64(b_lo, hi128), idesc, accum);
+                accum = 1;
+                b_lo += (uint32_t)N * 2u;
+                if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += dil; } else { a_cb += cs8; }
               }
               if (s == MS - 1) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
+              if (++slot == p.n_slots) { slot = 0; par ^= 1u; }
             }
+            if (s == MS - 1) { slot0 = slot; par0 = par; }
             if (ok) umma_commit(bar_acc_full(c & 1, s));
           }
         }
@@ -230,18 +236,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
           const int t = t_start + r;
           const bool inside = t >= 0 && t < p.L;
           const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N + ch0 * 8);
+          uint32_t rr[kCPT * 8];
+          __syncwarp();
 #pragma unroll
-          for (int q = 0; q < kCPT; ++q) {
-            uint32_t rr[8];
-            __syncwarp();
+          for (int q = 0; q < kCPT; ++q)
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                         : "=r"(rr[q * 8 + 0]), "=r"(rr[q * 8 + 1]), "=r"(rr[q * 8 + 2]), "=r"(rr[q * 8 + 3]),
+                           "=r"(rr[q * 8 + 4]), "=r"(rr[q * 8 + 5]), "=r"(rr[q * 8 + 6]), "=r"(rr[q * 8 + 7])
                          : "r"(t_addr + (uint32_t)(q * 8))
                          : "memory");
-            tmem_ld_wait();
-            float v[8];
+          tmem_ld_wait();                                        // one wait for all the loads of this sub-tile
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[e]) + bias_c[q * 8 + e];
+          for (int q = 0; q < kCPT; ++q) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_c + q * 8), b1 = *reinterpret_cast<const float4*>(bias_c + q * 8 + 4);
+            v[0] = __uint_as_float(rr[q * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[q * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(rr[q * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[q * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(rr[q * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[q * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(rr[q * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[q * 8 + 7]) + b1.w;
             if (second) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) { xr[s][q * 8 + e] += v[e]; v[e] = xr[s][q * 8 + e]; }

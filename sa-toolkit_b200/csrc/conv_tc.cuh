@@ -186,6 +186,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   return d;
 }
+// The same descriptor as two 32-bit halves: only the start field (low 14 bits of `lo`) changes
+// between MMAs, so the issue loop updates it with one integer add.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // Instruction descriptor, kind::f16: fp32 accumulate, A/B fp16 (0) or bf16 (1), both K-major,
 // M = 128, N = n.   bits [4,6) c_format=1 | [7,10) a_format | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4
 __device__ __forceinline__ uint32_t make_idesc(int n, bool bf16) {
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it % p.n_abuf, use = it / p.n_abuf;
+        const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         if (use > 0 && !mbar_wait(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
         const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
         mbar_arrive_expect_tx(bar_a_full(buf), a_bytes);
@@ -293,19 +301,21 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
   } else if (warp == 1) {
     // ===== W producer: weight stages through the ring (once, when resident) =====
     if (lane == 0) {
-      int wit = 0;
+      int slot = 0;
+      uint32_t par = 1;                                           // parity of the previous use of `slot`
+      bool wrapped = false;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         if (p.w_resident && tile != (int)blockIdx.x) break;
         bool ok = true;
-        for (int i = 0; i < n_iters && ok; ++i, ++wit) {
-          const int slot = wit % p.n_wstages, use = wit / p.n_wstages;
-          if (use > 0) ok = mbar_wait(bar_w_empty(slot), (use - 1) & 1, p.error_flag);
+        for (int i = 0; i < n_iters && ok; ++i) {
+          if (wrapped) ok = mbar_wait(bar_w_empty(slot), par, p.error_flag);
           if (!ok) break;
           const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
           const uint32_t bytes = (uint32_t)k16 * N * 32u;
           mbar_arrive_expect_tx(bar_w_full(slot), bytes);
           bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
                     bar_w_full(slot));
+          if (++slot == p.n_wstages) { slot = 0; par ^= 1u; wrapped = true; }
         }
         if (!ok) break;
       }
@@ -315,36 +325,43 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N, (p.flags & EPI_BF16) != 0);
       const int row_lo = p.row_lo[phase];
-      int it = 0, wit = 0;
+      const uint32_t hi128 = desc_hi(128u);
+      const uint32_t cs8 = chunk_stride >> 3;                     // two channel chunks, in 16-byte units
+      const uint32_t b_lo0 = desc_lo(smem_u32(w_smem), (uint32_t)N * 16u);
+      int it = 0, wslot = 0;
+      uint32_t wpar = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
-        const int buf = it % p.n_abuf, use = it / p.n_abuf;
-        const int acc = it % kNumAcc, acc_use = it / kNumAcc;
+        const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
+        const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
         if (acc_use > 0) ok = mbar_wait(bar_acc_empty(acc), (acc_use - 1) & 1, p.error_flag);
         if (ok) ok = mbar_wait(bar_a_full(buf), use & 1, p.error_flag);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t a_base = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
+        // descriptor bookkeeping in 16-byte units: start(tap, cb, ms) = a0 + tap*tap_step + cb*cs8 + ms*128
+        const uint32_t a_lo0 = desc_lo(smem_u32(a_smem) + (uint32_t)buf * a_bytes, chunk_stride) +
+                               (uint32_t)(p.tap_base[phase] - row_lo);
         const uint32_t d_base = tmem_base + (uint32_t)(acc * kAccCols);
-        int step = 0;
+        uint32_t a_tap = a_lo0, a_cb = 0, accum = 0;
+        int cb = 0;
         for (int i = 0; i < n_iters; ++i) {
-          int slot, wuse;
-          if (p.w_resident) { slot = i; wuse = 0; } else { slot = wit % p.n_wstages; wuse = wit / p.n_wstages; ++wit; }
-          ok = mbar_wait(bar_w_full(slot), wuse & 1, p.error_flag);
+          int slot;
+          uint32_t wuse_par;
+          if (p.w_resident) { slot = i; wuse_par = 0; }
+          else { slot = wslot; wuse_par = wpar; if (++wslot == p.n_wstages) { wslot = 0; wpar ^= 1u; } }
+          ok = mbar_wait(bar_w_full(slot), wuse_par, p.error_flag);
           if (!ok) break;
           tc_fence_after();
           const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
-          for (int kk = 0; kk < k16; ++kk, ++step) {
-            const int tap = step / k16_per_tap, cb = step - tap * k16_per_tap;
-            const int off = p.tap_base[phase] + tap * p.tap_step - row_lo;        // staged row of output row m0
-            const uint32_t a_addr = a_base + (uint32_t)(2 * cb) * chunk_stride + (uint32_t)off * 16u;
-            const uint64_t bdesc = make_smem_desc(smem_u32(w_smem) + (uint32_t)slot * stage_bytes + (uint32_t)kk * N * 32u,
-                                                  (uint32_t)N * 16u, 128u);
+          uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
+          for (int kk = 0; kk < k16; ++kk) {
+            const uint64_t bdesc = desc64(b_lo, hi128);
 #pragma unroll
-            for (int ms = 0; ms < MSUB; ++ms) {
-              const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)ms * 128u * 16u, chunk_stride, 128u);
-              umma_f16(d_base + (uint32_t)ms * N, adesc, bdesc, idesc, step > 0 ? 1u : 0u);
-            }
+            for (int ms = 0; ms < MSUB; ++ms)
+              umma_f16(d_base + (uint32_t)ms * N, desc64(a_tap + a_cb + (uint32_t)ms * 128u, hi128), bdesc, idesc, accum);
+            accum = 1;
+            b_lo += (uint32_t)N * 2u;
+            if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += (uint32_t)p.tap_step; } else { a_cb += cs8; }
           }
           if (!p.w_resident) umma_commit(bar_w_empty(slot));     // slot free once these MMAs have read it
         }
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     const uint32_t flags = p.flags;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it % kNumAcc, acc_use = it / kNumAcc;
+      const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
       if (!mbar_wait(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
       tc_fence_after();
       const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
