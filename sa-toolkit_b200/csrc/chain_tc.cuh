@@ -5,8 +5,9 @@
 //     x -> [ lrelu -> conv1(k, d) -> lrelu -> conv2(k, 1) -> + x ] for d in (1, 3, 5)
 // and folds the multi-receptive-field combine (archi.py:82-86) into the last epilogue.
 //
-//   bufA  [C/8][PAD + MS*128 + PAD][8] 16-bit   lrelu(x)            operand of conv1
-//   bufT  same shape                            lrelu(conv1 + b)    operand of conv2
+//   bufA  [PAD + MS*128 + PAD rows][C] 16-bit, UMMA K-major swizzled (row = 2C bytes: SWIZZLE_128B /
+//         64B / 32B for C = 64 / 32 / 16)         lrelu(x)            operand of conv1
+//   bufT  same shape                              lrelu(conv1 + b)    operand of conv2
 //   x     fp32 residual stream, in REGISTERS of the epilogue threads (one thread owns a row
 //         of a sub-tile and half of the channels for the whole ResBlock)
 //   D     fp32 accumulators in TMEM, two buffers per sub-tile (conv parity)
@@ -41,7 +42,8 @@ struct ChainParams {
   float* sum32;             // MRF running sum, fp32 blocked
   float* out32;             // stage output (EPI_OUT32)
   void* out16;              // lrelu(stage output), 16-bit blocked (EPI_OUT16)
-  const void* w;            // weights of the n_convs convs, conv-major, each [k16 step][2][C][8]
+  const void* w;            // weights of the n_convs convs, conv-major, each [tap][C rows][C] pre-swizzled
+  int desc_base_offset;     // debug switch, see conv_tc.cuh
   const float* bias;        // [n_convs][C]
   int* error_flag;
   int L;                    // rows per item
@@ -59,13 +61,13 @@ struct ChainParams {
 
 template <int C, int MS>
 __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const __grid_constant__ ChainParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int N = C;
   constexpr int R = MS * 128;
   constexpr int ROWS = R + 2 * kChainPad;
-  constexpr int CHUNKS = C / 8;
-  constexpr uint32_t kChunkStride = ROWS * 16u;
-  constexpr uint32_t kBufBytes = CHUNKS * kChunkStride;
+  constexpr uint32_t RB = 2u * C;                                // row bytes: 128 / 64 / 32
+  constexpr uint32_t kBufBytes = ROWS * RB;
   constexpr int kCPT = C / 16;                                   // 8-channel chunks per epilogue thread
   constexpr uint32_t kTmemNeed = 2u * MS * N;
   constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
@@ -99,13 +101,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   for (int i = threadIdx.x; i < p.n_convs * C; i += kChainThreads) bias_s[i] = p.bias[i];
-  // zero the slack rows of both staged tiles (never written afterwards)
-  for (int i = threadIdx.x; i < 2 * CHUNKS * 2 * kChainPad; i += kChainThreads) {
-    const int buf = i / (CHUNKS * 2 * kChainPad), rem = i % (CHUNKS * 2 * kChainPad);
-    const int ch = rem / (2 * kChainPad), r = rem % (2 * kChainPad);
-    const int row = r < kChainPad ? r : R + r;                   // [0,PAD) and [PAD+R, PAD+R+PAD)
-    *reinterpret_cast<uint4*>(smem + buf * kBufBytes + ch * kChunkStride + row * 16) = make_uint4(0, 0, 0, 0);
-  }
+  // zero both staged tiles once: the PAD slack rows are never written afterwards
+  for (uint32_t i = threadIdx.x; i < 2 * kBufBytes / 16; i += kChainThreads)
+    *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -134,24 +132,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N, bf16);
-      const uint32_t hi128 = desc_hi(128u);
-      const uint32_t cs8 = kChunkStride >> 3;
-      const uint32_t b_lo0 = desc_lo(smem_u32(w_smem), (uint32_t)N * 16u);
+      const uint32_t hi = desc_hi(RB);
+      const int bo = p.desc_base_offset;
+      constexpr uint32_t row16 = RB >> 4;
+      const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
       int it = 0, slot0 = 0;                                     // slot0 / par0: first weight stage of the running conv
       uint32_t par0 = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
         for (int c = 0; c < p.n_convs && ok; ++c) {
-          const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA), kChunkStride) + (uint32_t)(kChainPad - p.pad[c]);
+          const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA)) + (uint32_t)(kChainPad - p.pad[c]) * row16;
           const uint32_t rdy_parity = (uint32_t)(it * (p.n_convs / 2) + c / 2) & 1u;
-          const uint32_t dil = (uint32_t)p.dil[c];
+          const uint32_t dil16 = (uint32_t)p.dil[c] * row16;
           for (int s = 0; s < MS && ok; ++s) {
             // inputs of sub-tiles s-1..s+1 are staged once ready[.][min(s+1, MS-1)] has completed
             ok = mbar_wait(bar_ready(c & 1, min(s + 1, MS - 1)), rdy_parity, p.error_flag);
             if (!ok) break;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
-            uint32_t a_tap = in_lo0 + (uint32_t)(s * 128), a_cb = 0, accum = 0;
+            uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16, a_cb = 0, accum = 0;
             int cb = 0, slot = slot0;
             uint32_t par = par0;
             for (int i = 0; i < p.stages_per_conv && ok; ++i) {
@@ -162,10 +161,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
               }
               uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
               for (int kk = 0; kk < p.k16_per_stage; ++kk) {
-                umma_f16(d_tmem, desc64(a_tap + a_cb, hi128), desc64(b_lo, hi128), idesc, accum);
+                // one panel (C <= 64): tap = one weight block [N rows][C]; K16 step kk sits at +32 B in the row
+                umma_f16(d_tmem, desc64(a_tap + a_cb, hi, bo), desc64(b_lo, hi, bo), idesc, accum);
                 accum = 1;
-                b_lo += (uint32_t)N * 2u;
-                if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += dil; } else { a_cb += cs8; }
+                if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += dil16; b_lo += (uint32_t)N * row16 - 2u * (uint32_t)(k16_per_tap - 1); }
+                else { a_cb += 2u; b_lo += 2u; }
               }
               if (s == MS - 1) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
               if (++slot == p.n_slots) { slot = 0; par ^= 1u; }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[s][q * 8 + e], 0.1f);
-          *reinterpret_cast<uint4*>(bufA + (ch0 + q) * kChunkStride + (kChainPad + r) * 16) = pack8(v, bf16);
+          *reinterpret_cast<uint4*>(bufA + swz((uint32_t)(kChainPad + r) * RB + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
             if (!last) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = inside ? lrelu_f(v[e], 0.1f) : 0.f;
-              *reinterpret_cast<uint4*>(out_buf + (ch0 + q) * kChunkStride + (kChainPad + r) * 16) = pack8(v, bf16);
+              *reinterpret_cast<uint4*>(out_buf + swz((uint32_t)(kChainPad + r) * RB + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
             } else if (inside && r >= p.halo && r < R - p.halo) {
               // final epilogue: multi-receptive-field combine + stores (v = x_final)
               const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
               if (p.flags & EPI_OUT16) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = lrelu_f(v[e], p.slope_out);
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx * 2) = pack8(v, bf16);
+                const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + ch0 + q) * 16;   // [B][1][L][C]
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(v, bf16);
               }
             }
           }

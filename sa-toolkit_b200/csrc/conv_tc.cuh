@@ -3,20 +3,24 @@
 //
 // Formulation ("time on M"):   D[t, co] = sum_j sum_ci  A[t + off_j, ci] * W_j[co, ci]
 //   M = 128 output time steps per MMA (MSUB sub-tiles per CTA tile), N = Cout tile, K = Cin per tap.
-//   A  activations, 16-bit, channel-blocked  [B][C/8][L][8]   (one time step of 8 channels = 16 B)
-//   W  weights, 16-bit, pre-packed on the host in MMA order [k16 step][2][N][8]
+//   A  activations, 16-bit, panel-blocked [B][C/PW][L][PW]
+//   W  weights, 16-bit, pre-packed + pre-swizzled on the host, [tap][panel][N][PW]
 //   D  fp32 accumulators in TMEM (MSUB * N columns, double buffered when they fit twice)
 //
-// Why this layout: in the no-swizzle K-major canonical layout of the UMMA shared-memory
-// descriptor a core matrix is 8 rows x 16 bytes with rows 16 B apart, 8-row groups SBO apart
-// and the two K-halves LBO apart.  Staging the input tile as [C/8][rows][8] makes SBO = 128 B
-// (rows are contiguous), so the operand of filter tap j is the SAME staged tile with the
-// descriptor start address advanced by off_j * 16 B: dilated taps cost no data movement and
-// no im2col; the +-(k-1)d/2 halo lives in shared memory.  TMA (cp.async.bulk.tensor) loads the
-// tile and zero-fills rows outside [0, L), which is exactly the per-layer zero padding of
-// the reference convs (nn.py:98-166).  Weights stream through an mbarrier ring with 1-D bulk
-// copies (or stay resident when the whole filter bank is small).  The polyphase transposed
-// convs (archi.py:47-59) are the same kernel: phase phi is a conv with taps at rows
+// Layout: 16-bit activations are "panel blocked" in HBM, [B][C/PW][L][PW] with PW = min(C, 64)
+// channels, so one time step of a panel is one row of 128 / 64 / 32 bytes -- exactly the row of
+// the UMMA K-major SWIZZLE_128B / 64B / 32B canonical layouts.  TMA (cp.async.bulk.tensor, same
+// swizzle mode) stages the input tile with its +-(k-1)d/2 halo as [panel][rows][PW]; rows are
+// contiguous, so the operand of filter tap j is the SAME staged tile with the descriptor start
+// address advanced by off_j rows: dilated taps cost no data movement and no im2col.  (The swizzle
+// XOR is a function of the absolute shared-memory address bits, so a start address in the middle
+// of an 8-row swizzle atom addresses the rows the TMA wrote.)  A first version used the
+// no-swizzle "interleaved" layout; ncu showed the tensor core reading it at ~16 B/cycle (3x off
+// the MMA rate for N = 256 and ~200 cycles per MMA for narrow N), see profiles/README.md.
+// TMA zero-fills rows outside [0, L): that is the per-layer zero padding of the reference convs
+// (nn.py:98-166).  Weights are pre-swizzled on the host and stream through an mbarrier ring
+// with 1-D bulk copies (or stay resident when the whole filter bank is small).  The polyphase
+// transposed convs (archi.py:47-59) are the same kernel: phase phi is a conv with taps at rows
 // (off_phi - m) whose output row is u*q + phi.
 //
 // Persistent CTAs: grid.x CTAs walk the (item, time-tile) list with stride grid.x, so barrier
@@ -54,13 +58,13 @@ enum : uint32_t {
 };
 
 struct ConvParams {
-  CUtensorMap tmap;         // activations [B][Cin/8][L_in][8], box {8, box_rows, box_chunks, 1}
+  CUtensorMap tmap;         // activations [B][Cin/PW][L_in][PW], box {PW, box_rows, 1, 1}, swizzle = row bytes
   const void* w;            // packed weights: phase p / n-tile t at w + (p * n_tiles + t) * w_tile_bytes
   const float* bias;        // [Cout_total]
   const float* res32;       // fp32 blocked [B][Cout_total/8][L_out][8]
   float* out32;
   float* sum32;
-  void* out16;              // 16-bit blocked
+  void* out16;              // 16-bit panel-blocked [B][Cout/out_pw][L_out][out_pw]
   int* error_flag;          // raised when a barrier wait times out
   int cin;                  // multiple of 16
   int cout_total;           // channels of the output tensor
@@ -73,8 +77,11 @@ struct ConvParams {
   int tap_base[kMaxPhases]; // row offset of tap 0 of each phase
   int n_taps[kMaxPhases];
   int row_lo[kMaxPhases];   // min tap offset of the phase (first staged row = m0 + row_lo)
-  int rows_alloc;           // staged rows per chunk (nseg * box_rows)
-  int box_rows, nseg, box_chunks;
+  int rows_alloc;           // staged rows per panel (nseg * box_rows), multiple of 8
+  int box_rows, nseg;
+  int pw;                   // input panel width in channels: 64, 32 or 16 (row bytes = 2 * pw)
+  int out_pw;               // panel width of the 16-bit output tensor
+  int desc_base_offset;     // debug: 1 = also fill the descriptor base_offset field from the start address
   int k16_per_stage;        // K=16 steps per weight stage
   int n_wstages;            // weight ring depth
   int w_resident;           // 1: all weight stages stay in smem (loaded once per CTA)
@@ -176,23 +183,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major, no swizzle (layout_type 0), version 1 (sm_100).
-//   bits [0,14) start >> 4 | [16,30) LBO >> 4 (between the two 16-byte K halves)
-//   | [32,46) SBO >> 4 (between 8-row groups) | [46,48) version = 1
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
+// UMMA shared-memory descriptor, K-major, swizzled canonical layout, version 1 (sm_100), as two
+// 32-bit halves (only the start field, low 14 bits of `lo`, changes between MMAs):
+//   lo: [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major; 1)
+//   hi: [0,14) SBO >> 4 (8 rows = 8 * row bytes) | [14,16) version = 1 | [17,20) base offset
+//       | [29,32) layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+  return (((8u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
 }
-// The same descriptor as two 32-bit halves: only the start field (low 14 bits of `lo`) changes
-// between MMAs, so the issue loop updates it with one integer add.
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
-  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi, int with_base_offset = 0) {
+  if (with_base_offset) hi |= ((lo >> 3) & 7u) << 17;            // (start address >> 7) & 7
+  return ((uint64_t)hi << 32) | lo;
 }
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// byte offset inside a swizzled buffer whose base is aligned to the swizzle pattern (8 rows)
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t row_bytes) {
+  const uint32_t mask = row_bytes == 128 ? 7u : row_bytes == 64 ? 3u : 1u;
+  return off ^ (((off >> 7) & mask) << 4);
+}
 
 // Instruction descriptor, kind::f16: fp32 accumulate, A/B fp16 (0) or bf16 (1), both K-major,
 // M = 128, N = n.   bits [4,6) c_format=1 | [7,10) a_format | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4
@@ -226,12 +235,13 @@ __device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, floa
 
 // ---------------------------------------------------------------------------------------
 // The kernel.  grid = (persistent CTAs, n_phases * n_tiles).  Dynamic smem:
-//   [A ring: n_abuf * (cin/8) * rows_alloc * 16][W ring: n_wstages * k16_per_stage * N * 32]
-//   [bias N*4][barriers][tmem holder]
+//   [A ring: n_abuf * (cin/pw) * rows_alloc * 2pw][W ring: n_wstages * k16_per_stage * N * 32]
+//   [bias N*4][barriers][tmem holder]      (base rounded up to 1024 B: swizzle pattern anchor)
 // ---------------------------------------------------------------------------------------
 template <int N, int MSUB>
 __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int phase = blockIdx.y / p.n_tiles, ntile = blockIdx.y % p.n_tiles;
 
@@ -240,9 +250,10 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
   constexpr uint32_t kTmemCols = (kNumAcc * kAccCols <= 32) ? 32 : (kNumAcc * kAccCols <= 64) ? 64
                                  : (kNumAcc * kAccCols <= 128) ? 128 : (kNumAcc * kAccCols <= 256) ? 256 : 512;
 
-  const int chunks = p.cin >> 3;
-  const uint32_t chunk_stride = (uint32_t)p.rows_alloc * 16u;
-  const uint32_t a_bytes = (uint32_t)chunks * chunk_stride;
+  const uint32_t row_bytes = (uint32_t)p.pw * 2u;                  // 128 / 64 / 32
+  const int panels = p.cin / p.pw;
+  const uint32_t panel_bytes = (uint32_t)p.rows_alloc * row_bytes; // multiple of the 8-row swizzle pattern
+  const uint32_t a_bytes = (uint32_t)panels * panel_bytes;
   const uint32_t stage_bytes = (uint32_t)p.k16_per_stage * N * 32u;
   uint8_t* a_smem = smem;
   uint8_t* w_smem = smem + (size_t)p.n_abuf * a_bytes;
@@ -292,10 +303,10 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         mbar_arrive_expect_tx(bar_a_full(buf), a_bytes);
         const int row0 = m0 + p.row_lo[phase];
         const uint32_t dst = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
-        for (int c = 0; c < chunks; c += p.box_chunks)
+        for (int c = 0; c < panels; ++c)
           for (int s = 0; s < p.nseg; ++s)
-            tma_load_4d(dst + (uint32_t)c * chunk_stride + (uint32_t)(s * p.box_rows) * 16u, &p.tmap, bar_a_full(buf), 0,
-                        row0 + s * p.box_rows, c, b);
+            tma_load_4d(dst + (uint32_t)c * panel_bytes + (uint32_t)(s * p.box_rows) * row_bytes, &p.tmap, bar_a_full(buf),
+                        0, row0 + s * p.box_rows, c, b);
       }
     }
   } else if (warp == 1) {
@@ -325,9 +336,12 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N, (p.flags & EPI_BF16) != 0);
       const int row_lo = p.row_lo[phase];
-      const uint32_t hi128 = desc_hi(128u);
-      const uint32_t cs8 = chunk_stride >> 3;                     // two channel chunks, in 16-byte units
-      const uint32_t b_lo0 = desc_lo(smem_u32(w_smem), (uint32_t)N * 16u);
+      const uint32_t hi = desc_hi(row_bytes);
+      const int bo = p.desc_base_offset;
+      const int spp = p.pw >> 4;                                  // K=16 steps per panel row
+      const uint32_t row16 = row_bytes >> 4;                      // one row, in 16-byte units
+      const uint32_t a_panel16 = panel_bytes >> 4, b_panel16 = ((uint32_t)N * row_bytes) >> 4;
+      const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
       int it = 0, wslot = 0;
       uint32_t wpar = 0;
       bool ok = true;
@@ -338,12 +352,14 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         if (ok) ok = mbar_wait(bar_a_full(buf), use & 1, p.error_flag);
         if (!ok) break;
         tc_fence_after();
-        // descriptor bookkeeping in 16-byte units: start(tap, cb, ms) = a0 + tap*tap_step + cb*cs8 + ms*128
-        const uint32_t a_lo0 = desc_lo(smem_u32(a_smem) + (uint32_t)buf * a_bytes, chunk_stride) +
-                               (uint32_t)(p.tap_base[phase] - row_lo);
+        // descriptor bookkeeping in 16-byte units:
+        //   A start(tap, panel, kk, ms) = a0 + (tap offset + ms*128) rows + panel * panel16 + kk * 2
+        //   B start(step)               = stage + (step / spp) * N rows + (step % spp) * 2
+        const uint32_t a_lo0 = desc_lo(smem_u32(a_smem) + (uint32_t)buf * a_bytes) +
+                               (uint32_t)(p.tap_base[phase] - row_lo) * row16;
         const uint32_t d_base = tmem_base + (uint32_t)(acc * kAccCols);
         uint32_t a_tap = a_lo0, a_cb = 0, accum = 0;
-        int cb = 0;
+        int cb = 0, kin = 0;                                      // cb: K16 step inside the tap; kin: inside the panel
         for (int i = 0; i < n_iters; ++i) {
           int slot;
           uint32_t wuse_par;
@@ -354,14 +370,18 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
           tc_fence_after();
           const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
           uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
+          int bk = 0;                                             // stages hold whole panels: starts at kk = 0
           for (int kk = 0; kk < k16; ++kk) {
-            const uint64_t bdesc = desc64(b_lo, hi128);
+            const uint64_t bdesc = desc64(b_lo, hi, bo);
 #pragma unroll
             for (int ms = 0; ms < MSUB; ++ms)
-              umma_f16(d_base + (uint32_t)ms * N, desc64(a_tap + a_cb + (uint32_t)ms * 128u, hi128), bdesc, idesc, accum);
+              umma_f16(d_base + (uint32_t)ms * N, desc64(a_tap + a_cb + (uint32_t)ms * 128u * row16, hi, bo), bdesc, idesc,
+                       accum);
             accum = 1;
-            b_lo += (uint32_t)N * 2u;
-            if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += (uint32_t)p.tap_step; } else { a_cb += cs8; }
+            if (++bk == spp) { bk = 0; b_lo += b_panel16 - 2u * (uint32_t)(spp - 1); } else { b_lo += 2u; }
+            if (++cb == k16_per_tap) { cb = 0; kin = 0; a_cb = 0; a_tap += (uint32_t)p.tap_step * row16; }
+            else if (++kin == spp) { kin = 0; a_cb += a_panel16 - 2u * (uint32_t)(spp - 1); }
+            else { a_cb += 2u; }
           }
           if (!p.w_resident) umma_commit(bar_w_empty(slot));     // slot free once these MMAs have read it
         }
@@ -379,6 +399,8 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     const int col0 = (N >= 32) ? half * kColsPerWarp : 0;
     const bool bf16 = (p.flags & EPI_BF16) != 0;
     const int cchunks_total = p.cout_total >> 3;
+    const int opc = p.out_pw >> 3;                                 // 8-channel chunks per output panel row
+    const int opanels = p.cout_total / p.out_pw;
     const uint32_t flags = p.flags;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -443,8 +465,10 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
                 float lo[8], hi[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { lo[e] = lrelu_f(v[e], p.slope_out); hi[e] = lrelu_f(v[8 + e], p.slope_out); }
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx0 * 2) = pack8(lo, bf16);
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + idx1 * 2) = pack8(hi, bf16);
+                const int cg = ntile * (N / 8) + c8;               // chunk index in the output tensor (even)
+                const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(lo, bf16);
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8(hi, bf16);
               }
             }
           }

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,6 +41,12 @@ const char* msgf(const char* fmt, const char* a, const char* b = "") {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// byte offset inside a swizzled block whose base is aligned to the swizzle pattern (conv_tc.cuh: swz)
+uint32_t swizzle_offset(uint32_t off, uint32_t row_bytes) {
+  const uint32_t mask = row_bytes == 128 ? 7u : row_bytes == 64 ? 3u : 1u;
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
 uint16_t to16(float f, bool bf16) {
   if (bf16) {
     __nv_bfloat16 h = __float2bfloat16_rn(f);
@@ -55,9 +62,9 @@ uint16_t to16(float f, bool bf16) {
 
 // ---- small CUDA-core helper kernels ------------------------------------------------------
 
-// x fp32 [B][Cin][T] -> 16-bit blocked [B][Cpad/8][T][8] (channels >= Cin are zero).
+// x fp32 [B][Cin][T] -> 16-bit panel-blocked [B][Cpad/pw][T][pw] (channels >= Cin are zero).
 __global__ void pack_input_kernel(const float* __restrict__ x, uint4* __restrict__ out, int Cin, int chunks, int T,
-                                  int bf16) {
+                                  int bf16, int pw) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -67,7 +74,8 @@ __global__ void pack_input_kernel(const float* __restrict__ x, uint4* __restrict
     const int c = c8 * 8 + e;
     v[e] = c < Cin ? __ldg(x + ((size_t)b * Cin + c) * T + t) : 0.f;
   }
-  out[((size_t)b * chunks + c8) * T + t] = tc::pack8(v, bf16 != 0);
+  const int cpp = pw >> 3;                    // chunks per panel row
+  out[(((size_t)b * (chunks / cpp) + c8 / cpp) * T + t) * cpp + c8 % cpp] = tc::pack8(v, bf16 != 0);
 }
 
 // fp32 blocked [B][C/8][L][8] -> fp32 [B][C][L]  (debug taps only)
@@ -130,38 +138,41 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct Plan {          // launch geometry of one conv on the tensor cores
-  int msub, rows_alloc, box_rows, nseg, box_chunks, k16_per_stage, n_wstages, w_resident, n_abuf;
+  int msub, rows_alloc, box_rows, nseg, k16_per_stage, n_wstages, w_resident, n_abuf;
   size_t smem;
 };
+
+int panel_width(int c) { return c >= 64 ? 64 : c; }
 
 constexpr size_t kResidentWeightBytes = 48 * 1024;   // keep the whole filter bank in smem below this
 
 bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int n_k16_max, int max_smem) {
-  const size_t fixed = (size_t)n * 4 + (8 + 2 * tc::kMaxStages) * 8 + 16;
+  const size_t fixed = (size_t)n * 4 + (8 + 2 * tc::kMaxStages) * 8 + 16 + 1024;   // + alignment slack
+  const int spp = panel_width(cin_pad) / 16;                    // weight stages hold whole panels
   for (int msub = (m_rows > 128 ? 2 : 1); msub >= 1; --msub) {
     const int rows = 128 * msub + span;
     const int nseg = (rows + 255) / 256;
     const int box_rows = (int)align_up((size_t)(rows + nseg - 1) / nseg, 8);
     if (box_rows > 256) continue;
     const int rows_alloc = nseg * box_rows;
-    const size_t a_bytes = (size_t)(cin_pad / 8) * rows_alloc * 16;
+    const size_t a_bytes = (size_t)cin_pad * 2 * rows_alloc;
     for (int n_abuf = 2; n_abuf >= 1; --n_abuf) {
       auto accept = [&](int k16, int stages, int resident) {
         pl.msub = msub; pl.rows_alloc = rows_alloc; pl.box_rows = box_rows; pl.nseg = nseg;
-        pl.box_chunks = (nseg == 1) ? std::min(cin_pad / 8, 256) : 1;
         pl.k16_per_stage = k16; pl.n_wstages = stages; pl.w_resident = resident; pl.n_abuf = n_abuf;
         pl.smem = n_abuf * a_bytes + (size_t)stages * k16 * n * 32 + fixed;
       };
       const size_t w_all = (size_t)n_k16_max * n * 32;
       if (w_all <= kResidentWeightBytes) {
-        const int k16 = std::max((n_k16_max + tc::kMaxStages - 1) / tc::kMaxStages, std::max(1, 8 * 1024 / (n * 32)));
+        int k16 = std::max((n_k16_max + tc::kMaxStages - 1) / tc::kMaxStages, std::max(1, 8 * 1024 / (n * 32)));
+        k16 = (k16 + spp - 1) / spp * spp;
         const int stages = (n_k16_max + k16 - 1) / k16;
         if (n_abuf * a_bytes + (size_t)stages * k16 * n * 32 + fixed <= (size_t)max_smem) {
           accept(k16, stages, 1);
           return true;
         }
       }
-      const int k16 = std::max(1, 16 * 1024 / (n * 32));
+      const int k16 = (std::max(1, 16 * 1024 / (n * 32)) + spp - 1) / spp * spp;
       for (int stages = 4; stages >= 2; --stages)
         if (n_abuf * a_bytes + (size_t)stages * k16 * n * 32 + fixed <= (size_t)max_smem) {
           accept(k16, stages, 0);
@@ -219,8 +230,8 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   const size_t stage = (size_t)ch.k16_per_stage * C * 32;
   auto need = [&](int ms, int slots) {
     const size_t rows = (size_t)ms * 128 + 2 * tc::kChainPad;
-    return 2 * (size_t)(C / 8) * rows * 16 + slots * stage + (size_t)tc::kChainMaxConvs * C * 4 +
-           (32 + 2 * tc::kChainMaxSlots) * 8 + 16;
+    return 2 * rows * (size_t)C * 2 + slots * stage + (size_t)tc::kChainMaxConvs * C * 4 +
+           (32 + 2 * tc::kChainMaxSlots) * 8 + 16 + 1024;
   };
   const int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
   if (slots > tc::kChainMaxSlots) return false;
@@ -296,18 +307,22 @@ struct Runner {
     int n_k16_max = 0;
     for (int ph = 0; ph < w.n_phases; ++ph) n_k16_max = std::max(n_k16_max, w.n_taps[ph] * (w.cin_pad / 16));
     if (!make_plan(pl, w.cin_pad, w.n, span, l_in, n_k16_max, ctx.max_smem)) return "conv does not fit in shared memory";
-    // tensor map over the input activation [B][cin_pad/8][l_in][8]
-    const cuuint64_t gdim[4] = {8, (cuuint64_t)l_in, (cuuint64_t)(w.cin_pad / 8), (cuuint64_t)a.B};
-    const cuuint64_t gstr[3] = {16, (cuuint64_t)l_in * 16, (cuuint64_t)(w.cin_pad / 8) * l_in * 16};
-    const cuuint32_t box[4] = {8, (cuuint32_t)pl.box_rows, (cuuint32_t)pl.box_chunks, 1};
+    // tensor map over the input activation [B][cin_pad/pw][l_in][pw], swizzle = row bytes
+    const int pw = panel_width(w.cin_pad);
+    const cuuint64_t rb = (cuuint64_t)pw * 2;
+    const cuuint64_t gdim[4] = {(cuuint64_t)pw, (cuuint64_t)l_in, (cuuint64_t)(w.cin_pad / pw), (cuuint64_t)a.B};
+    const cuuint64_t gstr[3] = {rb, (cuuint64_t)l_in * rb, (cuuint64_t)(w.cin_pad / pw) * l_in * rb};
+    const cuuint32_t box[4] = {(cuuint32_t)pw, (cuuint32_t)pl.box_rows, 1, 1};
+    const CUtensorMapSwizzle swz = pw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                     : CU_TENSOR_MAP_SWIZZLE_32B;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = reinterpret_cast<encode_tiled_fn>(ctx.encode_fn)(
         &p.tmap, a.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in16),
-        gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for L=%d chunks=%d box_rows=%d", (int)r, l_in,
-               w.cin_pad / 8, pl.box_rows);
+      snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for L=%d panels=%d box_rows=%d", (int)r, l_in,
+               w.cin_pad / pw, pl.box_rows);
       return g_msg;
     }
     p.w = w.d_w;
@@ -321,7 +336,8 @@ struct Runner {
     p.l_out = l_in * p.out_stride;
     p.n_phases = w.n_phases;
     p.n_tiles = w.n_tiles;
-    p.rows_alloc = pl.rows_alloc; p.box_rows = pl.box_rows; p.nseg = pl.nseg; p.box_chunks = pl.box_chunks;
+    p.rows_alloc = pl.rows_alloc; p.box_rows = pl.box_rows; p.nseg = pl.nseg;
+    p.pw = pw; p.out_pw = panel_width(ly.cout); p.desc_base_offset = ctx.desc_base_offset;
     p.k16_per_stage = pl.k16_per_stage;
     p.n_wstages = pl.n_wstages; p.w_resident = pl.w_resident; p.n_abuf = pl.n_abuf;
     p.m_tiles = (l_in + 128 * pl.msub - 1) / (128 * pl.msub);
@@ -354,6 +370,7 @@ struct Runner {
     memset(&p, 0, sizeof(p));
     p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
     p.w = ch.d_w; p.bias = ch.d_bias; p.error_flag = ctx.d_error;
+    p.desc_base_offset = ctx.desc_base_offset;
     p.L = L; p.n_convs = ch.n_convs; p.ktaps = ch.k;
     for (int c = 0; c < ch.n_convs; ++c) { p.dil[c] = ch.dil[c]; p.pad[c] = ch.pad[c]; }
     p.halo = ch.halo;
@@ -411,25 +428,29 @@ const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed,
       max_taps = std::max(max_taps, w.n_taps[ph]);
     }
   }
-  w.tile_bytes = (size_t)max_taps * k16_per_tap * w.n * 32;
+  // one (phase, n_tile) block = [tap][panel][N rows][pw] with the UMMA K-major swizzle applied
+  const int pw = panel_width(w.cin_pad), panels = w.cin_pad / pw, rb = pw * 2;
+  const size_t panel_bytes = (size_t)w.n * rb;
+  w.tile_bytes = (size_t)max_taps * panels * panel_bytes;
   w.bytes = w.tile_bytes * w.n_phases * w.n_tiles;
   std::vector<uint16_t> host(w.bytes / 2, 0);
   for (int ph = 0; ph < w.n_phases; ++ph)
     for (int t = 0; t < w.n_tiles; ++t) {
-      uint16_t* tile = host.data() + ((size_t)(ph * w.n_tiles + t) * w.tile_bytes) / 2;
+      uint8_t* tile = reinterpret_cast<uint8_t*>(host.data()) + (size_t)(ph * w.n_tiles + t) * w.tile_bytes;
       for (int tap = 0; tap < w.n_taps[ph]; ++tap) {
         const int j = transposed ? ((ph + pad) % stride + stride * tap) : tap;
-        for (int cb = 0; cb < k16_per_tap; ++cb) {
-          uint16_t* step = tile + (size_t)(tap * k16_per_tap + cb) * w.n * 16;
-          for (int h = 0; h < 2; ++h)
-            for (int r = 0; r < w.n; ++r)
-              for (int e = 0; e < 8; ++e) {
-                const int ci = cb * 16 + h * 8 + e, co = t * w.n + r;
-                float v = 0.f;
-                if (ci < cin)
-                  v = transposed ? folded[((size_t)ci * cout + co) * k + j] : folded[((size_t)co * cin + ci) * k + j];
-                step[((size_t)h * w.n + r) * 8 + e] = to16(v, bf16);
-              }
+        for (int pn = 0; pn < panels; ++pn) {
+          uint8_t* blk = tile + (size_t)(tap * panels + pn) * panel_bytes;
+          for (int r = 0; r < w.n; ++r)
+            for (int kq = 0; kq < pw; ++kq) {
+              const int ci = pn * pw + kq, co = t * w.n + r;
+              float v = 0.f;
+              if (ci < cin)
+                v = transposed ? folded[((size_t)ci * cout + co) * k + j] : folded[((size_t)co * cin + ci) * k + j];
+              const uint32_t off = swizzle_offset((uint32_t)r * rb + (uint32_t)kq * 2, rb);
+              const uint16_t h = to16(v, bf16);
+              memcpy(blk + off, &h, 2);
+            }
         }
       }
     }
@@ -456,19 +477,18 @@ const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* 
   const int k16_per_tap = c / 16;
   if (c == 64) { ch.k16_per_stage = k16_per_tap; ch.stages_per_conv = k; }     // one tap (8 KB) per stage
   else { ch.k16_per_stage = k * k16_per_tap; ch.stages_per_conv = 1; }         // the whole conv per stage
-  const size_t conv_elems = (size_t)k * k16_per_tap * c * 16;
-  std::vector<uint16_t> host(conv_elems * n_convs);
+  const int rb = 2 * c;                                          // one panel: row = all C channels
+  const size_t tap_bytes = (size_t)c * rb, conv_bytes = (size_t)k * tap_bytes;
+  std::vector<uint16_t> host(conv_bytes * n_convs / 2);
   for (int cv = 0; cv < n_convs; ++cv)
-    for (int tap = 0; tap < k; ++tap)
-      for (int cb = 0; cb < k16_per_tap; ++cb) {
-        uint16_t* step = host.data() + cv * conv_elems + (size_t)(tap * k16_per_tap + cb) * c * 16;
-        for (int h = 0; h < 2; ++h)
-          for (int r = 0; r < c; ++r)
-            for (int e = 0; e < 8; ++e) {
-              const int ci = cb * 16 + h * 8 + e;
-              step[((size_t)h * c + r) * 8 + e] = to16(folded[cv][((size_t)r * c + ci) * k + tap], bf16);
-            }
-      }
+    for (int tap = 0; tap < k; ++tap) {
+      uint8_t* blk = reinterpret_cast<uint8_t*>(host.data()) + cv * conv_bytes + tap * tap_bytes;
+      for (int r = 0; r < c; ++r)
+        for (int ci = 0; ci < c; ++ci) {
+          const uint16_t h = to16(folded[cv][((size_t)r * c + ci) * k + tap], bf16);
+          memcpy(blk + swizzle_offset((uint32_t)r * rb + (uint32_t)ci * 2, rb), &h, 2);
+        }
+    }
   std::vector<float> hb((size_t)n_convs * c);
   for (int cv = 0; cv < n_convs; ++cv) memcpy(hb.data() + (size_t)cv * c, bias[cv], c * sizeof(float));
   TC_CUDA(cudaMalloc(&ch.d_w, host.size() * 2));
@@ -501,6 +521,7 @@ const char* tc_init(tc_context& ctx, int device) {
   TC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx.h_error), sizeof(int), cudaHostAllocMapped));
   *ctx.h_error = 0;
   TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
+  if (const char* env = getenv("SATOOLS_B200_DESC_BASE_OFFSET")) ctx.desc_base_offset = atoi(env);
   ctx.ready = true;
   return nullptr;
 }
@@ -569,7 +590,8 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     const int cpad = (int)align_up(cfg.input_dim, 16);
     dim3 g((unsigned)((a.T + 127) / 128), (unsigned)(cpad / 8), (unsigned)a.B);
     run.mark(15);
-    pack_input_kernel<<<g, 128, 0, st>>>(a.x, reinterpret_cast<uint4*>(XIN16), cfg.input_dim, cpad / 8, a.T, a.bf16 ? 1 : 0);
+    pack_input_kernel<<<g, 128, 0, st>>>(a.x, reinterpret_cast<uint4*>(XIN16), cfg.input_dim, cpad / 8, a.T, a.bf16 ? 1 : 0,
+                                         panel_width(cpad));
     ++*launches;
     TC_CUDA(cudaGetLastError());
   }

@@ -9,7 +9,7 @@ namespace sa {
 constexpr int kTcMaxPhases = 8;
 
 // Packed 16-bit weights of one conv for the implicit-GEMM kernel (conv_tc.cuh):
-// [phase][n_tile][k16 step = tap * cin_pad/16 + cb][2][N][8].
+// [phase][n_tile][tap][panel][N rows][pw], each [N][pw] block in the UMMA K-major swizzled layout.
 struct tc_weights {
   void* d_w = nullptr;
   int n = 0;                 // N per MMA (Cout tile)
@@ -24,7 +24,7 @@ struct tc_weights {
 };
 
 // One ResBlock1 packed for the fused narrow-stage kernel (chain_tc.cuh): the 2*n_dilations convs in
-// execution order (convs1[0], convs2[0], convs1[1], ...), each [k16 step][2][C][8]; bias [n_convs][C].
+// execution order (convs1[0], convs2[0], convs1[1], ...), each [tap][C rows][C] swizzled; bias [n_convs][C].
 struct tc_chain {
   void* d_w = nullptr;
   float* d_bias = nullptr;
@@ -40,6 +40,7 @@ struct tc_context {
   int* h_error = nullptr;     // mapped pinned flag raised by a kernel whose barrier wait timed out
   int* d_error = nullptr;     // device alias of h_error
   int max_smem = 0;
+  int desc_base_offset = 0;   // debug: fill the UMMA descriptor base_offset field (SATOOLS_B200_DESC_BASE_OFFSET=1)
 };
 
 struct tc_layer {
