@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
 
   if (warp == 0) {
     // ===== weight producer: stage g = (conv counter, stage in conv); slot = g % n_slots =====
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int slot = 0;
       uint32_t par = 1;                                          // parity of the previous use of `slot`
       bool wrapped = false, ok = true;
@@ -121,16 +122,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
           for (int i = 0; i < p.stages_per_conv; ++i) {
             if (wrapped) ok = mbar_wait(bar_w_empty(slot), par, p.error_flag);
             if (!ok) break;
-            mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
-            bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes,
-                      static_cast<const uint8_t*>(p.w) + (size_t)(c * p.stages_per_conv + i) * stage_bytes, stage_bytes,
-                      bar_w_full(slot));
+            if (leader) {
+              mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
+              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes,
+                        static_cast<const uint8_t*>(p.w) + (size_t)(c * p.stages_per_conv + i) * stage_bytes, stage_bytes,
+                        bar_w_full(slot));
+            }
+            __syncwarp();
             if (++slot == p.n_slots) { slot = 0; par ^= 1u; wrapped = true; }
           }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc(N, bf16);
       const uint32_t hi = desc_hi(RB);
       const int bo = p.desc_base_offset;
@@ -162,16 +167,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
               uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
               for (int kk = 0; kk < p.k16_per_stage; ++kk) {
                 // one panel (C <= 64): tap = one weight block [N rows][C]; K16 step kk sits at +32 B in the row
-                umma_f16(d_tmem, desc64(a_tap + a_cb, hi, bo), desc64(b_lo, hi, bo), idesc, accum);
+                const uint64_t adesc = desc64(a_tap + a_cb, hi, bo), bdesc = desc64(b_lo, hi, bo);
+                if (leader) umma_f16(d_tmem, adesc, bdesc, idesc, accum);
                 accum = 1;
                 if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += dil16; b_lo += (uint32_t)N * row16 - 2u * (uint32_t)(k16_per_tap - 1); }
                 else { a_cb += 2u; b_lo += 2u; }
               }
-              if (s == MS - 1) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
+              if (s == MS - 1 && leader) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
+              __syncwarp();
               if (++slot == p.n_slots) { slot = 0; par ^= 1u; }
             }
             if (s == MS - 1) { slot0 = slot; par0 = par; }
-            if (ok) umma_commit(bar_acc_full(c & 1, s));
+            if (ok && leader) umma_commit(bar_acc_full(c & 1, s));
+            __syncwarp();
           }
         }
       }

@@ -131,6 +131,16 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
   return true;
 }
+// One lane of a converged warp.  The role loops below run warp-uniformly (all 32 lanes walk the
+// tiles and poll the barriers) and only the TMA / MMA / commit instruction itself is issued by
+// the elected lane: descriptors and addresses then stay in uniform registers.  (Running the
+// whole loop under `if (lane == 0)` made ptxas wrap every UTCHMMA in an ELECT/BRA uniformization
+// loop with R2UR moves and the kernel became MMA-issue bound; see profiles/README.md.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -294,24 +304,29 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
 
   if (warp == 0) {
     // ===== A producer: one TMA tile per work item =====
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         if (use > 0 && !mbar_wait(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
         const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
-        mbar_arrive_expect_tx(bar_a_full(buf), a_bytes);
         const int row0 = m0 + p.row_lo[phase];
         const uint32_t dst = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
-        for (int c = 0; c < panels; ++c)
-          for (int s = 0; s < p.nseg; ++s)
-            tma_load_4d(dst + (uint32_t)c * panel_bytes + (uint32_t)(s * p.box_rows) * row_bytes, &p.tmap, bar_a_full(buf),
-                        0, row0 + s * p.box_rows, c, b);
+        if (leader) {
+          mbar_arrive_expect_tx(bar_a_full(buf), a_bytes);
+          for (int c = 0; c < panels; ++c)
+            for (int s = 0; s < p.nseg; ++s)
+              tma_load_4d(dst + (uint32_t)c * panel_bytes + (uint32_t)(s * p.box_rows) * row_bytes, &p.tmap,
+                          bar_a_full(buf), 0, row0 + s * p.box_rows, c, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===== W producer: weight stages through the ring (once, when resident) =====
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int slot = 0;
       uint32_t par = 1;                                           // parity of the previous use of `slot`
       bool wrapped = false;
@@ -323,17 +338,21 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
           if (!ok) break;
           const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
           const uint32_t bytes = (uint32_t)k16 * N * 32u;
-          mbar_arrive_expect_tx(bar_w_full(slot), bytes);
-          bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
-                    bar_w_full(slot));
+          if (leader) {
+            mbar_arrive_expect_tx(bar_w_full(slot), bytes);
+            bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
+                      bar_w_full(slot));
+          }
+          __syncwarp();
           if (++slot == p.n_wstages) { slot = 0; par ^= 1u; wrapped = true; }
         }
         if (!ok) break;
       }
     }
   } else if (warp == 2) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc(N, (p.flags & EPI_BF16) != 0);
       const int row_lo = p.row_lo[phase];
       const uint32_t hi = desc_hi(row_bytes);
@@ -374,20 +393,25 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
           for (int kk = 0; kk < k16; ++kk) {
             const uint64_t bdesc = desc64(b_lo, hi, bo);
 #pragma unroll
-            for (int ms = 0; ms < MSUB; ++ms)
-              umma_f16(d_base + (uint32_t)ms * N, desc64(a_tap + a_cb + (uint32_t)ms * 128u * row16, hi, bo), bdesc, idesc,
-                       accum);
+            for (int ms = 0; ms < MSUB; ++ms) {
+              const uint64_t adesc = desc64(a_tap + a_cb + (uint32_t)ms * 128u * row16, hi, bo);
+              if (leader) umma_f16(d_base + (uint32_t)ms * N, adesc, bdesc, idesc, accum);
+            }
             accum = 1;
             if (++bk == spp) { bk = 0; b_lo += b_panel16 - 2u * (uint32_t)(spp - 1); } else { b_lo += 2u; }
             if (++cb == k16_per_tap) { cb = 0; kin = 0; a_cb = 0; a_tap += (uint32_t)p.tap_step * row16; }
             else if (++kin == spp) { kin = 0; a_cb += a_panel16 - 2u * (uint32_t)(spp - 1); }
             else { a_cb += 2u; }
           }
-          if (!p.w_resident) umma_commit(bar_w_empty(slot));     // slot free once these MMAs have read it
+          if (!p.w_resident && leader) umma_commit(bar_w_empty(slot));   // slot free once these MMAs have read it
+          __syncwarp();
         }
         if (!ok) break;
-        umma_commit(bar_a_empty(buf));                            // A tile consumed
-        umma_commit(bar_acc_full(acc));                           // accumulators complete
+        if (leader) {
+          umma_commit(bar_a_empty(buf));                          // A tile consumed
+          umma_commit(bar_acc_full(acc));                         // accumulators complete
+        }
+        __syncwarp();
       }
     }
   } else {
