@@ -43,7 +43,6 @@ struct ChainParams {
   float* out32;             // stage output (EPI_OUT32)
   void* out16;              // lrelu(stage output), 16-bit blocked (EPI_OUT16)
   const void* w;            // weights of the n_convs convs, conv-major, each [tap][C rows][C] pre-swizzled
-  int desc_base_offset;     // debug switch, see conv_tc.cuh
   const float* bias;        // [n_convs][C]
   int* error_flag;
   int L;                    // rows per item
@@ -133,14 +132,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
           }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues; lean body, see conv_tc.cuh) =====
     {
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc(N, bf16);
-      const uint32_t hi = desc_hi(RB);
-      const int bo = p.desc_base_offset;
+      constexpr uint32_t hi = ((8u * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : RB == 64 ? 4u : 6u) << 29);
       constexpr uint32_t row16 = RB >> 4;
+      constexpr uint32_t b_tap16 = ((uint32_t)N * RB) >> 4;      // one tap = one [N rows][C] weight block
+      constexpr int K16 = C / 16;                                // K=16 steps per tap
       const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
+      const int taps_per_stage = p.k16_per_stage / K16;
       int it = 0, slot0 = 0;                                     // slot0 / par0: first weight stage of the running conv
       uint32_t par0 = 0;
       bool ok = true;
@@ -155,8 +156,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
             if (!ok) break;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
-            uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16, a_cb = 0, accum = 0;
-            int cb = 0, slot = slot0;
+            uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16, accum = 0;
+            int slot = slot0;
             uint32_t par = par0;
             for (int i = 0; i < p.stages_per_conv && ok; ++i) {
               if (s == 0) {                                      // later sub-tiles reuse the landed stage
@@ -164,14 +165,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
                 if (!ok) break;
                 tc_fence_after();
               }
-              uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
-              for (int kk = 0; kk < p.k16_per_stage; ++kk) {
-                // one panel (C <= 64): tap = one weight block [N rows][C]; K16 step kk sits at +32 B in the row
-                const uint64_t adesc = desc64(a_tap + a_cb, hi, bo), bdesc = desc64(b_lo, hi, bo);
-                if (leader) umma_f16(d_tmem, adesc, bdesc, idesc, accum);
-                accum = 1;
-                if (++cb == k16_per_tap) { cb = 0; a_cb = 0; a_tap += dil16; b_lo += (uint32_t)N * row16 - 2u * (uint32_t)(k16_per_tap - 1); }
-                else { a_cb += 2u; b_lo += 2u; }
+              uint32_t b_tap = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
+              for (int tp = 0; tp < taps_per_stage; ++tp) {
+#pragma unroll
+                for (int kk = 0; kk < K16; ++kk) {
+                  if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, accum);
+                  accum = 1;
+                }
+                a_tap += dil16;
+                b_tap += b_tap16;
               }
               if (s == MS - 1 && leader) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
               __syncwarp();

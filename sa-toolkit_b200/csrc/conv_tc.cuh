@@ -79,9 +79,7 @@ struct ConvParams {
   int row_lo[kMaxPhases];   // min tap offset of the phase (first staged row = m0 + row_lo)
   int rows_alloc;           // staged rows per panel (nseg * box_rows), multiple of 8
   int box_rows, nseg;
-  int pw;                   // input panel width in channels: 64, 32 or 16 (row bytes = 2 * pw)
   int out_pw;               // panel width of the 16-bit output tensor
-  int desc_base_offset;     // debug: 1 = also fill the descriptor base_offset field from the start address
   int k16_per_stage;        // K=16 steps per weight stage
   int n_wstages;            // weight ring depth
   int w_resident;           // 1: all weight stages stay in smem (loaded once per CTA)
@@ -203,10 +201,10 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t row_bytes) {
   const uint32_t layout = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
   return (((8u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
 }
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi, int with_base_offset = 0) {
-  if (with_base_offset) hi |= ((lo >> 3) & 7u) << 17;            // (start address >> 7) & 7
-  return ((uint64_t)hi << 32) | lo;
-}
+// The base-offset field stays 0: the hardware applies the swizzle XOR to the absolute shared-memory
+// address bits, so a start address in the middle of an 8-row atom is fine (verified on B200: setting
+// base_offset = (start >> 7) & 7 breaks the result, leaving it 0 is bit-exact).
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // byte offset inside a swizzled buffer whose base is aligned to the swizzle pattern (8 rows)
 __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t row_bytes) {
   const uint32_t mask = row_bytes == 128 ? 7u : row_bytes == 64 ? 3u : 1u;
@@ -248,7 +246,7 @@ __device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, floa
 //   [A ring: n_abuf * (cin/pw) * rows_alloc * 2pw][W ring: n_wstages * k16_per_stage * N * 32]
 //   [bias N*4][barriers][tmem holder]      (base rounded up to 1024 B: swizzle pattern anchor)
 // ---------------------------------------------------------------------------------------
-template <int N, int MSUB>
+template <int N, int MSUB, int PW>
 __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -260,8 +258,9 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
   constexpr uint32_t kTmemCols = (kNumAcc * kAccCols <= 32) ? 32 : (kNumAcc * kAccCols <= 64) ? 64
                                  : (kNumAcc * kAccCols <= 128) ? 128 : (kNumAcc * kAccCols <= 256) ? 256 : 512;
 
-  const uint32_t row_bytes = (uint32_t)p.pw * 2u;                  // 128 / 64 / 32
-  const int panels = p.cin / p.pw;
+  constexpr uint32_t row_bytes = (uint32_t)PW * 2u;                // 128 / 64 / 32
+  constexpr int SPP = PW / 16;                                     // K=16 steps per panel row
+  const int panels = p.cin / PW;
   const uint32_t panel_bytes = (uint32_t)p.rows_alloc * row_bytes; // multiple of the 8-row swizzle pattern
   const uint32_t a_bytes = (uint32_t)panels * panel_bytes;
   const uint32_t stage_bytes = (uint32_t)p.k16_per_stage * N * 32u;
@@ -351,19 +350,25 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     }
   } else if (warp == 2) {
     // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    // The loop body is kept as lean as the microbenchmark in tools/mma_bench2.cu (which reaches
+    // the hardware rate: 128 / 64 / 48 / 40 / 39 cycles per MMA for N = 256 .. 16): all
+    // bookkeeping happens per (tap, panel) weight block, the SPP x MSUB MMAs of a block are
+    // fully unrolled and differ only by constant adds on the descriptor start field.
     {
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc(N, (p.flags & EPI_BF16) != 0);
       const int row_lo = p.row_lo[phase];
-      const uint32_t hi = desc_hi(row_bytes);
-      const int bo = p.desc_base_offset;
-      const int spp = p.pw >> 4;                                  // K=16 steps per panel row
-      const uint32_t row16 = row_bytes >> 4;                      // one row, in 16-byte units
-      const uint32_t a_panel16 = panel_bytes >> 4, b_panel16 = ((uint32_t)N * row_bytes) >> 4;
+      constexpr uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u) << 29);
+      constexpr uint32_t row16 = row_bytes >> 4;                  // one row, in 16-byte units
+      constexpr uint32_t b_block16 = ((uint32_t)N * row_bytes) >> 4;
+      const uint32_t a_panel16 = panel_bytes >> 4;
       const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
+      const uint32_t tap_step16 = (uint32_t)p.tap_step * row16;
+      const int blocks_per_stage = p.k16_per_stage / SPP;
+      const int n_blocks_total = n_taps * panels;
       int it = 0, wslot = 0;
       uint32_t wpar = 0;
-      bool ok = true;
+      bool ok = true, resident_ready = false;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
@@ -371,42 +376,42 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         if (ok) ok = mbar_wait(bar_a_full(buf), use & 1, p.error_flag);
         if (!ok) break;
         tc_fence_after();
-        // descriptor bookkeeping in 16-byte units:
-        //   A start(tap, panel, kk, ms) = a0 + (tap offset + ms*128) rows + panel * panel16 + kk * 2
-        //   B start(step)               = stage + (step / spp) * N rows + (step % spp) * 2
-        const uint32_t a_lo0 = desc_lo(smem_u32(a_smem) + (uint32_t)buf * a_bytes) +
-                               (uint32_t)(p.tap_base[phase] - row_lo) * row16;
         const uint32_t d_base = tmem_base + (uint32_t)(acc * kAccCols);
-        uint32_t a_tap = a_lo0, a_cb = 0, accum = 0;
-        int cb = 0, kin = 0;                                      // cb: K16 step inside the tap; kin: inside the panel
+        uint32_t a_tap = desc_lo(smem_u32(a_smem) + (uint32_t)buf * a_bytes) + (uint32_t)(p.tap_base[phase] - row_lo) * row16;
+        uint32_t a_blk = a_tap, accum = 0;
+        int panel = 0, blk = 0;
         for (int i = 0; i < n_iters; ++i) {
-          int slot;
-          uint32_t wuse_par;
-          if (p.w_resident) { slot = i; wuse_par = 0; }
-          else { slot = wslot; wuse_par = wpar; if (++wslot == p.n_wstages) { wslot = 0; wpar ^= 1u; } }
-          ok = mbar_wait(bar_w_full(slot), wuse_par, p.error_flag);
+          int slot = i;
+          if (!p.w_resident) {
+            slot = wslot;
+            ok = mbar_wait(bar_w_full(slot), wpar, p.error_flag);
+            if (++wslot == p.n_wstages) { wslot = 0; wpar ^= 1u; }
+          } else if (!resident_ready) {
+            ok = mbar_wait(bar_w_full(slot), 0, p.error_flag);
+          }
           if (!ok) break;
           tc_fence_after();
-          const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
-          uint32_t b_lo = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
-          int bk = 0;                                             // stages hold whole panels: starts at kk = 0
-          for (int kk = 0; kk < k16; ++kk) {
-            const uint64_t bdesc = desc64(b_lo, hi, bo);
+          uint32_t b_blk = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
+          const int nb = min(blocks_per_stage, n_blocks_total - blk);
+          for (int bi = 0; bi < nb; ++bi, ++blk) {
 #pragma unroll
-            for (int ms = 0; ms < MSUB; ++ms) {
-              const uint64_t adesc = desc64(a_tap + a_cb + (uint32_t)ms * 128u * row16, hi, bo);
-              if (leader) umma_f16(d_base + (uint32_t)ms * N, adesc, bdesc, idesc, accum);
+            for (int kk = 0; kk < SPP; ++kk) {
+              const uint64_t bdesc = desc64(b_blk + 2u * kk, hi);
+#pragma unroll
+              for (int ms = 0; ms < MSUB; ++ms) {
+                const uint64_t adesc = desc64(a_blk + 2u * kk + (uint32_t)ms * 128u * row16, hi);
+                if (leader) umma_f16(d_base + (uint32_t)ms * N, adesc, bdesc, idesc, accum);
+              }
+              accum = 1;
             }
-            accum = 1;
-            if (++bk == spp) { bk = 0; b_lo += b_panel16 - 2u * (uint32_t)(spp - 1); } else { b_lo += 2u; }
-            if (++cb == k16_per_tap) { cb = 0; kin = 0; a_cb = 0; a_tap += (uint32_t)p.tap_step * row16; }
-            else if (++kin == spp) { kin = 0; a_cb += a_panel16 - 2u * (uint32_t)(spp - 1); }
-            else { a_cb += 2u; }
+            b_blk += b_block16;
+            if (++panel == panels) { panel = 0; a_tap += tap_step16; a_blk = a_tap; } else { a_blk += a_panel16; }
           }
           if (!p.w_resident && leader) umma_commit(bar_w_empty(slot));   // slot free once these MMAs have read it
           __syncwarp();
         }
         if (!ok) break;
+        resident_ready = true;
         if (leader) {
           umma_commit(bar_a_empty(buf));                          // A tile consumed
           umma_commit(bar_acc_full(acc));                         // accumulators complete

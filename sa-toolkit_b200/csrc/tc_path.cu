@@ -183,7 +183,7 @@ bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int n_k16_max
   return false;
 }
 
-template <int N, int MSUB>
+template <int N, int MSUB, int PW>
 cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
   static int occ_cache[16] = {0};
   static size_t occ_smem[16] = {0};
@@ -192,13 +192,13 @@ cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int 
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<N, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<N, MSUB, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
     int occ = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::conv_tc_kernel<N, MSUB>, tc::kThreads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::conv_tc_kernel<N, MSUB, PW>, tc::kThreads, smem);
     if (e != cudaSuccess) return e;
     constexpr int acc_cols = N * MSUB * ((2 * N * MSUB <= 512) ? 2 : 1);
     constexpr int tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
@@ -208,18 +208,18 @@ cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int 
   tc::ConvParams p = p_in;
   const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev] / grid_y));
   dim3 grid((unsigned)ctas, (unsigned)grid_y, 1);
-  tc::conv_tc_kernel<N, MSUB><<<grid, tc::kThreads, smem, st>>>(p);
+  tc::conv_tc_kernel<N, MSUB, PW><<<grid, tc::kThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t dispatch(int n, int msub, const tc::ConvParams& p, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
-#define SA_CASE(NN)                                                                       \
-  case NN: return msub == 2 ? launch_one<NN, 2>(p, grid_y, smem, n_sm, st) : launch_one<NN, 1>(p, grid_y, smem, n_sm, st);
-  switch (n) {
-    SA_CASE(16) SA_CASE(32) SA_CASE(64) SA_CASE(128) SA_CASE(256)
-    default: return cudaErrorInvalidValue;
-  }
+cudaError_t dispatch(int n, int msub, int pw, const tc::ConvParams& p, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
+#define SA_CASE(NN, PP)                                                                   \
+  if (n == NN && pw == PP)                                                                \
+    return msub == 2 ? launch_one<NN, 2, PP>(p, grid_y, smem, n_sm, st) : launch_one<NN, 1, PP>(p, grid_y, smem, n_sm, st);
+  SA_CASE(256, 64) SA_CASE(128, 64) SA_CASE(64, 64) SA_CASE(32, 64) SA_CASE(16, 64)
+  SA_CASE(32, 32) SA_CASE(16, 32) SA_CASE(16, 16)
 #undef SA_CASE
+  return cudaErrorInvalidValue;
 }
 
 // ---- fused ResBlock (chain) launch -------------------------------------------------------
@@ -337,7 +337,7 @@ struct Runner {
     p.n_phases = w.n_phases;
     p.n_tiles = w.n_tiles;
     p.rows_alloc = pl.rows_alloc; p.box_rows = pl.box_rows; p.nseg = pl.nseg;
-    p.pw = pw; p.out_pw = panel_width(ly.cout); p.desc_base_offset = ctx.desc_base_offset;
+    p.out_pw = panel_width(ly.cout);
     p.k16_per_stage = pl.k16_per_stage;
     p.n_wstages = pl.n_wstages; p.w_resident = pl.w_resident; p.n_abuf = pl.n_abuf;
     p.m_tiles = (l_in + 128 * pl.msub - 1) / (128 * pl.msub);
@@ -347,7 +347,7 @@ struct Runner {
     p.slope_out = e.slope_out;
     p.n_blocks = e.n_blocks;
     mark(tag);
-    cudaError_t ce = dispatch(w.n, pl.msub, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream);
+    cudaError_t ce = dispatch(w.n, pl.msub, pw, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream);
     if (ce != cudaSuccess) return msgf("conv_tc launch: %s", cudaGetErrorString(ce));
     ++*launches;
     return nullptr;
@@ -370,7 +370,6 @@ struct Runner {
     memset(&p, 0, sizeof(p));
     p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
     p.w = ch.d_w; p.bias = ch.d_bias; p.error_flag = ctx.d_error;
-    p.desc_base_offset = ctx.desc_base_offset;
     p.L = L; p.n_convs = ch.n_convs; p.ktaps = ch.k;
     for (int c = 0; c < ch.n_convs; ++c) { p.dil[c] = ch.dil[c]; p.pad[c] = ch.pad[c]; }
     p.halo = ch.halo;
@@ -521,7 +520,6 @@ const char* tc_init(tc_context& ctx, int device) {
   TC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx.h_error), sizeof(int), cudaHostAllocMapped));
   *ctx.h_error = 0;
   TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
-  if (const char* env = getenv("SATOOLS_B200_DESC_BASE_OFFSET")) ctx.desc_base_offset = atoi(env);
   ctx.ready = true;
   return nullptr;
 }

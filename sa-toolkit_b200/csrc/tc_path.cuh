@@ -40,7 +40,6 @@ struct tc_context {
   int* h_error = nullptr;     // mapped pinned flag raised by a kernel whose barrier wait timed out
   int* d_error = nullptr;     // device alias of h_error
   int max_smem = 0;
-  int desc_base_offset = 0;   // debug: fill the UMMA descriptor base_offset field (SATOOLS_B200_DESC_BASE_OFFSET=1)
 };
 
 struct tc_layer {
