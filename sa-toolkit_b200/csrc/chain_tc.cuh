@@ -58,7 +58,9 @@ struct ChainParams {
   float n_blocks;
 };
 
-template <int C, int MS>
+// K = filter taps.  Weight ring: C = 64 streams one tap ([64 rows][64], 8 KB) per stage through K
+// slots (slot = tap, parity = conv counter & 1); C <= 32 holds a whole conv per stage in 2 slots.
+template <int C, int MS, int K>
 __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -72,12 +74,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
 
+  constexpr int SPC = (C == 64) ? K : 1;                         // weight stages per conv
+  constexpr int NSLOTS = (C == 64) ? K : 2;
+  constexpr int K16 = C / 16;                                    // K=16 steps per tap
+  constexpr uint32_t kTapBytes = (uint32_t)N * RB;               // one tap = one [N rows][C] weight block
+  constexpr uint32_t stage_bytes = (C == 64) ? kTapBytes : (uint32_t)K * kTapBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = (uint32_t)p.k16_per_stage * N * 32u;
   uint8_t* bufA = smem;
   uint8_t* bufT = smem + kBufBytes;
   uint8_t* w_smem = smem + 2 * kBufBytes;
-  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)p.n_slots * stage_bytes);
+  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)NSLOTS * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kChainMaxConvs * C);
   // barrier slots: ready[2][8] acc_full[2][8] w_full[16] w_empty[16]
   auto bar_ready = [&](int buf, int s) { return smem_u32(&bars[buf * 8 + s]); };
@@ -87,7 +93,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32 + 2 * kChainMaxSlots);
 
   const int valid_rows = R - 2 * p.halo;
-  const int k16_per_tap = C / 16;
   const bool bf16 = (p.flags & EPI_BF16) != 0;
 
   if (warp == 0 && lane == 0) {
@@ -110,78 +115,75 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===== weight producer: stage g = (conv counter, stage in conv); slot = g % n_slots =====
+    // ===== weight producer =====
     {
       const bool leader = elect_one();
-      int slot = 0;
-      uint32_t par = 1;                                          // parity of the previous use of `slot`
-      bool wrapped = false, ok = true;
+      uint32_t cc = 0;                                           // conv counter of this CTA
+      bool ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x)
-        for (int c = 0; c < p.n_convs && ok; ++c)
-          for (int i = 0; i < p.stages_per_conv; ++i) {
-            if (wrapped) ok = mbar_wait(bar_w_empty(slot), par, p.error_flag);
+        for (int c = 0; c < p.n_convs && ok; ++c, ++cc) {
+          const uint8_t* src = static_cast<const uint8_t*>(p.w) + (size_t)c * SPC * stage_bytes;
+#pragma unroll 1
+          for (int i = 0; i < SPC; ++i) {
+            const int slot = (C == 64) ? i : (int)(cc & 1u);
+            const uint32_t use = (C == 64) ? cc : (cc >> 1);       // how often this slot has been filled before
+            if (use > 0) ok = mbar_wait(bar_w_empty(slot), (use - 1) & 1u, p.error_flag);
             if (!ok) break;
             if (leader) {
               mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
-              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes,
-                        static_cast<const uint8_t*>(p.w) + (size_t)(c * p.stages_per_conv + i) * stage_bytes, stage_bytes,
+              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, src + (size_t)i * stage_bytes, stage_bytes,
                         bar_w_full(slot));
             }
             __syncwarp();
-            if (++slot == p.n_slots) { slot = 0; par ^= 1u; wrapped = true; }
           }
+        }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform loop, one elected lane issues; lean body, see conv_tc.cuh) =====
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    // Straight-line code per (conv, sub-tile): K * K16 MMAs whose descriptors differ by constant
+    // adds; the only waits are the activation-ready barrier and, on sub-tile 0, the weight stages.
     {
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc(N, bf16);
       constexpr uint32_t hi = ((8u * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : RB == 64 ? 4u : 6u) << 29);
       constexpr uint32_t row16 = RB >> 4;
-      constexpr uint32_t b_tap16 = ((uint32_t)N * RB) >> 4;      // one tap = one [N rows][C] weight block
-      constexpr int K16 = C / 16;                                // K=16 steps per tap
+      constexpr uint32_t tap16 = kTapBytes >> 4;
       const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
-      const int taps_per_stage = p.k16_per_stage / K16;
-      int it = 0, slot0 = 0;                                     // slot0 / par0: first weight stage of the running conv
-      uint32_t par0 = 0;
+      uint32_t it = 0, cc = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
-        for (int c = 0; c < p.n_convs && ok; ++c) {
+        for (int c = 0; c < p.n_convs && ok; ++c, ++cc) {
           const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA)) + (uint32_t)(kChainPad - p.pad[c]) * row16;
-          const uint32_t rdy_parity = (uint32_t)(it * (p.n_convs / 2) + c / 2) & 1u;
+          const uint32_t rdy_parity = (it * (uint32_t)(p.n_convs / 2) + (uint32_t)(c / 2)) & 1u;
           const uint32_t dil16 = (uint32_t)p.dil[c] * row16;
-          for (int s = 0; s < MS && ok; ++s) {
-            // inputs of sub-tiles s-1..s+1 are staged once ready[.][min(s+1, MS-1)] has completed
-            ok = mbar_wait(bar_ready(c & 1, min(s + 1, MS - 1)), rdy_parity, p.error_flag);
-            if (!ok) break;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
-            uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16, accum = 0;
-            int slot = slot0;
-            uint32_t par = par0;
-            for (int i = 0; i < p.stages_per_conv && ok; ++i) {
-              if (s == 0) {                                      // later sub-tiles reuse the landed stage
-                ok = mbar_wait(bar_w_full(slot), par, p.error_flag);
-                if (!ok) break;
-                tc_fence_after();
-              }
-              uint32_t b_tap = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
-              for (int tp = 0; tp < taps_per_stage; ++tp) {
+          const uint32_t w_par = (C == 64) ? (cc & 1u) : ((cc >> 1) & 1u);
+          const uint32_t b_conv = b_lo0 + ((C == 64) ? 0u : (cc & 1u) * (stage_bytes >> 4));
 #pragma unroll
-                for (int kk = 0; kk < K16; ++kk) {
-                  if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, accum);
-                  accum = 1;
+          for (int s = 0; s < MS; ++s) {
+            // inputs of sub-tiles s-1..s+1 are staged once ready[.][min(s+1, MS-1)] has completed
+            if (ok) ok = mbar_wait(bar_ready(c & 1, (s + 1 < MS) ? s + 1 : MS - 1), rdy_parity, p.error_flag);
+            if (ok) {
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
+              uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16;
+#pragma unroll
+              for (int tap = 0; tap < K; ++tap) {
+                if (s == 0 && (C == 64 || tap == 0)) {           // later sub-tiles reuse the landed weights
+                  ok = ok && mbar_wait(bar_w_full((C == 64) ? tap : (int)(cc & 1u)), w_par, p.error_flag);
+                  tc_fence_after();
                 }
+                const uint32_t b_tap = b_conv + (uint32_t)tap * tap16;
+#pragma unroll
+                for (int kk = 0; kk < K16; ++kk)
+                  if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, (tap | kk) ? 1u : 0u);
                 a_tap += dil16;
-                b_tap += b_tap16;
+                if (s == MS - 1 && (C == 64 || tap == K - 1)) {  // last sub-tile: the slot may be refilled
+                  if (leader) umma_commit(bar_w_empty((C == 64) ? tap : (int)(cc & 1u)));
+                }
               }
-              if (s == MS - 1 && leader) umma_commit(bar_w_empty(slot));   // last sub-tile: the slot may be refilled
+              if (leader) umma_commit(bar_acc_full(c & 1, s));
               __syncwarp();
-              if (++slot == p.n_slots) { slot = 0; par ^= 1u; }
             }
-            if (s == MS - 1) { slot0 = slot; par0 = par; }
-            if (ok && leader) umma_commit(bar_acc_full(c & 1, s));
-            __syncwarp();
           }
         }
       }

@@ -235,8 +235,9 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   };
   const int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
   if (slots > tc::kChainMaxSlots) return false;
+  if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;          // instantiated tap counts
   int ms;
-  if (C == 64) ms = need(4, slots) <= (size_t)max_smem ? 4 : 3;
+  if (C == 64) ms = (ch.k == 11) ? 3 : 4;
   else if (C == 32) ms = 4;
   else ms = 8;
   if (need(ms, slots) > (size_t)max_smem) return false;
@@ -245,7 +246,7 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   return true;
 }
 
-template <int C, int MS>
+template <int C, int MS, int K>
 cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaStream_t st) {
   static bool attr_set[16] = {false};
   static int occ_cache[16] = {0};
@@ -254,13 +255,13 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
     int occ = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS>, tc::kChainThreads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K>, tc::kChainThreads, smem);
     if (e != cudaSuccess) return e;
     constexpr int need = 2 * MS * C;
     constexpr int cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -268,7 +269,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
     occ_smem[dev] = smem;
   }
   const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev]));
-  tc::resblock_chain_kernel<C, MS><<<ctas, tc::kChainThreads, smem, st>>>(p);
+  tc::resblock_chain_kernel<C, MS, K><<<ctas, tc::kChainThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -380,10 +381,12 @@ struct Runner {
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
     cudaError_t ce = cudaErrorInvalidValue;
-    if (ch.c == 64 && pl.ms == 4) ce = launch_chain<64, 4>(p, pl.smem, a.n_sm, a.stream);
-    else if (ch.c == 64 && pl.ms == 3) ce = launch_chain<64, 3>(p, pl.smem, a.n_sm, a.stream);
-    else if (ch.c == 32 && pl.ms == 4) ce = launch_chain<32, 4>(p, pl.smem, a.n_sm, a.stream);
-    else if (ch.c == 16 && pl.ms == 8) ce = launch_chain<16, 8>(p, pl.smem, a.n_sm, a.stream);
+#define SA_CHAIN(CC, MM, KK) \
+    if (ch.c == CC && pl.ms == MM && ch.k == KK) ce = launch_chain<CC, MM, KK>(p, pl.smem, a.n_sm, a.stream);
+    SA_CHAIN(64, 4, 3) SA_CHAIN(64, 4, 7) SA_CHAIN(64, 3, 11)
+    SA_CHAIN(32, 4, 3) SA_CHAIN(32, 4, 7) SA_CHAIN(32, 4, 11)
+    SA_CHAIN(16, 8, 3) SA_CHAIN(16, 8, 7) SA_CHAIN(16, 8, 11)
+#undef SA_CHAIN
     if (ce != cudaSuccess) return msgf("resblock_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
     *done = true;
