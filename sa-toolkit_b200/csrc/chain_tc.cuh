@@ -25,7 +25,10 @@
 // are released on the last sub-tile, which lets the next conv's weights stream in behind.
 //
 // Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = epilogue (TMEM lane group = warp % 4, channel half = (warp - 2) / 4).
+// warps 2..9 = epilogue, TMEM lane group = warp % 4.  C = 64: both warp quads work on the same
+// sub-tile, each taking half of the channels (the MMAs of a sub-tile are long enough to hide
+// it).  C <= 32: a sub-tile's MMAs are short, so the two warp quads own alternating sub-tiles
+// (a thread owns a full row) and two sub-tile epilogues run concurrently.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -69,7 +72,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   constexpr int ROWS = R + 2 * kChainPad;
   constexpr uint32_t RB = 2u * C;                                // row bytes: 128 / 64 / 32
   constexpr uint32_t kBufBytes = ROWS * RB;
-  constexpr int kCPT = C / 16;                                   // 8-channel chunks per epilogue thread
+  constexpr int G = (C <= 32) ? 2 : 1;                           // epilogue warp groups owning alternating sub-tiles
+  constexpr int kCPT = (G == 1) ? C / 16 : C / 8;                // 8-channel chunks per epilogue thread
+  constexpr int kOwn = MS / G;                                   // sub-tiles whose rows a thread owns
+  static_assert(MS % G == 0, "MS must be a multiple of the group count");
   constexpr uint32_t kTmemNeed = 2u * MS * N;
   constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 8; ++s) {
-      mbar_init(bar_ready(0, s), 8); mbar_init(bar_ready(1, s), 8);
+      mbar_init(bar_ready(0, s), 8 / G); mbar_init(bar_ready(1, s), 8 / G);
       mbar_init(bar_acc_full(0, s), 1); mbar_init(bar_acc_full(1, s), 1);
     }
     for (int i = 0; i < kChainMaxSlots; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
@@ -160,8 +166,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
           const uint32_t b_conv = b_lo0 + ((C == 64) ? 0u : (cc & 1u) * (stage_bytes >> 4));
 #pragma unroll
           for (int s = 0; s < MS; ++s) {
-            // inputs of sub-tiles s-1..s+1 are staged once ready[.][min(s+1, MS-1)] has completed
+            // inputs of sub-tiles s-1..s+1 must be staged.  Each epilogue group finishes its sub-tiles in
+            // order, so ready[s+1] implies ready[s-1] (G = 2) or everything before it (G = 1).
             if (ok) ok = mbar_wait(bar_ready(c & 1, (s + 1 < MS) ? s + 1 : MS - 1), rdy_parity, p.error_flag);
+            if (G == 2 && s + 1 < MS && ok) ok = mbar_wait(bar_ready(c & 1, s), rdy_parity, p.error_flag);
             if (ok) {
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
@@ -191,10 +199,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   } else {
     // ===== epilogue warps =====
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int ch0 = half * kCPT;                                 // first 8-channel chunk of this thread
+    const int half = (warp - 2) >> 2;                            // warp quad: channel half (G = 1) or sub-tile parity (G = 2)
+    const int ch0 = (G == 1) ? half * kCPT : 0;                  // first 8-channel chunk of this thread
     const int cchunks = C / 8;
-    float xr[MS][kCPT * 8];                                      // fp32 residual stream of this thread
+    float xr[kOwn][kCPT * 8];                                    // fp32 residual stream of this thread
+#define SA_MINE(s) (G == 1 || ((s) & 1) == half)
+#define SA_XI(s) ((G == 1) ? (s) : (s) / 2)
     int it = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
       // ---- P0: load x, keep it in registers, stage lrelu(x) ----
 #pragma unroll
       for (int s = 0; s < MS; ++s) {
+        if (!SA_MINE(s)) continue;
         const int r = s * 128 + lg * 32 + lane;
         const int t = t_start + r;
         const bool inside = t >= 0 && t < p.L;
@@ -213,18 +224,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
             const float* src = p.x32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
             a = ldg_f4(src); c4 = ldg_f4(src + 4);
           }
-          xr[s][q * 8 + 0] = a.x; xr[s][q * 8 + 1] = a.y; xr[s][q * 8 + 2] = a.z; xr[s][q * 8 + 3] = a.w;
-          xr[s][q * 8 + 4] = c4.x; xr[s][q * 8 + 5] = c4.y; xr[s][q * 8 + 6] = c4.z; xr[s][q * 8 + 7] = c4.w;
+          xr[SA_XI(s)][q * 8 + 0] = a.x; xr[SA_XI(s)][q * 8 + 1] = a.y; xr[SA_XI(s)][q * 8 + 2] = a.z; xr[SA_XI(s)][q * 8 + 3] = a.w;
+          xr[SA_XI(s)][q * 8 + 4] = c4.x; xr[SA_XI(s)][q * 8 + 5] = c4.y; xr[SA_XI(s)][q * 8 + 6] = c4.z; xr[SA_XI(s)][q * 8 + 7] = c4.w;
         }
       }
 #pragma unroll
       for (int s = 0; s < MS; ++s) {
+        if (!SA_MINE(s)) continue;
         const int r = s * 128 + lg * 32 + lane;
 #pragma unroll
         for (int q = 0; q < kCPT; ++q) {
           float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[s][q * 8 + e], 0.1f);
+          for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[SA_XI(s)][q * 8 + e], 0.1f);
           *reinterpret_cast<uint4*>(bufA + swz((uint32_t)(kChainPad + r) * RB + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
         uint8_t* out_buf = second ? bufA : bufT;
 #pragma unroll
         for (int s = 0; s < MS; ++s) {
+          if (!SA_MINE(s)) continue;
           if (!ok) break;
           ok = mbar_wait(bar_acc_full(c & 1, s), acc_parity, p.error_flag);
           if (!ok) break;
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
             v[6] = __uint_as_float(rr[q * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[q * 8 + 7]) + b1.w;
             if (second) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { xr[s][q * 8 + e] += v[e]; v[e] = xr[s][q * 8 + e]; }
+              for (int e = 0; e < 8; ++e) { xr[SA_XI(s)][q * 8 + e] += v[e]; v[e] = xr[SA_XI(s)][q * 8 + e]; }
             }
             if (!last) {
 #pragma unroll
@@ -310,6 +323,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
       }
     }
   }
+#undef SA_MINE
+#undef SA_XI
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
