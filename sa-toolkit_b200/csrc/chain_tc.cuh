@@ -27,8 +27,8 @@
 // Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..9 = epilogue, TMEM lane group = warp % 4.  C = 64: both warp quads work on the same
 // sub-tile, each taking half of the channels (the MMAs of a sub-tile are long enough to hide
-// it).  C <= 32: a sub-tile's MMAs are short, so the two warp quads own alternating sub-tiles
-// (a thread owns a full row) and two sub-tile epilogues run concurrently.
+// it).  (An alternative mapping where the two warp quads own alternating sub-tiles exists behind
+// the constant G below; it measured slower.)
 #pragma once
 #include "conv_tc.cuh"
 
@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   constexpr int ROWS = R + 2 * kChainPad;
   constexpr uint32_t RB = 2u * C;                                // row bytes: 128 / 64 / 32
   constexpr uint32_t kBufBytes = ROWS * RB;
-  constexpr int G = (C <= 32) ? 2 : 1;                           // epilogue warp groups owning alternating sub-tiles
+  // G = 2 (the two warp quads own alternating sub-tiles) was measured SLOWER for C <= 32 on B200 (stage 3: 7.4 ->
+  // 13.0 ms, stage 4: 9.5 -> 14.1 ms: the unrolled epilogue bodies double and fall out of the instruction cache),
+  // so every width uses one group.  The code path is kept for experiments.
+  constexpr int G = 1;                                           // epilogue warp groups owning alternating sub-tiles
   constexpr int kCPT = (G == 1) ? C / 16 : C / 8;                // 8-channel chunks per epilogue thread
   constexpr int kOwn = MS / G;                                   // sub-tiles whose rows a thread owns
   static_assert(MS % G == 0, "MS must be a multiple of the group count");
