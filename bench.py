@@ -111,7 +111,7 @@ def cpu_port_runner(state):
     return lambda x: otc.generator_forward(p, x)
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU implementation of the path (torch-CPU port of
     archi.py:77-91; the reference is Python and /root/reference does not travel to the GPU box),
     all host threads, each step a bounded sample (2 utterances) of the same batch."""
@@ -138,14 +138,14 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = t_audio / dt
     sample = f"{per_step} utterances of the 64-item batch per step, {args.steps} steps, fp32, torch {torch.__version__} CPU"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "hifigan_audio_seconds_per_second", "value": v, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, "cpu"),
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0})
 
 
 def workload_config(args, where):
@@ -158,6 +158,16 @@ def workload_config(args, where):
 
 
 def main():
+    # Only the final JSON line may reach stdout: NCCL / torch print banners from C code, so fd 1 is
+    # pointed at stderr until the result is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -173,7 +183,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch.distributed as dist
@@ -291,7 +301,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
