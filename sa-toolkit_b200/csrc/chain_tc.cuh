@@ -8,8 +8,7 @@
 //   bufA  [PAD + MS*128 + PAD rows][C] 16-bit, UMMA K-major swizzled (row = 2C bytes: SWIZZLE_128B /
 //         64B / 32B for C = 64 / 32 / 16)         lrelu(x)            operand of conv1
 //   bufT  same shape                              lrelu(conv1 + b)    operand of conv2
-//   x     fp32 residual stream, in REGISTERS of the epilogue threads (one thread owns a row
-//         of a sub-tile and half of the channels for the whole ResBlock)
+//   x     fp32 residual stream, in REGISTERS of the epilogue threads (one thread owns one row)
 //   D     fp32 accumulators in TMEM, two buffers per sub-tile (conv parity)
 //
 // Same implicit-GEMM formulation as conv_tc.cuh: time on M, Cout on N, the staged tile is the
@@ -24,18 +23,20 @@
 // eight epilogue warps drain sub-tile s.  Weights of one conv sit in a ring (slot = stage) and
 // are released on the last sub-tile, which lets the next conv's weights stream in behind.
 //
-// Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = epilogue, TMEM lane group = warp % 4.  C = 64: both warp quads work on the same
-// sub-tile, each taking half of the channels (the MMAs of a sub-tile are long enough to hide
-// it).  (An alternative mapping where the two warp quads own alternating sub-tiles exists behind
-// the constant G below; it measured slower.)
+// Warp roles (64 + 128*MS threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
+// then one epilogue warp quad per sub-tile (TMEM lane group = warp % 4): ONE THREAD OWNS ONE ROW of
+// the tile for the whole ResBlock, so the residual stream is a fixed xr[C] in its registers, there
+// is no loop over sub-tiles (small code, every sub-tile epilogue runs concurrently) and each quad
+// talks to the MMA warp through its own acc_full / ready barriers.  (Earlier mappings -- all 8
+// warps on one sub-tile, or two groups on alternating sub-tiles -- were 2-4x slower: ~250
+// instructions per 256 elements and 32 KB of unrolled code, profiles/README.md.)
 #pragma once
 #include "conv_tc.cuh"
 
 namespace sa {
 namespace tc {
 
-constexpr int kChainThreads = 320;
+__host__ __device__ constexpr int chain_threads(int ms) { return 64 + 128 * ms; }
 constexpr int kChainPad = 32;            // slack rows on both sides of the staged tile (>= max tap reach 25)
 constexpr int kChainMaxConvs = 8;
 constexpr int kChainMaxSlots = 16;
@@ -64,7 +65,7 @@ struct ChainParams {
 // K = filter taps.  Weight ring: C = 64 streams one tap ([64 rows][64], 8 KB) per stage through K
 // slots (slot = tap, parity = conv counter & 1); C <= 32 holds a whole conv per stage in 2 slots.
 template <int C, int MS, int K>
-__global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const __grid_constant__ ChainParams p) {
+__global__ void __launch_bounds__(chain_threads(MS), 1) resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int N = C;
@@ -72,13 +73,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
   constexpr int ROWS = R + 2 * kChainPad;
   constexpr uint32_t RB = 2u * C;                                // row bytes: 128 / 64 / 32
   constexpr uint32_t kBufBytes = ROWS * RB;
-  // G = 2 (the two warp quads own alternating sub-tiles) was measured SLOWER for C <= 32 on B200 (stage 3: 7.4 ->
-  // 13.0 ms, stage 4: 9.5 -> 14.1 ms: the unrolled epilogue bodies double and fall out of the instruction cache),
-  // so every width uses one group.  The code path is kept for experiments.
-  constexpr int G = 1;                                           // epilogue warp groups owning alternating sub-tiles
-  constexpr int kCPT = (G == 1) ? C / 16 : C / 8;                // 8-channel chunks per epilogue thread
-  constexpr int kOwn = MS / G;                                   // sub-tiles whose rows a thread owns
-  static_assert(MS % G == 0, "MS must be a multiple of the group count");
+  constexpr int kThreads_ = chain_threads(MS);
+  constexpr int kCPT = C / 8;                                    // 8-channel chunks per row = per epilogue thread
   constexpr uint32_t kTmemNeed = 2u * MS * N;
   constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
@@ -106,16 +102,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 8; ++s) {
-      mbar_init(bar_ready(0, s), 8 / G); mbar_init(bar_ready(1, s), 8 / G);
+      mbar_init(bar_ready(0, s), 4); mbar_init(bar_ready(1, s), 4);    // the 4 warps of the sub-tile's quad
       mbar_init(bar_acc_full(0, s), 1); mbar_init(bar_acc_full(1, s), 1);
     }
     for (int i = 0; i < kChainMaxSlots; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
-  for (int i = threadIdx.x; i < p.n_convs * C; i += kChainThreads) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_convs * C; i += kThreads_) bias_s[i] = p.bias[i];
   // zero both staged tiles once: the PAD slack rows are never written afterwards
-  for (uint32_t i = threadIdx.x; i < 2 * kBufBytes / 16; i += kChainThreads)
+  for (uint32_t i = threadIdx.x; i < 2 * kBufBytes / 16; i += kThreads_)
     *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -169,10 +165,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
           const uint32_t b_conv = b_lo0 + ((C == 64) ? 0u : (cc & 1u) * (stage_bytes >> 4));
 #pragma unroll
           for (int s = 0; s < MS; ++s) {
-            // inputs of sub-tiles s-1..s+1 must be staged.  Each epilogue group finishes its sub-tiles in
-            // order, so ready[s+1] implies ready[s-1] (G = 2) or everything before it (G = 1).
-            if (ok) ok = mbar_wait(bar_ready(c & 1, (s + 1 < MS) ? s + 1 : MS - 1), rdy_parity, p.error_flag);
-            if (G == 2 && s + 1 < MS && ok) ok = mbar_wait(bar_ready(c & 1, s), rdy_parity, p.error_flag);
+            // inputs of sub-tiles s-1..s+1 must be staged (s-1 was waited for in the previous iteration)
+            if (ok) ok = mbar_wait(bar_ready(c & 1, s), rdy_parity, p.error_flag);
+            if (s + 1 < MS && ok) ok = mbar_wait(bar_ready(c & 1, s + 1), rdy_parity, p.error_flag);
             if (ok) {
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
@@ -200,99 +195,79 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
       }
     }
   } else {
-    // ===== epilogue warps =====
+    // ===== epilogue: warp quad (warp - 2) / 4 owns sub-tile s; this thread owns row r of the tile =====
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;                            // warp quad: channel half (G = 1) or sub-tile parity (G = 2)
-    const int ch0 = (G == 1) ? half * kCPT : 0;                  // first 8-channel chunk of this thread
-    const int cchunks = C / 8;
-    float xr[kOwn][kCPT * 8];                                    // fp32 residual stream of this thread
-#define SA_MINE(s) (G == 1 || ((s) & 1) == half)
-#define SA_XI(s) ((G == 1) ? (s) : (s) / 2)
-    int it = 0;
+    const int s = (warp - 2) >> 2;
+    const int r = s * 128 + lg * 32 + lane;
+    constexpr int cchunks = C / 8;
+    float xr[C];                                                 // fp32 residual stream of this row
+    const uint32_t row_off = (uint32_t)(kChainPad + r) * RB;
+    uint32_t it = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_item, mt = tile - b * p.tiles_per_item;
-      const int t_start = mt * valid_rows - p.halo;              // global row of tile row 0
-      // ---- P0: load x, keep it in registers, stage lrelu(x) ----
+      const int t = mt * valid_rows - p.halo + r;                // global row of this thread
+      const bool inside = t >= 0 && t < p.L;
+      const bool keep = inside && r >= p.halo && r < R - p.halo; // rows this tile is responsible for
+      // ---- load x, keep it in registers, stage lrelu(x) ----
 #pragma unroll
-      for (int s = 0; s < MS; ++s) {
-        if (!SA_MINE(s)) continue;
-        const int r = s * 128 + lg * 32 + lane;
-        const int t = t_start + r;
-        const bool inside = t >= 0 && t < p.L;
-#pragma unroll
-        for (int q = 0; q < kCPT; ++q) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
-          if (inside) {
-            const float* src = p.x32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
-            a = ldg_f4(src); c4 = ldg_f4(src + 4);
-          }
-          xr[SA_XI(s)][q * 8 + 0] = a.x; xr[SA_XI(s)][q * 8 + 1] = a.y; xr[SA_XI(s)][q * 8 + 2] = a.z; xr[SA_XI(s)][q * 8 + 3] = a.w;
-          xr[SA_XI(s)][q * 8 + 4] = c4.x; xr[SA_XI(s)][q * 8 + 5] = c4.y; xr[SA_XI(s)][q * 8 + 6] = c4.z; xr[SA_XI(s)][q * 8 + 7] = c4.w;
+      for (int q = 0; q < kCPT; ++q) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
+        if (inside) {
+          const float* src = p.x32 + (((size_t)b * cchunks + q) * (size_t)p.L + t) * 8;
+          a = ldg_f4(src); c4 = ldg_f4(src + 4);
         }
+        xr[q * 8 + 0] = a.x; xr[q * 8 + 1] = a.y; xr[q * 8 + 2] = a.z; xr[q * 8 + 3] = a.w;
+        xr[q * 8 + 4] = c4.x; xr[q * 8 + 5] = c4.y; xr[q * 8 + 6] = c4.z; xr[q * 8 + 7] = c4.w;
       }
 #pragma unroll
-      for (int s = 0; s < MS; ++s) {
-        if (!SA_MINE(s)) continue;
-        const int r = s * 128 + lg * 32 + lane;
+      for (int q = 0; q < kCPT; ++q) {
+        float v[8];
 #pragma unroll
-        for (int q = 0; q < kCPT; ++q) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[SA_XI(s)][q * 8 + e], 0.1f);
-          *reinterpret_cast<uint4*>(bufA + swz((uint32_t)(kChainPad + r) * RB + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_ready(0, s));
+        for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[q * 8 + e], 0.1f);
+        *reinterpret_cast<uint4*>(bufA + swz(row_off + (uint32_t)q * 16u, RB)) = pack8(v, bf16);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready(0, s));
       // ---- the convs ----
-      for (int c = 0; c < p.n_convs && ok; ++c) {
-        const uint32_t acc_parity = (uint32_t)(it * (p.n_convs / 2) + c / 2) & 1u;
+#pragma unroll 1
+      for (int c = 0; c < p.n_convs; ++c) {
+        const uint32_t acc_parity = (it * (uint32_t)(p.n_convs / 2) + (uint32_t)(c / 2)) & 1u;
         const bool second = (c & 1) != 0;                        // conv2 of a pair: x += ..
         const bool last = (c == p.n_convs - 1);
-        const float* bias_c = bias_s + c * C + ch0 * 8;
+        const float* bias_c = bias_s + c * C;
         uint8_t* out_buf = second ? bufA : bufT;
+        ok = mbar_wait(bar_acc_full(c & 1, s), acc_parity, p.error_flag);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N);
 #pragma unroll
-        for (int s = 0; s < MS; ++s) {
-          if (!SA_MINE(s)) continue;
-          if (!ok) break;
-          ok = mbar_wait(bar_acc_full(c & 1, s), acc_parity, p.error_flag);
-          if (!ok) break;
-          tc_fence_after();
-          const int r = s * 128 + lg * 32 + lane;
-          const int t = t_start + r;
-          const bool inside = t >= 0 && t < p.L;
-          const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N + ch0 * 8);
-          uint32_t rr[kCPT * 8];
+        for (int g = 0; g < C / 16; ++g) {                       // 16 columns = 2 channel chunks per TMEM round trip
+          uint32_t rr[16];
           __syncwarp();
+          tmem_ld16(t_addr + (uint32_t)(g * 16), rr);
+          tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < kCPT; ++q)
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(rr[q * 8 + 0]), "=r"(rr[q * 8 + 1]), "=r"(rr[q * 8 + 2]), "=r"(rr[q * 8 + 3]),
-                           "=r"(rr[q * 8 + 4]), "=r"(rr[q * 8 + 5]), "=r"(rr[q * 8 + 6]), "=r"(rr[q * 8 + 7])
-                         : "r"(t_addr + (uint32_t)(q * 8))
-                         : "memory");
-          tmem_ld_wait();                                        // one wait for all the loads of this sub-tile
-#pragma unroll
-          for (int q = 0; q < kCPT; ++q) {
+          for (int h = 0; h < 2; ++h) {
+            const int q = g * 2 + h;
             float v[8];
             const float4 b0 = *reinterpret_cast<const float4*>(bias_c + q * 8), b1 = *reinterpret_cast<const float4*>(bias_c + q * 8 + 4);
-            v[0] = __uint_as_float(rr[q * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[q * 8 + 1]) + b0.y;
-            v[2] = __uint_as_float(rr[q * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[q * 8 + 3]) + b0.w;
-            v[4] = __uint_as_float(rr[q * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[q * 8 + 5]) + b1.y;
-            v[6] = __uint_as_float(rr[q * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[q * 8 + 7]) + b1.w;
+            v[0] = __uint_as_float(rr[h * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[h * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(rr[h * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[h * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(rr[h * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[h * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(rr[h * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[h * 8 + 7]) + b1.w;
             if (second) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { xr[SA_XI(s)][q * 8 + e] += v[e]; v[e] = xr[SA_XI(s)][q * 8 + e]; }
+              for (int e = 0; e < 8; ++e) { xr[q * 8 + e] += v[e]; v[e] = xr[q * 8 + e]; }
             }
             if (!last) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = inside ? lrelu_f(v[e], 0.1f) : 0.f;
-              *reinterpret_cast<uint4*>(out_buf + swz((uint32_t)(kChainPad + r) * RB + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
-            } else if (inside && r >= p.halo && r < R - p.halo) {
+              *reinterpret_cast<uint4*>(out_buf + swz(row_off + (uint32_t)q * 16u, RB)) = pack8(v, bf16);
+            } else if (keep) {
               // final epilogue: multi-receptive-field combine + stores (v = x_final)
-              const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
+              const size_t idx = (((size_t)b * cchunks + q) * (size_t)p.L + t) * 8;
               if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
                 const float4 s0 = ldg_f4(p.sum32 + idx), s1 = ldg_f4(p.sum32 + idx + 4);
                 v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
@@ -311,23 +286,21 @@ __global__ void __launch_bounds__(kChainThreads, 1) resblock_chain_kernel(const 
               if (p.flags & EPI_OUT16) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = lrelu_f(v[e], p.slope_out);
-                const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + ch0 + q) * 16;   // [B][1][L][C]
+                const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + q) * 16;   // [B][1][L][C]
                 *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(v, bf16);
               }
             }
           }
-          if (!last) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_ready(second ? 0 : 1, s));
-          }
+        }
+        if (!last) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_ready(second ? 0 : 1, s));
         }
       }
     }
   }
-#undef SA_MINE
-#undef SA_XI
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -237,9 +237,8 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   if (slots > tc::kChainMaxSlots) return false;
   if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;          // instantiated tap counts
   int ms;
-  if (C == 64) ms = (ch.k == 11) ? 3 : 4;
-  else if (C == 32) ms = 4;
-  else ms = 8;
+  if (C == 64) ms = (ch.k == 11) ? 3 : 4;       // smem: 2 staged tiles + K weight taps
+  else ms = 6;                                   // 64 + 128*6 = 832 threads; TMEM 2*6*C <= 512
   if (need(ms, slots) > (size_t)max_smem) return false;
   if (ms * 128 - 2 * ch.halo < 64) return false;
   pl.ms = ms; pl.n_slots = slots; pl.smem = need(ms, slots);
@@ -261,7 +260,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
   }
   if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
     int occ = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K>, tc::kChainThreads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K>, tc::chain_threads(MS), smem);
     if (e != cudaSuccess) return e;
     constexpr int need = 2 * MS * C;
     constexpr int cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -269,7 +268,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
     occ_smem[dev] = smem;
   }
   const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev]));
-  tc::resblock_chain_kernel<C, MS, K><<<ctas, tc::kChainThreads, smem, st>>>(p);
+  tc::resblock_chain_kernel<C, MS, K><<<ctas, tc::chain_threads(MS), smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -384,8 +383,8 @@ struct Runner {
 #define SA_CHAIN(CC, MM, KK) \
     if (ch.c == CC && pl.ms == MM && ch.k == KK) ce = launch_chain<CC, MM, KK>(p, pl.smem, a.n_sm, a.stream);
     SA_CHAIN(64, 4, 3) SA_CHAIN(64, 4, 7) SA_CHAIN(64, 3, 11)
-    SA_CHAIN(32, 4, 3) SA_CHAIN(32, 4, 7) SA_CHAIN(32, 4, 11)
-    SA_CHAIN(16, 8, 3) SA_CHAIN(16, 8, 7) SA_CHAIN(16, 8, 11)
+    SA_CHAIN(32, 6, 3) SA_CHAIN(32, 6, 7) SA_CHAIN(32, 6, 11)
+    SA_CHAIN(16, 6, 3) SA_CHAIN(16, 6, 7) SA_CHAIN(16, 6, 11)
 #undef SA_CHAIN
     if (ce != cudaSuccess) return msgf("resblock_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
