@@ -65,7 +65,8 @@ struct ChainParams {
 // K = filter taps.  Weight ring: C = 64 streams one tap ([64 rows][64], 8 KB) per stage through K
 // slots (slot = tap, parity = conv counter & 1); C <= 32 holds a whole conv per stage in 2 slots.
 template <int C, int MS, int K>
-__global__ void __launch_bounds__(chain_threads(MS), 1) resblock_chain_kernel(const __grid_constant__ ChainParams p) {
+__global__ void __launch_bounds__(chain_threads(MS), (C <= 32 && MS <= 3) ? 2 : 1)
+resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int N = C;

@@ -223,6 +223,8 @@ cudaError_t dispatch(int n, int msub, int pw, const tc::ConvParams& p, int grid_
 }
 
 // ---- fused ResBlock (chain) launch -------------------------------------------------------
+int g_chain_ms_narrow = 6;      // sub-tiles per CTA for C <= 32 (SATOOLS_B200_CHAIN_MS=3 -> two CTAs per SM)
+
 struct ChainPlan { int ms, n_slots; size_t smem; };
 
 bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
@@ -238,7 +240,7 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;          // instantiated tap counts
   int ms;
   if (C == 64) ms = (ch.k == 11) ? 3 : 4;       // smem: 2 staged tiles + K weight taps
-  else ms = 6;                                   // 64 + 128*6 = 832 threads; TMEM 2*6*C <= 512
+  else ms = g_chain_ms_narrow;                   // 6: one CTA/SM (832 threads); 3: two CTAs/SM (448 threads each)
   if (need(ms, slots) > (size_t)max_smem) return false;
   if (ms * 128 - 2 * ch.halo < 64) return false;
   pl.ms = ms; pl.n_slots = slots; pl.smem = need(ms, slots);
@@ -385,6 +387,8 @@ struct Runner {
     SA_CHAIN(64, 4, 3) SA_CHAIN(64, 4, 7) SA_CHAIN(64, 3, 11)
     SA_CHAIN(32, 6, 3) SA_CHAIN(32, 6, 7) SA_CHAIN(32, 6, 11)
     SA_CHAIN(16, 6, 3) SA_CHAIN(16, 6, 7) SA_CHAIN(16, 6, 11)
+    SA_CHAIN(32, 3, 3) SA_CHAIN(32, 3, 7) SA_CHAIN(32, 3, 11)
+    SA_CHAIN(16, 3, 3) SA_CHAIN(16, 3, 7) SA_CHAIN(16, 3, 11)
 #undef SA_CHAIN
     if (ce != cudaSuccess) return msgf("resblock_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
@@ -522,6 +526,10 @@ const char* tc_init(tc_context& ctx, int device) {
   TC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx.h_error), sizeof(int), cudaHostAllocMapped));
   *ctx.h_error = 0;
   TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
+  if (const char* env = getenv("SATOOLS_B200_CHAIN_MS")) {
+    const int v = atoi(env);
+    if (v == 3 || v == 6) g_chain_ms_narrow = v;
+  }
   ctx.ready = true;
   return nullptr;
 }
