@@ -166,8 +166,9 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
           const uint32_t b_conv = b_lo0 + ((C == 64) ? 0u : (cc & 1u) * (stage_bytes >> 4));
 #pragma unroll
           for (int s = 0; s < MS; ++s) {
-            // inputs of sub-tiles s-1..s+1 must be staged (s-1 was waited for in the previous iteration)
-            if (ok) ok = mbar_wait(bar_ready(c & 1, s), rdy_parity, p.error_flag);
+            // inputs of sub-tiles s-1..s+1 must be staged; s-1 and s were confirmed in earlier iterations
+            // (an already-complete try_wait still costs ~90 cycles on this single issuing warp)
+            if (s == 0 && ok) ok = mbar_wait(bar_ready(c & 1, 0), rdy_parity, p.error_flag);
             if (s + 1 < MS && ok) ok = mbar_wait(bar_ready(c & 1, s + 1), rdy_parity, p.error_flag);
             if (ok) {
               tc_fence_after();

@@ -444,60 +444,73 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
           const bool valid = t < p.m_rows;
           const size_t orow = (size_t)t * p.out_stride + phase;
           const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0);
+          // The residual of up to 64 columns (4 groups) is requested before the first TMEM round trip, so a
+          // tile costs kColsPerWarp/64 dependent HBM latencies per sub-tile instead of kColsPerWarp/16.
+          constexpr int kGroups = kColsPerWarp / 16;
+          constexpr int kBatch = kGroups < 4 ? kGroups : 4;
 #pragma unroll 1
-          for (int g = 0; g < kColsPerWarp / 16; ++g) {            // 16 columns = 2 channel chunks per step
-            uint32_t r[16];
-            __syncwarp();                                          // tcgen05.ld is .sync.aligned
-            tmem_ld16(t_addr + (uint32_t)(g * 16), r);
-            const int c8 = (col0 >> 3) + g * 2;                    // first channel chunk inside this n-tile
-            const size_t idx0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
-            const size_t idx1 = idx0 + (size_t)p.l_out * 8;
-            float4 qr[4], qs[4];
-            if (valid) {                                           // issue every global load before waiting on TMEM
-              if (flags & EPI_RES) {
-                qr[0] = ldg_f4(p.res32 + idx0); qr[1] = ldg_f4(p.res32 + idx0 + 4);
-                qr[2] = ldg_f4(p.res32 + idx1); qr[3] = ldg_f4(p.res32 + idx1 + 4);
+          for (int g0 = 0; g0 < kGroups; g0 += kBatch) {
+            float4 qr[kBatch][4];
+            if (valid && (flags & EPI_RES)) {
+#pragma unroll
+              for (int gi = 0; gi < kBatch; ++gi) {
+                const int c8 = (col0 >> 3) + (g0 + gi) * 2;
+                const size_t i0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
+                const size_t i1 = i0 + (size_t)p.l_out * 8;
+                qr[gi][0] = ldg_f4(p.res32 + i0); qr[gi][1] = ldg_f4(p.res32 + i0 + 4);
+                qr[gi][2] = ldg_f4(p.res32 + i1); qr[gi][3] = ldg_f4(p.res32 + i1 + 4);
               }
-              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
+            }
+#pragma unroll
+            for (int gi = 0; gi < kBatch; ++gi) {
+              const int g = g0 + gi;
+              uint32_t r[16];
+              __syncwarp();                                        // tcgen05.ld is .sync.aligned
+              tmem_ld16(t_addr + (uint32_t)(g * 16), r);
+              const int c8 = (col0 >> 3) + g * 2;                  // first channel chunk inside this n-tile
+              const size_t idx0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
+              const size_t idx1 = idx0 + (size_t)p.l_out * 8;
+              float4 qs[4];
+              if (valid && (flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
                 qs[0] = ldg_f4(p.sum32 + idx0); qs[1] = ldg_f4(p.sum32 + idx0 + 4);
                 qs[2] = ldg_f4(p.sum32 + idx1); qs[3] = ldg_f4(p.sum32 + idx1 + 4);
               }
-            }
-            tmem_ld_wait();
-            if (valid) {
-              float v[16];
+              tmem_ld_wait();
+              if (valid) {
+                float v[16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
-              if (flags & EPI_RES) {
+                for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
+                if (flags & EPI_RES) {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) { v[4 * h] += qr[h].x; v[4 * h + 1] += qr[h].y; v[4 * h + 2] += qr[h].z; v[4 * h + 3] += qr[h].w; }
-              }
-              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
+                  for (int h = 0; h < 4; ++h) { v[4 * h] += qr[gi][h].x; v[4 * h + 1] += qr[gi][h].y; v[4 * h + 2] += qr[gi][h].z; v[4 * h + 3] += qr[gi][h].w; }
                 }
-              }
-              if (flags & EPI_SUM_FIN) {
+                if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;            // xs / num_kernels
-              }
-              if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-                stg_f4(p.sum32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx0 + 4, v[4], v[5], v[6], v[7]);
-                stg_f4(p.sum32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + idx1 + 4, v[12], v[13], v[14], v[15]);
-              }
-              if (flags & EPI_OUT32) {
-                stg_f4(p.out32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx0 + 4, v[4], v[5], v[6], v[7]);
-                stg_f4(p.out32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + idx1 + 4, v[12], v[13], v[14], v[15]);
-              }
-              if (flags & EPI_OUT16) {
-                float lo[8], hi[8];
+                  for (int h = 0; h < 4; ++h) {
+                    v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
+                  }
+                }
+                if (flags & EPI_SUM_FIN) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { lo[e] = lrelu_f(v[e], p.slope_out); hi[e] = lrelu_f(v[8 + e], p.slope_out); }
-                const int cg = ntile * (N / 8) + c8;               // chunk index in the output tensor (even)
-                const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(lo, bf16);
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8(hi, bf16);
+                  for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;            // xs / num_kernels
+                }
+                if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
+                  stg_f4(p.sum32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx0 + 4, v[4], v[5], v[6], v[7]);
+                  stg_f4(p.sum32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + idx1 + 4, v[12], v[13], v[14], v[15]);
+                }
+                if (flags & EPI_OUT32) {
+                  stg_f4(p.out32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx0 + 4, v[4], v[5], v[6], v[7]);
+                  stg_f4(p.out32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + idx1 + 4, v[12], v[13], v[14], v[15]);
+                }
+                if (flags & EPI_OUT16) {
+                  float lo[8], hi[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { lo[e] = lrelu_f(v[e], p.slope_out); hi[e] = lrelu_f(v[8 + e], p.slope_out); }
+                  const int cg = ntile * (N / 8) + c8;               // chunk index in the output tensor (even)
+                  const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
+                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(lo, bf16);
+                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8(hi, bf16);
+                }
               }
             }
           }
