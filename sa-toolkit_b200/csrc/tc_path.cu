@@ -149,7 +149,11 @@ constexpr size_t kResidentWeightBytes = 48 * 1024;   // keep the whole filter ba
 bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int n_k16_max, int max_smem) {
   const size_t fixed = (size_t)n * 4 + (8 + 2 * tc::kMaxStages) * 8 + 16 + 1024;   // + alignment slack
   const int spp = panel_width(cin_pad) / 16;                    // weight stages hold whole panels
-  for (int msub = (m_rows > 128 ? 2 : 1); msub >= 1; --msub) {
+  // 128-row tiles for the widest layers let the A tile and the accumulator double-buffer (256-row tiles of
+  // C = 256 fill shared memory and TMEM); SATOOLS_B200_MSUB_WIDE=2 restores 256-row tiles.
+  static const int msub_wide = getenv("SATOOLS_B200_MSUB_WIDE") ? atoi(getenv("SATOOLS_B200_MSUB_WIDE")) : 2;
+  const int msub_max = (m_rows > 128 ? 2 : 1);
+  for (int msub = (cin_pad >= 256 && n >= 256) ? std::min(msub_max, msub_wide) : msub_max; msub >= 1; --msub) {
     const int rows = 128 * msub + span;
     const int nseg = (rows + 255) / 256;
     const int box_rows = (int)align_up((size_t)(rows + nseg - 1) / nseg, 8);
