@@ -23,10 +23,11 @@
 // eight epilogue warps drain sub-tile s.  Weights of one conv sit in a ring (slot = stage) and
 // are released on the last sub-tile, which lets the next conv's weights stream in behind.
 //
-// Warp roles (64 + 128*MS threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
-// then one epilogue warp quad per sub-tile (TMEM lane group = warp % 4): ONE THREAD OWNS ONE ROW of
-// the tile for the whole ResBlock, so the residual stream is a fixed xr[C] in its registers, there
-// is no loop over sub-tiles (small code, every sub-tile epilogue runs concurrently) and each quad
+// Warp roles (64 + 32*WPS*MS threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
+// then WPS (4 or 8) epilogue warps per sub-tile (TMEM lane group = warp % 4; with 8 warps the second
+// quad takes the upper half of the channels): ONE THREAD OWNS ONE ROW (or half of it) of the tile
+// for the whole ResBlock, so the residual stream is a fixed array in its registers, there is no
+// loop over sub-tiles (small code, every sub-tile epilogue runs concurrently) and each sub-tile
 // talks to the MMA warp through its own acc_full / ready barriers.  (Earlier mappings -- all 8
 // warps on one sub-tile, or two groups on alternating sub-tiles -- were 2-4x slower: ~250
 // instructions per 256 elements and 32 KB of unrolled code, profiles/README.md.)
@@ -36,7 +37,7 @@
 namespace sa {
 namespace tc {
 
-__host__ __device__ constexpr int chain_threads(int ms) { return 64 + 128 * ms; }
+__host__ __device__ constexpr int chain_threads(int ms, int wps) { return 64 + 32 * wps * ms; }
 constexpr int kChainPad = 32;            // slack rows on both sides of the staged tile (>= max tap reach 25)
 constexpr int kChainMaxConvs = 8;
 constexpr int kChainMaxSlots = 16;
@@ -62,10 +63,12 @@ struct ChainParams {
   float n_blocks;
 };
 
-// K = filter taps.  Weight ring: C = 64 streams one tap ([64 rows][64], 8 KB) per stage through K
-// slots (slot = tap, parity = conv counter & 1); C <= 32 holds a whole conv per stage in 2 slots.
-template <int C, int MS, int K>
-__global__ void __launch_bounds__(chain_threads(MS), (C <= 32 && MS <= 3) ? 2 : 1)
+// K = filter taps, WPS = epilogue warps per sub-tile.  Weight ring: C = 64 streams one tap ([64 rows][64],
+// 8 KB) per stage through p.n_slots >= K slots (a ring deeper than one conv lets the first taps of the
+// next conv land before the current conv's last sub-tile is done); C <= 32 holds a whole conv per stage
+// in 2 slots.
+template <int C, int MS, int K, int WPS>
+__global__ void __launch_bounds__(chain_threads(MS, WPS), (C <= 32 && MS <= 3) ? 2 : 1)
 resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -74,14 +77,16 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int ROWS = R + 2 * kChainPad;
   constexpr uint32_t RB = 2u * C;                                // row bytes: 128 / 64 / 32
   constexpr uint32_t kBufBytes = ROWS * RB;
-  constexpr int kThreads_ = chain_threads(MS);
-  constexpr int kCPT = C / 8;                                    // 8-channel chunks per row = per epilogue thread
+  constexpr int kThreads_ = chain_threads(MS, WPS);
+  constexpr int kCPT = C / 8 / (WPS / 4);                        // 8-channel chunks per epilogue thread
+  static_assert(WPS == 4 || WPS == 8, "4 or 8 epilogue warps per sub-tile");
+  static_assert(kCPT >= 2 && kCPT % 2 == 0, "a thread handles pairs of channel chunks");
   constexpr uint32_t kTmemNeed = 2u * MS * N;
   constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
 
   constexpr int SPC = (C == 64) ? K : 1;                         // weight stages per conv
-  constexpr int NSLOTS = (C == 64) ? K : 2;
+  const int NSLOTS = (C == 64) ? p.n_slots : 2;
   constexpr int K16 = C / 16;                                    // K=16 steps per tap
   constexpr uint32_t kTapBytes = (uint32_t)N * RB;               // one tap = one [N rows][C] weight block
   constexpr uint32_t stage_bytes = (C == 64) ? kTapBytes : (uint32_t)K * kTapBytes;
@@ -103,7 +108,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 8; ++s) {
-      mbar_init(bar_ready(0, s), 4); mbar_init(bar_ready(1, s), 4);    // the 4 warps of the sub-tile's quad
+      mbar_init(bar_ready(0, s), WPS); mbar_init(bar_ready(1, s), WPS);   // the warps owning the sub-tile
       mbar_init(bar_acc_full(0, s), 1); mbar_init(bar_acc_full(1, s), 1);
     }
     for (int i = 0; i < kChainMaxSlots; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
@@ -124,16 +129,15 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     // ===== weight producer =====
     {
       const bool leader = elect_one();
-      uint32_t cc = 0;                                           // conv counter of this CTA
-      bool ok = true;
+      int slot = 0;
+      uint32_t par = 1;                                          // parity of the previous use of `slot`
+      bool wrapped = false, ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x)
-        for (int c = 0; c < p.n_convs && ok; ++c, ++cc) {
+        for (int c = 0; c < p.n_convs && ok; ++c) {
           const uint8_t* src = static_cast<const uint8_t*>(p.w) + (size_t)c * SPC * stage_bytes;
 #pragma unroll 1
           for (int i = 0; i < SPC; ++i) {
-            const int slot = (C == 64) ? i : (int)(cc & 1u);
-            const uint32_t use = (C == 64) ? cc : (cc >> 1);       // how often this slot has been filled before
-            if (use > 0) ok = mbar_wait(bar_w_empty(slot), (use - 1) & 1u, p.error_flag);
+            if (wrapped) ok = mbar_wait(bar_w_empty(slot), par, p.error_flag);
             if (!ok) break;
             if (leader) {
               mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
@@ -141,6 +145,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
                         bar_w_full(slot));
             }
             __syncwarp();
+            if (++slot == NSLOTS) { slot = 0; par ^= 1u; wrapped = true; }
           }
         }
     }
@@ -155,15 +160,17 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       constexpr uint32_t row16 = RB >> 4;
       constexpr uint32_t tap16 = kTapBytes >> 4;
       const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
-      uint32_t it = 0, cc = 0;
+      uint32_t it = 0;
+      int slot0 = 0;                                             // ring position of the running conv's first stage
+      uint32_t par0 = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
-        for (int c = 0; c < p.n_convs && ok; ++c, ++cc) {
+        for (int c = 0; c < p.n_convs && ok; ++c) {
           const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA)) + (uint32_t)(kChainPad - p.pad[c]) * row16;
           const uint32_t rdy_parity = (it * (uint32_t)(p.n_convs / 2) + (uint32_t)(c / 2)) & 1u;
           const uint32_t dil16 = (uint32_t)p.dil[c] * row16;
-          const uint32_t w_par = (C == 64) ? (cc & 1u) : ((cc >> 1) & 1u);
-          const uint32_t b_conv = b_lo0 + ((C == 64) ? 0u : (cc & 1u) * (stage_bytes >> 4));
+          int slot_end = slot0;
+          uint32_t par_end = par0;
 #pragma unroll
           for (int s = 0; s < MS; ++s) {
             // inputs of sub-tiles s-1..s+1 must be staged; s-1 and s were confirmed in earlier iterations
@@ -174,35 +181,45 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
               uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16;
+              int slot = slot0;
+              uint32_t par = par0;
+              uint32_t b_tap = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
 #pragma unroll
               for (int tap = 0; tap < K; ++tap) {
                 if (s == 0 && (C == 64 || tap == 0)) {           // later sub-tiles reuse the landed weights
-                  ok = ok && mbar_wait(bar_w_full((C == 64) ? tap : (int)(cc & 1u)), w_par, p.error_flag);
+                  ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);
                   tc_fence_after();
                 }
-                const uint32_t b_tap = b_conv + (uint32_t)tap * tap16;
 #pragma unroll
                 for (int kk = 0; kk < K16; ++kk)
                   if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, (tap | kk) ? 1u : 0u);
                 a_tap += dil16;
                 if (s == MS - 1 && (C == 64 || tap == K - 1)) {  // last sub-tile: the slot may be refilled
-                  if (leader) umma_commit(bar_w_empty((C == 64) ? tap : (int)(cc & 1u)));
+                  if (leader) umma_commit(bar_w_empty(slot));
+                }
+                if (C == 64 || tap == K - 1) {                   // next weight stage
+                  if (++slot == NSLOTS) { slot = 0; par ^= 1u; b_tap = b_lo0; } else { b_tap += (stage_bytes >> 4); }
+                } else {
+                  b_tap += tap16;                                // C <= 32: taps are consecutive inside the stage
                 }
               }
+              slot_end = slot; par_end = par;
               if (leader) umma_commit(bar_acc_full(c & 1, s));
               __syncwarp();
             }
           }
+          slot0 = slot_end; par0 = par_end;
         }
       }
     }
   } else {
-    // ===== epilogue: warp quad (warp - 2) / 4 owns sub-tile s; this thread owns row r of the tile =====
+    // ===== epilogue: warps (warp - 2) / WPS own sub-tile s; this thread owns row r (channel chunks ch0..) =====
     const int lg = warp & 3;
-    const int s = (warp - 2) >> 2;
+    const int s = (warp - 2) / WPS;
+    const int ch0 = (WPS == 8) ? (((warp - 2) % WPS) >> 2) * kCPT : 0;   // first 8-channel chunk of this thread
     const int r = s * 128 + lg * 32 + lane;
     constexpr int cchunks = C / 8;
-    float xr[C];                                                 // fp32 residual stream of this row
+    float xr[kCPT * 8];                                          // fp32 residual stream of this thread's channels
     const uint32_t row_off = (uint32_t)(kChainPad + r) * RB;
     uint32_t it = 0;
     bool ok = true;
@@ -216,7 +233,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       for (int q = 0; q < kCPT; ++q) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
         if (inside) {
-          const float* src = p.x32 + (((size_t)b * cchunks + q) * (size_t)p.L + t) * 8;
+          const float* src = p.x32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
           a = ldg_f4(src); c4 = ldg_f4(src + 4);
         }
         xr[q * 8 + 0] = a.x; xr[q * 8 + 1] = a.y; xr[q * 8 + 2] = a.z; xr[q * 8 + 3] = a.w;
@@ -227,7 +244,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[q * 8 + e], 0.1f);
-        *reinterpret_cast<uint4*>(bufA + swz(row_off + (uint32_t)q * 16u, RB)) = pack8(v, bf16);
+        *reinterpret_cast<uint4*>(bufA + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -238,14 +255,14 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
         const uint32_t acc_parity = (it * (uint32_t)(p.n_convs / 2) + (uint32_t)(c / 2)) & 1u;
         const bool second = (c & 1) != 0;                        // conv2 of a pair: x += ..
         const bool last = (c == p.n_convs - 1);
-        const float* bias_c = bias_s + c * C;
+        const float* bias_c = bias_s + c * C + ch0 * 8;
         uint8_t* out_buf = second ? bufA : bufT;
         ok = mbar_wait(bar_acc_full(c & 1, s), acc_parity, p.error_flag);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N + ch0 * 8);
 #pragma unroll
-        for (int g = 0; g < C / 16; ++g) {                       // 16 columns = 2 channel chunks per TMEM round trip
+        for (int g = 0; g < kCPT / 2; ++g) {                     // 16 columns = 2 channel chunks per TMEM round trip
           uint32_t rr[16];
           __syncwarp();
           tmem_ld16(t_addr + (uint32_t)(g * 16), rr);
@@ -266,10 +283,10 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
             if (!last) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = inside ? lrelu_f(v[e], 0.1f) : 0.f;
-              *reinterpret_cast<uint4*>(out_buf + swz(row_off + (uint32_t)q * 16u, RB)) = pack8(v, bf16);
+              *reinterpret_cast<uint4*>(out_buf + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
             } else if (keep) {
               // final epilogue: multi-receptive-field combine + stores (v = x_final)
-              const size_t idx = (((size_t)b * cchunks + q) * (size_t)p.L + t) * 8;
+              const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
               if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
                 const float4 s0 = ldg_f4(p.sum32 + idx), s1 = ldg_f4(p.sum32 + idx + 4);
                 v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
@@ -288,7 +305,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
               if (p.flags & EPI_OUT16) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = lrelu_f(v[e], p.slope_out);
-                const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + q) * 16;   // [B][1][L][C]
+                const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + ch0 + q) * 16;   // [B][1][L][C]
                 *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(v, bf16);
               }
             }

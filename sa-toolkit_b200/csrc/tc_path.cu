@@ -151,7 +151,7 @@ bool make_plan(Plan& pl, int cin_pad, int n, int span, int m_rows, int n_k16_max
   const int spp = panel_width(cin_pad) / 16;                    // weight stages hold whole panels
   // 128-row tiles for the widest layers let the A tile and the accumulator double-buffer (256-row tiles of
   // C = 256 fill shared memory and TMEM); SATOOLS_B200_MSUB_WIDE=2 restores 256-row tiles.
-  static const int msub_wide = getenv("SATOOLS_B200_MSUB_WIDE") ? atoi(getenv("SATOOLS_B200_MSUB_WIDE")) : 2;
+  static const int msub_wide = getenv("SATOOLS_B200_MSUB_WIDE") ? atoi(getenv("SATOOLS_B200_MSUB_WIDE")) : 1;
   const int msub_max = (m_rows > 128 ? 2 : 1);
   for (int msub = (cin_pad >= 256 && n >= 256) ? std::min(msub_max, msub_wide) : msub_max; msub >= 1; --msub) {
     const int rows = 128 * msub + span;
@@ -229,7 +229,7 @@ cudaError_t dispatch(int n, int msub, int pw, const tc::ConvParams& p, int grid_
 // ---- fused ResBlock (chain) launch -------------------------------------------------------
 int g_chain_ms_narrow = 6;      // sub-tiles per CTA for C <= 32 (SATOOLS_B200_CHAIN_MS=3 -> two CTAs per SM)
 
-struct ChainPlan { int ms, n_slots; size_t smem; };
+struct ChainPlan { int ms, wps, n_slots; size_t smem; };
 
 bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   const int C = ch.c;
@@ -239,19 +239,21 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
     return 2 * rows * (size_t)C * 2 + slots * stage + (size_t)tc::kChainMaxConvs * C * 4 +
            (32 + 2 * tc::kChainMaxSlots) * 8 + 16 + 1024;
   };
-  const int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
-  if (slots > tc::kChainMaxSlots) return false;
   if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;          // instantiated tap counts
-  int ms;
-  if (C == 64) ms = (ch.k == 11) ? 3 : 4;       // smem: 2 staged tiles + K weight taps
-  else ms = g_chain_ms_narrow;                   // 6: one CTA/SM (832 threads); 3: two CTAs/SM (448 threads each)
+  // C = 64: 3 sub-tiles with 8 epilogue warps each (an epilogue then fits inside one sub-tile's MMA time) and as
+  // many weight-tap slots as shared memory allows (>= K); C <= 32: 6 sub-tiles, 4 warps each, 2 whole-conv slots.
+  const int ms = (C == 64) ? 3 : g_chain_ms_narrow;
+  const int wps = (C == 64) ? 8 : 4;
+  int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
   if (need(ms, slots) > (size_t)max_smem) return false;
+  if (C == 64)
+    while (slots < tc::kChainMaxSlots && slots < 2 * ch.stages_per_conv && need(ms, slots + 1) <= (size_t)max_smem) ++slots;
   if (ms * 128 - 2 * ch.halo < 64) return false;
-  pl.ms = ms; pl.n_slots = slots; pl.smem = need(ms, slots);
+  pl.ms = ms; pl.wps = wps; pl.n_slots = slots; pl.smem = need(ms, slots);
   return true;
 }
 
-template <int C, int MS, int K>
+template <int C, int MS, int K, int WPS>
 cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaStream_t st) {
   static bool attr_set[16] = {false};
   static int occ_cache[16] = {0};
@@ -260,13 +262,13 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
     int occ = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K>, tc::chain_threads(MS), smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K, WPS>, tc::chain_threads(MS, WPS), smem);
     if (e != cudaSuccess) return e;
     constexpr int need = 2 * MS * C;
     constexpr int cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -274,7 +276,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
     occ_smem[dev] = smem;
   }
   const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev]));
-  tc::resblock_chain_kernel<C, MS, K><<<ctas, tc::chain_threads(MS), smem, st>>>(p);
+  tc::resblock_chain_kernel<C, MS, K, WPS><<<ctas, tc::chain_threads(MS, WPS), smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -386,13 +388,13 @@ struct Runner {
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
     cudaError_t ce = cudaErrorInvalidValue;
-#define SA_CHAIN(CC, MM, KK) \
-    if (ch.c == CC && pl.ms == MM && ch.k == KK) ce = launch_chain<CC, MM, KK>(p, pl.smem, a.n_sm, a.stream);
-    SA_CHAIN(64, 4, 3) SA_CHAIN(64, 4, 7) SA_CHAIN(64, 3, 11)
-    SA_CHAIN(32, 6, 3) SA_CHAIN(32, 6, 7) SA_CHAIN(32, 6, 11)
-    SA_CHAIN(16, 6, 3) SA_CHAIN(16, 6, 7) SA_CHAIN(16, 6, 11)
-    SA_CHAIN(32, 3, 3) SA_CHAIN(32, 3, 7) SA_CHAIN(32, 3, 11)
-    SA_CHAIN(16, 3, 3) SA_CHAIN(16, 3, 7) SA_CHAIN(16, 3, 11)
+#define SA_CHAIN(CC, MM, KK, WW) \
+    if (ch.c == CC && pl.ms == MM && ch.k == KK && pl.wps == WW) ce = launch_chain<CC, MM, KK, WW>(p, pl.smem, a.n_sm, a.stream);
+    SA_CHAIN(64, 3, 3, 8) SA_CHAIN(64, 3, 7, 8) SA_CHAIN(64, 3, 11, 8)
+    SA_CHAIN(32, 6, 3, 4) SA_CHAIN(32, 6, 7, 4) SA_CHAIN(32, 6, 11, 4)
+    SA_CHAIN(16, 6, 3, 4) SA_CHAIN(16, 6, 7, 4) SA_CHAIN(16, 6, 11, 4)
+    SA_CHAIN(32, 3, 3, 4) SA_CHAIN(32, 3, 7, 4) SA_CHAIN(32, 3, 11, 4)
+    SA_CHAIN(16, 3, 3, 4) SA_CHAIN(16, 3, 7, 4) SA_CHAIN(16, 3, 11, 4)
 #undef SA_CHAIN
     if (ce != cudaSuccess) return msgf("resblock_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
