@@ -23,6 +23,7 @@
  *                           as Python exceptions from torch)
  *   sa_hifigan_set_profiling / sa_hifigan_get_profile  (no reference counterpart; the reference has
  *                           no profiler hooks) per-launch CUDA-event timing
+ *   sa_hifigan_chain_timing  (no reference counterpart) in-kernel cycle accounting of the fused kernels
  *   sa_hifigan_set_debug_tap  (no reference counterpart; exposes stage activations so the
  *                           parity tests can localise a mismatch)
  *
@@ -157,6 +158,12 @@ int sa_hifigan_get_profile(sa_hifigan* h, float* ms, int32_t* tags, int32_t max_
 /* Wait for `stream` and report any device-side failure of the work enqueued so far (a CUDA
  * error, or a tensor-core kernel that gave up waiting on a barrier).  0 = all good. */
 int sa_hifigan_check(sa_hifigan* h, void* stream);
+
+/* Diagnostics (enabled by SATOOLS_B200_CHAIN_TIMING=1 in the environment at finalize time): cycle
+ * counters of the fused ResBlock kernels of the most recent forward, 8 int64 per launch in launch
+ * order (MMA warp: total, wait-activations, wait-weights, issue; one epilogue warp: total, load+stage x,
+ * wait-accumulator, work), summed over CTAs.  Returns the number of launches written. */
+int sa_hifigan_chain_timing(sa_hifigan* h, int64_t* out, int32_t max_launches);
 
 /* Kernel launches enqueued by the most recent forward on this handle. */
 int64_t sa_hifigan_last_launch_count(const sa_hifigan* h);

@@ -58,6 +58,8 @@ struct ChainParams {
   int halo;                 // H
   int tiles_per_item, total_tiles;
   int k16_per_stage, stages_per_conv, n_slots;
+  long long* timing;        // optional [8] cycle counters (diagnostics): MMA warp: total, wait ready, wait weights,
+                            // issue; epilogue warp 2: total, x load + staging, wait accumulator, work
   uint32_t flags;           // EPI_* of the final epilogue (SUM_SET / SUM_ADD / SUM_FIN / OUT32 / OUT16 / BF16)
   float slope_out;
   float n_blocks;
@@ -164,6 +166,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       int slot0 = 0;                                             // ring position of the running conv's first stage
       uint32_t par0 = 0;
       bool ok = true;
+      const bool timing = p.timing != nullptr;
+      long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
         for (int c = 0; c < p.n_convs && ok; ++c) {
           const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA)) + (uint32_t)(kChainPad - p.pad[c]) * row16;
@@ -175,8 +179,10 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
           for (int s = 0; s < MS; ++s) {
             // inputs of sub-tiles s-1..s+1 must be staged; s-1 and s were confirmed in earlier iterations
             // (an already-complete try_wait still costs ~90 cycles on this single issuing warp)
+            const long long tr0 = timing ? clock64() : 0;
             if (s == 0 && ok) ok = mbar_wait(bar_ready(c & 1, 0), rdy_parity, p.error_flag);
             if (s + 1 < MS && ok) ok = mbar_wait(bar_ready(c & 1, s + 1), rdy_parity, p.error_flag);
+            if (timing) t_ready += clock64() - tr0;
             if (ok) {
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
@@ -187,8 +193,10 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
               for (int tap = 0; tap < K; ++tap) {
                 if (s == 0 && (C == 64 || tap == 0)) {           // later sub-tiles reuse the landed weights
+                  const long long tw0 = timing ? clock64() : 0;
                   ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);
                   tc_fence_after();
+                  if (timing) t_w += clock64() - tw0;
                 }
 #pragma unroll
                 for (int kk = 0; kk < K16; ++kk)
@@ -211,6 +219,13 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
           slot0 = slot_end; par0 = par_end;
         }
       }
+      if (timing && lane == 0) {
+        const long long tot = clock64() - t_begin;
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 0), (unsigned long long)tot);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_ready);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 2), (unsigned long long)t_w);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 3), (unsigned long long)(tot - t_ready - t_w));
+      }
     }
   } else {
     // ===== epilogue: warps (warp - 2) / WPS own sub-tile s; this thread owns row r (channel chunks ch0..) =====
@@ -223,7 +238,10 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     const uint32_t row_off = (uint32_t)(kChainPad + r) * RB;
     uint32_t it = 0;
     bool ok = true;
+    const bool timing = p.timing != nullptr && warp == 2;
+    long long t_p0 = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+      const long long tp0 = timing ? clock64() : 0;
       const int b = tile / p.tiles_per_item, mt = tile - b * p.tiles_per_item;
       const int t = mt * valid_rows - p.halo + r;                // global row of this thread
       const bool inside = t >= 0 && t < p.L;
@@ -249,6 +267,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(0, s));
+      if (timing) t_p0 += clock64() - tp0;
       // ---- the convs ----
 #pragma unroll 1
       for (int c = 0; c < p.n_convs; ++c) {
@@ -257,9 +276,11 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
         const bool last = (c == p.n_convs - 1);
         const float* bias_c = bias_s + c * C + ch0 * 8;
         uint8_t* out_buf = second ? bufA : bufT;
+        const long long ta0 = timing ? clock64() : 0;
         ok = mbar_wait(bar_acc_full(c & 1, s), acc_parity, p.error_flag);
         if (!ok) break;
         tc_fence_after();
+        if (timing) t_acc += clock64() - ta0;
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N + ch0 * 8);
 #pragma unroll
         for (int g = 0; g < kCPT / 2; ++g) {                     // 16 columns = 2 channel chunks per TMEM round trip
@@ -318,6 +339,13 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
           if (lane == 0) mbar_arrive(bar_ready(second ? 0 : 1, s));
         }
       }
+    }
+    if (timing && lane == 0) {
+      const long long tot = clock64() - t_begin;
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 4), (unsigned long long)tot);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 5), (unsigned long long)t_p0);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 6), (unsigned long long)t_acc);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 7), (unsigned long long)(tot - t_p0 - t_acc));
     }
   }
   tc_fence_before();

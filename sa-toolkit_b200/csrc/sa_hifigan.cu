@@ -580,6 +580,11 @@ int sa_hifigan_check(sa_hifigan* h, void* stream) {
   return SA_OK;
 }
 
+int sa_hifigan_chain_timing(sa_hifigan* h, int64_t* out, int32_t max_launches) {
+  if (!h || !out) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  return sa::tc_read_chain_timing(h->tc, reinterpret_cast<long long*>(out), max_launches);
+}
+
 int sa_hifigan_set_profiling(sa_hifigan* h, int32_t enable) {
   if (!h) return fail(SA_ERR_INVALID_ARG, "NULL handle");
   h->prof_on = enable != 0;

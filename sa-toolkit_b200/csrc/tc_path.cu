@@ -378,6 +378,7 @@ struct Runner {
     memset(&p, 0, sizeof(p));
     p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
     p.w = ch.d_w; p.bias = ch.d_bias; p.error_flag = ctx.d_error;
+    p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 8 * ctx.timing_launches++ : nullptr;
     p.L = L; p.n_convs = ch.n_convs; p.ktaps = ch.k;
     for (int c = 0; c < ch.n_convs; ++c) { p.dil[c] = ch.dil[c]; p.pad[c] = ch.pad[c]; }
     p.halo = ch.halo;
@@ -532,12 +533,23 @@ const char* tc_init(tc_context& ctx, int device) {
   TC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx.h_error), sizeof(int), cudaHostAllocMapped));
   *ctx.h_error = 0;
   TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
+  if (const char* env = getenv("SATOOLS_B200_CHAIN_TIMING")) {
+    if (atoi(env) != 0) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx.d_timing), 64 * 8 * sizeof(long long)));
+  }
   if (const char* env = getenv("SATOOLS_B200_CHAIN_MS")) {
     const int v = atoi(env);
     if (v == 3 || v == 6) g_chain_ms_narrow = v;
   }
   ctx.ready = true;
   return nullptr;
+}
+
+int tc_read_chain_timing(tc_context& ctx, long long* out, int max_launches) {
+  if (!ctx.d_timing) return 0;
+  const int n = std::min(ctx.timing_launches, max_launches);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, ctx.d_timing, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
 }
 
 bool tc_error_raised(const tc_context& ctx) {
@@ -569,6 +581,10 @@ size_t tc_workspace_bytes(const sa_hifigan_cfg& cfg, int B, int T) {
 const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launches) {
   if (!ctx.ready) return "tensor-core context not initialised";
   if (tc_error_raised(ctx)) return "a tcgen05 kernel of an earlier forward timed out on an mbarrier (protocol bug)";
+  if (ctx.d_timing) {
+    ctx.timing_launches = 0;
+    cudaMemsetAsync(ctx.d_timing, 0, 64 * 8 * sizeof(long long), a.stream);
+  }
   const sa_hifigan_cfg& cfg = *a.cfg;
   const Sizes s = sizes(cfg, a.B, a.T);
   char* base = static_cast<char*>(a.workspace);

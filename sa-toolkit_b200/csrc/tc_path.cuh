@@ -40,6 +40,8 @@ struct tc_context {
   int* h_error = nullptr;     // mapped pinned flag raised by a kernel whose barrier wait timed out
   int* d_error = nullptr;     // device alias of h_error
   int max_smem = 0;
+  long long* d_timing = nullptr;   // diagnostics: [64 launches][8] cycle counters of the fused kernels (SATOOLS_B200_CHAIN_TIMING=1)
+  int timing_launches = 0;
 };
 
 struct tc_layer {
@@ -80,6 +82,7 @@ const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* 
 void tc_free_chain(tc_chain& ch);
 const char* tc_init(tc_context& ctx, int device);
 bool tc_error_raised(const tc_context& ctx);
+int tc_read_chain_timing(tc_context& ctx, long long* out, int max_launches);
 size_t tc_workspace_bytes(const sa_hifigan_cfg& cfg, int B, int T);
 const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launches);
 

@@ -54,6 +54,7 @@ SYMBOLS = {
     "sa_hifigan_set_debug_tap": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "sa_hifigan_last_launch_count": (C.c_int64, [C.c_void_p]),
     "sa_hifigan_check": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sa_hifigan_chain_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "sa_hifigan_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "sa_hifigan_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
 }

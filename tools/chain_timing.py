@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Print the in-kernel cycle accounting of the fused ResBlock kernels (SATOOLS_B200_CHAIN_TIMING=1)."""
+import ctypes as C
+import os
+import sys
+
+os.environ["SATOOLS_B200_CHAIN_TIMING"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "sa-toolkit_b200")):
+    sys.path.insert(0, p)
+import torch
+from satools_b200 import CoreHifiGan, conditioning, _lib
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+torch.manual_seed(0)
+gen = CoreHifiGan(imput_dim=504, precision="fp16").to("cuda:0")
+x = torch.from_numpy(conditioning.batch(7, [750] * B)).to("cuda:0")
+for _ in range(2):
+    gen(x)
+gen.check()
+lib = _lib.load()
+buf = (C.c_int64 * (64 * 8))()
+n = lib.sa_hifigan_chain_timing(gen._handle, buf, 64)
+names = ["mma_total", "mma_wait_ready", "mma_wait_w", "mma_issue", "epi_total", "epi_load_x", "epi_wait_acc", "epi_work"]
+labels = ["c64 k3", "c64 k7", "c64 k11", "c32 k3", "c32 k7", "c32 k11", "c16 k3", "c16 k7", "c16 k11"]
+print("per-CTA average cycles (148 CTAs)")
+for i in range(n):
+    v = [buf[i * 8 + j] / 148.0 for j in range(8)]
+    tot = v[0] or 1.0
+    print(f"{labels[i] if i < len(labels) else i:8s} " + " ".join(f"{nm}={val/1e3:8.0f}k({100*val/ (tot if j < 4 else (v[4] or 1)):3.0f}%)" for j, (nm, val) in enumerate(zip(names, v))))
