@@ -82,7 +82,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   // TM (tap-major, C = 64): for tap { for sub-tile { MMAs } }: a tap's weights serve every sub-tile and are
   // released at once, so a short ring streams them (measured with the sub-tile-major order: 14% of the MMA
   // warp's time waiting for weights, 22% for activations); one ready / acc_full barrier per conv.
-  constexpr bool TM = (C == 64);
+  constexpr bool TM = false;     // measured slower on B200 (stage 2: 7.7 -> 9.1 ms: the epilogue no longer overlaps the MMAs)
   constexpr int kThreads_ = chain_threads(MS, WPS);
   constexpr int kCPT = C / 8 / (WPS / 4);                        // 8-channel chunks per epilogue thread
   static_assert(WPS == 4 || WPS == 8, "4 or 8 epilogue warps per sub-tile");
@@ -299,8 +299,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       for (int q = 0; q < kCPT; ++q) {
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = lrelu_f(xr[q * 8 + e], 0.1f);
-        *reinterpret_cast<uint4*>(bufA + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
+        for (int e = 0; e < 8; ++e) v[e] = xr[q * 8 + e];
+        *reinterpret_cast<uint4*>(bufA + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8_lrelu(v, 0.1f, true, bf16);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -340,9 +340,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
               for (int e = 0; e < 8; ++e) { xr[q * 8 + e] += v[e]; v[e] = xr[q * 8 + e]; }
             }
             if (!last) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = inside ? lrelu_f(v[e], 0.1f) : 0.f;
-              *reinterpret_cast<uint4*>(out_buf + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8(v, bf16);
+              *reinterpret_cast<uint4*>(out_buf + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8_lrelu(v, 0.1f, inside, bf16);
             } else if (keep) {
               // final epilogue: multi-receptive-field combine + stores (v = x_final)
               const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
@@ -362,10 +360,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
                 stg_f4(p.out32 + idx, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx + 4, v[4], v[5], v[6], v[7]);
               }
               if (p.flags & EPI_OUT16) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = lrelu_f(v[e], p.slope_out);
                 const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + ch0 + q) * 16;   // [B][1][L][C]
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(v, bf16);
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(v, p.slope_out, true, bf16);
               }
             }
           }

@@ -236,6 +236,34 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], bool bf16) {
   return o;
 }
 
+// 8 fp32 -> 8 x 16-bit with leaky-ReLU applied in packed 16-bit arithmetic: h = round(v); h = max(h, slope*h)
+// (slope < 1).  One convert + two packed ops per PAIR of values instead of ~4 fp32 ops per value: the
+// epilogues of the narrow layers are instruction-issue bound (profiles/README.md).  `keep` = false zeroes
+// the result (rows outside the utterance).  Both the per-layer and the fused kernels use this routine, so
+// their outputs stay bit-identical.
+__device__ __forceinline__ uint4 pack8_lrelu(const float (&v)[8], float slope, bool keep, bool bf16) {
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+  if (bf16) {
+    const __nv_bfloat162 s2 = __float2bfloat162_rn(slope);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      h = __hmax2(h, __hmul2(h, s2));
+      ow[i] = keep ? *reinterpret_cast<uint32_t*>(&h) : 0u;
+    }
+  } else {
+    const __half2 s2 = __float2half2_rn(slope);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      h = __hmax2(h, __hmul2(h, s2));
+      ow[i] = keep ? *reinterpret_cast<uint32_t*>(&h) : 0u;
+    }
+  }
+  return o;
+}
+
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
@@ -505,11 +533,11 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
                 if (flags & EPI_OUT16) {
                   float lo[8], hi[8];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) { lo[e] = lrelu_f(v[e], p.slope_out); hi[e] = lrelu_f(v[8 + e], p.slope_out); }
+                  for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi[e] = v[8 + e]; }
                   const int cg = ntile * (N / 8) + c8;               // chunk index in the output tensor (even)
                   const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
-                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8(lo, bf16);
-                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8(hi, bf16);
+                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(lo, p.slope_out, true, bf16);
+                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8_lrelu(hi, p.slope_out, true, bf16);
                 }
               }
             }

@@ -244,9 +244,10 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   // many weight-tap slots as shared memory allows (>= K); C <= 32: 6 sub-tiles, 4 warps each, 2 whole-conv slots.
   const int ms = (C == 64) ? 3 : g_chain_ms_narrow;
   const int wps = (C == 64) ? 8 : 4;
-  int slots = ch.stages_per_conv == 1 ? 2 : 6;
+  int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
   if (need(ms, slots) > (size_t)max_smem) return false;
-  if (C == 64) slots = 6;                            // tap-major order: a short ring of weight taps streams
+  if (C == 64)                                       // sub-tile-major order needs >= one conv of taps; take what fits
+    while (slots < tc::kChainMaxSlots && slots < 2 * ch.stages_per_conv && need(ms, slots + 1) <= (size_t)max_smem) ++slots;
   if (ms * 128 - 2 * ch.halo < 64) return false;
   pl.ms = ms; pl.wps = wps; pl.n_slots = slots; pl.smem = need(ms, slots);
   return true;
