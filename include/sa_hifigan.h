@@ -160,9 +160,10 @@ int sa_hifigan_get_profile(sa_hifigan* h, float* ms, int32_t* tags, int32_t max_
 int sa_hifigan_check(sa_hifigan* h, void* stream);
 
 /* Diagnostics (enabled by SATOOLS_B200_CHAIN_TIMING=1 in the environment at finalize time): cycle
- * counters of the fused ResBlock kernels of the most recent forward, 8 int64 per launch in launch
+ * counters of the fused ResBlock kernels of the most recent forward, 16 int64 per launch in launch
  * order (MMA warp: total, wait-activations, wait-weights, issue; one epilogue warp: total, load+stage x,
- * wait-accumulator, work), summed over CTAs.  Returns the number of launches written. */
+ * wait-accumulator, work, of which TMEM loads, of which fence+arrive; rest unused), summed over CTAs.
+ * Returns the number of launches written. */
 int sa_hifigan_chain_timing(sa_hifigan* h, int64_t* out, int32_t max_launches);
 
 /* Kernel launches enqueued by the most recent forward on this handle. */

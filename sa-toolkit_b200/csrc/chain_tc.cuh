@@ -58,7 +58,7 @@ struct ChainParams {
   int halo;                 // H
   int tiles_per_item, total_tiles;
   int k16_per_stage, stages_per_conv, n_slots;
-  long long* timing;        // optional [8] cycle counters (diagnostics): MMA warp: total, wait ready, wait weights,
+  long long* timing;        // optional [16] cycle counters (diagnostics): MMA warp: total, wait ready, wait weights,
                             // issue; epilogue warp 2: total, x load + staging, wait accumulator, work
   uint32_t flags;           // EPI_* of the final epilogue (SUM_SET / SUM_ADD / SUM_FIN / OUT32 / OUT16 / BF16)
   float slope_out;
@@ -277,7 +277,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     uint32_t it = 0;
     bool ok = true;
     const bool timing = p.timing != nullptr && warp == 2;
-    long long t_p0 = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
+    long long t_p0 = 0, t_acc = 0, t_ld = 0, t_fence = 0, t_begin = timing ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
       const long long tp0 = timing ? clock64() : 0;
       const int b = tile / p.tiles_per_item, mt = tile - b * p.tiles_per_item;
@@ -323,9 +323,11 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
         for (int g = 0; g < kCPT / 2; ++g) {                     // 16 columns = 2 channel chunks per TMEM round trip
           uint32_t rr[16];
+          const long long tl0 = timing ? clock64() : 0;
           __syncwarp();
           tmem_ld16(t_addr + (uint32_t)(g * 16), rr);
           tmem_ld_wait();
+          if (timing) t_ld += clock64() - tl0;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int q = g * 2 + h;
@@ -367,10 +369,12 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
           }
         }
         if (!last) {
+          const long long tf0 = timing ? clock64() : 0;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_ready(second ? 0 : 1, TM ? 0 : s));
+          if (timing) t_fence += clock64() - tf0;
         }
       }
     }
@@ -380,6 +384,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 5), (unsigned long long)t_p0);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 6), (unsigned long long)t_acc);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 7), (unsigned long long)(tot - t_p0 - t_acc));
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 8), (unsigned long long)t_ld);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 9), (unsigned long long)t_fence);
     }
   }
   tc_fence_before();

@@ -378,7 +378,7 @@ struct Runner {
     memset(&p, 0, sizeof(p));
     p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
     p.w = ch.d_w; p.bias = ch.d_bias; p.error_flag = ctx.d_error;
-    p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 8 * ctx.timing_launches++ : nullptr;
+    p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 16 * ctx.timing_launches++ : nullptr;
     p.L = L; p.n_convs = ch.n_convs; p.ktaps = ch.k;
     for (int c = 0; c < ch.n_convs; ++c) { p.dil[c] = ch.dil[c]; p.pad[c] = ch.pad[c]; }
     p.halo = ch.halo;
@@ -534,7 +534,7 @@ const char* tc_init(tc_context& ctx, int device) {
   *ctx.h_error = 0;
   TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
   if (const char* env = getenv("SATOOLS_B200_CHAIN_TIMING")) {
-    if (atoi(env) != 0) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx.d_timing), 64 * 8 * sizeof(long long)));
+    if (atoi(env) != 0) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx.d_timing), 64 * 16 * sizeof(long long)));
   }
   if (const char* env = getenv("SATOOLS_B200_CHAIN_MS")) {
     const int v = atoi(env);
@@ -548,7 +548,7 @@ int tc_read_chain_timing(tc_context& ctx, long long* out, int max_launches) {
   if (!ctx.d_timing) return 0;
   const int n = std::min(ctx.timing_launches, max_launches);
   cudaDeviceSynchronize();
-  cudaMemcpy(out, ctx.d_timing, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, ctx.d_timing, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
   return n;
 }
 
@@ -583,7 +583,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
   if (tc_error_raised(ctx)) return "a tcgen05 kernel of an earlier forward timed out on an mbarrier (protocol bug)";
   if (ctx.d_timing) {
     ctx.timing_launches = 0;
-    cudaMemsetAsync(ctx.d_timing, 0, 64 * 8 * sizeof(long long), a.stream);
+    cudaMemsetAsync(ctx.d_timing, 0, 64 * 16 * sizeof(long long), a.stream);
   }
   const sa_hifigan_cfg& cfg = *a.cfg;
   const Sizes s = sizes(cfg, a.B, a.T);
