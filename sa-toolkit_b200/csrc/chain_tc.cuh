@@ -33,6 +33,7 @@
 // instructions per 256 elements and 32 KB of unrolled code, profiles/README.md.)
 #pragma once
 #include "conv_tc.cuh"
+#include <type_traits>
 
 namespace sa {
 namespace tc {
@@ -274,6 +275,9 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     constexpr int cchunks = C / 8;
     float xr[kCPT * 8];                                          // fp32 residual stream of this thread's channels
     const uint32_t row_off = (uint32_t)(kChainPad + r) * RB;
+    uint32_t soff[kCPT];                                         // swizzled staging offsets of this thread's chunks (tile invariant)
+#pragma unroll
+    for (int q = 0; q < kCPT; ++q) soff[q] = swz(row_off + (uint32_t)(ch0 + q) * 16u, RB);
     uint32_t it = 0;
     bool ok = true;
     const bool timing = p.timing != nullptr && warp == 2;
@@ -300,23 +304,23 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = xr[q * 8 + e];
-        *reinterpret_cast<uint4*>(bufA + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8_lrelu(v, 0.1f, true, bf16);
+        *reinterpret_cast<uint4*>(bufA + soff[q]) = pack8_lrelu(v, 0.1f, true, bf16);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(0, TM ? 0 : s));
       if (timing) t_p0 += clock64() - tp0;
-      // ---- the convs ----
-#pragma unroll 1
-      for (int c = 0; c < p.n_convs; ++c) {
+      // ---- the convs: (conv1, conv2) pairs; one generic step with compile-time flags so the residual add, the
+      // final stores and the staging stores are straight-line code without predicated moves ----
+      auto step = [&](auto second_c, auto last_c, int c) {
+        constexpr bool second = decltype(second_c)::value;       // conv2 of a pair: x += ..
+        constexpr bool last = decltype(last_c)::value;           // last conv of the block: final epilogue
         const uint32_t acc_parity = (it * (uint32_t)(p.n_convs / 2) + (uint32_t)(c / 2)) & 1u;
-        const bool second = (c & 1) != 0;                        // conv2 of a pair: x += ..
-        const bool last = (c == p.n_convs - 1);
         const float* bias_c = bias_s + c * C + ch0 * 8;
         uint8_t* out_buf = second ? bufA : bufT;
         const long long ta0 = timing ? clock64() : 0;
-        ok = mbar_wait(bar_acc_full(c & 1, TM ? 0 : s), acc_parity, p.error_flag);
-        if (!ok) break;
+        ok = ok && mbar_wait(bar_acc_full(c & 1, TM ? 0 : s), acc_parity, p.error_flag);
+        if (!ok) return;
         tc_fence_after();
         if (timing) t_acc += clock64() - ta0;
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((c & 1) * MS + s) * N + ch0 * 8);
@@ -337,12 +341,12 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
             v[2] = __uint_as_float(rr[h * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[h * 8 + 3]) + b0.w;
             v[4] = __uint_as_float(rr[h * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[h * 8 + 5]) + b1.y;
             v[6] = __uint_as_float(rr[h * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[h * 8 + 7]) + b1.w;
-            if (second) {
+            if constexpr (second) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { xr[q * 8 + e] += v[e]; v[e] = xr[q * 8 + e]; }
+              for (int e = 0; e < 8; ++e) { v[e] += xr[q * 8 + e]; xr[q * 8 + e] = v[e]; }
             }
-            if (!last) {
-              *reinterpret_cast<uint4*>(out_buf + swz(row_off + (uint32_t)(ch0 + q) * 16u, RB)) = pack8_lrelu(v, 0.1f, inside, bf16);
+            if constexpr (!last) {
+              *reinterpret_cast<uint4*>(out_buf + soff[q]) = pack8_lrelu(v, 0.1f, inside, bf16);
             } else if (keep) {
               // final epilogue: multi-receptive-field combine + stores (v = x_final)
               const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
@@ -368,7 +372,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
             }
           }
         }
-        if (!last) {
+        if constexpr (!last) {
           const long long tf0 = timing ? clock64() : 0;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
@@ -376,7 +380,15 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
           if (lane == 0) mbar_arrive(bar_ready(second ? 0 : 1, TM ? 0 : s));
           if (timing) t_fence += clock64() - tf0;
         }
+      };
+      const int n_pairs = p.n_convs / 2;
+#pragma unroll 1
+      for (int m = 0; m + 1 < n_pairs && ok; ++m) {
+        step(std::false_type{}, std::false_type{}, 2 * m);
+        step(std::true_type{}, std::false_type{}, 2 * m + 1);
       }
+      step(std::false_type{}, std::false_type{}, 2 * (n_pairs - 1));
+      step(std::true_type{}, std::true_type{}, 2 * (n_pairs - 1) + 1);
     }
     if (timing && lane == 0) {
       const long long tot = clock64() - t_begin;
