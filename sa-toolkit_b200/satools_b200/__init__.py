@@ -9,5 +9,6 @@ Public surface:
 from .archi import CoreHifiGan, ResBlock1  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from . import scheduler  # noqa: F401
+from . import synth  # noqa: F401
 
-__all__ = ["CoreHifiGan", "ResBlock1", "install", "uninstall", "scheduler"]
+__all__ = ["CoreHifiGan", "ResBlock1", "install", "uninstall", "scheduler", "synth"]
