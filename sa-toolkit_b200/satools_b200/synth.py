@@ -68,19 +68,23 @@ def synthesize_corpus(gen, feats: Dict[str, np.ndarray], *, rank: int = 0, world
         wav = np.zeros(320 * n + 1, dtype=out[ids[short[0]]].dtype if short else
                        {torch.float32: np.float32, torch.float16: np.float16, torch.int16: np.int16}[out_dtype])
         windows = scheduler.chunks(n, chunk_frames)
-        # windows of one utterance have (almost) equal lengths: run them as one batch
-        T = max(rhi - rlo for rlo, rhi, _, _ in windows)
-        xb = _pad_batch([x[:, rlo:rhi] for rlo, rhi, _, _ in windows], T)
-        # padding a window on the right must not change its kept part: the last window is the only short one and
-        # ends at the true end of the utterance, where zero BN/F0 padding is what the unchunked run sees, too
-        for w0 in range(0, len(windows), max_items):
-            y = run(xb[w0:w0 + max_items])
-            for k, (rlo, rhi, klo, khi) in enumerate(windows[w0:w0 + max_items]):
-                lo, hi = 320 * (klo - rlo), 320 * (khi - rlo)
-                if klo == 0:
-                    wav[:1 + 320 * khi] = y[k, 0, :1 + hi]
-                else:
-                    wav[1 + 320 * klo:1 + 320 * khi] = y[k, 0, 1 + lo:1 + hi]
+        # Windows are batched only with windows of the same length: padding a window with extra frames is NOT
+        # what the unchunked run sees at the end of the utterance (there the convs zero-pad; padded frames would
+        # carry the speaker one-hot), and the difference would reach the last 20 frames.
+        by_len: Dict[int, List[int]] = {}
+        for k, (rlo, rhi, _, _) in enumerate(windows):
+            by_len.setdefault(rhi - rlo, []).append(k)
+        for T, ks in sorted(by_len.items()):
+            for w0 in range(0, len(ks), max_items):
+                group = ks[w0:w0 + max_items]
+                y = run(np.stack([np.ascontiguousarray(x[:, windows[k][0]:windows[k][1]]) for k in group]))
+                for j, k in enumerate(group):
+                    rlo, rhi, klo, khi = windows[k]
+                    lo, hi = 320 * (klo - rlo), 320 * (khi - rlo)
+                    if klo == 0:
+                        wav[:1 + 320 * khi] = y[j, 0, :1 + hi]
+                    else:
+                        wav[1 + 320 * klo:1 + 320 * khi] = y[j, 0, 1 + lo:1 + hi]
         out[ids[i]] = wav
     if original_len:
         for u in out:
