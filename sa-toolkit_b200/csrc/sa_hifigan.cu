@@ -73,6 +73,8 @@ struct sa_hifigan {
   int n_sm = 148;
   sa::tc_context tc;
   std::vector<sa::tc_chain> chains;     // [n_stages * n_resblocks], fused narrow-stage ResBlocks
+  cudaStream_t side_stream = nullptr;   // second stream of sa_hifigan_synthesize_host
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // per-launch profiling: one event before every launch + one closing event
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -217,6 +219,9 @@ void sa_hifigan_destroy(sa_hifigan* h) {
     cudaSetDevice(h->device);
     free_device_weights(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaSetDevice(cur);
   }
   delete h;
@@ -606,12 +611,23 @@ int sa_hifigan_get_profile(sa_hifigan* h, float* ms, int32_t* tags, int32_t max_
   return n;
 }
 
+// Host-buffer entry: the batch is cut into two halves that run on two internal streams, so the H2D / D2H copies
+// of one half overlap the kernels of the other (the reference does audio.to(device) -> convert -> .cpu() strictly
+// one after the other, bin/pipeline.py:104-149).  Scratch layout: [x | y | workspace] per half.
+static int host_halves(int B) { return B >= 8 ? 2 : 1; }
+
+static size_t host_part_bytes(const sa_hifigan* h, int B, int T, int y_dtype) {
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  return align_up((size_t)B * h->cfg.input_dim * T * sizeof(float), 256) +
+         align_up((size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz, 256) + sa_hifigan_workspace_bytes(h, B, T);
+}
+
 size_t sa_hifigan_host_scratch_bytes(const sa_hifigan* h, int32_t B, int32_t T, int32_t y_dtype) {
   if (!h || B < 1 || T < 1) return 0;
-  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
-  const size_t xb = align_up((size_t)B * h->cfg.input_dim * T * sizeof(float), 256);
-  const size_t yb = align_up((size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz, 256);
-  return xb + yb + sa_hifigan_workspace_bytes(h, B, T);
+  const int nh = host_halves(B);
+  size_t total = 0;
+  for (int i = 0; i < nh; ++i) total += align_up(host_part_bytes(h, (B + nh - 1 - i) / nh, T, y_dtype), 256);
+  return total;
 }
 
 int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
@@ -624,23 +640,47 @@ int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, in
   if (dev_scratch_bytes < need) return fail(SA_ERR_WORKSPACE, "dev_scratch too small: %zu < %zu", dev_scratch_bytes, need);
   if (reinterpret_cast<uintptr_t>(dev_scratch) & 255) return fail(SA_ERR_INVALID_ARG, "dev_scratch must be 256-byte aligned");
   const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
-  const size_t x_bytes = (size_t)B * h->cfg.input_dim * T * sizeof(float);
-  const size_t y_bytes = (size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz;
-  char* base = static_cast<char*>(dev_scratch);
-  float* xd = reinterpret_cast<float*>(base);
-  void* yd = base + align_up(x_bytes, 256);
-  void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
-  const size_t ws_bytes = dev_scratch_bytes - align_up(x_bytes, 256) - align_up(y_bytes, 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int cur = -1;
   SA_CUDA(cudaGetDevice(&cur));
   if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
-  SA_CUDA(cudaMemcpyAsync(xd, x_host, x_bytes, cudaMemcpyHostToDevice, st));
-  int rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, ws_bytes, stream);
-  if (rc == SA_OK) {
-    SA_CUDA(cudaMemcpyAsync(y_host, yd, y_bytes, cudaMemcpyDeviceToHost, st));
-    SA_CUDA(cudaStreamSynchronize(st));
+  const int nh = host_halves(B);
+  if (nh > 1 && !h->side_stream) {
+    SA_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
+  if (nh > 1) {                                   // side stream starts after the caller's stream reaches this point
+    SA_CUDA(cudaEventRecord(h->ev_fork, st));
+    SA_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+  }
+  const int64_t Lout = sa_hifigan_output_length(h, T);
+  char* base = static_cast<char*>(dev_scratch);
+  int rc = SA_OK, b0 = 0;
+  int64_t launches = 0;
+  for (int i = 0; i < nh && rc == SA_OK; ++i) {
+    const int Bi = (B + nh - 1 - i) / nh;
+    cudaStream_t si = (i == 0) ? st : h->side_stream;
+    const size_t x_bytes = (size_t)Bi * h->cfg.input_dim * T * sizeof(float);
+    const size_t y_bytes = (size_t)Bi * (size_t)Lout * esz;
+    float* xd = reinterpret_cast<float*>(base);
+    void* yd = base + align_up(x_bytes, 256);
+    void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+    const size_t ws_bytes = sa_hifigan_workspace_bytes(h, Bi, T);
+    SA_CUDA(cudaMemcpyAsync(xd, x_host + (size_t)b0 * h->cfg.input_dim * T, x_bytes, cudaMemcpyHostToDevice, si));
+    rc = sa_hifigan_forward(h, xd, Bi, T, frames_per_item ? frames_per_item + b0 : nullptr, yd, y_dtype, ws, ws_bytes, si);
+    launches += h->launches;
+    if (rc == SA_OK)
+      SA_CUDA(cudaMemcpyAsync(static_cast<char*>(y_host) + (size_t)b0 * Lout * esz, yd, y_bytes, cudaMemcpyDeviceToHost, si));
+    base += align_up(host_part_bytes(h, Bi, T, y_dtype), 256);
+    b0 += Bi;
+  }
+  h->launches = launches;
+  if (nh > 1) {
+    SA_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+    SA_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
+  if (rc == SA_OK) SA_CUDA(cudaStreamSynchronize(st));
   if (cur != h->device) cudaSetDevice(cur);
   return rc;
 }

@@ -256,3 +256,15 @@ def test_fused_and_per_layer_paths_are_bit_identical():
     finally:
         del os.environ["SATOOLS_B200_FUSED"]
     np.testing.assert_array_equal(y_fused, y_layer)
+
+
+def test_host_entry_two_stream_split_equals_device_entry():
+    """sa_hifigan_synthesize_host cuts batches of >= 8 items into two halves on two streams; the result is the
+    same as one device-resident forward."""
+    gen = dev_gen(0, "fp16")
+    x = conditioning.batch(77, [30, 28, 25, 31, 22, 30, 27, 29, 26])
+    y = run(gen, x)
+    yh = gen.synthesize_host(torch.from_numpy(x).pin_memory())
+    np.testing.assert_array_equal(yh.numpy(), y)
+    pcm = gen.synthesize_host(torch.from_numpy(x).pin_memory(), out_dtype=torch.int16)
+    np.testing.assert_array_equal(pcm.numpy(), np.clip(np.rint(y * 32767.0), -32768, 32767).astype(np.int16))
