@@ -13,6 +13,7 @@
 #include "tc_path.cuh"
 #include "conv_tc.cuh"
 #include "chain_tc.cuh"
+#include "chain3_tc.cuh"
 
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -280,6 +281,25 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
   return cudaGetLastError();
 }
 
+// ---- whole-stage fused launch (three ResBlocks in one kernel, C <= 32) -------------------------
+int g_use_chain3 = 1;           // SATOOLS_B200_CHAIN3=0 falls back to one fused kernel per ResBlock
+
+template <int C, int MS>
+cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::stage_chain3_kernel<C, MS, 3, 7, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int ctas = std::max(1, std::min(p.total_tiles, n_sm));
+  tc::stage_chain3_kernel<C, MS, 3, 7, 11><<<ctas, tc::chain_threads(MS, 4), smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 struct Epi {
   uint32_t flags = 0;
   const float* res32 = nullptr;
@@ -363,6 +383,40 @@ struct Runner {
 
   // One whole ResBlock1 on a narrow stage, fused (chain_tc.cuh).  Returns "" (empty, not an
   // error) when this block must run layer by layer instead.
+  // The three ResBlocks of a stage in one kernel (chain3_tc.cuh); *done = false: run them one by one instead.
+  const char* chain3(const tc_chain* ch, int nrb, const float* x32, int L, const Epi& e, int tag, bool* done) {
+    *done = false;
+    if (!g_use_chain3 || nrb != 3 || !ch[0].d_w || !ch[1].d_w || !ch[2].d_w) return nullptr;
+    const int C = ch[0].c;
+    if ((C != 16 && C != 32) || ch[0].k != 3 || ch[1].k != 7 || ch[2].k != 11) return nullptr;
+    if (ch[0].n_convs != ch[1].n_convs || ch[0].n_convs != ch[2].n_convs) return nullptr;
+    const int ms = (C == 16) ? 4 : 3;
+    const int halo = std::max(ch[0].halo, std::max(ch[1].halo, ch[2].halo));
+    const int valid = ms * 128 - 2 * halo;
+    if (valid < 64 || L < 2 * valid) return nullptr;
+    const size_t rows = (size_t)ms * 128 + 2 * tc::kChainPad;
+    const size_t smem = 6 * rows * (size_t)C * 2 + (size_t)(3 + 7 + 11) * C * C * 2 + 3 * (size_t)tc::kChainMaxConvs * C * 4 + 80 * 8 + 16 + 1024;
+    if (smem > (size_t)ctx.max_smem) return nullptr;
+    tc::Chain3Params p;
+    memset(&p, 0, sizeof(p));
+    p.x32 = x32; p.out32 = e.out32; p.out16 = e.out16; p.error_flag = ctx.d_error;
+    for (int j = 0; j < 3; ++j) {
+      p.w[j] = ch[j].d_w; p.bias[j] = ch[j].d_bias;
+      for (int c = 0; c < ch[j].n_convs; ++c) { p.dil[j][c] = ch[j].dil[c]; p.pad[j][c] = ch[j].pad[c]; }
+    }
+    p.L = L; p.n_convs = ch[0].n_convs; p.halo = halo;
+    p.tiles_per_item = (L + valid - 1) / valid;
+    p.total_tiles = p.tiles_per_item * a.B;
+    p.flags = (e.flags & (tc::EPI_OUT32 | tc::EPI_OUT16)) | (a.bf16 ? tc::EPI_BF16 : 0u);
+    p.slope_out = e.slope_out;
+    mark(tag);
+    cudaError_t ce = (C == 16) ? launch_chain3<16, 4>(p, smem, a.n_sm, a.stream) : launch_chain3<32, 3>(p, smem, a.n_sm, a.stream);
+    if (ce != cudaSuccess) return msgf("stage_chain3 launch: %s", cudaGetErrorString(ce));
+    ++*launches;
+    *done = true;
+    return nullptr;
+  }
+
   bool chain_usable(const tc_chain& ch, int L) const {
     ChainPlan pl;
     if (!ch.d_w || !chain_plan(pl, ch, ctx.max_smem)) return false;
@@ -536,6 +590,7 @@ const char* tc_init(tc_context& ctx, int device) {
   if (const char* env = getenv("SATOOLS_B200_CHAIN_TIMING")) {
     if (atoi(env) != 0) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx.d_timing), 64 * 16 * sizeof(long long)));
   }
+  if (const char* env = getenv("SATOOLS_B200_CHAIN3")) g_use_chain3 = atoi(env);
   if (const char* env = getenv("SATOOLS_B200_CHAIN_MS")) {
     const int v = atoi(env);
     if (v == 3 || v == 6) g_chain_ms_narrow = v;
@@ -650,6 +705,18 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     const bool last_rb_fused = a.chains && run.chain_usable(a.chains[i * nrb + nrb - 1], L);
     float* H32 = last_rb_fused ? R32 : X32;
     Hout = H32;
+    if (a.chains) {                                 // narrowest stages: the whole stage in one kernel
+      Epi fin;
+      if (last_stage || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = R32; }
+      if (!last_stage) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = 0.1f; }
+      bool done = false;
+      if ((err = run.chain3(a.chains + i * nrb, nrb, X32, L, fin, 16 * (1 + i) + 1, &done))) return err;
+      if (done) {
+        Hout = R32;
+        if ((err = unblock_tap(SA_TAP_STAGE0 + i, up.cout, L))) return err;
+        continue;
+      }
+    }
     for (int j = 0; j < nrb; ++j) {
       const int tag = 16 * (1 + i) + 1 + j;
       // multi-receptive-field epilogue of this block's last conv (archi.py:82-86)
