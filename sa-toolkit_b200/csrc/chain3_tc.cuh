@@ -12,7 +12,9 @@
 // swizzled layout (two buffers per chain), time on M, taps as row-shifted descriptors, accumulators in TMEM
 // (one per chain and sub-tile: the next conv of a chain only starts after that chain's epilogue has drained
 // it), one epilogue warp quad per sub-tile (one thread = one row, for all three chains).  All chains use
-// the largest halo (that of K2) so that they produce the same valid rows.
+// the largest halo (that of K2) so that they produce the same valid rows.  Synchronisation is per (chain,
+// conv), not per sub-tile: with three chains in flight the MMA warp rarely has to wait, and every barrier
+// check costs it ~90 cycles even when it is already complete.
 #pragma once
 #include "chain_tc.cuh"
 
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < 3; ++j) {
       for (int s = 0; s < 8; ++s) {
-        mbar_init(bar_ready(j, 0, s), 4); mbar_init(bar_ready(j, 1, s), 4);
+        mbar_init(bar_ready(j, 0, s), 4 * MS); mbar_init(bar_ready(j, 1, s), 4 * MS);   // only s = 0 is used
         mbar_init(bar_acc_full(j, s), 1);
       }
       mbar_init(bar_w_full(j), 1); mbar_init(bar_w_empty(j), 1);
@@ -131,12 +133,11 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
       const uint32_t dil16 = (uint32_t)p.dil[j][c] * row16;
       const uint32_t b_lo0 = desc_lo(smem_u32(w_smem) + kWOff[j]);
       ok = ok && mbar_wait(bar_w_full(j), n & 1u, p.error_flag);
+      ok = ok && mbar_wait(bar_ready(j, c & 1, 0), rdy_parity, p.error_flag);      // every sub-tile of this chain staged
+      if (!ok) return;
+      tc_fence_after();
 #pragma unroll
       for (int s = 0; s < MS; ++s) {
-        if (s == 0 && ok) ok = mbar_wait(bar_ready(j, c & 1, 0), rdy_parity, p.error_flag);
-        if (s + 1 < MS && ok) ok = mbar_wait(bar_ready(j, c & 1, s + 1), rdy_parity, p.error_flag);
-        if (!ok) return;
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)((j * MS + s) * N);
         uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16;
         uint32_t b_tap = b_lo0;
@@ -148,10 +149,11 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
           a_tap += dil16;
           b_tap += tap16;
         }
-        if (leader) umma_commit(bar_acc_full(j, s));
-        __syncwarp();
       }
-      if (leader) umma_commit(bar_w_empty(j));                   // the whole conv's weights are consumed
+      if (leader) {
+        umma_commit(bar_acc_full(j, 0));                         // all sub-tiles of this chain's conv
+        umma_commit(bar_w_empty(j));                             // and its weights are consumed
+      }
       __syncwarp();
     };
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it)
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar_ready(0, 0, s)); mbar_arrive(bar_ready(1, 0, s)); mbar_arrive(bar_ready(2, 0, s)); }
+      if (lane == 0) { mbar_arrive(bar_ready(0, 0, 0)); mbar_arrive(bar_ready(1, 0, 0)); mbar_arrive(bar_ready(2, 0, 0)); }
       // ---- one conv of one chain ----
       auto step = [&](auto second_c, auto last_c, auto j_c, int c) {
         constexpr bool second = decltype(second_c)::value;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
         constexpr int j = decltype(j_c)::value;
         const float* bias_c = bias_s + (j * kChainMaxConvs + c) * C;
         uint8_t* out_buf = buf(j, second ? 0 : 1);
-        ok = ok && mbar_wait(bar_acc_full(j, s), n & 1u, p.error_flag);
+        ok = ok && mbar_wait(bar_acc_full(j, 0), n & 1u, p.error_flag);
         if (!ok) return;
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((j * MS + s) * N);
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_ready(j, second ? 0 : 1, s));
+          if (lane == 0) mbar_arrive(bar_ready(j, second ? 0 : 1, 0));
         } else {
           tc_fence_before();                                     // TMEM reads done before the next tile's MMAs
         }
