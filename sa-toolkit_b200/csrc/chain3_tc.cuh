@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarpW = 4 * MS, kWarpMma = 4 * MS + 1;          // epilogue warps first, MMA issuer last (see chain_tc.cuh)
   // smem: buf[chain][A|T], weights (one conv per chain), bias, barriers
   auto buf = [&](int j, int t) { return smem + (uint32_t)(j * 2 + t) * kBufBytes; };
   uint8_t* w_smem = smem + 6 * kBufBytes;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   const bool bf16 = (p.flags & EPI_BF16) != 0;
   const int n_pairs = p.n_convs / 2;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpW && lane == 0) {
     for (int j = 0; j < 3; ++j) {
       for (int s = 0; s < 8; ++s) {
         mbar_init(bar_ready(j, 0, s), 4 * MS); mbar_init(bar_ready(j, 1, s), 4 * MS);   // only s = 0 is used
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   for (int i = threadIdx.x; i < 3 * p.n_convs * C; i += kThreads_) {
     const int j = i / (p.n_convs * C), rem = i - j * p.n_convs * C;
     bias_s[j * kChainMaxConvs * C + rem] = p.bias[j][rem];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
+  if (warp == kWarpW) {
     // ===== weight producer: conv c of chain j into chain j's slot =====
     const bool leader = elect_one();
     uint32_t n = 0;                                              // how often each slot has been filled
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
       for (int c = 0; c < p.n_convs && ok; ++c, ++n)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          if (n > 0) ok = ok && mbar_wait(bar_w_empty(j), (n - 1) & 1u, p.error_flag);
+          if (n > 0) ok = ok && mbar_wait_relaxed(bar_w_empty(j), (n - 1) & 1u, p.error_flag);
           if (!ok) break;
           const uint32_t bytes = (uint32_t)KS[j] * kTapBytes;
           if (leader) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
           }
           __syncwarp();
         }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===== MMA issuer: conv by conv, the three chains in turn =====
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(N, bf16);
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   } else {
     // ===== epilogue: warp quad (warp - 2) / 4 owns sub-tile s; this thread owns row r for all three chains =====
     const int lg = warp & 3;
-    const int s = (warp - 2) >> 2;
+    const int s = warp >> 2;
     const int r = s * 128 + lg * 32 + lane;
     constexpr int cchunks = C / 8;
     float xr[3][C];                                              // the three residual streams of this row
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
         constexpr int j = decltype(j_c)::value;
         const float* bias_c = bias_s + (j * kChainMaxConvs + c) * C;
         uint8_t* out_buf = buf(j, second ? 0 : 1);
-        ok = ok && mbar_wait(bar_acc_full(j, 0), n & 1u, p.error_flag);
+        ok = ok && mbar_wait_relaxed(bar_acc_full(j, 0), n & 1u, p.error_flag);
         if (!ok) return;
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((j * MS + s) * N);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

@@ -26,11 +26,12 @@
 // Persistent CTAs: grid.x CTAs walk the (item, time-tile) list with stride grid.x, so barrier
 // setup, TMEM allocation and (resident) weights are paid once and the three pipelines overlap
 // across tiles:
-//   warp 0      A producer: TMA tile loads into a 1- or 2-deep ring            (a_full / a_empty)
-//   warp 1      W producer: bulk copies of weight stages                       (w_full / w_empty)
-//   warp 2      MMA issuer (one thread) + TMEM owner                           (acc_full / acc_empty)
-//   warps 3..10 epilogue: TMEM -> registers -> bias / residual / MRF sum / leaky-ReLU -> global,
+//   warps 0..7  epilogue: TMEM -> registers -> bias / residual / MRF sum / leaky-ReLU -> global,
 //               two warps per TMEM lane group, each taking half of the N columns
+//   warp 8      A producer: TMA tile loads into a 1- or 2-deep ring            (a_full / a_empty)
+//   warp 9      W producer: bulk copies of weight stages                       (w_full / w_empty)
+//   warp 10     MMA issuer (one elected lane) + TMEM owner                     (acc_full / acc_empty)
+//   (the issuer is the last warp: the scheduler prefers the highest eligible warp id)
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -123,6 +124,21 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {          // ~2 s at 2 GHz
+      if (error_flag) atomicExch(error_flag, 1);
+      return false;
+    }
+  }
+  return true;
+}
+// Same, for the producer and epilogue warps: back off between polls so that waiting warps do not take
+// issue slots from the MMA warp (the scheduler picks the highest warp id among the eligible warps; the
+// MMA issuer is therefore also the LAST warp of the CTA).
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) {
       if (error_flag) atomicExch(error_flag, 1);
       return false;
     }
@@ -311,7 +327,8 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
   const int n_iters = (n_k16 + p.k16_per_stage - 1) / p.k16_per_stage;   // weight stages per tile
   const uint8_t* w_tile = static_cast<const uint8_t*>(p.w) + (size_t)(phase * p.n_tiles + ntile) * p.w_tile_bytes;
 
-  if (warp == 0 && lane == 0) {
+  constexpr int kWarpA = kEpiWarps, kWarpW = kEpiWarps + 1, kWarpMma = kEpiWarps + 2;
+  if (warp == kWarpA && lane == 0) {
     prefetch_tmap(&p.tmap);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_a_full(i), 1);
@@ -322,21 +339,21 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = p.bias[ntile * N + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
+  if (warp == kWarpA) {
     // ===== A producer: one TMA tile per work item =====
     {
       const bool leader = elect_one();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
-        if (use > 0 && !mbar_wait(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
+        if (use > 0 && !mbar_wait_relaxed(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
         const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
         const int row0 = m0 + p.row_lo[phase];
         const uint32_t dst = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
@@ -350,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpW) {
     // ===== W producer: weight stages through the ring (once, when resident) =====
     {
       const bool leader = elect_one();
@@ -361,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         if (p.w_resident && tile != (int)blockIdx.x) break;
         bool ok = true;
         for (int i = 0; i < n_iters && ok; ++i) {
-          if (wrapped) ok = mbar_wait(bar_w_empty(slot), par, p.error_flag);
+          if (wrapped) ok = mbar_wait_relaxed(bar_w_empty(slot), par, p.error_flag);
           if (!ok) break;
           const int k16 = min(p.k16_per_stage, n_k16 - i * p.k16_per_stage);
           const uint32_t bytes = (uint32_t)k16 * N * 32u;
@@ -376,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         if (!ok) break;
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == kWarpMma) {
     // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
     // The loop body is kept as lean as the microbenchmark in tools/mma_bench2.cu (which reaches
     // the hardware rate: 128 / 64 / 48 / 40 / 39 cycles per MMA for N = 256 .. 16): all
@@ -448,9 +465,9 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       }
     }
   } else {
-    // ===== epilogue: warps 3..10; TMEM lane group = warp % 4; column half = (warp - 3) / 4 =====
+    // ===== epilogue: warps 0..7; TMEM lane group = warp % 4; column half = warp / 4 =====
     const int lg = warp & 3;
-    const int half = (warp - 3) >> 2;
+    const int half = warp >> 2;
     constexpr int kColsPerWarp = (N >= 32) ? N / 2 : N;            // N = 16: only half 0 has columns
     const bool has_cols = (N >= 32) || half == 0;
     const int col0 = (N >= 32) ? half * kColsPerWarp : 0;
@@ -462,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
-      if (!mbar_wait(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
+      if (!mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
       tc_fence_after();
       const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
       if (has_cols) {
@@ -551,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
