@@ -58,6 +58,19 @@ def load_peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic():
+    """DRAM bytes of one forward of this workload from the committed ncu launch list (dram__bytes_read.sum +
+    dram__bytes_write.sum summed over the launches of one step); None when the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_launches_fp16_v9_summary.txt")
+    try:
+        import re
+        m = re.search(r"DRAM traffic ([0-9.]+) GB", open(path).read())
+        return {"traffic": float(m.group(1)) * 1e9, "traffic_unit": "bytes per step (ncu, all launches of one forward)",
+                "traffic_source": "profiles/r1_launches_fp16_v9_summary.txt"}
+    except Exception:
+        return {"traffic": None}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -259,7 +272,7 @@ def main():
     achieved = flops_step / ms_per_step                           # TFLOP/s over the timed region
     dominant = max(range(n_sections), key=lambda i: sec_ms[i])
     roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
+                "frac": round(achieved / peaks["tflops"], 4), **ncu_traffic(),
                 "peak_source": peaks["source"] + ", sustained bf16 (kernels timed inside a long step)",
                 "kernel": "whole conv chain of one forward (conv_pre + 5 x (upsampler + 18 ResBlock convs) + tail)",
                 "algorithmic_gflop_per_step": round(flops_step, 1), "profiled_ms_per_step": round(conv_ms, 3),
