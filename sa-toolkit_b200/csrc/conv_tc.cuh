@@ -67,6 +67,8 @@ struct ConvParams {
   float* sum32;
   void* out16;              // 16-bit panel-blocked [B][Cout/out_pw][L_out][out_pw]
   int* error_flag;          // raised when a barrier wait times out
+  long long* timing;        // optional [16] cycle counters (diagnostics): MMA warp total / wait A / wait W / wait acc-empty;
+                            // epilogue warp 0 total / wait acc-full; A producer total / wait a-empty
   int cin;                  // multiple of 16
   int cout_total;           // channels of the output tensor
   int m_rows;               // valid output rows per item on the M axis (L for conv, L_in for convT)
@@ -414,11 +416,16 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       int it = 0, wslot = 0;
       uint32_t wpar = 0;
       bool ok = true, resident_ready = false;
+      const bool timing = p.timing != nullptr;
+      long long t_a = 0, t_w = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
+        long long tq = timing ? clock64() : 0;
         if (acc_use > 0) ok = mbar_wait(bar_acc_empty(acc), (acc_use - 1) & 1, p.error_flag);
+        if (timing) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
         if (ok) ok = mbar_wait(bar_a_full(buf), use & 1, p.error_flag);
+        if (timing) t_a += clock64() - tq;
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(acc * kAccCols);
@@ -427,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         int panel = 0, blk = 0;
         for (int i = 0; i < n_iters; ++i) {
           int slot = i;
+          const long long tw0 = timing ? clock64() : 0;
           if (!p.w_resident) {
             slot = wslot;
             ok = mbar_wait(bar_w_full(slot), wpar, p.error_flag);
@@ -434,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
           } else if (!resident_ready) {
             ok = mbar_wait(bar_w_full(slot), 0, p.error_flag);
           }
+          if (timing) t_w += clock64() - tw0;
           if (!ok) break;
           tc_fence_after();
           uint32_t b_blk = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
@@ -463,6 +472,12 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
         }
         __syncwarp();
       }
+      if (timing && lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 0), (unsigned long long)(clock64() - t_begin));
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_a);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 2), (unsigned long long)t_w);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 3), (unsigned long long)t_acc);
+      }
     }
   } else {
     // ===== epilogue: warps 0..7; TMEM lane group = warp % 4; column half = warp / 4 =====
@@ -477,9 +492,13 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     const int opanels = p.cout_total / p.out_pw;
     const uint32_t flags = p.flags;
     int it = 0;
+    const bool timing = p.timing != nullptr && warp == 0;
+    long long t_full = 0, t_begin = timing ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
+      const long long tf0 = timing ? clock64() : 0;
       if (!mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
+      if (timing) t_full += clock64() - tf0;
       tc_fence_after();
       const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
       if (has_cols) {
@@ -564,6 +583,10 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(acc));              // this warp is done with the accumulator buffer
+    }
+    if (timing && lane == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 4), (unsigned long long)(clock64() - t_begin));
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 5), (unsigned long long)t_full);
     }
   }
   tc_fence_before();

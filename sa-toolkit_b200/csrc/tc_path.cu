@@ -357,6 +357,7 @@ struct Runner {
     p.bias = ly.d_bias;
     p.res32 = e.res32; p.out32 = e.out32; p.sum32 = e.sum32; p.out16 = e.out16;
     p.error_flag = ctx.d_error;
+    p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 16 * ctx.timing_launches++ : nullptr;
     p.cin = w.cin_pad;
     p.cout_total = ly.cout;
     p.m_rows = l_in;

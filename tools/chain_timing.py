@@ -22,9 +22,9 @@ lib = _lib.load()
 buf = (C.c_int64 * (64 * 16))()
 n = lib.sa_hifigan_chain_timing(gen._handle, buf, 64)
 names = ["mma_total", "mma_wait_ready", "mma_wait_w", "mma_issue", "epi_total", "epi_load_x", "epi_wait_acc", "epi_work", "epi_tmem_ld", "epi_fence"]
-labels = ["c64 k3", "c64 k7", "c64 k11", "c32 k3", "c32 k7", "c32 k11", "c16 k3", "c16 k7", "c16 k11"]
-print("per-CTA average cycles (148 CTAs)")
+labels = []
+print("cycle counters per launch (timed launches in order: conv_tc launches = MMA warp [total, wait A, wait W, wait acc-empty], epilogue warp 0 [total, wait acc-full]; fused kernels as in sa_hifigan.h), summed over CTAs / 148")
 for i in range(n):
     v = [buf[i * 16 + j] / 148.0 for j in range(10)]
     tot = v[0] or 1.0
-    print(f"{labels[i] if i < len(labels) else i:8s} " + " ".join(f"{nm}={val/1e3:8.0f}k({100*val/ (tot if j < 4 else (v[4] or 1)):3.0f}%)" for j, (nm, val) in enumerate(zip(names, v))))
+    print(f"launch {i:2d} " + " ".join(f"{val/1e3:7.0f}k({100*val/ (tot if j < 4 else (v[4] or 1)):3.0f}%)" for j, val in enumerate(v)))
