@@ -139,6 +139,14 @@ size_t sa_hifigan_host_scratch_bytes(const sa_hifigan* h, int32_t B, int32_t T, 
 int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
                                const int32_t* frames_per_item, void* y_host, int32_t y_dtype,
                                void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+/* Stream-ordered form of the same sequence: enqueues H2D copy, forward and D2H copy on `stream`
+ * and returns without waiting.  x_host, y_host and dev_scratch stay owned by the call until the
+ * caller has synchronized `stream`.  Two streams used alternately (each with its own buffers)
+ * overlap the copies of one batch with the kernels of the other -- the pipeline's DataLoader
+ * prefetch (bin/pipeline.py:91-101) moved to the device side. */
+int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
+                                     const int32_t* frames_per_item, void* y_host, int32_t y_dtype,
+                                     void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
 /* Debug tap: while `out` is non-NULL every following forward also writes activation `tap`
  * as fp32 [B,C,L] to `out` (device memory, caller sized: conv_pre B*initial_channels*T,

@@ -87,6 +87,7 @@ struct ConvParams {
   int n_wstages;            // weight ring depth
   int w_resident;           // 1: all weight stages stay in smem (loaded once per CTA)
   int n_abuf;               // A-tile ring depth (1 or 2)
+  int cluster;              // 1: launched as 2-CTA clusters; weight stages are multicast (each CTA loads half)
   int m_tiles;              // time tiles per item
   int total_tiles;          // m_tiles * B
   uint32_t w_tile_bytes;
@@ -170,6 +171,27 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
+}
+// Multicast variants for 2-CTA clusters: the data lands at the same CTA-relative offset in every CTA of
+// `mask`, and so does the mbarrier complete_tx / arrive.
+__device__ __forceinline__ void bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -338,22 +360,30 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       mbar_init(bar_acc_full(i), 1);
       mbar_init(bar_acc_empty(i), kEpiWarps);
     }
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), p.cluster ? 2 : 1); }
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = p.bias[ntile * N + i];
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();              // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // In cluster mode both CTAs of a pair must run the same number of tiles (they share the weight ring's pace):
+  // every CTA runs n_rounds rounds; a round past the end recomputes the last tile without storing it.
+  const int n_rounds = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int round) { return min((int)blockIdx.x + round * (int)gridDim.x, p.total_tiles - 1); };
+  auto is_dummy = [&](int round) { return (int)blockIdx.x + round * (int)gridDim.x >= p.total_tiles; };
+  const int my_rounds = p.cluster ? n_rounds : (((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
 
   if (warp == kWarpA) {
     // ===== A producer: one TMA tile per work item =====
     {
       const bool leader = elect_one();
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (; it < my_rounds; ++it) {
+        const int tile = tile_of(it);
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         if (use > 0 && !mbar_wait_relaxed(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
         const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
@@ -376,8 +406,9 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       int slot = 0;
       uint32_t par = 1;                                           // parity of the previous use of `slot`
       bool wrapped = false;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        if (p.w_resident && tile != (int)blockIdx.x) break;
+      const uint32_t crank = p.cluster ? cluster_ctarank() : 0u;
+      for (int round = 0; round < my_rounds; ++round) {
+        if (p.w_resident && round != 0) break;
         bool ok = true;
         for (int i = 0; i < n_iters && ok; ++i) {
           if (wrapped) ok = mbar_wait_relaxed(bar_w_empty(slot), par, p.error_flag);
@@ -386,8 +417,14 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
           const uint32_t bytes = (uint32_t)k16 * N * 32u;
           if (leader) {
             mbar_arrive_expect_tx(bar_w_full(slot), bytes);
-            bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
-                      bar_w_full(slot));
+            if (p.cluster) {                                      // this CTA fetches its half and multicasts it to the pair
+              const uint32_t half = bytes >> 1;
+              bulk_load_mc(smem_u32(w_smem) + (uint32_t)slot * stage_bytes + crank * half,
+                           w_tile + (size_t)i * stage_bytes + crank * half, half, bar_w_full(slot), (uint16_t)0x3);
+            } else {
+              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
+                        bar_w_full(slot));
+            }
           }
           __syncwarp();
           if (++slot == p.n_wstages) { slot = 0; par ^= 1u; wrapped = true; }
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       bool ok = true, resident_ready = false;
       const bool timing = p.timing != nullptr;
       long long t_a = 0, t_w = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+      for (; it < my_rounds && ok; ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
         long long tq = timing ? clock64() : 0;
@@ -461,7 +498,10 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
             b_blk += b_block16;
             if (++panel == panels) { panel = 0; a_tap += tap_step16; a_blk = a_tap; } else { a_blk += a_panel16; }
           }
-          if (!p.w_resident && leader) umma_commit(bar_w_empty(slot));   // slot free once these MMAs have read it
+          if (!p.w_resident && leader) {                          // slot free once these MMAs have read it
+            if (p.cluster) umma_commit_mc(bar_w_empty(slot), (uint16_t)0x3);   // ... in both CTAs' rings
+            else umma_commit(bar_w_empty(slot));
+          }
           __syncwarp();
         }
         if (!ok) break;
@@ -494,7 +534,9 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
     int it = 0;
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_full = 0, t_begin = timing ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (; it < my_rounds; ++it) {
+      const int tile = tile_of(it);
+      const bool dummy = is_dummy(it);
       const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
       const long long tf0 = timing ? clock64() : 0;
       if (!mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
@@ -505,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
 #pragma unroll
         for (int ms = 0; ms < MSUB; ++ms) {
           const int t = m0 + ms * 128 + lg * 32 + lane;            // output row on the M axis
-          const bool valid = t < p.m_rows;
+          const bool valid = t < p.m_rows && !dummy;
           const size_t orow = (size_t)t * p.out_stride + phase;
           const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0);
           // The residual of up to 64 columns (4 groups) is requested before the first TMEM round trip, so a
@@ -591,6 +633,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();              // no CTA leaves while its peer may still multicast into it
   if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

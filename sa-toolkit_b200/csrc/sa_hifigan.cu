@@ -627,7 +627,40 @@ size_t sa_hifigan_host_scratch_bytes(const sa_hifigan* h, int32_t B, int32_t T, 
   const int nh = host_halves(B);
   size_t total = 0;
   for (int i = 0; i < nh; ++i) total += align_up(host_part_bytes(h, (B + nh - 1 - i) / nh, T, y_dtype), 256);
-  return total;
+  return std::max(total, align_up(host_part_bytes(h, B, T, y_dtype), 256));   // the _async entry does not split
+}
+
+// Stream-ordered variant: H2D copy, forward and D2H copy are enqueued on `stream` and the call returns.  A caller
+// that alternates two streams (with their own pinned buffers and scratch) overlaps the copies of one batch with
+// the kernels of the other across calls; see satools_b200/synth.py.
+int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
+                                     const int32_t* frames_per_item, void* y_host, int32_t y_dtype, void* dev_scratch,
+                                     size_t dev_scratch_bytes, void* stream) {
+  if (!h || !x_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
+  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2");
+  if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
+    return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
+  const size_t need = align_up(host_part_bytes(h, B, T, y_dtype), 256);
+  if (dev_scratch_bytes < need) return fail(SA_ERR_WORKSPACE, "dev_scratch too small: %zu < %zu", dev_scratch_bytes, need);
+  if (reinterpret_cast<uintptr_t>(dev_scratch) & 255) return fail(SA_ERR_INVALID_ARG, "dev_scratch must be 256-byte aligned");
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cur = -1;
+  SA_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
+  const int64_t Lout = sa_hifigan_output_length(h, T);
+  char* base = static_cast<char*>(dev_scratch);
+  const size_t x_bytes = (size_t)B * h->cfg.input_dim * T * sizeof(float);
+  const size_t y_bytes = (size_t)B * (size_t)Lout * esz;
+  float* xd = reinterpret_cast<float*>(base);
+  void* yd = base + align_up(x_bytes, 256);
+  void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+  SA_CUDA(cudaMemcpyAsync(xd, x_host, x_bytes, cudaMemcpyHostToDevice, st));
+  int rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, sa_hifigan_workspace_bytes(h, B, T), st);
+  if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(y_host, yd, y_bytes, cudaMemcpyDeviceToHost, st));
+  if (cur != h->device) cudaSetDevice(cur);
+  return rc;
 }
 
 int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,

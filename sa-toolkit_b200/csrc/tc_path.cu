@@ -134,6 +134,75 @@ __global__ void conv_post_blocked_kernel(const float* __restrict__ h, const floa
   }
 }
 
+// conv_post over the 16-bit blocked stage output (archi.py:87-90).  The producer has already applied
+// lrelu(0.01); ReflectionPad1d((1,0)) is the index map xp[i] = x[i == 0 ? 1 : i - 1]; zero padding of the k = 7
+// conv is the range check.  Each thread owns one padded position: it reads its row once (C 16-bit values),
+// forms the 7 per-tap partial sums in registers, and the block exchanges them through shared memory, so the
+// kernel reads every activation exactly once (249 outputs per 256-thread block).
+template <bool BF16>
+__global__ void __launch_bounds__(256) conv_post16_k7_kernel(const uint4* __restrict__ h16, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, void* y, int C, int PW, int L,
+                                                             int y_dtype) {
+  constexpr int K = 7, kOut = 256 - (K - 1);
+  extern __shared__ float4 post_smem[];
+  float4* ws = post_smem;                                   // [C][2] float4: taps 0-3, taps 4-6 + 0
+  float* part = reinterpret_cast<float*>(post_smem + 2 * C);   // [K][256]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float* wr = w + i * K;
+    ws[2 * i] = make_float4(wr[0], wr[1], wr[2], wr[3]);
+    ws[2 * i + 1] = make_float4(wr[4], wr[5], wr[6], 0.f);
+  }
+  __syncthreads();
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int n0 = blockIdx.x * kOut;
+  const int i = n0 - (K - 1) / 2 + tid;                     // padded position owned by this thread
+  const int Lout = L + 1;
+  float p[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) p[j] = 0.f;
+  if (i >= 0 && i < Lout) {
+    const int src = (i == 0) ? 1 : i - 1;
+    const int opc = PW >> 3;
+    for (int c8 = 0; c8 < (C >> 3); ++c8) {
+      const int panel = c8 / opc, within = c8 - panel * opc;
+      const uint4 q = __ldg(h16 + (((size_t)b * (C / PW) + panel) * L + src) * opc + within);
+      const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 v;
+        if (BF16) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qw[e]));
+        else v = __half22float2(*reinterpret_cast<const __half2*>(&qw[e]));
+        const float vv[2] = {v.x, v.y};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 w0 = ws[2 * (c8 * 8 + e * 2 + u)], w1 = ws[2 * (c8 * 8 + e * 2 + u) + 1];
+          p[0] = fmaf(w0.x, vv[u], p[0]); p[1] = fmaf(w0.y, vv[u], p[1]);
+          p[2] = fmaf(w0.z, vv[u], p[2]); p[3] = fmaf(w0.w, vv[u], p[3]);
+          p[4] = fmaf(w1.x, vv[u], p[4]); p[5] = fmaf(w1.y, vv[u], p[5]);
+          p[6] = fmaf(w1.z, vv[u], p[6]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) part[j * 256 + tid] = p[j];
+  __syncthreads();
+  const int n = n0 + tid;
+  if (tid >= kOut || n >= Lout) return;
+  float acc = __ldg(bias);
+#pragma unroll
+  for (int j = 0; j < K; ++j) acc += part[j * 256 + tid + j];
+  const float v = tanhf(acc);
+  const size_t o = (size_t)b * Lout + n;
+  if (y_dtype == SA_DTYPE_F32) reinterpret_cast<float*>(y)[o] = v;
+  else if (y_dtype == SA_DTYPE_F16) reinterpret_cast<__half*>(y)[o] = __float2half_rn(v);
+  else {
+    float s = rintf(v * 32767.f);
+    s = fminf(fmaxf(s, -32768.f), 32767.f);
+    reinterpret_cast<int16_t*>(y)[o] = (int16_t)s;
+  }
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -211,7 +280,33 @@ cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int 
     occ_smem[dev] = smem;
   }
   tc::ConvParams p = p_in;
-  const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev] / grid_y));
+  int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev] / grid_y));
+  // Wide layers stream their weights from L2 once per tile; CTA pairs (2-CTA clusters) fetch half a stage each and
+  // multicast it.  Measured on B200: no gain at cluster size 2 (the L2 slices, not the request count, are the cap; profiles/README.md), so it is opt-in: SATOOLS_B200_CLUSTER=1.
+  static const int use_cluster = getenv("SATOOLS_B200_CLUSTER") ? atoi(getenv("SATOOLS_B200_CLUSTER")) : 0;
+  if (use_cluster && N >= 256 && p.cin >= 256 && !p.w_resident && ctas >= 2) {
+    static int max_clusters[16] = {0};
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(tc::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (max_clusters[dev] == 0) {
+      cfg.gridDim = dim3(2 * (unsigned)n_sm, 1, 1);
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc::conv_tc_kernel<N, MSUB, PW>, &cfg) != cudaSuccess || nc < 1) nc = n_sm / 2;
+      max_clusters[dev] = nc;
+    }
+    ctas = std::min(ctas & ~1, 2 * std::max(1, max_clusters[dev] / grid_y));
+    p.cluster = 1;
+    cfg.gridDim = dim3((unsigned)ctas, (unsigned)grid_y, 1);
+    return cudaLaunchKernelEx(&cfg, tc::conv_tc_kernel<N, MSUB, PW>, p);
+  }
+  p.cluster = 0;
   dim3 grid((unsigned)ctas, (unsigned)grid_y, 1);
   tc::conv_tc_kernel<N, MSUB, PW><<<grid, tc::kThreads, smem, st>>>(p);
   return cudaGetLastError();
@@ -690,6 +785,9 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     if ((err = unblock_tap(SA_TAP_CONV_PRE, cfg.initial_channels, a.T))) return err;
   }
   int L = a.T;
+  // The last stage hands conv_post its lrelu(0.01)-activated output in the 16-bit blocked layout (half the bytes of
+  // the fp32 stream, read once); other filter lengths keep the fp32 hand-off.
+  const bool post16 = a.layers[L_post].k == 7 && a.layers[L_post].cin % 8 == 0;
   for (int i = 0; i < nst; ++i) {
     const tc_layer& up = a.layers[L_up(i)];
     {                                               // archi.py:80-81
@@ -708,8 +806,8 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     Hout = H32;
     if (a.chains) {                                 // narrowest stages: the whole stage in one kernel
       Epi fin;
-      if (last_stage || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = R32; }
-      if (!last_stage) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = 0.1f; }
+      if ((last_stage && !post16) || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = R32; }
+      if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = last_stage ? 0.01f : 0.1f; }
       bool done = false;
       if ((err = run.chain3(a.chains + i * nrb, nrb, X32, L, fin, 16 * (1 + i) + 1, &done))) return err;
       if (done) {
@@ -725,8 +823,8 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       fin.sum32 = S32; fin.n_blocks = (float)nrb;
       if (nrb > 1) fin.flags |= (j == 0) ? tc::EPI_SUM_SET : (j == nrb - 1 ? tc::EPI_SUM_FIN : tc::EPI_SUM_ADD);
       if (j == nrb - 1) {
-        if (last_stage || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = H32; }
-        if (!last_stage) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = 0.1f; }
+        if ((last_stage && !post16) || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = H32; }
+        if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = last_stage ? 0.01f : 0.1f; }
       }
       if (a.chains) {                               // narrow stages: the whole ResBlock in one kernel
         bool done = false;
@@ -754,6 +852,17 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     const int threads = 256;
     dim3 g((unsigned)((L + 1 + threads - 1) / threads), (unsigned)a.B);
     run.mark(16 * (nst + 1));
+    if (post16) {
+      dim3 g16((unsigned)((L + 1 + 249) / 250), (unsigned)a.B);
+      const size_t sm = (size_t)post.cin * 32 + 7 * 256 * sizeof(float);
+      const int pw = panel_width(post.cin);
+      if (a.bf16)
+        conv_post16_k7_kernel<true><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(P16), post.d_w32, post.d_bias, a.y,
+                                                          post.cin, pw, L, a.y_dtype);
+      else
+        conv_post16_k7_kernel<false><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(P16), post.d_w32, post.d_bias, a.y,
+                                                           post.cin, pw, L, a.y_dtype);
+    } else
     conv_post_blocked_kernel<<<g, threads, post.cin * post.k * sizeof(float), st>>>(Hout, post.d_w32, post.d_bias, a.y,
                                                                                     post.cin, L, post.k, 0.01f, a.y_dtype);
     ++*launches;

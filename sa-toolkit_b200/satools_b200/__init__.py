@@ -5,10 +5,12 @@ Public surface:
   install()            rebind satools.hifigan.archi.CoreHifiGan to it (install.py)
   scheduler            length-balanced utterance sharding for multi-GPU runs (scheduler.py)
   synth                host-side batch driver: bucket, pad, convert, trim (synth.py)
+  HostPipeline         two-deep H2D / generator / D2H pipeline over host batches (pipeline.py)
 """
 from .archi import CoreHifiGan, ResBlock1  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from . import scheduler  # noqa: F401
 from . import synth  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
-__all__ = ["CoreHifiGan", "ResBlock1", "install", "uninstall", "scheduler", "synth"]
+__all__ = ["CoreHifiGan", "ResBlock1", "install", "uninstall", "scheduler", "synth", "HostPipeline"]

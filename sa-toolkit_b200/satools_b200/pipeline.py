@@ -1,0 +1,94 @@
+"""Two-deep host pipeline over sa_hifigan_synthesize_host_async.
+
+The reference keeps the GPU fed through a DataLoader that prefetches the next batch while the current
+one is converted, then does `.to(device)`, convert and `.cpu()` back to back
+(/root/reference/satools/satools/bin/pipeline.py:91-101,104-149).  Here each batch is one stream-ordered
+C-ABI call (H2D copy -> generator -> D2H copy); two slots with their own stream, device scratch and
+pinned output alternate, so the copies of one batch run under the kernels of the other.
+
+    pipe = HostPipeline(gen)
+    t0 = pipe.submit(x0_pinned)
+    t1 = pipe.submit(x1_pinned)          # H2D of batch 1 overlaps the kernels of batch 0
+    y0 = pipe.result(t0)                 # waits for slot 0 only
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .archi import _OUT_DTYPE
+
+
+class _Slot:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.scratch: Optional[torch.Tensor] = None
+        self.ticket = -1                   # ticket in flight (or finished, not yet collected) in this slot
+        self.keep = None                   # host objects the enqueued call still reads / writes
+        self.out: Optional[torch.Tensor] = None
+
+
+class HostPipeline:
+    def __init__(self, gen, depth: int = 2, device=None):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.gen = gen
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("HostPipeline needs a CUDA device (no CPU fallback)")
+        self._slots: List[_Slot] = [_Slot(self.device) for _ in range(depth)]
+        self._next = 0
+        self.launches = 0
+
+    def submit(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32,
+               frames_per_item: Optional[Sequence[int]] = None) -> int:
+        """Enqueue one batch (CPU fp32 [B, imput_dim, T], pinned for overlap).  Returns a ticket for result().
+        `out` (pinned CPU [B, 1, 320*T+1]) and x_host must not be touched until result(ticket) returned."""
+        if x_host.is_cuda:
+            raise ValueError("submit takes a CPU tensor")
+        lib = _lib.load()
+        ticket = self._next
+        slot = self._slots[ticket % len(self._slots)]
+        if slot.ticket >= 0:
+            slot.stream.synchronize()                       # the slot's previous batch (result() may be skipped)
+        x_host = x_host.to(torch.float32).contiguous()
+        B, _, T = x_host.shape
+        if out is None:
+            out = torch.empty((B, 1, self.gen.output_length(T)), dtype=out_dtype, pin_memory=True)
+        with torch.cuda.device(self.device):
+            self.gen._ensure_ready(self.device)
+            h = self.gen._handle
+            need = lib.sa_hifigan_host_scratch_bytes(h, B, T, _OUT_DTYPE[out.dtype])
+            if slot.scratch is None or slot.scratch.numel() < need:
+                slot.scratch = None
+                slot.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+            fpi = None
+            if frames_per_item is not None:
+                fpi = (C.c_int32 * B)(*[int(v) for v in frames_per_item])
+            _lib.check(lib.sa_hifigan_synthesize_host_async(h, x_host.data_ptr(), B, T, fpi, out.data_ptr(),
+                                                            _OUT_DTYPE[out.dtype], slot.scratch.data_ptr(),
+                                                            slot.scratch.numel(), slot.stream.cuda_stream))
+            self.launches += int(lib.sa_hifigan_last_launch_count(h))
+        slot.ticket, slot.keep, slot.out = ticket, (x_host, fpi), out
+        self._next += 1
+        return ticket
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Wait for the batch of `ticket` and return its waveform tensor (CPU)."""
+        slot = self._slots[ticket % len(self._slots)]
+        if slot.ticket != ticket:
+            raise KeyError(f"ticket {ticket} is not in flight (already overwritten or never submitted)")
+        slot.stream.synchronize()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().sa_hifigan_check(self.gen._handle, slot.stream.cuda_stream))
+        out, slot.keep, slot.out, slot.ticket = slot.out, None, None, -1
+        return out
+
+    def drain(self) -> None:
+        for slot in self._slots:
+            if slot.ticket >= 0:
+                slot.stream.synchronize()
+                slot.keep, slot.out, slot.ticket = None, None, -1

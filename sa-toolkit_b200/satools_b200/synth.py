@@ -55,12 +55,28 @@ def synthesize_corpus(gen, feats: Dict[str, np.ndarray], *, rank: int = 0, world
         y = gen.synthesize_host(xh, out_dtype=out_dtype, device=dev)
         return y.numpy()
 
-    short = [i for i in mine if lengths[i] <= chunk_frames]
-    for batch in scheduler.batches(short, lengths, max_items=max_items, max_padded_frames=max_padded_frames):
-        T = max(max(lengths[i] for i in batch), 2)
-        y = run(_pad_batch([feats[ids[i]] for i in batch], T))
+    # Batches go through the two-deep pipeline: batch k+1 is padded, pinned and enqueued (its H2D copy runs)
+    # while the kernels of batch k are still busy; the waveforms of batch k are trimmed after that.
+    from .pipeline import HostPipeline
+    pipe = HostPipeline(gen, depth=2, device=dev)
+
+    def collect(ticket: int, batch: Sequence[int]) -> None:
+        y = pipe.result(ticket).numpy()
         for b, i in enumerate(batch):
             out[ids[i]] = y[b, 0, :320 * lengths[i] + 1].copy()
+
+    short = [i for i in mine if lengths[i] <= chunk_frames]
+    pending = None
+    for batch in scheduler.batches(short, lengths, max_items=max_items, max_padded_frames=max_padded_frames):
+        T = max(max(lengths[i] for i in batch), 2)
+        xh = torch.from_numpy(_pad_batch([feats[ids[i]] for i in batch], T)).pin_memory()
+        ticket = pipe.submit(xh, out_dtype=out_dtype)
+        if pending is not None:
+            collect(*pending)
+        pending = (ticket, batch)
+    if pending is not None:
+        collect(*pending)
+    pipe.drain()
     for i in mine:
         if lengths[i] <= chunk_frames:
             continue

@@ -268,3 +268,26 @@ def test_host_entry_two_stream_split_equals_device_entry():
     np.testing.assert_array_equal(yh.numpy(), y)
     pcm = gen.synthesize_host(torch.from_numpy(x).pin_memory(), out_dtype=torch.int16)
     np.testing.assert_array_equal(pcm.numpy(), np.clip(np.rint(y * 32767.0), -32768, 32767).astype(np.int16))
+
+
+def test_host_pipeline_overlapped_batches_equal_blocking_calls():
+    """HostPipeline keeps two batches in flight on two streams (sa_hifigan_synthesize_host_async); every batch
+    must come back exactly as the blocking entry returns it, whatever its neighbour in the pipeline is."""
+    from satools_b200 import HostPipeline
+    gen = dev_gen(0, "fp16")
+    batches = [conditioning.batch(90 + k, lens) for k, lens in
+               enumerate([[30, 28, 25], [12, 40, 33, 18, 22, 31, 27, 29, 26], [64], [20, 20]])]
+    want = [gen.synthesize_host(torch.from_numpy(x).pin_memory()).numpy().copy() for x in batches]
+    pipe = HostPipeline(gen, depth=2)
+    tickets, got = [], []
+    for k, x in enumerate(batches):
+        tickets.append(pipe.submit(torch.from_numpy(x).pin_memory()))
+        if k >= 1:
+            got.append(pipe.result(tickets[k - 1]).numpy().copy())
+    got.append(pipe.result(tickets[-1]).numpy().copy())
+    for w, g in zip(want, got):
+        np.testing.assert_array_equal(g, w)
+    with pytest.raises(KeyError):
+        pipe.result(tickets[0])
+    pcm = pipe.result(pipe.submit(torch.from_numpy(batches[0]).pin_memory(), out_dtype=torch.int16)).numpy()
+    np.testing.assert_array_equal(pcm, np.clip(np.rint(want[0] * 32767.0), -32768, 32767).astype(np.int16))
