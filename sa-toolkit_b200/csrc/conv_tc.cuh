@@ -60,6 +60,7 @@ enum : uint32_t {
 
 struct ConvParams {
   CUtensorMap tmap;         // activations [B][Cin/PW][L_in][PW], box {PW, box_rows, 1, 1}, swizzle = row bytes
+  CUtensorMap wmap;         // conv_pair_tc.cuh only: packed weights as [rows][64] 16-bit, box {64, rows of one stage}
   const void* w;            // packed weights: phase p / n-tile t at w + (p * n_tiles + t) * w_tile_bytes
   const float* bias;        // [Cout_total]
   const float* res32;       // fp32 blocked [B][Cout_total/8][L_out][8]

@@ -12,6 +12,7 @@
 //   S32    multi-receptive-field sum                fp32    E
 #include "tc_path.cuh"
 #include "conv_tc.cuh"
+#include "conv_pair_tc.cuh"
 #include "chain_tc.cuh"
 #include "chain3_tc.cuh"
 
@@ -395,6 +396,79 @@ cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cuda
   return cudaGetLastError();
 }
 
+// ---- CTA-pair kernel (conv_pair_tc.cuh): plan + launch ------------------------------------
+int use_pair() {              // SATOOLS_B200_PAIR=0: wide layers on the single-CTA kernel
+  static const int v = getenv("SATOOLS_B200_PAIR") ? atoi(getenv("SATOOLS_B200_PAIR")) : 1;
+  return v;
+}
+bool make_plan_pair(Plan& pl, int cin_pad, int n, int span, int m_rows, int max_smem) {
+  const size_t fixed = (size_t)n * 4 + (8 + 2 * tc::kMaxStages) * 8 + 16 + 1024;
+  const size_t block_bytes = (size_t)(n / 2) * 128;              // one [N/2][64] weight block (4 K-steps)
+  const int bps = (int)std::max<size_t>(1, 16 * 1024 / block_bytes);
+  const size_t stage_bytes = bps * block_bytes;
+  const int msub_max = (n == 128 && m_rows > 128) ? 2 : 1;       // 2 x N accumulator columns must fit TMEM twice
+  for (int msub = msub_max; msub >= 1; --msub) {
+    const int rows = 128 * msub + span;
+    const int nseg = (rows + 255) / 256;
+    const int box_rows = (int)align_up((size_t)(rows + nseg - 1) / nseg, 8);
+    if (box_rows > 256) continue;
+    const int rows_alloc = nseg * box_rows;
+    const size_t a_bytes = (size_t)cin_pad * 2 * rows_alloc;
+    // A double-buffered when at least three weight stages still fit (two cannot hide the L2 latency of a 16 KB stage)
+    for (int n_abuf = 2; n_abuf >= 1; --n_abuf) {
+      if (n_abuf * a_bytes + fixed >= (size_t)max_smem) continue;
+      const int stages = (int)std::min<size_t>(tc::kMaxStages, ((size_t)max_smem - fixed - n_abuf * a_bytes) / stage_bytes);
+      if (stages < (n_abuf == 2 ? 3 : 2)) continue;
+      pl.msub = msub; pl.rows_alloc = rows_alloc; pl.box_rows = box_rows; pl.nseg = nseg;
+      pl.k16_per_stage = 4 * bps; pl.n_wstages = stages; pl.w_resident = 0; pl.n_abuf = n_abuf;
+      pl.smem = n_abuf * a_bytes + stages * stage_bytes + fixed;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int N, int MSUB>
+cudaError_t launch_pair(const tc::ConvParams& p, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  static int max_clusters[16] = {0};
+  static size_t mc_smem[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_pair_kernel<N, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(tc::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0 || mc_smem[dev] != smem) {     // co-resident pairs (a GPC with an odd SM count strands one)
+    cfg.gridDim = dim3(2 * (unsigned)n_sm, 1, 1);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc::conv_pair_kernel<N, MSUB>, &cfg) != cudaSuccess || nc < 1) nc = n_sm / 2 - 4;
+    max_clusters[dev] = nc;
+    mc_smem[dev] = smem;
+  }
+  const int pairs = std::max(1, std::min((p.total_tiles + 1) / 2, max_clusters[dev] / grid_y));
+  cfg.gridDim = dim3(2 * (unsigned)pairs, (unsigned)grid_y, 1);
+  return cudaLaunchKernelEx(&cfg, tc::conv_pair_kernel<N, MSUB>, p);
+}
+
+cudaError_t dispatch_pair(int n, int msub, const tc::ConvParams& p, int grid_y, size_t smem, int n_sm, cudaStream_t st) {
+  if (n == 256 && msub == 1) return launch_pair<256, 1>(p, grid_y, smem, n_sm, st);
+  if (n == 128 && msub == 2) return launch_pair<128, 2>(p, grid_y, smem, n_sm, st);
+  if (n == 128 && msub == 1) return launch_pair<128, 1>(p, grid_y, smem, n_sm, st);
+  return cudaErrorInvalidValue;
+}
+
 struct Epi {
   uint32_t flags = 0;
   const float* res32 = nullptr;
@@ -429,7 +503,11 @@ struct Runner {
     Plan pl;
     int n_k16_max = 0;
     for (int ph = 0; ph < w.n_phases; ++ph) n_k16_max = std::max(n_k16_max, w.n_taps[ph] * (w.cin_pad / 16));
-    if (!make_plan(pl, w.cin_pad, w.n, span, l_in, n_k16_max, ctx.max_smem)) return "conv does not fit in shared memory";
+    if (w.pair) {
+      if (!make_plan_pair(pl, w.cin_pad, w.n, span, l_in, ctx.max_smem)) return "conv (CTA pair) does not fit in shared memory";
+    } else if (!make_plan(pl, w.cin_pad, w.n, span, l_in, n_k16_max, ctx.max_smem)) {
+      return "conv does not fit in shared memory";
+    }
     // tensor map over the input activation [B][cin_pad/pw][l_in][pw], swizzle = row bytes
     const int pw = panel_width(w.cin_pad);
     const cuuint64_t rb = (cuuint64_t)pw * 2;
@@ -447,6 +525,20 @@ struct Runner {
       snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for L=%d panels=%d box_rows=%d", (int)r, l_in,
                w.cin_pad / pw, pl.box_rows);
       return g_msg;
+    }
+    if (w.pair) {       // the packed weights as rows of 128 bytes; one box = this CTA's half of one stage
+      const cuuint64_t wdim[2] = {64, (cuuint64_t)(w.bytes / 128)};
+      const cuuint64_t wstr[1] = {128};
+      const cuuint32_t wbox[2] = {64, (cuuint32_t)((pl.k16_per_stage / 4) * (w.n / 2))};
+      const cuuint32_t wes[2] = {1, 1};
+      r = reinterpret_cast<encode_tiled_fn>(ctx.encode_fn)(
+          &p.wmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w.d_w, wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for the weights (%zu rows, box %u)", (int)r,
+                 w.bytes / 128, wbox[1]);
+        return g_msg;
+      }
     }
     p.w = w.d_w;
     p.bias = ly.d_bias;
@@ -471,7 +563,8 @@ struct Runner {
     p.slope_out = e.slope_out;
     p.n_blocks = e.n_blocks;
     mark(tag);
-    cudaError_t ce = dispatch(w.n, pl.msub, pw, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream);
+    cudaError_t ce = w.pair ? dispatch_pair(w.n, pl.msub, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream)
+                            : dispatch(w.n, pl.msub, pw, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream);
     if (ce != cudaSuccess) return msgf("conv_tc launch: %s", cudaGetErrorString(ce));
     ++*launches;
     return nullptr;
@@ -570,6 +663,9 @@ const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed,
   w.cin_pad = (int)align_up(cin, 16);
   w.n = cout > 256 ? 256 : cout;
   w.n_tiles = cout / w.n;
+  // Wide layers (N = 256 / 128, 64-channel panels) run on CTA pairs; their weights are packed in half tiles.
+  w.pair = (use_pair() && (w.n == 256 || w.n == 128) && w.cin_pad % 64 == 0) ? 1 : 0;
+  const int pack_n = w.pair ? w.n / 2 : w.n, pack_tiles = cout / pack_n;
   const int k16_per_tap = w.cin_pad / 16;
   int max_taps = 0;
   if (!transposed) {
@@ -592,20 +688,20 @@ const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed,
   }
   // one (phase, n_tile) block = [tap][panel][N rows][pw] with the UMMA K-major swizzle applied
   const int pw = panel_width(w.cin_pad), panels = w.cin_pad / pw, rb = pw * 2;
-  const size_t panel_bytes = (size_t)w.n * rb;
+  const size_t panel_bytes = (size_t)pack_n * rb;
   w.tile_bytes = (size_t)max_taps * panels * panel_bytes;
-  w.bytes = w.tile_bytes * w.n_phases * w.n_tiles;
+  w.bytes = w.tile_bytes * w.n_phases * pack_tiles;
   std::vector<uint16_t> host(w.bytes / 2, 0);
   for (int ph = 0; ph < w.n_phases; ++ph)
-    for (int t = 0; t < w.n_tiles; ++t) {
-      uint8_t* tile = reinterpret_cast<uint8_t*>(host.data()) + (size_t)(ph * w.n_tiles + t) * w.tile_bytes;
+    for (int t = 0; t < pack_tiles; ++t) {
+      uint8_t* tile = reinterpret_cast<uint8_t*>(host.data()) + (size_t)(ph * pack_tiles + t) * w.tile_bytes;
       for (int tap = 0; tap < w.n_taps[ph]; ++tap) {
         const int j = transposed ? ((ph + pad) % stride + stride * tap) : tap;
         for (int pn = 0; pn < panels; ++pn) {
           uint8_t* blk = tile + (size_t)(tap * panels + pn) * panel_bytes;
-          for (int r = 0; r < w.n; ++r)
+          for (int r = 0; r < pack_n; ++r)
             for (int kq = 0; kq < pw; ++kq) {
-              const int ci = pn * pw + kq, co = t * w.n + r;
+              const int ci = pn * pw + kq, co = t * pack_n + r;
               float v = 0.f;
               if (ci < cin)
                 v = transposed ? folded[((size_t)ci * cout + co) * k + j] : folded[((size_t)co * cin + ci) * k + j];

@@ -14,6 +14,8 @@ struct tc_weights {
   void* d_w = nullptr;
   int n = 0;                 // N per MMA (Cout tile)
   int n_tiles = 0;           // Cout / N
+  int pair = 0;              // 1: packed in N/2-row half tiles for the CTA-pair kernel (conv_pair_tc.cuh):
+                             //    [phase][2 * n_tile + half][tap][panel][N/2][64]; tile_bytes = one half tile
   int n_phases = 0;          // 1 for Conv1d, stride for ConvTranspose1d
   int cin_pad = 0;           // Cin rounded up to 16
   int n_taps[kTcMaxPhases] = {0};
