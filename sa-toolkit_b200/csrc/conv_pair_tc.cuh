@@ -18,7 +18,7 @@
 //   * every TMA load (A and W, both CTAs) completes on the LEADER's (rank 0) a_full / w_full barriers
 //     (.cta_group::2 loads may signal the peer CTA's barrier); the leader's elected MMA lane issues
 //     tcgen05.mma.cta_group::2 and releases smem slots / publishes accumulators in BOTH CTAs with multicast commits.
-//   * each CTA's 8 epilogue warps drain their own TMEM (their 128 rows x N columns) and arrive on the leader's
+//   * each CTA's 16 epilogue warps drain their own TMEM (their 128 rows x N columns) and arrive on the leader's
 //     acc_empty barrier (remote mbarrier.arrive for the peer).
 #pragma once
 #include "conv_tc.cuh"
@@ -31,34 +31,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default (.release.cta) semantics on purpose: a
+// .release.cluster arrive makes the warp wait (MEMBAR) until all its earlier global stores are performed, which
+// serialised the epilogue behind its own output stores (ncu: membar stall, profiles/README.md).  The hand-back only
+// has to order the TMEM reads, and tcgen05.fence::before_thread_sync does that.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag) {
-  if (mbar_try_wait_cluster(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      if (error_flag) atomicExch(error_flag, 1);
-      return false;
-    }
-  }
-  return true;
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA loads of a CTA pair: data into this CTA's shared memory, completion bytes onto `bar` (a shared::cluster
 // address, here always the leader's barrier).
@@ -101,10 +79,15 @@ __device__ __forceinline__ uint32_t make_idesc_pair(int n, bool bf16) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
+// 16 epilogue warps (four per TMEM lane group, each a quarter of the N columns): the epilogue of the wide layers is
+// what the MMA waits for (residual reads + three output streams), and twice the warps keep twice the loads in flight.
+constexpr int kPairEpiWarps = 16;
+constexpr int kPairThreads = (kPairEpiWarps + 3) * 32;   // + A producer, W producer, MMA issuer
+
 // Dynamic smem (identical layout in both CTAs -- the MMA addresses both through one descriptor):
 //   [A ring: n_abuf * (cin/64) * rows_alloc * 128][W ring: n_wstages * stage rows * 128][bias N*4][barriers][tmem holder]
 template <int N, int MSUB>
-__global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
   // first 128-byte row of this CTA's half tile inside the packed weight buffer
   const int w_row0 = (int)(((size_t)(phase * p.n_tiles + ntile) * 2 + crank) * (p.w_tile_bytes / row_bytes));
 
-  constexpr int kWarpA = kEpiWarps, kWarpW = kEpiWarps + 1, kWarpMma = kEpiWarps + 2;
+  constexpr int kWarpA = kPairEpiWarps, kWarpW = kPairEpiWarps + 1, kWarpMma = kPairEpiWarps + 2;
   if (warp == kWarpA && lane == 0) {
     prefetch_tmap(&p.tmap);
     prefetch_tmap(&p.wmap);
@@ -150,13 +133,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       mbar_init(bar_a_full(i), 1);                 // leader: its producer's arrive.expect_tx (bytes of both CTAs)
       mbar_init(bar_a_empty(i), 1);                // multicast commit
       mbar_init(bar_acc_full(i), 1);               // multicast commit
-      mbar_init(bar_acc_empty(i), 2 * kEpiWarps);  // leader: epilogue warps of both CTAs
+      mbar_init(bar_acc_empty(i), 2 * kPairEpiWarps);  // leader: epilogue warps of both CTAs
     }
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc_pair(smem_u32(tmem_holder), kTmemCols);
-  for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = p.bias[ntile * N + i];
+  for (int i = threadIdx.x; i < N; i += kPairThreads) bias_s[i] = p.bias[ntile * N + i];
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                              // both CTAs' barriers and TMEM exist before any cross-CTA signal
@@ -229,9 +212,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         const int acc = it & 1, acc_use = it >> 1;
         long long tq = timing ? clock64() : 0;
-        if (acc_use > 0) ok = mbar_wait_cluster(bar_acc_empty(acc), (acc_use - 1) & 1, p.error_flag);
+        if (acc_use > 0) ok = mbar_wait(bar_acc_empty(acc), (acc_use - 1) & 1, p.error_flag);
         if (timing) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
-        if (ok) ok = mbar_wait_cluster(bar_a_full(buf), use & 1, p.error_flag);
+        if (ok) ok = mbar_wait(bar_a_full(buf), use & 1, p.error_flag);
         if (timing) t_a += clock64() - tq;
         if (!ok) break;
         tc_fence_after();
@@ -242,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
         for (int i = 0; i < n_iters; ++i) {
           const long long tw0 = timing ? clock64() : 0;
           const int slot = wslot;
-          ok = mbar_wait_cluster(bar_w_full(slot), wpar, p.error_flag);
+          ok = mbar_wait(bar_w_full(slot), wpar, p.error_flag);
           if (++wslot == p.n_wstages) { wslot = 0; wpar ^= 1u; }
           if (timing) t_w += clock64() - tw0;
           if (!ok) break;
@@ -281,99 +264,115 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_con
       }
     }
   } else {
-    // ===== epilogue (both CTAs): own TMEM lanes; identical to conv_tc.cuh but for the acc_empty arrive =====
+    // ===== epilogue (both CTAs): own TMEM lanes; the arithmetic is conv_tc.cuh's =====
+    // A warp owns 32 rows x N/4 columns of every sub-tile: U = MSUB * N/64 units of 16 columns per tile.  The
+    // residual reads do not depend on the MMA: the lines of the NEXT tile are prefetched into L2 while this tile is
+    // processed (no registers), and inside a tile the registers of unit u+1 are loaded (from L2) under unit u.
     const int lg = warp & 3;
-    const int half = warp >> 2;
-    constexpr int kColsPerWarp = N / 2;
-    const int col0 = half * kColsPerWarp;
+    const int quarter = warp >> 2;
+    constexpr int kColsPerWarp = N / 4;
+    constexpr int kGroups = kColsPerWarp / 16;
+    constexpr int U = MSUB * kGroups;
+    const int col0 = quarter * kColsPerWarp;
     const bool bf16 = (p.flags & EPI_BF16) != 0;
     const int cchunks_total = p.cout_total >> 3;
     const int opc = p.out_pw >> 3;
     const int opanels = p.cout_total / p.out_pw;
     const uint32_t flags = p.flags;
+    const bool has_res = (flags & EPI_RES) != 0;
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_full = 0, t_begin = timing ? clock64() : 0;
+    const int row_in_tile = lg * 32 + lane;
+    // element index of (item b, n-tile channel chunk c8, output row orow) in the fp32 blocked tensors
+    auto idx32 = [&](int b, int c8, size_t orow) {
+      return (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
+    };
+    float4 qr[2][4];
+    // residual of unit u of round `round`: into registers (q != nullptr) or just into L2
+    auto fetch_res = [&](int round, int u, float4* q) {
+      if (!has_res || round >= n_rounds || is_dummy(round)) return;
+      const int tile = tile_of(round);
+      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+      const int t = m0 + (u / kGroups) * 128 + row_in_tile;
+      if (t >= p.m_rows) return;
+      const size_t i0 = idx32(b, (col0 >> 3) + (u % kGroups) * 2, (size_t)t * p.out_stride + phase);
+      const size_t i1 = i0 + (size_t)p.l_out * 8;
+      if (q) {
+        q[0] = ldg_f4(p.res32 + i0); q[1] = ldg_f4(p.res32 + i0 + 4);
+        q[2] = ldg_f4(p.res32 + i1); q[3] = ldg_f4(p.res32 + i1 + 4);
+      } else {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res32 + i0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res32 + i1));
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) fetch_res(0, u, nullptr);
     for (int it = 0; it < n_rounds; ++it) {
       const int tile = tile_of(it);
       const bool dummy = is_dummy(it);
       const int acc = it & 1, acc_use = it >> 1;
+#pragma unroll
+      for (int u = 0; u < U; ++u) fetch_res(it + 1, u, nullptr);
+      fetch_res(it, 0, qr[0]);
       const long long tf0 = timing ? clock64() : 0;
       if (!mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
       if (timing) t_full += clock64() - tf0;
       tc_fence_after();
       const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
 #pragma unroll
-      for (int ms = 0; ms < MSUB; ++ms) {
-        const int t = m0 + ms * 128 + lg * 32 + lane;
+      for (int u = 0; u < U; ++u) {
+        const int ms = u / kGroups, g = u % kGroups;
+        const int t = m0 + ms * 128 + row_in_tile;
         const bool valid = t < p.m_rows && !dummy;
         const size_t orow = (size_t)t * p.out_stride + phase;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0);
-        constexpr int kGroups = kColsPerWarp / 16;
-        constexpr int kBatch = 4;
-#pragma unroll 1
-        for (int g0 = 0; g0 < kGroups; g0 += kBatch) {
-          float4 qr[kBatch][4];
-          if (valid && (flags & EPI_RES)) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0 + g * 16);
+        uint32_t r[16];
+        __syncwarp();                                        // tcgen05.ld is .sync.aligned
+        tmem_ld16(t_addr, r);
+        const int c8 = (col0 >> 3) + g * 2;                  // first channel chunk inside this n-tile
+        const size_t idx0 = idx32(b, c8, orow);
+        const size_t idx1 = idx0 + (size_t)p.l_out * 8;
+        float4 qs[4];
+        if (valid && (flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
+          qs[0] = ldg_f4(p.sum32 + idx0); qs[1] = ldg_f4(p.sum32 + idx0 + 4);
+          qs[2] = ldg_f4(p.sum32 + idx1); qs[3] = ldg_f4(p.sum32 + idx1 + 4);
+        }
+        tmem_ld_wait();
+        float v[16];
 #pragma unroll
-            for (int gi = 0; gi < kBatch; ++gi) {
-              const int c8 = (col0 >> 3) + (g0 + gi) * 2;
-              const size_t i0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
-              const size_t i1 = i0 + (size_t)p.l_out * 8;
-              qr[gi][0] = ldg_f4(p.res32 + i0); qr[gi][1] = ldg_f4(p.res32 + i0 + 4);
-              qr[gi][2] = ldg_f4(p.res32 + i1); qr[gi][3] = ldg_f4(p.res32 + i1 + 4);
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
+        if (u + 1 < U) fetch_res(it, u + 1, qr[(u + 1) & 1]);
+        if (valid && has_res) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) { v[4 * h] += qr[u & 1][h].x; v[4 * h + 1] += qr[u & 1][h].y; v[4 * h + 2] += qr[u & 1][h].z; v[4 * h + 3] += qr[u & 1][h].w; }
+        }
+        if (valid) {
+          if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
             }
           }
+          if (flags & EPI_SUM_FIN) {
 #pragma unroll
-          for (int gi = 0; gi < kBatch; ++gi) {
-            const int g = g0 + gi;
-            uint32_t r[16];
-            __syncwarp();
-            tmem_ld16(t_addr + (uint32_t)(g * 16), r);
-            const int c8 = (col0 >> 3) + g * 2;
-            const size_t idx0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
-            const size_t idx1 = idx0 + (size_t)p.l_out * 8;
-            float4 qs[4];
-            if (valid && (flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
-              qs[0] = ldg_f4(p.sum32 + idx0); qs[1] = ldg_f4(p.sum32 + idx0 + 4);
-              qs[2] = ldg_f4(p.sum32 + idx1); qs[3] = ldg_f4(p.sum32 + idx1 + 4);
-            }
-            tmem_ld_wait();
-            if (valid) {
-              float v[16];
+            for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;            // xs / num_kernels
+          }
+          if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
+            stg_f4(p.sum32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx0 + 4, v[4], v[5], v[6], v[7]);
+            stg_f4(p.sum32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + idx1 + 4, v[12], v[13], v[14], v[15]);
+          }
+          if (flags & EPI_OUT32) {
+            stg_f4(p.out32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx0 + 4, v[4], v[5], v[6], v[7]);
+            stg_f4(p.out32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + idx1 + 4, v[12], v[13], v[14], v[15]);
+          }
+          if (flags & EPI_OUT16) {
+            float lo[8], hi8[8];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
-              if (flags & EPI_RES) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) { v[4 * h] += qr[gi][h].x; v[4 * h + 1] += qr[gi][h].y; v[4 * h + 2] += qr[gi][h].z; v[4 * h + 3] += qr[gi][h].w; }
-              }
-              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
-                }
-              }
-              if (flags & EPI_SUM_FIN) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;
-              }
-              if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-                stg_f4(p.sum32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx0 + 4, v[4], v[5], v[6], v[7]);
-                stg_f4(p.sum32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + idx1 + 4, v[12], v[13], v[14], v[15]);
-              }
-              if (flags & EPI_OUT32) {
-                stg_f4(p.out32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx0 + 4, v[4], v[5], v[6], v[7]);
-                stg_f4(p.out32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + idx1 + 4, v[12], v[13], v[14], v[15]);
-              }
-              if (flags & EPI_OUT16) {
-                float lo[8], hi8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
-                const int cg = ntile * (N / 8) + c8;
-                const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(lo, p.slope_out, true, bf16);
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8_lrelu(hi8, p.slope_out, true, bf16);
-              }
-            }
+            for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
+            const int cg = ntile * (N / 8) + c8;               // chunk index in the output tensor (even)
+            const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(lo, p.slope_out, true, bf16);
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8_lrelu(hi8, p.slope_out, true, bf16);
           }
         }
       }

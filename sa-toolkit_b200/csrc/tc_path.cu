@@ -445,7 +445,7 @@ cudaError_t launch_pair(const tc::ConvParams& p, int grid_y, size_t smem, int n_
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(tc::kThreads, 1, 1);
+  cfg.blockDim = dim3(tc::kPairThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cfg.attrs = at;

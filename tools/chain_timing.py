@@ -28,3 +28,13 @@ for i in range(n):
     v = [buf[i * 16 + j] / 148.0 for j in range(10)]
     tot = v[0] or 1.0
     print(f"launch {i:2d} " + " ".join(f"{val/1e3:7.0f}k({100*val/ (tot if j < 4 else (v[4] or 1)):3.0f}%)" for j, val in enumerate(v)))
+
+# Per-launch device time of the same forward (CUDA events) next to the MMA-warp cycle count: cycles / time is
+# the SM clock the kernel actually ran at (clock64 counts SM cycles; under a power cap it is well below the
+# nominal 1965 MHz), and the difference to the in-kernel total is launch + ramp + tail overhead.
+prof = gen.profile(x, repeats=3)
+kern = [(t, ms) for t, ms in prof if (t % 16) != 15 and t < 16 * 6]      # drop pack_input and the tail
+print("launch  tag   event_ms   mma_total_kcycles   implied_MHz")
+for i, (t, ms) in enumerate(kern[:n]):
+    cyc = buf[i * 16 + 0] / 148.0
+    print(f"{i:4d} {t:5d} {ms:9.4f} {cyc/1e3:12.0f} {cyc / (ms * 1e3) if ms > 0 else 0:12.0f}")
