@@ -560,6 +560,9 @@ struct Runner {
     p.total_tiles = p.m_tiles * a.B;
     p.w_tile_bytes = (uint32_t)w.tile_bytes;
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+    // diagnostics only (results become wrong): drop epilogue streams to time what each costs
+    static const uint32_t dbg_mask = getenv("SATOOLS_B200_DEBUG_EPI_MASK") ? (uint32_t)strtoul(getenv("SATOOLS_B200_DEBUG_EPI_MASK"), nullptr, 16) : 0u;
+    p.flags &= ~dbg_mask;
     p.slope_out = e.slope_out;
     p.n_blocks = e.n_blocks;
     mark(tag);
