@@ -84,22 +84,6 @@ __device__ __forceinline__ uint32_t make_idesc_pair(int n, bool bf16) {
 constexpr int kPairEpiWarps = 16;
 constexpr int kPairThreads = (kPairEpiWarps + 3) * 32;   // + A producer, W producer, MMA issuer
 
-// 4 x 4 transpose of 16-byte items inside every aligned group of four lanes: on entry lane j (= lane & 3) holds
-// a[k] = item (row j, piece k); on exit a[k] = item (row k, piece j).  Two butterfly rounds, 16 SHFL.
-__device__ __forceinline__ uint4 shfl_xor_u4(uint4 x, int m) {
-  x.x = __shfl_xor_sync(0xffffffffu, x.x, m); x.y = __shfl_xor_sync(0xffffffffu, x.y, m);
-  x.z = __shfl_xor_sync(0xffffffffu, x.z, m); x.w = __shfl_xor_sync(0xffffffffu, x.w, m);
-  return x;
-}
-__device__ __forceinline__ void quad_transpose(uint4 (&a)[4], int j) {
-  const bool b0 = (j & 1) != 0, b1 = (j & 2) != 0;
-  uint4 r;
-  r = shfl_xor_u4(b0 ? a[0] : a[1], 1); if (b0) a[0] = r; else a[1] = r;
-  r = shfl_xor_u4(b0 ? a[2] : a[3], 1); if (b0) a[2] = r; else a[3] = r;
-  r = shfl_xor_u4(b1 ? a[0] : a[2], 2); if (b1) a[0] = r; else a[2] = r;
-  r = shfl_xor_u4(b1 ? a[1] : a[3], 2); if (b1) a[1] = r; else a[3] = r;
-}
-
 // Dynamic smem (identical layout in both CTAs -- the MMA addresses both through one descriptor):
 //   [A ring: n_abuf * (cin/64) * rows_alloc * 128][W ring: n_wstages * stage rows * 128][bias N*4][barriers][tmem holder]
 template <int N, int MSUB>
@@ -280,127 +264,24 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
       }
     }
   } else {
-    // ===== epilogue (both CTAs): own TMEM lanes; the arithmetic is conv_tc.cuh's =====
-    // A warp owns 32 rows x N/4 columns of every sub-tile: U = MSUB * N/64 units of 16 columns per tile.  All
-    // addresses are one 64-bit base per (tile, sub-tile) plus small strides: the first version recomputed the
-    // blocked-tensor indices per unit and spent ~200 issued instructions per unit on it (ncu, profiles/README.md).
+    // ===== epilogue (both CTAs): own TMEM lanes, a quarter of the N columns per warp (epi_tile, conv_tc.cuh) =====
     const int lg = warp & 3;
-    const int quarter = warp >> 2;
-    constexpr int kColsPerWarp = N / 4;
-    constexpr int kGroups = kColsPerWarp / 16;
-    constexpr int U = MSUB * kGroups;
-    static_assert(kGroups % 2 == 0, "units are stored in pairs");
-    const int col0 = quarter * kColsPerWarp;
-    const bool bf16 = (p.flags & EPI_BF16) != 0;
-    const uint32_t flags = p.flags;
-    const bool has_res = (flags & EPI_RES) != 0;
-    const bool has_sum_in = (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) != 0;
+    const int col0 = (warp >> 2) * (N / 4);
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_full = 0, t_begin = timing ? clock64() : 0;
-    const int row_in_tile = lg * 32 + lane;
-    const int j4 = lane & 3;
-    const int m_rows = p.m_rows, out_stride = p.out_stride;
-    const size_t l_out = (size_t)p.l_out;
-    const size_t plane = l_out * 8;                          // floats between consecutive 8-channel chunks (fp32 tensors)
-    const int chunk0 = ntile * (N / 8) + (col0 >> 3);        // first 8-channel chunk of this warp in the output tensor
-    const int cchunks_total = p.cout_total >> 3;
-    // 16-bit output: 64-channel panels of 128-byte rows (Cout >= 128 here); this lane stores chunk (chunk0 + 4h + j4)
-    const size_t panel16 = l_out * 128;
-    const float* const res32 = p.res32;
-    const float* const sum_in = p.sum32;
-    float* const sum32 = p.sum32;
-    float* const out32 = p.out32;
-    uint8_t* const out16 = static_cast<uint8_t*>(p.out16);
-    float4 qr[2][4];
-    uint4 pk[4];                                             // 16-bit output of two consecutive units: 64 bytes of this row
     for (int it = 0; it < n_rounds; ++it) {
       const int acc = it & 1, acc_use = it >> 1;
-      const bool dummy = is_dummy(it);
       const int tile = tile_of(it);
       const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
-      const int t0 = m0 + row_in_tile;
-      // fp32 element offset of (item b, chunk0, output row of sub-tile 0); sub-tile ms adds ms * 128 * out_stride rows
-      const size_t base32 = (((size_t)b * cchunks_total + chunk0) * l_out + (size_t)t0 * out_stride + phase) * 8;
-      const size_t ms_step32 = (size_t)128 * out_stride * 8;
-      auto fetch_res = [&](int u, float4 (&q)[4]) {
-        const int ms = u / kGroups, g = u % kGroups;
-        if (!has_res || dummy || t0 + ms * 128 >= m_rows) return;
-        const float* a0 = res32 + base32 + ms * ms_step32 + (size_t)(2 * g) * plane;
-        const float* a1 = a0 + plane;
-        q[0] = ldg_f4(a0); q[1] = ldg_f4(a0 + 4); q[2] = ldg_f4(a1); q[3] = ldg_f4(a1 + 4);
+      auto wait_acc = [&]() {
+        const long long tf0 = timing ? clock64() : 0;
+        const bool ok = mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag);
+        if (timing) t_full += clock64() - tf0;
+        return ok;
       };
-      fetch_res(0, qr[0]);                                   // does not depend on the accumulator
-      const long long tf0 = timing ? clock64() : 0;
-      if (!mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
-      if (timing) t_full += clock64() - tf0;
-      tc_fence_after();
-      if (!dummy) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int ms = u / kGroups, g = u % kGroups;
-          const int t = t0 + ms * 128;
-          const bool valid = t < m_rows;
-          const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0 + g * 16);
-          uint32_t r[16];
-          __syncwarp();                                        // tcgen05.ld is .sync.aligned
-          tmem_ld16(t_addr, r);
-          const size_t i0 = base32 + ms * ms_step32 + (size_t)(2 * g) * plane, i1 = i0 + plane;
-          float4 qs[4];
-          if (valid && has_sum_in) {
-            qs[0] = ldg_f4(sum_in + i0); qs[1] = ldg_f4(sum_in + i0 + 4);
-            qs[2] = ldg_f4(sum_in + i1); qs[3] = ldg_f4(sum_in + i1 + 4);
-          }
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
-          if (u + 1 < U) fetch_res(u + 1, qr[(u + 1) & 1]);
-          if (valid) {
-            if (has_res) {
-#pragma unroll
-              for (int h = 0; h < 4; ++h) { v[4 * h] += qr[u & 1][h].x; v[4 * h + 1] += qr[u & 1][h].y; v[4 * h + 2] += qr[u & 1][h].z; v[4 * h + 3] += qr[u & 1][h].w; }
-            }
-            if (has_sum_in) {
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
-              }
-            }
-            if (flags & EPI_SUM_FIN) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;            // xs / num_kernels
-            }
-            if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-              stg_f4(sum32 + i0, v[0], v[1], v[2], v[3]); stg_f4(sum32 + i0 + 4, v[4], v[5], v[6], v[7]);
-              stg_f4(sum32 + i1, v[8], v[9], v[10], v[11]); stg_f4(sum32 + i1 + 4, v[12], v[13], v[14], v[15]);
-            }
-            if (flags & EPI_OUT32) {
-              stg_f4(out32 + i0, v[0], v[1], v[2], v[3]); stg_f4(out32 + i0 + 4, v[4], v[5], v[6], v[7]);
-              stg_f4(out32 + i1, v[8], v[9], v[10], v[11]); stg_f4(out32 + i1 + 4, v[12], v[13], v[14], v[15]);
-            }
-          }
-          if (flags & EPI_OUT16) {
-            // Thread-per-row stores put every lane of a warp store into a different 128-byte line (32 L1 wavefronts
-            // per instruction).  The 64 bytes a thread holds after two units are transposed inside lane quads
-            // instead, so one instruction writes 64 contiguous bytes of 8 rows.
-            float lo[8], hi8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
-            pk[(u & 1) * 2] = pack8_lrelu(lo, p.slope_out, true, bf16);
-            pk[(u & 1) * 2 + 1] = pack8_lrelu(hi8, p.slope_out, true, bf16);
-            if (u & 1) {
-              quad_transpose(pk, j4);
-              const int cg = chunk0 + (g - 1) * 2 + j4;          // this lane's 8-channel chunk of the output row
-              const int tq = t - j4;                             // row of the quad's first lane
-              uint8_t* o = out16 + ((size_t)b * (cchunks_total >> 3) + (cg >> 3)) * panel16 +
-                           ((size_t)tq * out_stride + phase) * 128 + (size_t)(cg & 7) * 16;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (tq + k < m_rows) *reinterpret_cast<uint4*>(o + (size_t)k * out_stride * 128) = pk[k];
-            }
-          }
-        }
-      }
+      if (!epi_tile<N, MSUB, N / 4>(p, bias_s, tmem_base + (uint32_t)(acc * kAccCols), b, m0, phase, ntile, lg, lane, col0,
+                                    is_dummy(it), wait_acc))
+        break;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(bar_acc_empty(acc), 0));   // the leader owns the accumulator hand-back

@@ -310,13 +310,154 @@ __device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, floa
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
+// 4 x 4 transpose of 16-byte items inside every aligned group of four lanes: on entry lane j (= lane & 3) holds
+// a[k] = item (row j, piece k); on exit a[k] = item (row k, piece j).  Two butterfly rounds, 16 SHFL.
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 x, int m) {
+  x.x = __shfl_xor_sync(0xffffffffu, x.x, m); x.y = __shfl_xor_sync(0xffffffffu, x.y, m);
+  x.z = __shfl_xor_sync(0xffffffffu, x.z, m); x.w = __shfl_xor_sync(0xffffffffu, x.w, m);
+  return x;
+}
+__device__ __forceinline__ void quad_transpose(uint4 (&a)[4], int j) {
+  const bool b0 = (j & 1) != 0, b1 = (j & 2) != 0;
+  uint4 r;
+  r = shfl_xor_u4(b0 ? a[0] : a[1], 1); if (b0) a[0] = r; else a[1] = r;
+  r = shfl_xor_u4(b0 ? a[2] : a[3], 1); if (b0) a[2] = r; else a[3] = r;
+  r = shfl_xor_u4(b1 ? a[0] : a[2], 2); if (b1) a[0] = r; else a[2] = r;
+  r = shfl_xor_u4(b1 ? a[1] : a[3], 2); if (b1) a[1] = r; else a[3] = r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Epilogue of one accumulator tile, shared by conv_tc_kernel and conv_pair_kernel.  The calling warp owns TMEM lanes
+// [32 lg, 32 lg + 32) = 32 output rows of every 128-row sub-tile, and COLS columns starting at col0 of the n-tile:
+// U = MSUB * COLS / 16 units of 16 columns.  Per unit: TMEM -> registers, + bias, + residual (fp32 stream),
+// multi-receptive-field sum, then the fp32 and / or 16-bit (leaky-ReLU'd) output streams.
+//   * All addresses are one 64-bit base per tile plus small strides (an earlier version recomputed the blocked-tensor
+//     indices per unit: ~200 issued instructions per unit, the epilogue was issue bound -- profiles/README.md).
+//   * The residual of unit u+1 is requested while unit u is processed; unit 0's before the accumulator is waited for.
+//   * 16-bit stores: thread-per-row stores put every lane of a warp store into a different 128-byte line.  When a
+//     thread ends up with 64 contiguous output bytes (two units), they are transposed inside lane quads instead, so
+//     one instruction writes 64 contiguous bytes of 8 rows.
+// wait_acc() is called after the first residual request and must return false on a barrier timeout.
+// ---------------------------------------------------------------------------------------
+template <int N, int MSUB, int COLS, typename WaitAcc>
+__device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_s, uint32_t tmem_acc, int b, int m0, int phase,
+                                         int ntile, int lg, int lane, int col0, bool dummy, WaitAcc&& wait_acc) {
+  constexpr int kGroups = COLS / 16;
+  constexpr int U = MSUB * kGroups;
+  constexpr bool kQuadStores = (kGroups % 2 == 0);
+  const uint32_t flags = p.flags;
+  const bool bf16 = (flags & EPI_BF16) != 0;
+  const bool has_res = (flags & EPI_RES) != 0;
+  const bool has_sum_in = (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) != 0;
+  const int m_rows = p.m_rows, out_stride = p.out_stride;
+  const size_t l_out = (size_t)p.l_out;
+  const size_t plane = l_out * 8;                            // floats between consecutive 8-channel chunks (fp32 tensors)
+  const int chunk0 = ntile * (N / 8) + (col0 >> 3);          // first 8-channel chunk of this warp in the output tensor
+  const int cchunks_total = p.cout_total >> 3;
+  const int t0 = m0 + lg * 32 + lane;
+  // fp32 element offset of (item b, chunk0, output row of sub-tile 0); sub-tile ms adds 128 * out_stride rows
+  const size_t base32 = (((size_t)b * cchunks_total + chunk0) * l_out + (size_t)t0 * out_stride + phase) * 8;
+  const size_t ms_step32 = (size_t)128 * out_stride * 8;
+  // 16-bit output [B][Cout / out_pw][L][out_pw]: rows of row16 bytes, opc chunks of 16 bytes per row
+  const int opc_shift = p.out_pw >= 64 ? 3 : p.out_pw >= 32 ? 2 : 1;
+  const size_t row16 = (size_t)p.out_pw * 2;
+  const size_t panel16 = l_out * row16;
+  const size_t item16 = (size_t)(cchunks_total >> opc_shift) * panel16;
+  uint8_t* const out16 = static_cast<uint8_t*>(p.out16);
+  // narrow tiles (one unit per sub-tile) run two CTAs per SM on a tight register budget: no load-ahead there
+  constexpr int QB = kQuadStores ? 2 : 1;
+  float4 qr[QB][4];
+  uint4 pk[kQuadStores ? 4 : 1];
+  auto fetch_res = [&](int u, float4 (&q)[4]) {
+    const int ms = u / kGroups, g = u % kGroups;
+    if (!has_res || dummy || t0 + ms * 128 >= m_rows) return;
+    const float* a0 = p.res32 + base32 + ms * ms_step32 + (size_t)(2 * g) * plane;
+    const float* a1 = a0 + plane;
+    q[0] = ldg_f4(a0); q[1] = ldg_f4(a0 + 4); q[2] = ldg_f4(a1); q[3] = ldg_f4(a1 + 4);
+  };
+  fetch_res(0, qr[0]);                                       // does not depend on the accumulator
+  if (!wait_acc()) return false;
+  tc_fence_after();
+  if (dummy) return true;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int ms = u / kGroups, g = u % kGroups;
+    const int t = t0 + ms * 128;
+    const bool valid = t < m_rows;
+    uint32_t r[16];
+    __syncwarp();                                            // tcgen05.ld is .sync.aligned
+    tmem_ld16(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ms * N + col0 + g * 16), r);
+    const size_t i0 = base32 + ms * ms_step32 + (size_t)(2 * g) * plane, i1 = i0 + plane;
+    float4 qs[4];
+    if (QB == 1 && u > 0) fetch_res(u, qr[0]);
+    if (valid && has_sum_in) {
+      qs[0] = ldg_f4(p.sum32 + i0); qs[1] = ldg_f4(p.sum32 + i0 + 4);
+      qs[2] = ldg_f4(p.sum32 + i1); qs[3] = ldg_f4(p.sum32 + i1 + 4);
+    }
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
+    if (QB == 2 && u + 1 < U) fetch_res(u + 1, qr[(u + 1) % QB]);
+    if (valid) {
+      if (has_res) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { v[4 * h] += qr[u % QB][h].x; v[4 * h + 1] += qr[u % QB][h].y; v[4 * h + 2] += qr[u % QB][h].z; v[4 * h + 3] += qr[u % QB][h].w; }
+      }
+      if (has_sum_in) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w; }
+      }
+      if (flags & EPI_SUM_FIN) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;              // xs / num_kernels
+      }
+      if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
+        stg_f4(p.sum32 + i0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + i0 + 4, v[4], v[5], v[6], v[7]);
+        stg_f4(p.sum32 + i1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + i1 + 4, v[12], v[13], v[14], v[15]);
+      }
+      if (flags & EPI_OUT32) {
+        stg_f4(p.out32 + i0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + i0 + 4, v[4], v[5], v[6], v[7]);
+        stg_f4(p.out32 + i1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + i1 + 4, v[12], v[13], v[14], v[15]);
+      }
+    }
+    if (flags & EPI_OUT16) {
+      float lo[8], hi8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
+      if constexpr (kQuadStores) {
+        pk[(u & 1) * 2] = pack8_lrelu(lo, p.slope_out, true, bf16);
+        pk[(u & 1) * 2 + 1] = pack8_lrelu(hi8, p.slope_out, true, bf16);
+        if (u & 1) {                                         // N >= 64 here, so rows are 128 bytes (out_pw = 64)
+          const int j4 = lane & 3;
+          quad_transpose(pk, j4);
+          const int cg = chunk0 + (g - 1) * 2 + j4;          // this lane's 8-channel chunk of the output row
+          const int tq = t - j4;                             // row of the quad's first lane
+          uint8_t* o = out16 + (size_t)b * item16 + (size_t)(cg >> 3) * panel16 + ((size_t)tq * out_stride + phase) * 128 +
+                       (size_t)(cg & 7) * 16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (tq + k < m_rows) *reinterpret_cast<uint4*>(o + (size_t)k * out_stride * 128) = pk[k];
+        }
+      } else if (valid) {
+        const int cg = chunk0 + g * 2;                       // even chunk; cg and cg + 1 share a panel row
+        uint8_t* o = out16 + (size_t)b * item16 + (size_t)(cg >> opc_shift) * panel16 +
+                     ((size_t)t * out_stride + phase) * row16 + (size_t)(cg & ((1 << opc_shift) - 1)) * 16;
+        *reinterpret_cast<uint4*>(o) = pack8_lrelu(lo, p.slope_out, true, bf16);
+        *reinterpret_cast<uint4*>(o + 16) = pack8_lrelu(hi8, p.slope_out, true, bf16);
+      }
+    }
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------
 // The kernel.  grid = (persistent CTAs, n_phases * n_tiles).  Dynamic smem:
 //   [A ring: n_abuf * (cin/pw) * rows_alloc * 2pw][W ring: n_wstages * k16_per_stage * N * 32]
 //   [bias N*4][barriers][tmem holder]      (base rounded up to 1024 B: swizzle pattern anchor)
 // ---------------------------------------------------------------------------------------
 template <int N, int MSUB, int PW>
-__global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -521,108 +662,27 @@ __global__ void __launch_bounds__(kThreads, (N <= 64) ? 2 : 1) conv_tc_kernel(co
       }
     }
   } else {
-    // ===== epilogue: warps 0..7; TMEM lane group = warp % 4; column half = warp / 4 =====
+    // ===== epilogue: warps 0..7; TMEM lane group = warp % 4; column half = warp / 4 (epi_tile above) =====
     const int lg = warp & 3;
     const int half = warp >> 2;
     constexpr int kColsPerWarp = (N >= 32) ? N / 2 : N;            // N = 16: only half 0 has columns
     const bool has_cols = (N >= 32) || half == 0;
     const int col0 = (N >= 32) ? half * kColsPerWarp : 0;
-    const bool bf16 = (p.flags & EPI_BF16) != 0;
-    const int cchunks_total = p.cout_total >> 3;
-    const int opc = p.out_pw >> 3;                                 // 8-channel chunks per output panel row
-    const int opanels = p.cout_total / p.out_pw;
-    const uint32_t flags = p.flags;
-    int it = 0;
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_full = 0, t_begin = timing ? clock64() : 0;
-    for (; it < my_rounds; ++it) {
+    for (int it = 0; it < my_rounds; ++it) {
       const int tile = tile_of(it);
-      const bool dummy = is_dummy(it);
       const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
-      const long long tf0 = timing ? clock64() : 0;
-      if (!mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag)) break;
-      if (timing) t_full += clock64() - tf0;
-      tc_fence_after();
       const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
-      if (has_cols) {
-#pragma unroll
-        for (int ms = 0; ms < MSUB; ++ms) {
-          const int t = m0 + ms * 128 + lg * 32 + lane;            // output row on the M axis
-          const bool valid = t < p.m_rows && !dummy;
-          const size_t orow = (size_t)t * p.out_stride + phase;
-          const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * kAccCols + ms * N + col0);
-          // The residual of up to 64 columns (4 groups) is requested before the first TMEM round trip, so a
-          // tile costs kColsPerWarp/64 dependent HBM latencies per sub-tile instead of kColsPerWarp/16.
-          constexpr int kGroups = kColsPerWarp / 16;
-          constexpr int kBatch = kGroups < 4 ? kGroups : 4;
-#pragma unroll 1
-          for (int g0 = 0; g0 < kGroups; g0 += kBatch) {
-            float4 qr[kBatch][4];
-            if (valid && (flags & EPI_RES)) {
-#pragma unroll
-              for (int gi = 0; gi < kBatch; ++gi) {
-                const int c8 = (col0 >> 3) + (g0 + gi) * 2;
-                const size_t i0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
-                const size_t i1 = i0 + (size_t)p.l_out * 8;
-                qr[gi][0] = ldg_f4(p.res32 + i0); qr[gi][1] = ldg_f4(p.res32 + i0 + 4);
-                qr[gi][2] = ldg_f4(p.res32 + i1); qr[gi][3] = ldg_f4(p.res32 + i1 + 4);
-              }
-            }
-#pragma unroll
-            for (int gi = 0; gi < kBatch; ++gi) {
-              const int g = g0 + gi;
-              uint32_t r[16];
-              __syncwarp();                                        // tcgen05.ld is .sync.aligned
-              tmem_ld16(t_addr + (uint32_t)(g * 16), r);
-              const int c8 = (col0 >> 3) + g * 2;                  // first channel chunk inside this n-tile
-              const size_t idx0 = (((size_t)b * cchunks_total + (size_t)ntile * (N / 8) + c8) * (size_t)p.l_out + orow) * 8;
-              const size_t idx1 = idx0 + (size_t)p.l_out * 8;
-              float4 qs[4];
-              if (valid && (flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
-                qs[0] = ldg_f4(p.sum32 + idx0); qs[1] = ldg_f4(p.sum32 + idx0 + 4);
-                qs[2] = ldg_f4(p.sum32 + idx1); qs[3] = ldg_f4(p.sum32 + idx1 + 4);
-              }
-              tmem_ld_wait();
-              if (valid) {
-                float v[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bias_s[col0 + g * 16 + e];
-                if (flags & EPI_RES) {
-#pragma unroll
-                  for (int h = 0; h < 4; ++h) { v[4 * h] += qr[gi][h].x; v[4 * h + 1] += qr[gi][h].y; v[4 * h + 2] += qr[gi][h].z; v[4 * h + 3] += qr[gi][h].w; }
-                }
-                if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
-#pragma unroll
-                  for (int h = 0; h < 4; ++h) {
-                    v[4 * h] += qs[h].x; v[4 * h + 1] += qs[h].y; v[4 * h + 2] += qs[h].z; v[4 * h + 3] += qs[h].w;
-                  }
-                }
-                if (flags & EPI_SUM_FIN) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;            // xs / num_kernels
-                }
-                if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-                  stg_f4(p.sum32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx0 + 4, v[4], v[5], v[6], v[7]);
-                  stg_f4(p.sum32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + idx1 + 4, v[12], v[13], v[14], v[15]);
-                }
-                if (flags & EPI_OUT32) {
-                  stg_f4(p.out32 + idx0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx0 + 4, v[4], v[5], v[6], v[7]);
-                  stg_f4(p.out32 + idx1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + idx1 + 4, v[12], v[13], v[14], v[15]);
-                }
-                if (flags & EPI_OUT16) {
-                  float lo[8], hi[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi[e] = v[8 + e]; }
-                  const int cg = ntile * (N / 8) + c8;               // chunk index in the output tensor (even)
-                  const size_t o16 = ((((size_t)b * opanels + cg / opc) * (size_t)p.l_out + orow) * opc + cg % opc) * 16;
-                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(lo, p.slope_out, true, bf16);
-                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16 + 16) = pack8_lrelu(hi, p.slope_out, true, bf16);
-                }
-              }
-            }
-          }
-        }
-      }
+      auto wait_acc = [&]() {
+        const long long tf0 = timing ? clock64() : 0;
+        const bool ok = mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag);
+        if (timing) t_full += clock64() - tf0;
+        return ok;
+      };
+      if (!epi_tile<N, MSUB, kColsPerWarp>(p, bias_s, tmem_base + (uint32_t)(acc * kAccCols), b, m0, phase, ntile, lg, lane,
+                                           col0, is_dummy(it) || !has_cols, wait_acc))
+        break;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(acc));              // this warp is done with the accumulator buffer
