@@ -582,7 +582,9 @@ struct Runner {
     const int C = ch[0].c;
     if ((C != 16 && C != 32) || ch[0].k != 3 || ch[1].k != 7 || ch[2].k != 11) return nullptr;
     if (ch[0].n_convs != ch[1].n_convs || ch[0].n_convs != ch[2].n_convs) return nullptr;
-    const int ms = (C == 16) ? 4 : 3;
+    // sub-tiles per CTA: more rows per tile amortise the 2 x halo recomputed rows, until registers run out
+    static const int ms16 = getenv("SATOOLS_B200_CHAIN3_MS16") ? atoi(getenv("SATOOLS_B200_CHAIN3_MS16")) : 5;   // measured: 4 -> 5.5 ms, 5 -> 5.15, 6 -> 5.2 (spills)
+    const int ms = (C == 16) ? ((ms16 >= 4 && ms16 <= 6) ? ms16 : 5) : 3;
     const int halo = std::max(ch[0].halo, std::max(ch[1].halo, ch[2].halo));
     const int valid = ms * 128 - 2 * halo;
     if (valid < 64 || L < 2 * valid) return nullptr;
@@ -602,7 +604,10 @@ struct Runner {
     p.flags = (e.flags & (tc::EPI_OUT32 | tc::EPI_OUT16)) | (a.bf16 ? tc::EPI_BF16 : 0u);
     p.slope_out = e.slope_out;
     mark(tag);
-    cudaError_t ce = (C == 16) ? launch_chain3<16, 4>(p, smem, a.n_sm, a.stream) : launch_chain3<32, 3>(p, smem, a.n_sm, a.stream);
+    cudaError_t ce = (C == 32) ? launch_chain3<32, 3>(p, smem, a.n_sm, a.stream)
+                     : (ms == 6) ? launch_chain3<16, 6>(p, smem, a.n_sm, a.stream)
+                     : (ms == 5) ? launch_chain3<16, 5>(p, smem, a.n_sm, a.stream)
+                                 : launch_chain3<16, 4>(p, smem, a.n_sm, a.stream);
     if (ce != cudaSuccess) return msgf("stage_chain3 launch: %s", cudaGetErrorString(ce));
     ++*launches;
     *done = true;
