@@ -60,14 +60,19 @@ def load_peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes of one forward of this workload from the committed ncu launch list (dram__bytes_read.sum +
-    dram__bytes_write.sum summed over the launches of one step); None when the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_launches_fp16_v9_summary.txt")
+    """DRAM bytes of one forward of this workload from the newest committed ncu launch list (dram__bytes_read.sum +
+    dram__bytes_write.sum summed over the launches of one step); None when no summary is present."""
+    import glob
+    import re
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_launches_fp16_v*_summary.txt")):
+        m = re.search(r"r(\d+)_launches_fp16_v(\d+)_summary", path)
+        if m and (best is None or (int(m.group(1)), int(m.group(2))) > best[0]):
+            best = ((int(m.group(1)), int(m.group(2))), path)
     try:
-        import re
-        m = re.search(r"DRAM traffic ([0-9.]+) GB", open(path).read())
+        m = re.search(r"DRAM traffic ([0-9.]+) GB", open(best[1]).read())
         return {"traffic": float(m.group(1)) * 1e9, "traffic_unit": "bytes per step (ncu, all launches of one forward)",
-                "traffic_source": "profiles/r1_launches_fp16_v9_summary.txt"}
+                "traffic_source": os.path.relpath(best[1], ROOT)}
     except Exception:
         return {"traffic": None}
 

@@ -88,7 +88,6 @@ struct ConvParams {
   int n_wstages;            // weight ring depth
   int w_resident;           // 1: all weight stages stay in smem (loaded once per CTA)
   int n_abuf;               // A-tile ring depth (1 or 2)
-  int cluster;              // 1: launched as 2-CTA clusters; weight stages are multicast (each CTA loads half)
   int m_tiles;              // time tiles per item
   int total_tiles;          // m_tiles * B
   uint32_t w_tile_bytes;
@@ -172,18 +171,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
-}
-// Multicast variants for 2-CTA clusters: the data lands at the same CTA-relative offset in every CTA of
-// `mask`, and so does the mbarrier complete_tx / arrive.
-__device__ __forceinline__ void bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -502,22 +489,18 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
       mbar_init(bar_acc_full(i), 1);
       mbar_init(bar_acc_empty(i), kEpiWarps);
     }
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), p.cluster ? 2 : 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = p.bias[ntile * N + i];
   tc_fence_before();
   __syncthreads();
-  if (p.cluster) cluster_sync_all();              // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  // In cluster mode both CTAs of a pair must run the same number of tiles (they share the weight ring's pace):
-  // every CTA runs n_rounds rounds; a round past the end recomputes the last tile without storing it.
-  const int n_rounds = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_of = [&](int round) { return min((int)blockIdx.x + round * (int)gridDim.x, p.total_tiles - 1); };
-  auto is_dummy = [&](int round) { return (int)blockIdx.x + round * (int)gridDim.x >= p.total_tiles; };
-  const int my_rounds = p.cluster ? n_rounds : (((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
+  // persistent CTAs: tile = blockIdx.x + round * gridDim.x
+  auto tile_of = [&](int round) { return (int)blockIdx.x + round * (int)gridDim.x; };
+  const int my_rounds = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kWarpA) {
     // ===== A producer: one TMA tile per work item =====
@@ -548,7 +531,6 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
       int slot = 0;
       uint32_t par = 1;                                           // parity of the previous use of `slot`
       bool wrapped = false;
-      const uint32_t crank = p.cluster ? cluster_ctarank() : 0u;
       for (int round = 0; round < my_rounds; ++round) {
         if (p.w_resident && round != 0) break;
         bool ok = true;
@@ -559,14 +541,8 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
           const uint32_t bytes = (uint32_t)k16 * N * 32u;
           if (leader) {
             mbar_arrive_expect_tx(bar_w_full(slot), bytes);
-            if (p.cluster) {                                      // this CTA fetches its half and multicasts it to the pair
-              const uint32_t half = bytes >> 1;
-              bulk_load_mc(smem_u32(w_smem) + (uint32_t)slot * stage_bytes + crank * half,
-                           w_tile + (size_t)i * stage_bytes + crank * half, half, bar_w_full(slot), (uint16_t)0x3);
-            } else {
-              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
-                        bar_w_full(slot));
-            }
+            bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, w_tile + (size_t)i * stage_bytes, bytes,
+                      bar_w_full(slot));
           }
           __syncwarp();
           if (++slot == p.n_wstages) { slot = 0; par ^= 1u; wrapped = true; }
@@ -640,10 +616,7 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
             b_blk += b_block16;
             if (++panel == panels) { panel = 0; a_tap += tap_step16; a_blk = a_tap; } else { a_blk += a_panel16; }
           }
-          if (!p.w_resident && leader) {                          // slot free once these MMAs have read it
-            if (p.cluster) umma_commit_mc(bar_w_empty(slot), (uint16_t)0x3);   // ... in both CTAs' rings
-            else umma_commit(bar_w_empty(slot));
-          }
+          if (!p.w_resident && leader) umma_commit(bar_w_empty(slot));   // slot free once these MMAs have read it
           __syncwarp();
         }
         if (!ok) break;
@@ -681,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
         return ok;
       };
       if (!epi_tile<N, MSUB, kColsPerWarp>(p, bias_s, tmem_base + (uint32_t)(acc * kAccCols), b, m0, phase, ntile, lg, lane,
-                                           col0, is_dummy(it) || !has_cols, wait_acc))
+                                           col0, !has_cols, wait_acc))
         break;
       tc_fence_before();
       __syncwarp();
@@ -694,7 +667,6 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster) cluster_sync_all();              // no CTA leaves while its peer may still multicast into it
   if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

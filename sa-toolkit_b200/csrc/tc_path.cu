@@ -281,33 +281,7 @@ cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int 
     occ_smem[dev] = smem;
   }
   tc::ConvParams p = p_in;
-  int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev] / grid_y));
-  // Wide layers stream their weights from L2 once per tile; CTA pairs (2-CTA clusters) fetch half a stage each and
-  // multicast it.  Measured on B200: no gain at cluster size 2 (the L2 slices, not the request count, are the cap; profiles/README.md), so it is opt-in: SATOOLS_B200_CLUSTER=1.
-  static const int use_cluster = getenv("SATOOLS_B200_CLUSTER") ? atoi(getenv("SATOOLS_B200_CLUSTER")) : 0;
-  if (use_cluster && N >= 256 && p.cin >= 256 && !p.w_resident && ctas >= 2) {
-    static int max_clusters[16] = {0};
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(tc::kThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    if (max_clusters[dev] == 0) {
-      cfg.gridDim = dim3(2 * (unsigned)n_sm, 1, 1);
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc::conv_tc_kernel<N, MSUB, PW>, &cfg) != cudaSuccess || nc < 1) nc = n_sm / 2;
-      max_clusters[dev] = nc;
-    }
-    ctas = std::min(ctas & ~1, 2 * std::max(1, max_clusters[dev] / grid_y));
-    p.cluster = 1;
-    cfg.gridDim = dim3((unsigned)ctas, (unsigned)grid_y, 1);
-    return cudaLaunchKernelEx(&cfg, tc::conv_tc_kernel<N, MSUB, PW>, p);
-  }
-  p.cluster = 0;
+  const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev] / grid_y));
   dim3 grid((unsigned)ctas, (unsigned)grid_y, 1);
   tc::conv_tc_kernel<N, MSUB, PW><<<grid, tc::kThreads, smem, st>>>(p);
   return cudaGetLastError();
