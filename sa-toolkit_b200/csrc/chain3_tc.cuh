@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
         if (inside) {
           const float* src = p.x32 + (((size_t)b * cchunks + q) * (size_t)p.L + t) * 8;
-          a = ldg_f4(src); c4 = ldg_f4(src + 4);
+          ldg_f8(src, a, c4);
         }
         float v[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
         const uint4 pk = pack8_lrelu(v, 0.1f, true, bf16);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
           for (int e = 0; e < 8; ++e) v[e] = ((xr[0][q * 8 + e] + xr[1][q * 8 + e]) + xr[2][q * 8 + e]) / 3.0f;
           const size_t idx = (((size_t)b * cchunks + q) * (size_t)p.L + t) * 8;
           if (p.flags & EPI_OUT32) {
-            stg_f4(p.out32 + idx, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx + 4, v[4], v[5], v[6], v[7]);
+            stg_f8(p.out32 + idx, v);
           }
           if (p.flags & EPI_OUT16) {
             const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + q) * 16;

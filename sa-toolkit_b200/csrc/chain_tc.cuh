@@ -297,7 +297,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
         if (inside) {
           const float* src = p.x32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
-          a = ldg_f4(src); c4 = ldg_f4(src + 4);
+          ldg_f8(src, a, c4);
         }
         xr[q * 8 + 0] = a.x; xr[q * 8 + 1] = a.y; xr[q * 8 + 2] = a.z; xr[q * 8 + 3] = a.w;
         xr[q * 8 + 4] = c4.x; xr[q * 8 + 5] = c4.y; xr[q * 8 + 6] = c4.z; xr[q * 8 + 7] = c4.w;
@@ -354,7 +354,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
               // final epilogue: multi-receptive-field combine + stores (v = x_final)
               const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
               if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
-                const float4 s0 = ldg_f4(p.sum32 + idx), s1 = ldg_f4(p.sum32 + idx + 4);
+                float4 s0, s1;
+                ldg_f8(p.sum32 + idx, s0, s1);
                 v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
                 v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
               }
@@ -363,10 +364,10 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
                 for (int e = 0; e < 8; ++e) v[e] = v[e] / p.n_blocks;
               }
               if (p.flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-                stg_f4(p.sum32 + idx, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + idx + 4, v[4], v[5], v[6], v[7]);
+                stg_f8(p.sum32 + idx, v);
               }
               if (p.flags & EPI_OUT32) {
-                stg_f4(p.out32 + idx, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + idx + 4, v[4], v[5], v[6], v[7]);
+                stg_f8(p.out32 + idx, v);
               }
               if (p.flags & EPI_OUT16) {
                 const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + ch0 + q) * 16;   // [B][1][L][C]

@@ -296,6 +296,24 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return *reinterpret_c
 __device__ __forceinline__ void stg_f4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
+// 256-bit global accesses (sm_100: LDG/STG.256): one 8-channel fp32 row (32 bytes, 32-byte aligned) per instruction.  The
+// rows of a warp are consecutive in the blocked fp32 tensors, so a warp instruction covers 1 KB = 8 full lines, where two
+// 128-bit instructions each touched the same 8 lines with half sectors.
+__device__ __forceinline__ void ldg_f8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_f8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg_u8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 
 // 4 x 4 transpose of 16-byte items inside every aligned group of four lanes: on entry lane j (= lane & 3) holds
 // a[k] = item (row j, piece k); on exit a[k] = item (row k, piece j).  Two butterfly rounds, 16 SHFL.
@@ -360,7 +378,8 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
     if (!has_res || dummy || t0 + ms * 128 >= m_rows) return;
     const float* a0 = p.res32 + base32 + ms * ms_step32 + (size_t)(2 * g) * plane;
     const float* a1 = a0 + plane;
-    q[0] = ldg_f4(a0); q[1] = ldg_f4(a0 + 4); q[2] = ldg_f4(a1); q[3] = ldg_f4(a1 + 4);
+    ldg_f8(a0, q[0], q[1]);
+    ldg_f8(a1, q[2], q[3]);
   };
   fetch_res(0, qr[0]);                                       // does not depend on the accumulator
   if (!wait_acc()) return false;
@@ -378,8 +397,8 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
     float4 qs[4];
     if (QB == 1 && u > 0) fetch_res(u, qr[0]);
     if (valid && has_sum_in) {
-      qs[0] = ldg_f4(p.sum32 + i0); qs[1] = ldg_f4(p.sum32 + i0 + 4);
-      qs[2] = ldg_f4(p.sum32 + i1); qs[3] = ldg_f4(p.sum32 + i1 + 4);
+      ldg_f8(p.sum32 + i0, qs[0], qs[1]);
+      ldg_f8(p.sum32 + i1, qs[2], qs[3]);
     }
     tmem_ld_wait();
     float v[16];
@@ -400,12 +419,12 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
         for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;              // xs / num_kernels
       }
       if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) {
-        stg_f4(p.sum32 + i0, v[0], v[1], v[2], v[3]); stg_f4(p.sum32 + i0 + 4, v[4], v[5], v[6], v[7]);
-        stg_f4(p.sum32 + i1, v[8], v[9], v[10], v[11]); stg_f4(p.sum32 + i1 + 4, v[12], v[13], v[14], v[15]);
+        stg_f8(p.sum32 + i0, v);
+        stg_f8(p.sum32 + i1, v + 8);
       }
       if (flags & EPI_OUT32) {
-        stg_f4(p.out32 + i0, v[0], v[1], v[2], v[3]); stg_f4(p.out32 + i0 + 4, v[4], v[5], v[6], v[7]);
-        stg_f4(p.out32 + i1, v[8], v[9], v[10], v[11]); stg_f4(p.out32 + i1 + 4, v[12], v[13], v[14], v[15]);
+        stg_f8(p.out32 + i0, v);
+        stg_f8(p.out32 + i1, v + 8);
       }
     }
     if (flags & EPI_OUT16) {
@@ -430,8 +449,7 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
         const int cg = chunk0 + g * 2;                       // even chunk; cg and cg + 1 share a panel row
         uint8_t* o = out16 + (size_t)b * item16 + (size_t)(cg >> opc_shift) * panel16 +
                      ((size_t)t * out_stride + phase) * row16 + (size_t)(cg & ((1 << opc_shift) - 1)) * 16;
-        *reinterpret_cast<uint4*>(o) = pack8_lrelu(lo, p.slope_out, true, bf16);
-        *reinterpret_cast<uint4*>(o + 16) = pack8_lrelu(hi8, p.slope_out, true, bf16);
+        stg_u8(o, pack8_lrelu(lo, p.slope_out, true, bf16), pack8_lrelu(hi8, p.slope_out, true, bf16));
       }
     }
   }
