@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
       step(T{}, T{}, J0{}, cl + 1); step(T{}, T{}, J1{}, cl + 1); step(T{}, T{}, J2{}, cl + 1); ++n;
       // ---- multi-receptive-field mean: xs = 0; xs += r0; xs += r1; xs += r2; x = xs / 3 (archi.py:82-86) ----
       if (keep && ok) {
+        uint4 pk16[kCPT];
 #pragma unroll
         for (int q = 0; q < kCPT; ++q) {
           float v[8];
@@ -267,10 +268,12 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
           if (p.flags & EPI_OUT32) {
             stg_f8(p.out32 + idx, v);
           }
-          if (p.flags & EPI_OUT16) {
-            const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + q) * 16;
-            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(v, p.slope_out, true, bf16);
-          }
+          if (p.flags & EPI_OUT16) pk16[q] = pack8_lrelu(v, p.slope_out, true, bf16);
+        }
+        if (p.flags & EPI_OUT16) {                                 // the row's C 16-bit values are contiguous: 32-byte stores
+          uint8_t* o = static_cast<uint8_t*>(p.out16) + ((size_t)b * (size_t)p.L + t) * cchunks * 16;
+#pragma unroll
+          for (int q = 0; q < kCPT; q += 2) stg_u8(o + q * 16, pk16[q], pk16[q + 1]);
         }
       }
     }

@@ -164,9 +164,17 @@ __global__ void __launch_bounds__(256) conv_post16_k7_kernel(const uint4* __rest
   if (i >= 0 && i < Lout) {
     const int src = (i == 0) ? 1 : i - 1;
     const int opc = PW >> 3;
+    uint4 q2[2];
     for (int c8 = 0; c8 < (C >> 3); ++c8) {
       const int panel = c8 / opc, within = c8 - panel * opc;
-      const uint4 q = __ldg(h16 + (((size_t)b * (C / PW) + panel) * L + src) * opc + within);
+      if ((c8 & 1) == 0) {                                  // two chunks = 32 contiguous, 32-byte aligned bytes: one 256-bit load
+        const uint4* src16 = h16 + (((size_t)b * (C / PW) + panel) * L + src) * opc + within;
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(q2[0].x), "=r"(q2[0].y), "=r"(q2[0].z), "=r"(q2[0].w), "=r"(q2[1].x), "=r"(q2[1].y), "=r"(q2[1].z),
+                       "=r"(q2[1].w)
+                     : "l"(src16));
+      }
+      const uint4 q = q2[c8 & 1];
       const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -865,7 +873,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
   int L = a.T;
   // The last stage hands conv_post its lrelu(0.01)-activated output in the 16-bit blocked layout (half the bytes of
   // the fp32 stream, read once); other filter lengths keep the fp32 hand-off.
-  const bool post16 = a.layers[L_post].k == 7 && a.layers[L_post].cin % 8 == 0;
+  const bool post16 = a.layers[L_post].k == 7 && a.layers[L_post].cin % 16 == 0;
   for (int i = 0; i < nst; ++i) {
     const tc_layer& up = a.layers[L_up(i)];
     {                                               // archi.py:80-81
