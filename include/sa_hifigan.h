@@ -123,9 +123,12 @@ int64_t sa_hifigan_output_length(const sa_hifigan* h, int64_t T);
 size_t sa_hifigan_workspace_bytes(const sa_hifigan* h, int32_t B, int32_t T);
 
 /* x: device, fp32, contiguous [B, input_dim, T], 16-byte aligned.
- * frames_per_item: NULL, or host int32[B] with the true frame count of each item; outputs of
- *   item b beyond 320*frames_per_item[b] are then unspecified but finite (the pipeline trims
- *   them, pipeline.py:156).  NULL reproduces the reference's padded semantics exactly.
+ * frames_per_item: NULL, or host int32[B] with the true frame count of each item; the
+ *   tensor-core modes then only compute the tiles that can reach the first
+ *   320*frames_per_item[b]+1 samples of item b (true length + 24 frames at every layer; the
+ *   receptive field of the generator is 20 frames), which stay bit-identical to the padded
+ *   run; the rest of item b's output is not written (the pipeline trims it, pipeline.py:156).
+ *   The array is copied during the call.  NULL reproduces the reference's padded semantics.
  * y: device, contiguous [B, 1, 320*T+1] of y_dtype (F32, F16 or PCM16).
  * stream: a cudaStream_t passed as void* (NULL = legacy default stream). */
 int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T,

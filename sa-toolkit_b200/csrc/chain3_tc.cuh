@@ -34,6 +34,7 @@ struct Chain3Params {
   int pad[3][kChainMaxConvs];
   int halo;                 // halo of the widest chain
   int tiles_per_item, total_tiles;
+  TileMapParams map;        // ragged batches: live-tile enumeration (conv_tc.cuh); tile axis = valid rows per tile
   uint32_t flags;           // EPI_OUT32 / EPI_OUT16 / EPI_BF16
   float slope_out;
 };
@@ -73,6 +74,8 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 78);
 
   const int valid_rows = R - 2 * p.halo;
+  __shared__ int tile_pre[kMaxMapItems + 1];
+  tilemap_build(tile_pre, p.map, p.L, valid_rows);                // visible after the __syncthreads() below
   const bool bf16 = (p.flags & EPI_BF16) != 0;
   const int n_pairs = p.n_convs / 2;
 
@@ -98,13 +101,14 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const int n_live = tilemap_total(tile_pre, p.map, p.total_tiles);
 
   if (warp == kWarpW) {
     // ===== weight producer: conv c of chain j into chain j's slot =====
     const bool leader = elect_one();
     uint32_t n = 0;                                              // how often each slot has been filled
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x)
+    for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x)
       for (int c = 0; c < p.n_convs && ok; ++c, ++n)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it)
+    for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it)
       for (int c = 0; c < p.n_convs && ok; ++c, ++n) {
         conv(std::integral_constant<int, K0>{}, std::integral_constant<int, 0>{}, c);
         if (ok) conv(std::integral_constant<int, K1>{}, std::integral_constant<int, 1>{}, c);
@@ -176,8 +180,9 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
     for (int q = 0; q < kCPT; ++q) soff[q] = swz(row_off + (uint32_t)q * 16u, RB);
     uint32_t it = 0, n = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
-      const int b = tile / p.tiles_per_item, mt = tile - b * p.tiles_per_item;
+    for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
+      int b, mt;
+      tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
       const int t = mt * valid_rows - p.halo + r;
       const bool inside = t >= 0 && t < p.L;
       const bool keep = inside && r >= p.halo && r < R - p.halo;

@@ -60,6 +60,7 @@ struct ChainParams {
   int pad[kChainMaxConvs];
   int halo;                 // H
   int tiles_per_item, total_tiles;
+  TileMapParams map;        // ragged batches: live-tile enumeration (conv_tc.cuh); tile axis = valid rows per tile
   int k16_per_stage, stages_per_conv, n_slots;
   long long* timing;        // optional [16] cycle counters (diagnostics): MMA warp: total, wait ready, wait weights,
                             // issue; epilogue warp 2: total, x load + staging, wait accumulator, work
@@ -114,6 +115,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32 + 2 * kChainMaxSlots);
 
   const int valid_rows = R - 2 * p.halo;
+  __shared__ int tile_pre[kMaxMapItems + 1];
+  tilemap_build(tile_pre, p.map, p.L, valid_rows);                // visible after the __syncthreads() below
   const bool bf16 = (p.flags & EPI_BF16) != 0;
 
   if (warp == kWarpW && lane == 0) {
@@ -135,6 +138,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const int n_live = tilemap_total(tile_pre, p.map, p.total_tiles);
 
   if (warp == kWarpW) {
     // ===== weight producer =====
@@ -143,7 +147,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       int slot = 0;
       uint32_t par = 1;                                          // parity of the previous use of `slot`
       bool wrapped = false, ok = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x)
         for (int c = 0; c < p.n_convs && ok; ++c) {
           const uint8_t* src = static_cast<const uint8_t*>(p.w) + (size_t)c * SPC * stage_bytes;
 #pragma unroll 1
@@ -177,7 +181,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       bool ok = true;
       const bool timing = p.timing != nullptr;
       long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
         for (int c = 0; c < p.n_convs && ok; ++c) {
           const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA)) + (uint32_t)(kChainPad - p.pad[c]) * row16;
           const uint32_t rdy_parity = (it * (uint32_t)(p.n_convs / 2) + (uint32_t)(c / 2)) & 1u;
@@ -285,9 +289,10 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     bool ok = true;
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_p0 = 0, t_acc = 0, t_ld = 0, t_fence = 0, t_begin = timing ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
       const long long tp0 = timing ? clock64() : 0;
-      const int b = tile / p.tiles_per_item, mt = tile - b * p.tiles_per_item;
+      int b, mt;
+      tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
       const int t = mt * valid_rows - p.halo + r;                // global row of this thread
       const bool inside = t >= 0 && t < p.L;
       const bool keep = inside && r >= p.halo && r < R - p.halo; // rows this tile is responsible for

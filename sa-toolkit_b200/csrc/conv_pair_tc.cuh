@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
   auto bar_w_empty = [&](int s) { return smem_u32(&bars[8 + kMaxStages + s]); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxStages);
 
+  __shared__ int tile_pre[kMaxMapItems + 1];
+  tilemap_build(tile_pre, p.map, p.m_rows, 128 * MSUB);          // visible after the __syncthreads() below
   const int n_taps = p.n_taps[phase];
   const int n_blocks_total = n_taps * panels;
   const int n_iters = (n_blocks_total + blocks_per_stage - 1) / blocks_per_stage;   // weight stages per tile
@@ -146,9 +148,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  const int n_rounds = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_of = [&](int round) { return min((int)blockIdx.x + round * (int)gridDim.x, p.total_tiles - 1); };
-  auto is_dummy = [&](int round) { return (int)blockIdx.x + round * (int)gridDim.x >= p.total_tiles; };
+  const int n_live = tilemap_total(tile_pre, p.map, p.total_tiles);
+  const int n_rounds = (n_live + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int round) { return min((int)blockIdx.x + round * (int)gridDim.x, n_live - 1); };
+  auto is_dummy = [&](int round) { return (int)blockIdx.x + round * (int)gridDim.x >= n_live; };
 
   if (warp == kWarpA) {
     // ===== A producer (both CTAs): this CTA's rows, completion on the leader's barrier =====
@@ -157,7 +160,9 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
       const int tile = tile_of(it);
       const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
       if (use > 0 && !mbar_wait_relaxed(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
-      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+      int b, mt;
+      tilemap_locate(tile_pre, p.map, p.m_tiles, tile, b, mt);
+      const int m0 = mt * (128 * MSUB);
       const int row0 = m0 + p.row_lo[phase];
       const uint32_t dst = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
       const uint32_t full0 = mapa_u32(bar_a_full(buf), 0);
@@ -272,7 +277,9 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
     for (int it = 0; it < n_rounds; ++it) {
       const int acc = it & 1, acc_use = it >> 1;
       const int tile = tile_of(it);
-      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+      int b, mt;
+      tilemap_locate(tile_pre, p.map, p.m_tiles, tile, b, mt);
+      const int m0 = mt * (128 * MSUB);
       auto wait_acc = [&]() {
         const long long tf0 = timing ? clock64() : 0;
         const bool ok = mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag);

@@ -58,6 +58,53 @@ enum : uint32_t {
   EPI_BF16 = 1u << 6        // 16-bit type is bf16 (else fp16)
 };
 
+// Ragged batches: when the caller gives the true length of every item (frames_per_item), the kernels enumerate only
+// the tiles that can reach an item's kept samples: rows [0, (frames + margin) * rows_per_frame) of every layer, margin >
+// receptive field of the whole generator (20 frames) so the kept region is bit-identical to the padded run.  Live
+// tiles are compacted with a prefix sum over the items (built by warp 0 of every CTA, n_items <= kMaxMapItems), so
+// the persistent CTAs stay balanced.
+constexpr int kMaxMapItems = 256;
+struct TileMapParams {
+  const int* frames;        // device [n_items]; nullptr: every item owns all its tiles (padded semantics)
+  int n_items;
+  int rows_per_frame;       // rows of this kernel's tile axis per input frame
+  int margin_frames;
+};
+// Called by all threads before a __syncthreads(); pre[i] = first live tile of item i, pre[n_items] = live tiles.
+__device__ __forceinline__ void tilemap_build(int* pre, const TileMapParams& m, int rows_full, int tile_rows) {
+  if (m.frames == nullptr || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int running = 0;
+  if (lane == 0) pre[0] = 0;
+  for (int base = 0; base < m.n_items; base += 32) {
+    const int b = base + lane;
+    int v = 0;
+    if (b < m.n_items) {
+      const int rows = min(rows_full, (m.frames[b] + m.margin_frames) * m.rows_per_frame);
+      v = (rows + tile_rows - 1) / tile_rows;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += u;
+    }
+    if (b < m.n_items) pre[b + 1] = running + v;
+    running += __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+__device__ __forceinline__ int tilemap_total(const int* pre, const TileMapParams& m, int total_full) {
+  return m.frames ? pre[m.n_items] : total_full;
+}
+__device__ __forceinline__ void tilemap_locate(const int* pre, const TileMapParams& m, int tiles_full, int tile, int& b, int& mt) {
+  if (m.frames == nullptr) { b = tile / tiles_full; mt = tile - b * tiles_full; return; }
+  int lo = 0, hi = m.n_items;                                // largest b with pre[b] <= tile
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pre[mid] <= tile) lo = mid; else hi = mid;
+  }
+  b = lo; mt = tile - pre[lo];
+}
+
 struct ConvParams {
   CUtensorMap tmap;         // activations [B][Cin/PW][L_in][PW], box {PW, box_rows, 1, 1}, swizzle = row bytes
   CUtensorMap wmap;         // conv_pair_tc.cuh only: packed weights as [rows][64] 16-bit, box {64, rows of one stage}
@@ -90,6 +137,7 @@ struct ConvParams {
   int n_abuf;               // A-tile ring depth (1 or 2)
   int m_tiles;              // time tiles per item
   int total_tiles;          // m_tiles * B
+  TileMapParams map;        // ragged batches: live-tile enumeration (map.frames == nullptr: all tiles)
   uint32_t w_tile_bytes;
   uint32_t flags;
   float slope_out;
@@ -492,6 +540,8 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
   auto bar_w_empty = [&](int s) { return smem_u32(&bars[8 + kMaxStages + s]); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxStages);
 
+  __shared__ int tile_pre[kMaxMapItems + 1];
+  tilemap_build(tile_pre, p.map, p.m_rows, 128 * MSUB);          // visible after the __syncthreads() below
   const int n_taps = p.n_taps[phase];
   const int k16_per_tap = p.cin >> 4;
   const int n_k16 = n_taps * k16_per_tap;
@@ -518,7 +568,8 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
   const uint32_t tmem_base = *tmem_holder;
   // persistent CTAs: tile = blockIdx.x + round * gridDim.x
   auto tile_of = [&](int round) { return (int)blockIdx.x + round * (int)gridDim.x; };
-  const int my_rounds = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_live = tilemap_total(tile_pre, p.map, p.total_tiles);
+  const int my_rounds = ((int)blockIdx.x < n_live) ? (n_live - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kWarpA) {
     // ===== A producer: one TMA tile per work item =====
@@ -529,7 +580,9 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
         const int tile = tile_of(it);
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
         if (use > 0 && !mbar_wait_relaxed(bar_a_empty(buf), (use - 1) & 1, p.error_flag)) break;
-        const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+        int b, mt;
+        tilemap_locate(tile_pre, p.map, p.m_tiles, tile, b, mt);
+        const int m0 = mt * (128 * MSUB);
         const int row0 = m0 + p.row_lo[phase];
         const uint32_t dst = smem_u32(a_smem) + (uint32_t)buf * a_bytes;
         if (leader) {
@@ -664,7 +717,9 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
     for (int it = 0; it < my_rounds; ++it) {
       const int tile = tile_of(it);
       const int acc = (kNumAcc == 2) ? (it & 1) : 0, acc_use = (kNumAcc == 2) ? (it >> 1) : it;
-      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * (128 * MSUB);
+      int b, mt;
+      tilemap_locate(tile_pre, p.map, p.m_tiles, tile, b, mt);
+      const int m0 = mt * (128 * MSUB);
       auto wait_acc = [&]() {
         const long long tf0 = timing ? clock64() : 0;
         const bool ok = mbar_wait_relaxed(bar_acc_full(acc), acc_use & 1, p.error_flag);

@@ -143,7 +143,7 @@ __global__ void conv_post_blocked_kernel(const float* __restrict__ h, const floa
 template <bool BF16>
 __global__ void __launch_bounds__(256) conv_post16_k7_kernel(const uint4* __restrict__ h16, const float* __restrict__ w,
                                                              const float* __restrict__ bias, void* y, int C, int PW, int L,
-                                                             int y_dtype) {
+                                                             int y_dtype, const int* __restrict__ frames, int keep_margin, int samples_per_frame) {
   constexpr int K = 7, kOut = 256 - (K - 1);
   extern __shared__ float4 post_smem[];
   float4* ws = post_smem;                                   // [C][2] float4: taps 0-3, taps 4-6 + 0
@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(256) conv_post16_k7_kernel(const uint4* __rest
   __syncthreads();
   const int b = blockIdx.y, tid = threadIdx.x;
   const int n0 = blockIdx.x * kOut;
+  // ragged batch: samples past the item's true length (+ margin) are never looked at; their inputs were not computed
+  if (frames != nullptr && n0 > (frames[b] + keep_margin) * samples_per_frame) return;
   const int i = n0 - (K - 1) / 2 + tid;                     // padded position owned by this thread
   const int Lout = L + 1;
   float p[K];
@@ -216,6 +218,9 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+constexpr int kStaticSmemReserve = 2048;   // >= static __shared__ of every kernel (tile_pre: (kMaxMapItems + 1) ints)
+constexpr int kRaggedMarginFrames = 24;    // > receptive field of the generator in frames (20) + the reflect-pad sample
+
 struct Plan {          // launch geometry of one conv on the tensor cores
   int msub, rows_alloc, box_rows, nseg, k16_per_stage, n_wstages, w_resident, n_abuf;
   size_t smem;
@@ -275,7 +280,7 @@ cudaError_t launch_one(const tc::ConvParams& p_in, int grid_y, size_t smem, int 
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<N, MSUB, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<N, MSUB, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
@@ -341,7 +346,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
@@ -369,7 +374,7 @@ cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cuda
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::stage_chain3_kernel<C, MS, 3, 7, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::stage_chain3_kernel<C, MS, 3, 7, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
@@ -419,7 +424,7 @@ cudaError_t launch_pair(const tc::ConvParams& p, int grid_y, size_t smem, int n_
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::conv_pair_kernel<N, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_pair_kernel<N, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
@@ -465,6 +470,12 @@ struct Runner {
   tc_context& ctx;
   const tc_forward_args& a;
   int64_t* launches;
+  const int* d_frames = nullptr;                 // device copy of frames_per_item (ragged batches), else nullptr
+  tc::TileMapParams tile_map(int rows) const {   // rows = rows per item on the kernel's tile axis
+    tc::TileMapParams m;
+    m.frames = d_frames; m.n_items = a.B; m.rows_per_frame = rows / a.T; m.margin_frames = kRaggedMarginFrames;
+    return m;
+  }
   void mark(int tag) { if (a.mark) a.mark(a.mark_ctx, tag, a.stream); }
 
   // One conv layer (all phases / n-tiles) on the tensor cores.  in16: blocked input with
@@ -540,6 +551,7 @@ struct Runner {
     p.n_wstages = pl.n_wstages; p.w_resident = pl.w_resident; p.n_abuf = pl.n_abuf;
     p.m_tiles = (l_in + 128 * pl.msub - 1) / (128 * pl.msub);
     p.total_tiles = p.m_tiles * a.B;
+    p.map = tile_map(l_in);
     p.w_tile_bytes = (uint32_t)w.tile_bytes;
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
     // diagnostics only (results become wrong): drop epilogue streams to time what each costs
@@ -583,6 +595,7 @@ struct Runner {
     p.L = L; p.n_convs = ch[0].n_convs; p.halo = halo;
     p.tiles_per_item = (L + valid - 1) / valid;
     p.total_tiles = p.tiles_per_item * a.B;
+    p.map = tile_map(L);
     p.flags = (e.flags & (tc::EPI_OUT32 | tc::EPI_OUT16)) | (a.bf16 ? tc::EPI_BF16 : 0u);
     p.slope_out = e.slope_out;
     mark(tag);
@@ -617,6 +630,7 @@ struct Runner {
     p.halo = ch.halo;
     p.tiles_per_item = (L + valid - 1) / valid;
     p.total_tiles = p.tiles_per_item * a.B;
+    p.map = tile_map(L);
     p.k16_per_stage = ch.k16_per_stage; p.stages_per_conv = ch.stages_per_conv; p.n_slots = pl.n_slots;
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
@@ -765,6 +779,7 @@ const char* tc_init(tc_context& ctx, int device) {
   if (!fn || q != cudaDriverEntryPointSuccess) return "cuTensorMapEncodeTiled not available from the driver";
   ctx.encode_fn = fn;
   TC_CUDA(cudaDeviceGetAttribute(&ctx.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  ctx.max_smem -= kStaticSmemReserve;            // the kernels' static shared memory (live-tile prefix of ragged batches)
   // error flag in mapped pinned host memory: kernels can raise it, the host reads it without a sync
   TC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx.h_error), sizeof(int), cudaHostAllocMapped));
   *ctx.h_error = 0;
@@ -794,7 +809,7 @@ bool tc_error_raised(const tc_context& ctx) {
 }
 
 namespace {
-struct Sizes { size_t e16, e32, xin; };
+struct Sizes { size_t e16, e32, xin, frames; };
 Sizes sizes(const sa_hifigan_cfg& cfg, int B, int T) {
   int64_t per_frame = cfg.initial_channels, rate = 1;
   for (int i = 0; i < cfg.n_stages; ++i) {
@@ -806,13 +821,14 @@ Sizes sizes(const sa_hifigan_cfg& cfg, int B, int T) {
   s.e16 = align_up(E * 2, 256);
   s.e32 = align_up(E * 4, 256);
   s.xin = align_up((size_t)B * T * align_up(cfg.input_dim, 16) * 2, 256);
+  s.frames = align_up((size_t)B * sizeof(int32_t), 256);
   return s;
 }
 }  // namespace
 
 size_t tc_workspace_bytes(const sa_hifigan_cfg& cfg, int B, int T) {
   const Sizes s = sizes(cfg, B, T);
-  return s.xin + 4 * s.e16 + 3 * s.e32;
+  return s.xin + 4 * s.e16 + 3 * s.e32 + s.frames;
 }
 
 const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launches) {
@@ -832,9 +848,20 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
   void* T16 = base; base += s.e16;
   float* X32 = reinterpret_cast<float*>(base); base += s.e32;
   float* R32 = reinterpret_cast<float*>(base); base += s.e32;
-  float* S32 = reinterpret_cast<float*>(base);
+  float* S32 = reinterpret_cast<float*>(base); base += s.e32;
+  // Ragged batch: the true lengths go to the device once; every launch then enumerates only the live tiles.
+  const int* d_frames = nullptr;
+  if (a.frames_per_item && a.B <= tc::kMaxMapItems && !(a.debug_out)) {
+    bool ragged = false;
+    for (int b = 0; b < a.B; ++b) ragged = ragged || a.frames_per_item[b] + kRaggedMarginFrames < a.T;
+    if (ragged) {
+      TC_CUDA(cudaMemcpyAsync(base, a.frames_per_item, (size_t)a.B * sizeof(int32_t), cudaMemcpyHostToDevice, a.stream));
+      d_frames = reinterpret_cast<const int*>(base);
+    }
+  }
   cudaStream_t st = a.stream;
   Runner run{ctx, a, launches};
+  run.d_frames = d_frames;
   const int nst = cfg.n_stages, nrb = cfg.n_resblocks, nd = cfg.n_dilations;
   auto L_up = [&](int i) { return 1 + i; };
   auto L_rb = [&](int i, int j, int which, int m) { return 1 + nst + ((i * nrb + j) * 2 + which) * nd + m; };
@@ -944,10 +971,10 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       const int pw = panel_width(post.cin);
       if (a.bf16)
         conv_post16_k7_kernel<true><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(P16), post.d_w32, post.d_bias, a.y,
-                                                          post.cin, pw, L, a.y_dtype);
+                                                          post.cin, pw, L, a.y_dtype, d_frames, kRaggedMarginFrames, L / a.T);
       else
         conv_post16_k7_kernel<false><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(P16), post.d_w32, post.d_bias, a.y,
-                                                           post.cin, pw, L, a.y_dtype);
+                                                           post.cin, pw, L, a.y_dtype, d_frames, kRaggedMarginFrames, L / a.T);
     } else
     conv_post_blocked_kernel<<<g, threads, post.cin * post.k * sizeof(float), st>>>(Hout, post.d_w32, post.d_bias, a.y,
                                                                                     post.cin, L, post.k, 0.01f, a.y_dtype);

@@ -70,7 +70,7 @@ def synthesize_corpus(gen, feats: Dict[str, np.ndarray], *, rank: int = 0, world
     for batch in scheduler.batches(short, lengths, max_items=max_items, max_padded_frames=max_padded_frames):
         T = max(max(lengths[i] for i in batch), 2)
         xh = torch.from_numpy(_pad_batch([feats[ids[i]] for i in batch], T)).pin_memory()
-        ticket = pipe.submit(xh, out_dtype=out_dtype)
+        ticket = pipe.submit(xh, out_dtype=out_dtype, frames_per_item=[max(lengths[i], 1) for i in batch])
         if pending is not None:
             collect(*pending)
         pending = (ticket, batch)

@@ -291,3 +291,45 @@ def test_host_pipeline_overlapped_batches_equal_blocking_calls():
         pipe.result(tickets[0])
     pcm = pipe.result(pipe.submit(torch.from_numpy(batches[0]).pin_memory(), out_dtype=torch.int16)).numpy()
     np.testing.assert_array_equal(pcm, np.clip(np.rint(want[0] * 32767.0), -32768, 32767).astype(np.int16))
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_ragged_batch_kept_samples_are_bit_identical_to_the_padded_run(precision):
+    """frames_per_item lets every kernel enumerate only the tiles that can reach an item's kept samples
+    (true length + 24 frames > the 20-frame receptive field).  The first 320 * frames + 1 samples of every item must
+    be bit-identical to the padded run (what the reference computes and then trims, pipeline.py:156), for the
+    device entry, the blocking host entry (two halves) and the pipelined host entry."""
+    from satools_b200 import HostPipeline
+    gen = dev_gen(1, precision)
+    frames = [300, 37, 212, 90, 2, 299, 150, 61, 120, 275, 33]
+    x = conditioning.batch(123, frames)                         # padded to the longest item, pipeline semantics
+    assert x.shape[2] == 300
+    y_pad = run(gen, x)
+    y_rag = run(gen, x, frames_per_item=frames)
+    xh = torch.from_numpy(x).pin_memory()
+    y_host = gen.synthesize_host(xh, frames_per_item=frames).numpy()
+    pipe = HostPipeline(gen)
+    y_pipe = pipe.result(pipe.submit(xh, frames_per_item=frames)).numpy()
+    for b, f in enumerate(frames):
+        n = 320 * f + 1
+        for name, y in (("device", y_rag), ("host", y_host), ("pipeline", y_pipe)):
+            np.testing.assert_array_equal(y[b, 0, :n], y_pad[b, 0, :n], err_msg=f"{name} entry, item {b} ({f} frames)")
+    # no ragged item: identical everywhere
+    full = [300] * len(frames)
+    np.testing.assert_array_equal(run(gen, x, frames_per_item=full), y_pad)
+
+
+def test_ragged_batch_full_size_properties():
+    """64 items of 10-15 s padded to 750 frames (the bench workload): kept samples identical to the padded run."""
+    gen = dev_gen(0, "fp16")
+    rng = np.random.default_rng(5)
+    frames = [int(v) for v in rng.integers(500, 751, size=64)]
+    frames[0] = 750
+    x = conditioning.batch(7, frames)
+    xd = torch.from_numpy(x).to("cuda:0")
+    y_pad = gen(xd)[0]
+    y_rag = gen(xd, frames_per_item=frames)[0]
+    gen.check()
+    for b, f in enumerate(frames):
+        n = 320 * f + 1
+        assert torch.equal(y_rag[b, 0, :n], y_pad[b, 0, :n]), f"item {b} ({f} frames)"
