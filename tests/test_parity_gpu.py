@@ -333,3 +333,38 @@ def test_ragged_batch_full_size_properties():
     for b, f in enumerate(frames):
         n = 320 * f + 1
         assert torch.equal(y_rag[b, 0, :n], y_pad[b, 0, :n]), f"item {b} ({f} frames)"
+
+
+def test_fp16_against_the_reference_op_sequence_under_cuda_autocast():
+    """also compare with what the reference itself computes on a GPU -- its op sequence (the torch port,
+    cuDNN convs) under torch.autocast(fp16), hifigan.py:99 -- on the same weights and input.  Both are measured against
+    the fp64 truth; the tensor-core path must not be worse than eager autocast by more than 3 dB.  The eager
+    throughput on this GPU is printed for context (profiles/README.md), not asserted."""
+    import time
+    gen = dev_gen(0, "fp16")
+    frames = [250] * 4
+    x = conditioning.batch(11, frames)
+    state = {k: v.detach().cpu() for k, v in gen.state_dict().items()}
+    truth = otc.generator_forward(otc.fold(state, torch.float64), torch.from_numpy(x).double()).numpy()
+    p_cuda = {k: (w.cuda(), b.cuda()) for k, (w, b) in otc.fold(state, torch.float32).items()}
+    xd = torch.from_numpy(x).to("cuda:0")
+    with torch.autocast("cuda", dtype=torch.float16):
+        y_eager = otc.generator_forward(p_cuda, xd).float().cpu().numpy()
+    y_tc = run(gen, x)
+    snr_eager, snr_tc = helpers.snr_db(truth, y_eager), helpers.snr_db(truth, y_tc)
+    print(f"SNR vs fp64 truth: torch CUDA autocast(fp16) eager {snr_eager:.1f} dB, tensor-core path {snr_tc:.1f} dB; "
+          f"path vs eager {helpers.snr_db(y_eager, y_tc):.1f} dB")
+    assert snr_tc >= snr_eager - 3.0
+    check(truth, y_tc, "fp16", "vs truth")
+    # context: eager autocast throughput of the same op sequence on this GPU (16 x 15 s)
+    xb = torch.from_numpy(conditioning.batch(12, [750] * 16)).to("cuda:0")
+    for fn, name in ((lambda: otc.generator_forward(p_cuda, xb), "torch eager autocast(fp16)"), (lambda: gen(xb), "tensor-core path")):
+        with torch.autocast("cuda", dtype=torch.float16):
+            fn(); fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        print(f"{name}: {16 * 15 / dt:.0f} audio-s/s ({1e3 * dt:.1f} ms per 16 x 15 s)")
