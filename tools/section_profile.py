@@ -16,6 +16,15 @@ gen = CoreHifiGan(imput_dim=504, precision="fp16").to("cuda:0")
 x = torch.from_numpy(conditioning.batch(7, [750] * B)).to("cuda:0")
 for _ in range(3):
     gen(x)
+ragged = os.environ.get("RAGGED") == "1"            # RAGGED=1: 10-15 s items padded to 15 s, true lengths passed along
+if ragged:
+    import numpy as np
+    frames = [int(v) for v in np.random.default_rng(0).integers(500, 751, size=B)]
+    x = torch.from_numpy(conditioning.batch(7, frames)[:, :, :750]).to("cuda:0")
+    if x.shape[2] < 750:
+        x = torch.nn.functional.pad(x, (0, 750 - x.shape[2]))
+    fwd = gen.forward
+    gen.forward = lambda t: fwd(t, frames_per_item=frames)
 prof = gen.profile(x, repeats=reps)
 sec = {}
 for tag, ms in prof:
