@@ -144,7 +144,9 @@ int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, in
                                void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 /* Stream-ordered form of the same sequence: enqueues H2D copy, forward and D2H copy on `stream`
  * and returns without waiting.  x_host, y_host and dev_scratch stay owned by the call until the
- * caller has synchronized `stream`.  Two streams used alternately (each with its own buffers)
+ * caller has synchronized `stream`.  The copies run on `stream`; the kernels of all in-flight
+ * calls of a handle run in submission order on one internal stream (event-linked to `stream`),
+ * so two batches never compete for the SMs.  Two streams used alternately (each with its own buffers)
  * overlap the copies of one batch with the kernels of the other -- the pipeline's DataLoader
  * prefetch (bin/pipeline.py:91-101) moved to the device side. */
 int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,

@@ -75,6 +75,10 @@ struct sa_hifigan {
   std::vector<sa::tc_chain> chains;     // [n_stages * n_resblocks], fused narrow-stage ResBlocks
   cudaStream_t side_stream = nullptr;   // second stream of sa_hifigan_synthesize_host
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // sa_hifigan_synthesize_host_async: the forwards of all in-flight calls run on ONE compute stream (in submission
+  // order), only the copies stay on the callers' streams -- two forwards on two streams would interleave their kernels
+  cudaStream_t compute_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr;
   // per-launch profiling: one event before every launch + one closing event
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -222,6 +226,9 @@ void sa_hifigan_destroy(sa_hifigan* h) {
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     cudaSetDevice(cur);
   }
   delete h;
@@ -656,8 +663,20 @@ int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t
   float* xd = reinterpret_cast<float*>(base);
   void* yd = base + align_up(x_bytes, 256);
   void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+  if (!h->compute_stream) {
+    SA_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  }
+  // copies on the caller's stream, kernels on the shared compute stream: H2D -> [ev_in] -> forward -> [ev_done] -> D2H.
+  // (An event may be re-recorded by the next call: a wait refers to the record that preceded it.)
   SA_CUDA(cudaMemcpyAsync(xd, x_host, x_bytes, cudaMemcpyHostToDevice, st));
-  int rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, sa_hifigan_workspace_bytes(h, B, T), st);
+  SA_CUDA(cudaEventRecord(h->ev_in, st));
+  SA_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_in, 0));
+  int rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, sa_hifigan_workspace_bytes(h, B, T),
+                              h->compute_stream);
+  SA_CUDA(cudaEventRecord(h->ev_done, h->compute_stream));
+  SA_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
   if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(y_host, yd, y_bytes, cudaMemcpyDeviceToHost, st));
   if (cur != h->device) cudaSetDevice(cur);
   return rc;
