@@ -904,8 +904,11 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
   for (int i = 0; i < nst; ++i) {
     const tc_layer& up = a.layers[L_up(i)];
     {                                               // archi.py:80-81
+      // The fused ResBlock kernels read the fp32 stage input only; lrelu(x) in 16 bits is for the per-layer convs.
+      bool all_fused = a.chains != nullptr;
+      for (int j = 0; j < nrb && all_fused; ++j) all_fused = run.chain_usable(a.chains[i * nrb + j], L * up.stride);
       Epi e;
-      e.flags = tc::EPI_OUT32 | tc::EPI_OUT16;
+      e.flags = tc::EPI_OUT32 | (all_fused ? 0u : tc::EPI_OUT16);
       e.out32 = X32; e.out16 = AX16; e.slope_out = 0.1f;
       if ((err = run.conv(up, P16, L, e, 16 * (1 + i)))) return err;
     }
