@@ -615,19 +615,24 @@ struct Runner {
     return L >= 2 * (pl.ms * 128 - 2 * ch.halo);                // short sequences: the per-layer path wastes less
   }
 
-  const char* chain(const tc_chain& ch, const float* x32, int L, const Epi& e, int tag, bool* done) {
+  // convs [c0, c1) of the block (default: all): a block can be run as two launches to halve the recomputed halo
+  const char* chain(const tc_chain& ch, const float* x32, int L, const Epi& e, int tag, bool* done, int c0 = 0, int c1 = -1) {
     *done = false;
     ChainPlan pl;
     if (!chain_usable(ch, L) || !chain_plan(pl, ch, ctx.max_smem)) return nullptr;
-    const int valid = pl.ms * 128 - 2 * ch.halo;
+    if (c1 < 0) c1 = ch.n_convs;
+    int halo = 0;
+    for (int c = c0; c < c1; ++c) halo += ch.pad[c];
+    const int valid = pl.ms * 128 - 2 * halo;
     tc::ChainParams p;
     memset(&p, 0, sizeof(p));
     p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
-    p.w = ch.d_w; p.bias = ch.d_bias; p.error_flag = ctx.d_error;
+    p.w = static_cast<const uint8_t*>(ch.d_w) + (size_t)c0 * ch.k * ch.c * ch.c * 2;
+    p.bias = ch.d_bias + (size_t)c0 * ch.c; p.error_flag = ctx.d_error;
     p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 16 * ctx.timing_launches++ : nullptr;
-    p.L = L; p.n_convs = ch.n_convs; p.ktaps = ch.k;
-    for (int c = 0; c < ch.n_convs; ++c) { p.dil[c] = ch.dil[c]; p.pad[c] = ch.pad[c]; }
-    p.halo = ch.halo;
+    p.L = L; p.n_convs = c1 - c0; p.ktaps = ch.k;
+    for (int c = c0; c < c1; ++c) { p.dil[c - c0] = ch.dil[c]; p.pad[c - c0] = ch.pad[c]; }
+    p.halo = halo;
     p.tiles_per_item = (L + valid - 1) / valid;
     p.total_tiles = p.tiles_per_item * a.B;
     p.map = tile_map(L);
@@ -897,15 +902,16 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     if ((err = run.conv(a.layers[0], XIN16, a.T, e, 0))) return err;
     if ((err = unblock_tap(SA_TAP_CONV_PRE, cfg.initial_channels, a.T))) return err;
   }
-  int L = a.T;
+  int L = a.T, split_launches = 0;
+  (void)split_launches;
   // The last stage hands conv_post its lrelu(0.01)-activated output in the 16-bit blocked layout (half the bytes of
   // the fp32 stream, read once); other filter lengths keep the fp32 hand-off.
   const bool post16 = a.layers[L_post].k == 7 && a.layers[L_post].cin % 16 == 0;
   for (int i = 0; i < nst; ++i) {
     const tc_layer& up = a.layers[L_up(i)];
+    bool all_fused = a.chains != nullptr;
     {                                               // archi.py:80-81
       // The fused ResBlock kernels read the fp32 stage input only; lrelu(x) in 16 bits is for the per-layer convs.
-      bool all_fused = a.chains != nullptr;
       for (int j = 0; j < nrb && all_fused; ++j) all_fused = run.chain_usable(a.chains[i * nrb + j], L * up.stride);
       Epi e;
       e.flags = tc::EPI_OUT32 | (all_fused ? 0u : tc::EPI_OUT16);
@@ -944,7 +950,20 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       }
       if (a.chains) {                               // narrow stages: the whole ResBlock in one kernel
         bool done = false;
-        if ((err = run.chain(a.chains[i * nrb + j], X32, L, fin, tag, &done))) return err;
+        const tc_chain& ch = a.chains[i * nrb + j];
+        // SATOOLS_B200_SPLIT: bit 0 = split the k = 11 blocks, bit 1 = also the k = 7 blocks
+        static const int split = getenv("SATOOLS_B200_SPLIT") ? atoi(getenv("SATOOLS_B200_SPLIT")) : 1;
+        if (all_fused && ch.n_convs == 6 && (((split & 1) && ch.k == 11) || ((split & 2) && ch.k == 7)) && run.chain_usable(ch, L)) {
+          // two launches (pairs 0-1 | pair 2): 30 instead of 60 halo rows per side, one extra fp32 round trip
+          float* TMP32 = reinterpret_cast<float*>(AX16);        // AX16 + A16 are dead in a fully fused stage
+          Epi mid;
+          mid.flags = tc::EPI_OUT32; mid.out32 = TMP32;
+          if ((err = run.chain(ch, X32, L, mid, tag, &done, 0, 4))) return err;
+          if (done && (err = run.chain(ch, TMP32, L, fin, tag, &done, 4, 6))) return err;
+          if (done) { ++split_launches; continue; }
+          return "split ResBlock launch failed";
+        }
+        if ((err = run.chain(ch, X32, L, fin, tag, &done))) return err;
         if (done) continue;
       }
       for (int m = 0; m < nd; ++m) {               // nn.py:169-174
