@@ -167,6 +167,13 @@ class CoreHifiGan(nn.Module):
             self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
         return (y, torch.empty((1)))
 
+    # ---- latency path: one CUDA graph launch instead of ~50 kernel launches ---------------------
+    def graphed(self, B: int, T: int, device=None, out_dtype: torch.dtype = torch.float32) -> "GraphedForward":
+        """Capture forward() for one fixed input shape [B, imput_dim, T] into a CUDA graph (single utterances,
+        `convert()` one file at a time, hubconf usage).  The returned callable copies x into a static buffer, replays
+        the graph and returns the static output tensor (overwritten by the next call)."""
+        return GraphedForward(self, B, T, device, out_dtype)
+
     # ---- host-buffer entry (anonymize pipeline: H2D, convert, D2H; pipeline.py:104-149) ----
     @torch.no_grad()
     def synthesize_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -336,3 +343,38 @@ class CoreHifiGan(nn.Module):
             state[k] = None
         state["_handle_pid"] = -1
         return state
+
+
+class GraphedForward:
+    """CoreHifiGan.forward for one fixed shape, captured once and replayed (see CoreHifiGan.graphed)."""
+
+    def __init__(self, gen: CoreHifiGan, B: int, T: int, device=None, out_dtype: torch.dtype = torch.float32):
+        self.gen = gen
+        self.device = torch.device(device) if device is not None else next(gen.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device (no CPU fallback)")
+        self.x = torch.zeros((B, gen.imput_dim, T), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up: weight fold, kernel attributes, workspace
+                gen.forward(self.x, out_dtype=out_dtype)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self._sig = gen._weights_sig
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.y, _ = gen.forward(self.x, out_dtype=out_dtype)
+        self.launches = gen.last_launch_count
+        self._ws = gen._workspace                         # the captured kernels point into this allocation
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if tuple(x.shape) != tuple(self.x.shape):
+            raise ValueError(f"graph was captured for {tuple(self.x.shape)}, got {tuple(x.shape)}")
+        if self.gen._signature() != self._sig:
+            raise RuntimeError("the generator's weights changed after the capture (folded weights are baked in); "
+                               "call CoreHifiGan.graphed() again")
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y, torch.empty((1))

@@ -368,3 +368,27 @@ def test_fp16_against_the_reference_op_sequence_under_cuda_autocast():
             torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / 3
         print(f"{name}: {16 * 15 / dt:.0f} audio-s/s ({1e3 * dt:.1f} ms per 16 x 15 s)")
+
+
+def test_cuda_graph_forward_equals_direct_forward_and_reports_latency():
+    """Latency path (BASELINE configs[0]: one 5 s utterance): the ~50 launches of a forward captured into one CUDA
+    graph give the same waveform as the direct call; launch-bound latency is printed for profiles/README.md."""
+    import time
+    gen = dev_gen(0, "fp16")
+    x = torch.from_numpy(conditioning.batch(21, [250])).to("cuda:0")
+    x2 = torch.from_numpy(conditioning.batch(22, [250])).to("cuda:0")
+    want, want2 = gen(x)[0].clone(), gen(x2)[0].clone()
+    g = gen.graphed(1, 250)
+    assert torch.equal(g(x)[0], want)
+    assert torch.equal(g(x2)[0], want2)                     # static buffers are refreshed per call
+    with pytest.raises(ValueError):
+        g(torch.zeros(1, 504, 251, device="cuda:0"))
+    for fn, name in ((lambda: gen(x), "direct"), (lambda: g(x), "graph")):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            fn()
+        torch.cuda.synchronize()
+        print(f"{name}: {1e3 * (time.perf_counter() - t0) / 50:.3f} ms per 5 s utterance ({g.launches} kernel launches)")
