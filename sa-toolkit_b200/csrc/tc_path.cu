@@ -556,7 +556,12 @@ struct Runner {
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
     // diagnostics only (results become wrong): drop epilogue streams to time what each costs
     static const uint32_t dbg_mask = getenv("SATOOLS_B200_DEBUG_EPI_MASK") ? (uint32_t)strtoul(getenv("SATOOLS_B200_DEBUG_EPI_MASK"), nullptr, 16) : 0u;
-    p.flags &= ~dbg_mask;
+    if (dbg_mask) {
+      static bool warned = false;
+      if (!warned) fprintf(stderr, "[satools_b200] SATOOLS_B200_DEBUG_EPI_MASK=%x: epilogue streams dropped, RESULTS ARE WRONG (timing only)\n", dbg_mask);
+      warned = true;
+      p.flags &= ~dbg_mask;
+    }
     p.slope_out = e.slope_out;
     p.n_blocks = e.n_blocks;
     mark(tag);
