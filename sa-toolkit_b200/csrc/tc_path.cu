@@ -580,6 +580,10 @@ struct Runner {
     if (!g_use_chain3 || nrb != 3 || !ch[0].d_w || !ch[1].d_w || !ch[2].d_w) return nullptr;
     const int C = ch[0].c;
     if ((C != 16 && C != 32) || ch[0].k != 3 || ch[1].k != 7 || ch[2].k != 11) return nullptr;
+    // C = 32: three per-ResBlock launches (6 sub-tiles each, the k = 11 block split in two) recompute 14 % halo rows
+    // instead of 45 % and now win (stage 3: 6.0 -> 5.5 ms); C = 16 stays whole-stage (4.9 vs 5.9 ms).
+    static const int c32 = getenv("SATOOLS_B200_CHAIN3_C32") ? atoi(getenv("SATOOLS_B200_CHAIN3_C32")) : 0;
+    if (C == 32 && !c32) return nullptr;
     if (ch[0].n_convs != ch[1].n_convs || ch[0].n_convs != ch[2].n_convs) return nullptr;
     // sub-tiles per CTA: more rows per tile amortise the 2 x halo recomputed rows, until registers run out
     static const int ms16 = getenv("SATOOLS_B200_CHAIN3_MS16") ? atoi(getenv("SATOOLS_B200_CHAIN3_MS16")) : 5;   // measured: 4 -> 5.5 ms, 5 -> 5.15, 6 -> 5.2 (spills)
