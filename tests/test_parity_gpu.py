@@ -392,3 +392,16 @@ def test_cuda_graph_forward_equals_direct_forward_and_reports_latency():
             fn()
         torch.cuda.synchronize()
         print(f"{name}: {1e3 * (time.perf_counter() - t0) / 50:.3f} ms per 5 s utterance ({g.launches} kernel launches)")
+
+
+def test_ragged_batch_larger_than_the_tile_map_falls_back_to_padded_semantics():
+    """The live-tile prefix lives in 1 KB of static shared memory (256 items); bigger batches ignore frames_per_item
+    and compute the padded batch -- same kept samples, and here the same tail too."""
+    gen = dev_gen(2, "fp16")
+    rng = np.random.default_rng(9)
+    frames = [int(v) for v in rng.integers(2, 41, size=260)]
+    frames[3] = 40
+    x = conditioning.batch(31, frames)
+    y_pad = run(gen, x)
+    y_rag = run(gen, x, frames_per_item=frames)
+    np.testing.assert_array_equal(y_rag, y_pad)
