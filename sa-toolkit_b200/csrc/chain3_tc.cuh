@@ -206,6 +206,17 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_ready(0, 0, 0)); mbar_arrive(bar_ready(1, 0, 0)); mbar_arrive(bar_ready(2, 0, 0)); }
+      // The x load above sits at the head of every tile's dependency chain: pull the next tile's rows into L2 now.
+      if (tile + (int)gridDim.x < n_live) {
+        int bn, mtn;
+        tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile + (int)gridDim.x, bn, mtn);
+        const int tn = mtn * valid_rows - p.halo + r;
+        if (tn >= 0 && tn < p.L) {
+#pragma unroll
+          for (int q = 0; q < kCPT; ++q)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + q) * (size_t)p.L + tn) * 8));
+        }
+      }
       // ---- one conv of one chain ----
       auto step = [&](auto second_c, auto last_c, auto j_c, int c) {
         constexpr bool second = decltype(second_c)::value;

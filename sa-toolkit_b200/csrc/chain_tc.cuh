@@ -317,6 +317,23 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(0, TM ? 0 : s));
+      // the multi-receptive-field partial sum is only needed by this tile's last epilogue: have it in L2 by then
+      if (keep && (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
+#pragma unroll
+        for (int q = 0; q < kCPT; ++q)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sum32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8));
+      }
+      // The x load above sits at the head of every tile's dependency chain: pull the next tile's rows into L2 now.
+      if (tile + (int)gridDim.x < n_live) {
+        int bn, mtn;
+        tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile + (int)gridDim.x, bn, mtn);
+        const int tn = mtn * valid_rows - p.halo + r;
+        if (tn >= 0 && tn < p.L) {
+#pragma unroll
+          for (int q = 0; q < kCPT; ++q)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + ch0 + q) * (size_t)p.L + tn) * 8));
+        }
+      }
       if (timing) t_p0 += clock64() - tp0;
       // ---- the convs: (conv1, conv2) pairs; one generic step with compile-time flags so the residual add, the
       // final stores and the staging stores are straight-line code without predicated moves ----
