@@ -135,6 +135,19 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T,
                        const int32_t* frames_per_item, void* y, int32_t y_dtype,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same forward fed with the conditioning PARTS instead of the concatenated tensor: what
+ * Net._forward (egs/vc/libritts/local/tuning/hifigan.py:83-97) builds with
+ *   x = cat([bn, F.interpolate(f0, T), F.interpolate(spk_id.unsqueeze(2), T)], dim=1)
+ * bn [B, n_bn, T], f0 [B, 1, T] (already normalised / transformed / interpolated to T) and
+ * spk [B, n_spk] (one-hot rows, constant in time), device fp32, n_bn + 1 + n_spk == input_dim.
+ * The [B, input_dim, T] tensor is never materialised; the result is bit-identical to
+ * sa_hifigan_forward on the concatenation.  Tensor-core modes only (fp32 parity mode:
+ * SA_ERR_UNSUPPORTED, assemble x). */
+int sa_hifigan_forward_parts(sa_hifigan* h, const float* bn, int32_t n_bn, const float* f0,
+                             const float* spk, int32_t n_spk, int32_t B, int32_t T,
+                             const int32_t* frames_per_item, void* y, int32_t y_dtype,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same with HOST buffers (pinned for full speed): copies x to the device, runs the forward,
  * copies y back and waits.  dev_scratch must hold
  * sa_hifigan_host_scratch_bytes(h,B,T,y_dtype) bytes (staging for x and y + the workspace). */
@@ -152,6 +165,16 @@ int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, in
 int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
                                      const int32_t* frames_per_item, void* y_host, int32_t y_dtype,
                                      void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* The stream-ordered host entry fed with the conditioning parts (see sa_hifigan_forward_parts):
+ * bn_host [B, n_bn, T], f0_host [B, 1, T], spk_host [B, n_spk] on the host (pinned for overlap):
+ * (n_bn + 1) / input_dim of the H2D bytes of the concatenated tensor.  Same dev_scratch size. */
+int sa_hifigan_synthesize_host_parts_async(sa_hifigan* h, const float* bn_host, int32_t n_bn,
+                                           const float* f0_host, const float* spk_host,
+                                           int32_t n_spk, int32_t B, int32_t T,
+                                           const int32_t* frames_per_item, void* y_host,
+                                           int32_t y_dtype, void* dev_scratch,
+                                           size_t dev_scratch_bytes, void* stream);
 
 /* Debug tap: while `out` is non-NULL every following forward also writes activation `tap`
  * as fp32 [B,C,L] to `out` (device memory, caller sized: conv_pre B*initial_channels*T,

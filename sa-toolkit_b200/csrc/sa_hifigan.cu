@@ -532,14 +532,25 @@ int forward_f32(sa_hifigan* h, const float* x, int B, int T, void* y, int y_dtyp
 
 extern "C" {
 
-int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, const int32_t* frames_per_item, void* y,
-                       int32_t y_dtype, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h || !x || !y || !workspace) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+// x, or (x == nullptr) the conditioning parts bn / f0 / spk
+static int forward_impl(sa_hifigan* h, const float* x, const float* bn, const float* f0, const float* spk, int32_t n_bn,
+                        int32_t n_spk, int32_t B, int32_t T, const int32_t* frames_per_item, void* y, int32_t y_dtype,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !y || !workspace || (!x && (!bn || !f0 || !spk))) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (!x) {
+    if (n_bn < 1 || n_spk < 0 || n_bn + 1 + n_spk != h->cfg.input_dim)
+      return fail(SA_ERR_INVALID_ARG, "n_bn + 1 + n_spk = %d + 1 + %d != input_dim %d", n_bn, n_spk, h->cfg.input_dim);
+    if (h->finalized && h->precision == SA_PRECISION_FP32)
+      return fail(SA_ERR_UNSUPPORTED, "the fp32 parity mode takes the assembled x (sa_hifigan_forward)");
+    if ((reinterpret_cast<uintptr_t>(bn) | reinterpret_cast<uintptr_t>(f0) | reinterpret_cast<uintptr_t>(spk)) & 3)
+      return fail(SA_ERR_INVALID_ARG, "bn / f0 / spk must be 4-byte aligned");
+    x = nullptr;
+  }
   if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
   if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2 frames (got B=%d T=%d)", B, T);
   if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
     return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+  if ((x && (reinterpret_cast<uintptr_t>(x) & 15)) || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return fail(SA_ERR_INVALID_ARG, "x must be 16-byte and workspace 256-byte aligned");
   const size_t need = sa_hifigan_workspace_bytes(h, B, T);
   if (workspace_bytes < need)
@@ -562,6 +573,7 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, cons
   } else {
     sa::tc_forward_args a;
     a.cfg = &h->cfg; a.x = x; a.B = B; a.T = T; a.frames_per_item = frames_per_item; a.y = y; a.y_dtype = y_dtype;
+    a.bn = bn; a.f0 = f0; a.spk = spk; a.n_bn = n_bn; a.n_spk = n_spk;
     a.workspace = workspace; a.stream = st; a.debug_tap = h->debug_tap; a.debug_out = h->debug_out;
     a.bf16 = h->precision == SA_PRECISION_BF16; a.n_sm = h->n_sm;
     std::vector<sa::tc_layer> layers(h->convs.size());
@@ -581,6 +593,21 @@ int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, cons
   h->mark(-1, st);
   if (cur != h->device) cudaSetDevice(cur);
   return rc;
+}
+
+int sa_hifigan_forward(sa_hifigan* h, const float* x, int32_t B, int32_t T, const int32_t* frames_per_item, void* y,
+                       int32_t y_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  return forward_impl(h, x, nullptr, nullptr, nullptr, 0, 0, B, T, frames_per_item, y, y_dtype, workspace, workspace_bytes,
+                      stream);
+}
+
+int sa_hifigan_forward_parts(sa_hifigan* h, const float* bn, int32_t n_bn, const float* f0, const float* spk, int32_t n_spk,
+                             int32_t B, int32_t T, const int32_t* frames_per_item, void* y, int32_t y_dtype, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!bn || !f0 || !spk) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  return forward_impl(h, nullptr, bn, f0, spk, n_bn, n_spk, B, T, frames_per_item, y, y_dtype, workspace, workspace_bytes,
+                      stream);
 }
 
 int sa_hifigan_check(sa_hifigan* h, void* stream) {
@@ -675,6 +702,59 @@ int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t
   SA_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_in, 0));
   int rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, sa_hifigan_workspace_bytes(h, B, T),
                               h->compute_stream);
+  SA_CUDA(cudaEventRecord(h->ev_done, h->compute_stream));
+  SA_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+  if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(y_host, yd, y_bytes, cudaMemcpyDeviceToHost, st));
+  if (cur != h->device) cudaSetDevice(cur);
+  return rc;
+}
+
+// Parts variant of the stream-ordered host entry: H2D of bn + f0 + spk (49 % of the bytes of x for the 504-channel
+// model), forward_parts on the compute stream, D2H.  Same scratch size and layout as the x variant.
+int sa_hifigan_synthesize_host_parts_async(sa_hifigan* h, const float* bn_host, int32_t n_bn, const float* f0_host,
+                                           const float* spk_host, int32_t n_spk, int32_t B, int32_t T,
+                                           const int32_t* frames_per_item, void* y_host, int32_t y_dtype, void* dev_scratch,
+                                           size_t dev_scratch_bytes, void* stream) {
+  if (!h || !bn_host || !f0_host || !spk_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
+  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2");
+  if (n_bn < 1 || n_spk < 0 || n_bn + 1 + n_spk != h->cfg.input_dim)
+    return fail(SA_ERR_INVALID_ARG, "n_bn + 1 + n_spk = %d + 1 + %d != input_dim %d", n_bn, n_spk, h->cfg.input_dim);
+  if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
+    return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
+  const size_t need = align_up(host_part_bytes(h, B, T, y_dtype), 256);
+  if (dev_scratch_bytes < need) return fail(SA_ERR_WORKSPACE, "dev_scratch too small: %zu < %zu", dev_scratch_bytes, need);
+  if (reinterpret_cast<uintptr_t>(dev_scratch) & 255) return fail(SA_ERR_INVALID_ARG, "dev_scratch must be 256-byte aligned");
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cur = -1;
+  SA_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
+  const int64_t Lout = sa_hifigan_output_length(h, T);
+  char* base = static_cast<char*>(dev_scratch);
+  const size_t x_bytes = (size_t)B * h->cfg.input_dim * T * sizeof(float);
+  const size_t y_bytes = (size_t)B * (size_t)Lout * esz;
+  const size_t bn_bytes = (size_t)B * n_bn * T * sizeof(float), f0_bytes = (size_t)B * T * sizeof(float);
+  const size_t spk_bytes = (size_t)B * n_spk * sizeof(float);
+  float* bnd = reinterpret_cast<float*>(base);                   // the three parts share the x staging region
+  float* f0d = reinterpret_cast<float*>(base + align_up(bn_bytes, 256));
+  float* spkd = reinterpret_cast<float*>(base + align_up(bn_bytes, 256) + align_up(f0_bytes, 256));
+  if (align_up(bn_bytes, 256) + align_up(f0_bytes, 256) + spk_bytes > align_up(x_bytes, 256))
+    return fail(SA_ERR_WORKSPACE, "parts do not fit the x staging region");
+  void* yd = base + align_up(x_bytes, 256);
+  void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+  if (!h->compute_stream) {
+    SA_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  }
+  SA_CUDA(cudaMemcpyAsync(bnd, bn_host, bn_bytes, cudaMemcpyHostToDevice, st));
+  SA_CUDA(cudaMemcpyAsync(f0d, f0_host, f0_bytes, cudaMemcpyHostToDevice, st));
+  if (spk_bytes) SA_CUDA(cudaMemcpyAsync(spkd, spk_host, spk_bytes, cudaMemcpyHostToDevice, st));
+  SA_CUDA(cudaEventRecord(h->ev_in, st));
+  SA_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_in, 0));
+  int rc = sa_hifigan_forward_parts(h, bnd, n_bn, f0d, spkd, n_spk, B, T, frames_per_item, yd, y_dtype, ws,
+                                    sa_hifigan_workspace_bytes(h, B, T), h->compute_stream);
   SA_CUDA(cudaEventRecord(h->ev_done, h->compute_stream));
   SA_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
   if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(y_host, yd, y_bytes, cudaMemcpyDeviceToHost, st));

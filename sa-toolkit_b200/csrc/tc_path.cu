@@ -80,6 +80,27 @@ __global__ void pack_input_kernel(const float* __restrict__ x, uint4* __restrict
   out[(((size_t)b * (chunks / cpp) + c8 / cpp) * T + t) * cpp + c8 % cpp] = tc::pack8(v, bf16 != 0);
 }
 
+// The same packed input straight from the conditioning parts (Net._forward, hifigan.py:83-97: x = cat(bn, f0, speaker
+// one-hot repeated over time)): the [B, 504, T] fp32 tensor is never materialised.  Bit-identical to packing cat(...).
+__global__ void pack_parts_kernel(const float* __restrict__ bn, const float* __restrict__ f0, const float* __restrict__ spk,
+                                  uint4* __restrict__ out, int n_bn, int n_spk, int chunks, int T, int bf16, int pw) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c8 * 8 + e;
+    float x = 0.f;
+    if (c < n_bn) x = __ldg(bn + ((size_t)b * n_bn + c) * T + t);
+    else if (c == n_bn) x = __ldg(f0 + (size_t)b * T + t);
+    else if (c < n_bn + 1 + n_spk) x = __ldg(spk + (size_t)b * n_spk + (c - n_bn - 1));
+    v[e] = x;
+  }
+  const int cpp = pw >> 3;
+  out[(((size_t)b * (chunks / cpp) + c8 / cpp) * T + t) * cpp + c8 % cpp] = tc::pack8(v, bf16 != 0);
+}
+
 // fp32 blocked [B][C/8][L][8] -> fp32 [B][C][L]  (debug taps only)
 __global__ void unblock_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int L) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -898,8 +919,12 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     const int cpad = (int)align_up(cfg.input_dim, 16);
     dim3 g((unsigned)((a.T + 127) / 128), (unsigned)(cpad / 8), (unsigned)a.B);
     run.mark(15);
-    pack_input_kernel<<<g, 128, 0, st>>>(a.x, reinterpret_cast<uint4*>(XIN16), cfg.input_dim, cpad / 8, a.T, a.bf16 ? 1 : 0,
-                                         panel_width(cpad));
+    if (a.x)
+      pack_input_kernel<<<g, 128, 0, st>>>(a.x, reinterpret_cast<uint4*>(XIN16), cfg.input_dim, cpad / 8, a.T, a.bf16 ? 1 : 0,
+                                           panel_width(cpad));
+    else
+      pack_parts_kernel<<<g, 128, 0, st>>>(a.bn, a.f0, a.spk, reinterpret_cast<uint4*>(XIN16), a.n_bn, a.n_spk, cpad / 8, a.T,
+                                           a.bf16 ? 1 : 0, panel_width(cpad));
     ++*launches;
     TC_CUDA(cudaGetLastError());
   }

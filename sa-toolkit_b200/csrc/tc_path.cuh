@@ -56,7 +56,11 @@ struct tc_layer {
 
 struct tc_forward_args {
   const sa_hifigan_cfg* cfg;
-  const float* x;
+  const float* x;                                             // [B, input_dim, T] fp32, or nullptr: the parts below
+  const float* bn = nullptr;                                  // [B, n_bn, T]   channels 0 .. n_bn-1      (hifigan.py:91-93)
+  const float* f0 = nullptr;                                  // [B, 1, T]      channel n_bn
+  const float* spk = nullptr;                                 // [B, n_spk]     channels n_bn+1 .., constant in time (hifigan.py:94-97)
+  int n_bn = 0, n_spk = 0;
   int B, T;
   const int32_t* frames_per_item;
   void* y;

@@ -48,11 +48,17 @@ SYMBOLS = {
     "sa_hifigan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
     "sa_hifigan_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
                                      C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_hifigan_forward_parts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]),
     "sa_hifigan_host_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "sa_hifigan_synthesize_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                              C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sa_hifigan_synthesize_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_hifigan_synthesize_host_parts_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                         C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_int32,
+                                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "sa_hifigan_set_debug_tap": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "sa_hifigan_last_launch_count": (C.c_int64, [C.c_void_p]),
     "sa_hifigan_check": (C.c_int, [C.c_void_p, C.c_void_p]),

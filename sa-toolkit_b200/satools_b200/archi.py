@@ -167,6 +167,39 @@ class CoreHifiGan(nn.Module):
             self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
         return (y, torch.empty((1)))
 
+    # ---- conditioning parts instead of the concatenated tensor (Net._forward, hifigan.py:83-97) ----
+    @torch.no_grad()
+    def forward_parts(self, bn: torch.Tensor, f0: torch.Tensor, spk_id: torch.Tensor,
+                      frames_per_item: Optional[Sequence[int]] = None,
+                      out_dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+        """bn [B, n_bn, T], f0 [B, 1, T] or [B, T] (normalised, transformed, at T frames), spk_id [B, n_spk]
+        (one-hot).  Equals forward(torch.cat([bn, f0, spk_id[:, :, None].expand(-1, -1, T)], 1)) bit for bit
+        without building that tensor."""
+        if not (bn.is_cuda and f0.is_cuda and spk_id.is_cuda):
+            raise RuntimeError("satools_b200.CoreHifiGan runs on CUDA (sm_100a) only; there is no CPU fallback.")
+        lib = _lib.load()
+        bn = bn.detach().to(torch.float32).contiguous()
+        B, n_bn, T = bn.shape
+        f0 = f0.detach().to(torch.float32).reshape(B, 1, -1).contiguous()
+        spk = spk_id.detach().to(torch.float32).reshape(B, -1).contiguous()
+        n_spk = spk.shape[1]
+        if f0.shape[2] != T or n_bn + 1 + n_spk != self.imput_dim:
+            raise ValueError(f"parts do not add up: bn {tuple(bn.shape)}, f0 {tuple(f0.shape)}, spk {tuple(spk.shape)}, "
+                             f"imput_dim {self.imput_dim}")
+        with torch.cuda.device(bn.device):
+            self._ensure_ready(bn.device)
+            ws = self._get_workspace(lib.sa_hifigan_workspace_bytes(self._handle, B, T), bn.device)
+            y = torch.empty((B, 1, self.output_length(T)), dtype=out_dtype, device=bn.device)
+            fpi = None
+            if frames_per_item is not None:
+                fpi = (C.c_int32 * B)(*[int(v) for v in frames_per_item])
+            stream = torch.cuda.current_stream(bn.device).cuda_stream
+            _lib.check(lib.sa_hifigan_forward_parts(self._handle, bn.data_ptr(), n_bn, f0.data_ptr(), spk.data_ptr(), n_spk,
+                                                    B, T, fpi, y.data_ptr(), _OUT_DTYPE[out_dtype], ws.data_ptr(),
+                                                    ws.numel(), stream))
+            self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
+        return (y, torch.empty((1)))
+
     # ---- latency path: one CUDA graph launch instead of ~50 kernel launches ---------------------
     def graphed(self, B: int, T: int, device=None, out_dtype: torch.dtype = torch.float32) -> "GraphedForward":
         """Capture forward() for one fixed input shape [B, imput_dim, T] into a CUDA graph (single utterances,

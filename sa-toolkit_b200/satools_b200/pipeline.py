@@ -76,6 +76,44 @@ class HostPipeline:
         self._next += 1
         return ticket
 
+    def submit_parts(self, bn: torch.Tensor, f0: torch.Tensor, spk_id: torch.Tensor, out: Optional[torch.Tensor] = None,
+                     out_dtype: torch.dtype = torch.float32, frames_per_item: Optional[Sequence[int]] = None) -> int:
+        """Like submit(), fed with the conditioning parts (CPU, pinned for overlap): bn [B, n_bn, T], f0 [B, 1, T] or
+        [B, T], spk_id [B, n_spk] one-hot -- about half the H2D bytes of the concatenated tensor."""
+        if bn.is_cuda or f0.is_cuda or spk_id.is_cuda:
+            raise ValueError("submit_parts takes CPU tensors")
+        lib = _lib.load()
+        ticket = self._next
+        slot = self._slots[ticket % len(self._slots)]
+        if slot.ticket >= 0:
+            slot.stream.synchronize()
+        bn = bn.to(torch.float32).contiguous()
+        B, n_bn, T = bn.shape
+        f0 = f0.to(torch.float32).reshape(B, 1, -1).contiguous()
+        spk = spk_id.to(torch.float32).reshape(B, -1).contiguous()
+        if f0.shape[2] != T:
+            raise ValueError(f"f0 has {f0.shape[2]} frames, bn {T}")
+        if out is None:
+            out = torch.empty((B, 1, self.gen.output_length(T)), dtype=out_dtype, pin_memory=True)
+        with torch.cuda.device(self.device):
+            self.gen._ensure_ready(self.device)
+            h = self.gen._handle
+            need = lib.sa_hifigan_host_scratch_bytes(h, B, T, _OUT_DTYPE[out.dtype])
+            if slot.scratch is None or slot.scratch.numel() < need:
+                slot.scratch = None
+                slot.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+            fpi = None
+            if frames_per_item is not None:
+                fpi = (C.c_int32 * B)(*[int(v) for v in frames_per_item])
+            _lib.check(lib.sa_hifigan_synthesize_host_parts_async(h, bn.data_ptr(), n_bn, f0.data_ptr(), spk.data_ptr(),
+                                                                  spk.shape[1], B, T, fpi, out.data_ptr(),
+                                                                  _OUT_DTYPE[out.dtype], slot.scratch.data_ptr(),
+                                                                  slot.scratch.numel(), slot.stream.cuda_stream))
+            self.launches += int(lib.sa_hifigan_last_launch_count(h))
+        slot.ticket, slot.keep, slot.out = ticket, (bn, f0, spk, fpi), out
+        self._next += 1
+        return ticket
+
     def result(self, ticket: int) -> torch.Tensor:
         """Wait for the batch of `ticket` and return its waveform tensor (CPU)."""
         slot = self._slots[ticket % len(self._slots)]

@@ -405,3 +405,45 @@ def test_ragged_batch_larger_than_the_tile_map_falls_back_to_padded_semantics():
     y_pad = run(gen, x)
     y_rag = run(gen, x, frames_per_item=frames)
     np.testing.assert_array_equal(y_rag, y_pad)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_forward_parts_equals_forward_on_the_reference_concatenation(precision):
+    """feed (bn, f0, speaker one-hot) instead of the [B, 504, T] tensor.  On the reference's own assembly
+    (tests/golden/net_forward.npz: x captured at the hifigan(x) boundary of Net._forward together with its bn and
+    spk inputs) the parts path must be bit-identical to forward(x); same for a ragged batch of the bench's structure."""
+    gen = dev_gen(1, precision)
+    z = np.load(os.path.join(helpers.GOLDEN, "net_forward.npz"))
+    for tag in ("plain", "quant_16_awgn_2"):
+        x, bn, spk = z[f"{tag}/x"], z[f"{tag}/bn"], z[f"{tag}/spk"].astype(np.float32)
+        f0 = x[:, 256:257]                                     # the processed F0 channel the reference concatenated
+        y_x = run(gen, x)
+        y_p, aux = gen.forward_parts(torch.from_numpy(bn).cuda(), torch.from_numpy(np.ascontiguousarray(f0)).cuda(),
+                                     torch.from_numpy(spk).cuda())
+        gen.check()
+        assert tuple(aux.shape) == (1,)
+        np.testing.assert_array_equal(y_p.cpu().numpy(), y_x, err_msg=tag)
+    frames = [120, 33, 77, 101, 64]
+    x = conditioning.batch(41, frames)
+    xd = torch.from_numpy(x).cuda()
+    y_x = gen(xd, frames_per_item=frames)[0]
+    y_p = gen.forward_parts(xd[:, :256].contiguous(), xd[:, 256].contiguous(), xd[:, 257:, 0].contiguous(),
+                            frames_per_item=frames)[0]
+    gen.check()
+    for b, f in enumerate(frames):
+        assert torch.equal(y_p[b, 0, :320 * f + 1], y_x[b, 0, :320 * f + 1])
+    # host entry fed with the parts (pinned CPU tensors): 257/504 of the H2D bytes, same waveform
+    from satools_b200 import HostPipeline
+    pipe = HostPipeline(gen)
+    xc = torch.from_numpy(x)
+    t = pipe.submit_parts(xc[:, :256].contiguous().pin_memory(), xc[:, 256].contiguous().pin_memory(),
+                          xc[:, 257:, 0].contiguous().pin_memory(), frames_per_item=frames)
+    y_h = pipe.result(t)
+    for b, f in enumerate(frames):
+        assert torch.equal(y_h[b, 0, :320 * f + 1], y_x[b, 0, :320 * f + 1].cpu())
+    with pytest.raises(ValueError):
+        gen.forward_parts(xd[:, :255].contiguous(), xd[:, 256].contiguous(), xd[:, 257:, 0].contiguous())
+    from satools_b200 import _lib
+    gen.precision = "fp32"
+    with pytest.raises(_lib.SaHifiganError, match="assembled x"):
+        gen.forward_parts(xd[:, :256].contiguous(), xd[:, 256].contiguous(), xd[:, 257:, 0].contiguous())
