@@ -936,8 +936,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     if ((err = run.conv(a.layers[0], XIN16, a.T, e, 0))) return err;
     if ((err = unblock_tap(SA_TAP_CONV_PRE, cfg.initial_channels, a.T))) return err;
   }
-  int L = a.T, split_launches = 0;
-  (void)split_launches;
+  int L = a.T;
   // The last stage hands conv_post its lrelu(0.01)-activated output in the 16-bit blocked layout (half the bytes of
   // the fp32 stream, read once); other filter lengths keep the fp32 hand-off.
   const bool post16 = a.layers[L_post].k == 7 && a.layers[L_post].cin % 16 == 0;
@@ -994,7 +993,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
           mid.flags = tc::EPI_OUT32; mid.out32 = TMP32;
           if ((err = run.chain(ch, X32, L, mid, tag, &done, 0, 4))) return err;
           if (done && (err = run.chain(ch, TMP32, L, fin, tag, &done, 4, 6))) return err;
-          if (done) { ++split_launches; continue; }
+          if (done) continue;
           return "split ResBlock launch failed";
         }
         if ((err = run.chain(ch, X32, L, fin, tag, &done))) return err;
