@@ -326,12 +326,15 @@ int sa_hifigan_finalize(sa_hifigan* h, int32_t precision) {
     SA_CUDA(cudaMalloc(&c.d_bias, c.cout * sizeof(float)));
     SA_CUDA(cudaMemcpy(c.d_bias, c.bias.data(), c.cout * sizeof(float), cudaMemcpyHostToDevice));
   }
-  const bool is_post = true;
-  (void)is_post;
   for (size_t li = 0; li < h->convs.size(); ++li) {
     sa_conv& c = h->convs[li];
-    const bool need_f32 = precision == SA_PRECISION_FP32 || (int)li == h->conv_post() ||
-                          !sa::tc_layer_supported(c.transposed, c.cin, c.cout, c.k);
+    const bool tc_ok = sa::tc_layer_supported(c.transposed, c.cin, c.cout, c.k, (int)li == h->conv_pre());
+    // The tensor-core forward runs every layer but conv_post through the tcgen05 kernels: a layer they cannot take
+    // (channel counts that are not whole panels / instantiated tiles) is refused here, not discovered at launch time.
+    if (precision != SA_PRECISION_FP32 && (int)li != h->conv_post() && !tc_ok)
+      return fail(SA_ERR_UNSUPPORTED, "%s: Cin=%d Cout=%d is not supported by the fp16/bf16 tensor-core path (channels after "
+                  "conv_pre must be 16, 32, 64, 128 or a multiple of 256); use precision fp32", c.name.c_str(), c.cin, c.cout);
+    const bool need_f32 = precision == SA_PRECISION_FP32 || (int)li == h->conv_post();
     if (need_f32) {
       // [Cin][k][Cout] from [Cout][Cin][k] (Conv1d) or [Cin][Cout][k] (ConvTranspose1d)
       std::vector<float> p((size_t)c.cin * c.k * c.cout);
@@ -547,7 +550,7 @@ static int forward_impl(sa_hifigan* h, const float* x, const float* bn, const fl
     x = nullptr;
   }
   if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
-  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2 frames (got B=%d T=%d)", B, T);
+  if (B < 1 || T < 1) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 1 frames (got B=%d T=%d)", B, T);
   if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
     return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
   if ((x && (reinterpret_cast<uintptr_t>(x) & 15)) || (reinterpret_cast<uintptr_t>(workspace) & 255))
@@ -672,7 +675,7 @@ int sa_hifigan_synthesize_host_async(sa_hifigan* h, const float* x_host, int32_t
                                      size_t dev_scratch_bytes, void* stream) {
   if (!h || !x_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
   if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
-  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2");
+  if (B < 1 || T < 1) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 1");
   if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
     return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
   const size_t need = align_up(host_part_bytes(h, B, T, y_dtype), 256);
@@ -717,7 +720,7 @@ int sa_hifigan_synthesize_host_parts_async(sa_hifigan* h, const float* bn_host, 
                                            size_t dev_scratch_bytes, void* stream) {
   if (!h || !bn_host || !f0_host || !spk_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
   if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
-  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2");
+  if (B < 1 || T < 1) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 1");
   if (n_bn < 1 || n_spk < 0 || n_bn + 1 + n_spk != h->cfg.input_dim)
     return fail(SA_ERR_INVALID_ARG, "n_bn + 1 + n_spk = %d + 1 + %d != input_dim %d", n_bn, n_spk, h->cfg.input_dim);
   if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
@@ -767,7 +770,7 @@ int sa_hifigan_synthesize_host(sa_hifigan* h, const float* x_host, int32_t B, in
                                size_t dev_scratch_bytes, void* stream) {
   if (!h || !x_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
   if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
-  if (B < 1 || T < 2) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 2");
+  if (B < 1 || T < 1) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 1");
   const size_t need = sa_hifigan_host_scratch_bytes(h, B, T, y_dtype);
   if (dev_scratch_bytes < need) return fail(SA_ERR_WORKSPACE, "dev_scratch too small: %zu < %zu", dev_scratch_bytes, need);
   if (reinterpret_cast<uintptr_t>(dev_scratch) & 255) return fail(SA_ERR_INVALID_ARG, "dev_scratch must be 256-byte aligned");

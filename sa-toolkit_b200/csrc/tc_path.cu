@@ -575,6 +575,7 @@ struct Runner {
     p.map = tile_map(l_in);
     p.w_tile_bytes = (uint32_t)w.tile_bytes;
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+#ifdef SA_DIAG   // diagnostic builds only (nvcc -DSA_DIAG): the shipped library has no switch that changes results
     // diagnostics only (results become wrong): drop epilogue streams to time what each costs
     static const uint32_t dbg_mask = getenv("SATOOLS_B200_DEBUG_EPI_MASK") ? (uint32_t)strtoul(getenv("SATOOLS_B200_DEBUG_EPI_MASK"), nullptr, 16) : 0u;
     if (dbg_mask) {
@@ -583,6 +584,7 @@ struct Runner {
       warned = true;
       p.flags &= ~dbg_mask;
     }
+#endif
     p.slope_out = e.slope_out;
     p.n_blocks = e.n_blocks;
     mark(tag);
@@ -688,10 +690,17 @@ struct Runner {
 
 }  // namespace
 
-bool tc_layer_supported(bool transposed, int cin, int cout, int k) {
-  (void)cin; (void)k;
-  if (cout % 16 != 0) return false;
-  if (cout > 256 && cout % 256 != 0) return false;
+// Whole panels only: the 16-bit activation tensors are [C / PW][L][PW] with PW = min(C, 64), and the kernels, the weight
+// packing and the tensor maps all count panels as C / PW.  A channel count that is not 16, 32 or a multiple of 64 is padded
+// up to the next such value (conv_pre's input: 257 -> 320, 504 -> 512); padded channels are zero in x and in the weights.
+int tc_cin_pad(int cin) { return cin > 64 ? (cin + 63) / 64 * 64 : cin > 32 ? 64 : cin > 16 ? 32 : 16; }
+
+// first_layer: the input is packed by pack_input_kernel (any Cin); otherwise it is the previous layer's output tensor,
+// whose channel count must already be a whole number of panels.
+bool tc_layer_supported(bool transposed, int cin, int cout, int k, bool first_layer) {
+  (void)k;
+  if (!first_layer && tc_cin_pad(cin) != cin) return false;
+  if (cout != 16 && cout != 32 && cout != 64 && cout != 128 && cout % 256 != 0) return false;   // instantiated N tiles
   if (transposed && cout > 256) return false;
   return true;
 }
@@ -699,7 +708,7 @@ bool tc_layer_supported(bool transposed, int cin, int cout, int k) {
 const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed, int cin, int cout, int k, int stride,
                             int pad, bool bf16) {
   tc_free_weights(w);
-  w.cin_pad = (int)align_up(cin, 16);
+  w.cin_pad = tc_cin_pad(cin);
   w.n = cout > 256 ? 256 : cout;
   w.n_tiles = cout / w.n;
   // Wide layers (N = 256 / 128, 64-channel panels) run on CTA pairs; their weights are packed in half tiles.
@@ -855,7 +864,7 @@ Sizes sizes(const sa_hifigan_cfg& cfg, int B, int T) {
   Sizes s;
   s.e16 = align_up(E * 2, 256);
   s.e32 = align_up(E * 4, 256);
-  s.xin = align_up((size_t)B * T * align_up(cfg.input_dim, 16) * 2, 256);
+  s.xin = align_up((size_t)B * T * tc_cin_pad(cfg.input_dim) * 2, 256);
   s.frames = align_up((size_t)B * sizeof(int32_t), 256);
   return s;
 }
@@ -916,7 +925,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
 
   // pack x -> 16-bit blocked
   {
-    const int cpad = (int)align_up(cfg.input_dim, 16);
+    const int cpad = tc_cin_pad(cfg.input_dim);
     dim3 g((unsigned)((a.T + 127) / 128), (unsigned)(cpad / 8), (unsigned)a.B);
     run.mark(15);
     if (a.x)

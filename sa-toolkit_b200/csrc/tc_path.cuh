@@ -17,7 +17,7 @@ struct tc_weights {
   int pair = 0;              // 1: packed in N/2-row half tiles for the CTA-pair kernel (conv_pair_tc.cuh):
                              //    [phase][2 * n_tile + half][tap][panel][N/2][64]; tile_bytes = one half tile
   int n_phases = 0;          // 1 for Conv1d, stride for ConvTranspose1d
-  int cin_pad = 0;           // Cin rounded up to 16
+  int cin_pad = 0;           // Cin rounded up to whole panels (tc_cin_pad)
   int n_taps[kTcMaxPhases] = {0};
   int tap_base[kTcMaxPhases] = {0};
   int tap_step = 1;          // informational for transposed convs (-1); convs use the layer dilation
@@ -78,7 +78,8 @@ struct tc_forward_args {
   void (*mark)(void* ctx, int tag, cudaStream_t s) = nullptr;
 };
 
-bool tc_layer_supported(bool transposed, int cin, int cout, int k);
+int tc_cin_pad(int cin);
+bool tc_layer_supported(bool transposed, int cin, int cout, int k, bool first_layer);
 const char* tc_pack_weights(tc_weights& w, const float* folded, bool transposed, int cin, int cout, int k,
                             int stride, int pad, bool bf16);
 void tc_free_weights(tc_weights& w);

@@ -45,7 +45,21 @@ def utterance(rng: np.random.Generator, frames: int, n_spk: int = N_SPEAKERS,
     return x
 
 
-def batch(seed: int, frames: Sequence[int], n_spk: int = N_SPEAKERS, pad_to: Optional[int] = None) -> np.ndarray:
+def quant_awgn_f0(f0: np.ndarray, rng: np.random.Generator, bins: int = 16, noise_db: float = 2.0) -> np.ndarray:
+    """Synthetic stand-in for f0_transformation="quant_16_awgn_2" (BASELINE configs[2]) on a normalised F0 track:
+    quantize_f0 = round(x * bins) / bins with unvoiced (== 0) frames kept at 0, then awgn_f0 = + N(0, sqrt(10^(dB/10)))
+    with unvoiced frames kept at 0 (/root/reference/satools/satools/hifigan/nn.py:28-62).  The reference draws the
+    noise from torch's global CPU RNG; here it comes from `rng` so the workload is reproducible on any host."""
+    uv = f0 == 0
+    q = np.round(f0 * bins) / bins
+    q[uv] = 0
+    q = q + rng.normal(0.0, np.sqrt(10.0 ** (noise_db / 10.0)), size=q.shape).astype(np.float32)
+    q[uv] = 0
+    return q.astype(np.float32)
+
+
+def batch(seed: int, frames: Sequence[int], n_spk: int = N_SPEAKERS, pad_to: Optional[int] = None,
+          f0_transformation: str = "") -> np.ndarray:
     """Batch padded to the longest item the way the pipeline pads (zeros in BN/F0, but the
     speaker one-hot stays on: it is interpolated over the padded length, hifigan.py:94-97)."""
     rng = np.random.default_rng(seed)
@@ -56,4 +70,8 @@ def batch(seed: int, frames: Sequence[int], n_spk: int = N_SPEAKERS, pad_to: Opt
         u = utterance(rng, n, n_spk, cb)
         out[b, :, :n] = u
         out[b, N_BN + 1:, n:] = u[N_BN + 1:, :1]
+    if f0_transformation:
+        if f0_transformation != "quant_16_awgn_2":
+            raise ValueError("only quant_16_awgn_2 is generated")
+        out[:, N_BN] = quant_awgn_f0(out[:, N_BN], np.random.default_rng(seed + 7919))
     return out

@@ -26,14 +26,24 @@ def state_sha256(state) -> str:
 _GEN_CACHE = {}
 
 
-def seeded_generator(seed: int, **kw):
+def seeded_generator(seed: int, imput_dim: int = 504, **kw):
     """satools_b200.CoreHifiGan with the reference's random init for `seed` (CPU parameters)."""
     from satools_b200 import CoreHifiGan
-    key = (seed, tuple(sorted(kw.items())))
+    key = (seed, imput_dim, tuple(sorted(kw.items())))
     if key not in _GEN_CACHE:
         torch.manual_seed(seed)
-        _GEN_CACHE[key] = CoreHifiGan(imput_dim=504, **kw)
+        _GEN_CACHE[key] = CoreHifiGan(imput_dim=imput_dim, **kw)
     return _GEN_CACHE[key]
+
+
+def case_input(name: str, meta: dict) -> np.ndarray:
+    """Conditioning tensor of a golden generator case: regenerated from the seed (Cin 504), or shipped with the
+    fixture (other input widths, tiny); the fixture's SHA-256 of x proves it is the tensor the reference saw."""
+    from satools_b200 import conditioning
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x = g["x"] if "x" in g.files else conditioning.batch(meta["cond_seed"], meta["frames"])
+    assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).digest() == g["x_sha256"].tobytes(), "conditioning drifted"
+    return x
 
 
 def numpy_state(gen):

@@ -69,7 +69,7 @@ GEN_CASES = sorted(helpers.manifest()["generator"].items())
 
 @pytest.mark.parametrize("name,meta", GEN_CASES)
 def test_state_regenerates_bit_exact(name, meta):
-    gen = helpers.seeded_generator(meta["seed"])
+    gen = helpers.seeded_generator(meta["seed"], meta.get("imput_dim", 504))
     assert len(gen.state_dict()) == 291
     assert helpers.state_sha256(gen.state_dict()) == meta["state_sha256"]
 
@@ -77,8 +77,8 @@ def test_state_regenerates_bit_exact(name, meta):
 @pytest.mark.parametrize("name,meta", GEN_CASES)
 def test_numpy_oracle_matches_reference(name, meta):
     g = np.load(os.path.join(helpers.GOLDEN, name + ".npz"))
-    gen = helpers.seeded_generator(meta["seed"])
-    x = conditioning.batch(meta["cond_seed"], meta["frames"])
+    gen = helpers.seeded_generator(meta["seed"], meta.get("imput_dim", 504))
+    x = helpers.case_input(name, meta)
     y, stages = onp.generator_forward(helpers.numpy_state(gen), x, return_stages=True)
     assert list(y.shape) == meta["y_shape"]
     assert helpers.max_abs(g["y_ref_fp64"], y) < 1e-12
@@ -90,8 +90,8 @@ def test_numpy_oracle_matches_reference(name, meta):
 @pytest.mark.parametrize("name,meta", GEN_CASES)
 def test_torch_cpu_port_matches_reference(name, meta):
     g = np.load(os.path.join(helpers.GOLDEN, name + ".npz"))
-    gen = helpers.seeded_generator(meta["seed"])
-    x = torch.from_numpy(conditioning.batch(meta["cond_seed"], meta["frames"]))
+    gen = helpers.seeded_generator(meta["seed"], meta.get("imput_dim", 504))
+    x = torch.from_numpy(helpers.case_input(name, meta))
     y = otc.generator_forward(otc.fold(gen.state_dict()), x).numpy()
     assert helpers.max_abs(g["y_ref_fp32"], y) < 2e-6      # fp32, fold order differs from the hook's
     assert helpers.snr_db(g["y_ref_fp64"], y) > 100

@@ -83,3 +83,22 @@ def test_two_rank_gloo_sharding_covers_corpus(tmp_path):
     r0, r1 = (torch.load(tmp_path / f"r{r}.pt") for r in (0, 1))
     assert sorted(r0["mine"] + r1["mine"]) == list(range(len(L)))
     assert r0["total"] == r1["total"] == [float(sum(L)), float(len(L))]
+
+
+def test_receptive_field_is_exactly_20_frames_each_side():
+    """RECEPTIVE_HALO_FRAMES by exact perturbation of the fp64 oracle (random weights, so every tap is non-zero):
+    changing frame f changes output samples of frames f-20 .. f+20 and nothing else, i.e. sample 1 + 320 k + s depends
+    on frames [k - 20, k + 20] -- a window [klo - 20, khi + 20) reproduces frames [klo, khi)."""
+    import numpy as np
+    import torch
+    import helpers
+    from oracle import hifigan_torch_cpu as otc
+    p = otc.fold(helpers.seeded_generator(0).state_dict(), torch.float64)
+    T, f = 100, 50
+    x = torch.from_numpy(np.random.default_rng(0).standard_normal((1, 504, T)))
+    y0 = otc.generator_forward(p, x).numpy()[0, 0]
+    x[:, :, f] += 1.0
+    y1 = otc.generator_forward(p, x).numpy()[0, 0]
+    changed = np.nonzero(y0 != y1)[0]
+    first_frame, last_frame = (changed.min() - 1) // 320, (changed.max() - 1) // 320
+    assert (first_frame, last_frame) == (f - scheduler.RECEPTIVE_HALO_FRAMES, f + scheduler.RECEPTIVE_HALO_FRAMES)
