@@ -15,6 +15,7 @@
 #include "conv_pair_tc.cuh"
 #include "chain_tc.cuh"
 #include "chain3_tc.cuh"
+#include "chain_group_tc.cuh"
 
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -404,6 +405,25 @@ cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cuda
   return cudaGetLastError();
 }
 
+// ---- grouped (block-Toeplitz) fused ResBlock for C <= 32 (chain_group_tc.cuh) -------------------
+int g_use_group = 1;            // SATOOLS_B200_GROUP=0: C <= 32 on the per-tap kernels (chain_tc / chain3_tc)
+
+template <int C, bool BF16>
+cudaError_t launch_group(const tc::GroupParams& p, size_t smem, int n_sm, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::group_chain_kernel<C, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int ctas = std::max(1, std::min((p.total_tiles + 1) / 2, n_sm));     // two tiles in flight per CTA
+  tc::group_chain_kernel<C, BF16><<<ctas, tc::kGrpThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 // ---- CTA-pair kernel (conv_pair_tc.cuh): plan + launch ------------------------------------
 int use_pair() {              // SATOOLS_B200_PAIR=0: wide layers on the single-CTA kernel
   static const int v = getenv("SATOOLS_B200_PAIR") ? atoi(getenv("SATOOLS_B200_PAIR")) : 1;
@@ -641,6 +661,57 @@ struct Runner {
     return nullptr;
   }
 
+  // Grouped kernel geometry for convs [c0, c1) of a block: halo (multiple of G), valid positions per tile, ring depth.
+  struct GroupPlan { int halo, valid, n_wstages; size_t smem; };
+  bool group_plan(GroupPlan& pl, const tc_chain& ch, int L, int c0, int c1) const {
+    if (!g_use_group || !ch.d_wg || (c0 & 1) || ((c1 - c0) & 1) || c1 <= c0) return false;
+    const int G = 64 / ch.c, R = tc::kGrpRows * G;
+    int halo = 0;
+    for (int c = c0; c < c1; ++c) halo += ch.pad[c];
+    halo = (halo + G - 1) / G * G;
+    pl.halo = halo;
+    pl.valid = R - 2 * halo;
+    if (L % G != 0 || pl.valid < R / 2 || L < 2 * pl.valid) return false;    // short sequences: the per-layer path wastes less
+    const size_t fixed = 4 * (size_t)tc::kGrpBufBytes + 3 * (size_t)tc::kGrpMaxPairs * ch.c * 4 + (6 + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
+    int stages = std::min(tc::kGrpMaxStages, 2 * ch.g_stages);              // two convs deep: the next conv streams in behind
+    while (stages > ch.g_stages && fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) --stages;
+    if (stages < ch.g_stages + 1 || fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) return false;
+    pl.n_wstages = stages;
+    pl.smem = fixed + (size_t)stages * tc::kGrpStageBytes;
+    return true;
+  }
+
+  // convs [c0, c1) of one ResBlock on the grouped kernel; *done = false: not applicable, use the per-tap kernels
+  const char* group(const tc_chain& ch, const float* x32, int L, const Epi& e, int tag, bool* done, int c0 = 0, int c1 = -1) {
+    *done = false;
+    if (c1 < 0) c1 = ch.n_convs;
+    GroupPlan pl;
+    if (!group_plan(pl, ch, L, c0, c1)) return nullptr;
+    tc::GroupParams p;
+    memset(&p, 0, sizeof(p));
+    p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
+    p.w = static_cast<const uint8_t*>(ch.d_wg) + (size_t)c0 * ch.g_stages * tc::kGrpStageBytes;
+    p.bias = ch.d_bias + (size_t)c0 * ch.c;
+    p.error_flag = ctx.d_error;
+    p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 16 * ctx.timing_launches++ : nullptr;
+    p.L = L; p.n_convs = c1 - c0;
+    for (int c = c0; c < c1; c += 2) p.dil[(c - c0) / 2] = ch.dil[c];
+    p.halo = pl.halo;
+    p.n_slices = ch.g_slices; p.stages_per_conv = ch.g_stages; p.n_wstages = pl.n_wstages;
+    p.tiles_per_item = (L + pl.valid - 1) / pl.valid;
+    p.total_tiles = p.tiles_per_item * a.B;
+    p.map = tile_map(L);
+    p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+    p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
+    mark(tag);
+    const cudaError_t ce = ch.c == 16 ? (a.bf16 ? launch_group<16, true>(p, pl.smem, a.n_sm, a.stream) : launch_group<16, false>(p, pl.smem, a.n_sm, a.stream))
+                                      : (a.bf16 ? launch_group<32, true>(p, pl.smem, a.n_sm, a.stream) : launch_group<32, false>(p, pl.smem, a.n_sm, a.stream));
+    if (ce != cudaSuccess) return msgf("group_chain launch: %s", cudaGetErrorString(ce));
+    ++*launches;
+    *done = true;
+    return nullptr;
+  }
+
   bool chain_usable(const tc_chain& ch, int L) const {
     ChainPlan pl;
     if (!ch.d_w || !chain_plan(pl, ch, ctx.max_smem)) return false;
@@ -801,11 +872,42 @@ const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* 
   TC_CUDA(cudaMemcpy(ch.d_w, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
   TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ch.d_bias), hb.size() * sizeof(float)));
   TC_CUDA(cudaMemcpy(ch.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // Grouped packing (chain_group_tc.cuh; tools/grouped_chain_model.py is the executable specification): G = 64 / C
+  // positions per 128-byte row; slice q = (position offset c = q / (C/16), channel block h = q % (C/16)) holds
+  //   B_q[g * C + co][kk] = W[co][h * 16 + kk][j = c - g]   for 0 <= j < k, else 0.
+  // Needs every conv1 padded by (k-1)/2 * d and every conv2 undilated (nn.py:96-166), at most kGrpMaxPairs pairs.
+  bool grouped = (c == 16 || c == 32) && (k & 1) && n_convs / 2 <= tc::kGrpMaxPairs;
+  for (int cv = 0; cv < n_convs && grouped; ++cv)
+    grouped = pad[cv] == (k - 1) / 2 * dil[cv] && ((cv & 1) == 0 || dil[cv] == 1);
+  if (grouped) {
+    const int G = 64 / c, cpp = c / 16;
+    ch.g_slices = (G + k - 1) * cpp;
+    ch.g_stages = (ch.g_slices + tc::kGrpSlicesPerStage - 1) / tc::kGrpSlicesPerStage;
+    const size_t conv_g = (size_t)ch.g_stages * tc::kGrpStageBytes;
+    std::vector<uint8_t> hg(conv_g * n_convs, 0);
+    for (int cv = 0; cv < n_convs; ++cv)
+      for (int q = 0; q < ch.g_slices; ++q) {
+        uint8_t* blk = hg.data() + cv * conv_g + (size_t)q * tc::kGrpSliceBytes;
+        const int cpos = q / cpp, h = q % cpp;
+        for (int g = 0; g < G; ++g) {
+          const int j = cpos - g;
+          if (j < 0 || j >= k) continue;
+          for (int co = 0; co < c; ++co)
+            for (int kk = 0; kk < 16; ++kk) {
+              const uint16_t hv = to16(folded[cv][((size_t)co * c + h * 16 + kk) * k + j], bf16);
+              memcpy(blk + swizzle_offset((uint32_t)(g * c + co) * 32u + (uint32_t)kk * 2u, 32), &hv, 2);
+            }
+        }
+      }
+    TC_CUDA(cudaMalloc(&ch.d_wg, hg.size()));
+    TC_CUDA(cudaMemcpy(ch.d_wg, hg.data(), hg.size(), cudaMemcpyHostToDevice));
+  }
   return nullptr;
 }
 
 void tc_free_chain(tc_chain& ch) {
   if (ch.d_w) cudaFree(ch.d_w);
+  if (ch.d_wg) cudaFree(ch.d_wg);
   if (ch.d_bias) cudaFree(ch.d_bias);
   ch = tc_chain();
 }
@@ -832,6 +934,7 @@ const char* tc_init(tc_context& ctx, int device) {
     if (atoi(env) != 0) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx.d_timing), 64 * 16 * sizeof(long long)));
   }
   if (const char* env = getenv("SATOOLS_B200_CHAIN3")) g_use_chain3 = atoi(env);
+  if (const char* env = getenv("SATOOLS_B200_GROUP")) g_use_group = atoi(env);
   if (const char* env = getenv("SATOOLS_B200_CHAIN_MS")) {
     const int v = atoi(env);
     if (v == 3 || v == 6) g_chain_ms_narrow = v;
@@ -952,9 +1055,14 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
   for (int i = 0; i < nst; ++i) {
     const tc_layer& up = a.layers[L_up(i)];
     bool all_fused = a.chains != nullptr;
+    bool stage_grouped = a.chains != nullptr;       // C <= 32: every ResBlock of the stage on the grouped kernel
+    for (int j = 0; j < nrb && stage_grouped; ++j) {
+      Runner::GroupPlan gp;
+      stage_grouped = run.group_plan(gp, a.chains[i * nrb + j], L * up.stride, 0, a.chains[i * nrb + j].n_convs);
+    }
     {                                               // archi.py:80-81
       // The fused ResBlock kernels read the fp32 stage input only; lrelu(x) in 16 bits is for the per-layer convs.
-      for (int j = 0; j < nrb && all_fused; ++j) all_fused = run.chain_usable(a.chains[i * nrb + j], L * up.stride);
+      for (int j = 0; j < nrb && all_fused && !stage_grouped; ++j) all_fused = run.chain_usable(a.chains[i * nrb + j], L * up.stride);
       Epi e;
       e.flags = tc::EPI_OUT32 | (all_fused ? 0u : tc::EPI_OUT16);
       e.out32 = X32; e.out16 = AX16; e.slope_out = 0.1f;
@@ -965,10 +1073,10 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     const bool tap_here = a.debug_out && a.debug_tap == SA_TAP_STAGE0 + i;
     // The fused kernel reads X32 (with halo) while other CTAs store results, so its fp32 stage
     // output goes to R32; the per-layer path writes it over the then-dead X32.
-    const bool last_rb_fused = a.chains && run.chain_usable(a.chains[i * nrb + nrb - 1], L);
+    const bool last_rb_fused = stage_grouped || (a.chains && run.chain_usable(a.chains[i * nrb + nrb - 1], L));
     float* H32 = last_rb_fused ? R32 : X32;
     Hout = H32;
-    if (a.chains) {                                 // narrowest stages: the whole stage in one kernel
+    if (a.chains && !stage_grouped) {               // narrowest stages on the per-tap kernels: the whole stage in one kernel
       Epi fin;
       if ((last_stage && !post16) || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = R32; }
       if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = last_stage ? 0.01f : 0.1f; }
@@ -993,6 +1101,11 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       if (a.chains) {                               // narrow stages: the whole ResBlock in one kernel
         bool done = false;
         const tc_chain& ch = a.chains[i * nrb + j];
+        if (stage_grouped) {                        // C <= 32: grouped (block-Toeplitz) kernel, one launch per ResBlock
+          if ((err = run.group(ch, X32, L, fin, tag, &done))) return err;
+          if (done) continue;
+          return "grouped ResBlock launch failed";
+        }
         // SATOOLS_B200_SPLIT: bit 0 = split the k = 11 blocks, bit 1 = also the k = 7 blocks
         static const int split = getenv("SATOOLS_B200_SPLIT") ? atoi(getenv("SATOOLS_B200_SPLIT")) : 1;
         if (all_fused && ch.n_convs == 6 && (((split & 1) && ch.k == 11) || ((split & 2) && ch.k == 7)) && run.chain_usable(ch, L)) {

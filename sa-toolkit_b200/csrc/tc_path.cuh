@@ -34,6 +34,10 @@ struct tc_chain {
   int dil[8] = {0}, pad[8] = {0};
   int halo = 0;
   int k16_per_stage = 0, stages_per_conv = 0;
+  // grouped (block-Toeplitz) packing for C <= 32 (chain_group_tc.cuh): per conv g_stages stages of 8 KB, each four
+  // [64 rows (g', co)][16 ci] blocks in the SWIZZLE_32B K-major layout; g_slices = (64 / C + k - 1) * C / 16 are used
+  void* d_wg = nullptr;
+  int g_slices = 0, g_stages = 0;
 };
 
 struct tc_context {

@@ -296,21 +296,35 @@ def test_config5_corpus_sharding_covers_and_matches_single_item_runs():
         assert helpers.max_abs(alone[:keep], got[u][:keep]) < 1e-5
 
 
-def test_fused_and_per_layer_paths_are_bit_identical():
-    """The fused ResBlock kernels and the per-layer kernels perform the same arithmetic in the same order."""
+def test_fused_and_per_layer_paths_agree():
+    """The per-tap fused kernels (C = 64) perform the per-layer arithmetic in the same order: bit-identical.  The grouped
+    kernels (C <= 32, chain_group_tc.cuh) keep the residual stream in tensor memory and let conv2 accumulate onto it, so
+    their fp32 sums are associated differently (last-bit differences that occasionally flip a 16-bit rounding): the two
+    paths must agree far below the fp16 operand noise (73 dB vs the truth)."""
     _need_gpu()
     x = conditioning.batch(12, [64, 50])
-    gen = copy.deepcopy(helpers.seeded_generator(0)).to("cuda:0")
-    gen.precision = "fp16"
-    y_fused = run(gen, x)
-    os.environ["SATOOLS_B200_FUSED"] = "0"
-    try:
-        gen2 = copy.deepcopy(helpers.seeded_generator(0)).to("cuda:0")   # new native handle reads the switch
-        gen2.precision = "fp16"
-        y_layer = run(gen2, x)
-    finally:
-        del os.environ["SATOOLS_B200_FUSED"]
-    np.testing.assert_array_equal(y_fused, y_layer)
+
+    def fresh(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            g = copy.deepcopy(helpers.seeded_generator(0)).to("cuda:0")   # a new native handle reads the switches
+            g.precision = "fp16"
+            return run(g, x)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = v
+
+    y_layer = fresh({"SATOOLS_B200_FUSED": "0"})
+    y_pertap = fresh({"SATOOLS_B200_GROUP": "0"})
+    y_default = fresh({})
+    np.testing.assert_array_equal(y_pertap, y_layer)
+    snr = helpers.snr_db(y_layer, y_default)
+    print(f"grouped kernels vs per-layer path: SNR {snr:.1f} dB, max-abs {helpers.max_abs(y_layer, y_default):.2e}")
+    assert snr >= 90.0
 
 
 def test_host_entry_two_stream_split_equals_device_entry():
