@@ -25,8 +25,12 @@
 //
 // Residual stream in tensor memory.  conv2 accumulates ON TOP of the residual: the fp32 stream x lives in the TMEM
 // columns that conv2 uses as accumulator (written once per tile with tcgen05.st, MMA with accumulate = 1), so
-// x_{m+1} = x_m + conv2(...) needs no registers and no add; the conv2 biases are added when the epilogue reads
-// (cumulative: x_{m+1} = D + b2_0 + .. + b2_m).  Sums differ from the per-layer path in the last fp32 bit only.
+// x_{m+1} = x_m + conv2(...) needs no registers and no add.  Sums differ from the per-layer path in the last fp32 bit only.
+//
+// Bias in the MMA.  The epilogue of these layers is instruction-issue bound (ncu: 6 instructions per element and phase
+// in the first version, more issue cycles than MMA cycles), so the bias add moves into the tensor pipe: every conv gets
+// one more slice whose A operand is a constant tile of ones (columns 0 and 1) and whose B block holds the bias split in
+// two 16-bit halves (hi + lo: exact to 2^-22 for fp16, 2^-16 for bf16).  conv2's bias then also lands in the residual.
 //
 // Two tiles per CTA ("streams").  With full (conv-granular) dependencies a single chain would leave the tensor pipe
 // idle during every epilogue, so each CTA works on two independent tiles of the same ResBlock: the MMA warp issues
@@ -42,34 +46,37 @@
 namespace sa {
 namespace tc {
 
-constexpr int kGrpMS = 2;                                  // sub-tiles (128 rows of 128 bytes) per stream tile
-constexpr int kGrpStreams = 2;
-constexpr int kGrpRows = kGrpMS * 128;                     // rows of one stream tile
+// NS streams (independent tiles in flight per CTA) of MS sub-tiles (128 rows of 128 bytes) each; NS * MS = 4 fills the
+// 512 TMEM columns.  (2, 2): 256-row tiles, less recomputed halo; (4, 1): four dependency chains for the MMA warp to
+// rotate over -- with two, the C = 16 kernel's MMA warp waited 57 % of the time for epilogues (in-kernel counters).
+constexpr int kGrpMaxStreams = 4;
 constexpr int kGrpPadRows = 8;                             // slack rows on both sides (one 1024-byte swizzle atom)
-constexpr int kGrpEpiWarps = kGrpStreams * kGrpMS * 4;     // 16
+constexpr int kGrpEpiWarps = 16;                           // NS * MS * 4
 constexpr int kGrpThreads = 32 * (kGrpEpiWarps + 2);       // 576
 constexpr int kGrpMaxStages = 12;                          // weight ring depth (runtime n_wstages <= this)
 constexpr uint32_t kGrpSliceBytes = 64 * 32;               // one Toeplitz block: [64 rows (g', co)][16 ci] 16-bit
 constexpr int kGrpSlicesPerStage = 4;
 constexpr uint32_t kGrpStageBytes = kGrpSlicesPerStage * kGrpSliceBytes;   // 8 KB
 constexpr int kGrpMaxPairs = 3;
-constexpr uint32_t kGrpBufBytes = (kGrpRows + 2 * kGrpPadRows) * 128;      // 34816 = 34 KB, multiple of 1024
+__host__ __device__ constexpr uint32_t grp_buf_bytes(int ms) { return (uint32_t)(ms * 128 + 2 * kGrpPadRows) * 128u; }   // multiple of 1024
+__host__ __device__ constexpr int grp_tile_positions(int c, int ms) { return ms * 128 * (64 / c); }
+constexpr uint32_t kGrpOnesBytes = 128 * 32;                               // A operand of the bias slice
 
 struct GroupParams {
   const float* x32;         // block input, fp32 blocked [B][C/8][L][8]
   float* sum32;             // MRF running sum, fp32 blocked
   float* out32;             // EPI_OUT32
   void* out16;              // EPI_OUT16: lrelu(output), 16-bit [B][1][L][C]
-  const void* w;            // n_convs convs, each stages_per_conv stages of 8 KB (4 Toeplitz slices, zero padded)
-  const float* bias;        // [n_convs][C]
+  const void* w;            // n_convs convs, each stages_per_conv stages of 8 KB (4 slices per stage: the n_slices
+                            // Toeplitz blocks, then the bias block, zero padded)
   int* error_flag;
   long long* timing;        // optional [16] cycle counters: MMA warp total / wait ready / wait weights
   int L;                    // positions per item (multiple of G)
   int n_convs;              // 2 * n_pairs
   int dil[kGrpMaxPairs];    // dilation of conv1 of each pair
   int halo;                 // recomputed positions per side (sum of all conv reaches), multiple of G
-  int n_slices;             // (G + k - 1) * C / 16
-  int stages_per_conv;      // ceil(n_slices / 4)
+  int n_slices;             // (G + k - 1) * C / 16 Toeplitz slices (+ 1 bias slice)
+  int stages_per_conv;      // ceil((n_slices + 1) / 4)
   int n_wstages;            // ring depth, >= stages_per_conv + 1
   int tiles_per_item, total_tiles;
   TileMapParams map;        // ragged batches (conv_tc.cuh); tile axis = valid positions per tile
@@ -87,9 +94,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int C, bool BF16>
+template <int C, bool BF16, int NS, int MS>
 __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __grid_constant__ GroupParams p) {
   static_assert(C == 16 || C == 32, "grouped formulation: C = 16 (G = 4) or C = 32 (G = 2)");
+  static_assert(NS * MS * 4 == kGrpEpiWarps && NS <= kGrpMaxStreams, "NS * MS sub-tiles of 2 x 64 TMEM columns fill the 512 columns");
+  constexpr int kGrpStreams = NS, kGrpMS = MS, kGrpRows = MS * 128;
+  constexpr uint32_t kGrpBufBytes = grp_buf_bytes(MS);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int G = 64 / C;                                      // positions per 128-byte row
@@ -99,18 +109,17 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   constexpr int kGroupsPerPos = C / 16;                          // 16-column TMEM groups per position
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpW = kGrpEpiWarps, kWarpMma = kGrpEpiWarps + 1;
-  // smem: buf[stream][A|T], weight ring, bias [n_convs][C] + cumulative conv2 bias [n_pairs][C], barriers
+  // smem: buf[stream][A|T], weight ring, ones tile (128 rows x 32 B, SWIZZLE_32B), barriers
   auto buf = [&](int st, int t) { return smem + (uint32_t)(st * 2 + t) * kGrpBufBytes; };
-  uint8_t* w_smem = smem + 4 * kGrpBufBytes;
-  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)p.n_wstages * kGrpStageBytes);
-  float* cbias_s = bias_s + 2 * kGrpMaxPairs * C;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cbias_s + kGrpMaxPairs * C);
-  // barriers: ready[stream][A|T] (4), acc_full[stream] (2), w_full[12], w_empty[12]
+  uint8_t* w_smem = smem + 2 * NS * kGrpBufBytes;
+  uint8_t* ones_smem = w_smem + (size_t)p.n_wstages * kGrpStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_smem + kGrpOnesBytes);
+  // barriers: ready[stream][A|T] (8), acc_full[stream] (4), w_full[12], w_empty[12]
   auto bar_ready = [&](int st, int t) { return smem_u32(&bars[st * 2 + t]); };
-  auto bar_acc_full = [&](int st) { return smem_u32(&bars[4 + st]); };
-  auto bar_w_full = [&](int i) { return smem_u32(&bars[6 + i]); };
-  auto bar_w_empty = [&](int i) { return smem_u32(&bars[6 + kGrpMaxStages + i]); };
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6 + 2 * kGrpMaxStages);
+  auto bar_acc_full = [&](int st) { return smem_u32(&bars[2 * kGrpMaxStreams + st]); };
+  auto bar_w_full = [&](int i) { return smem_u32(&bars[3 * kGrpMaxStreams + i]); };
+  auto bar_w_empty = [&](int i) { return smem_u32(&bars[3 * kGrpMaxStreams + kGrpMaxStages + i]); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3 * kGrpMaxStreams + 2 * kGrpMaxStages);
 
   const int valid = R - 2 * p.halo;
   __shared__ int tile_pre[kMaxMapItems + 1];
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
 
   if (warp == kWarpW && lane == 0) {
     for (int st = 0; st < kGrpStreams; ++st) {
-      mbar_init(bar_ready(st, 0), kGrpMS * 4);                   // the eight warps of the stream
+      mbar_init(bar_ready(st, 0), kGrpMS * 4);                   // the warps of the stream
       mbar_init(bar_ready(st, 1), kGrpMS * 4);
       mbar_init(bar_acc_full(st), 1);
     }
@@ -128,17 +137,17 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), 512);
-  for (int i = threadIdx.x; i < p.n_convs * C; i += kGrpThreads) bias_s[i] = p.bias[i];
-  for (int i = threadIdx.x; i < n_pairs * C; i += kGrpThreads) {  // b2_0 + .. + b2_m per channel
-    const int m = i / C, ch = i - m * C;
-    float s = 0.f;
-    for (int mm = 0; mm <= m; ++mm) s += p.bias[(2 * mm + 1) * C + ch];
-    cbias_s[i] = s;
-  }
   // zero the four staged tiles once: the leading slack rows are never written, everything else only ever holds finite
   // 16-bit activations (a Toeplitz block multiplies positions outside its taps by an exact 0)
-  for (uint32_t i = threadIdx.x; i < 4 * kGrpBufBytes / 16; i += kGrpThreads)
+  for (uint32_t i = threadIdx.x; i < 2 * NS * kGrpBufBytes / 16; i += kGrpThreads)
     *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
+  // the ones tile: A operand of the bias slice, [128 rows][16] with 1.0 in columns 0 and 1 (K-major, SWIZZLE_32B:
+  // the 16-byte chunk at linear offset o lives at o ^ (((o >> 7) & 1) << 4); chunk 0 of every 32-byte row is even)
+  for (uint32_t i = threadIdx.x; i < kGrpOnesBytes / 16; i += kGrpThreads) {
+    const uint32_t o = i * 16u;
+    const uint32_t one2 = bf16 ? 0x00003F80u | 0x3F800000u : 0x00003C00u | 0x3C000000u;   // {1.0, 1.0}
+    *reinterpret_cast<uint4*>(ones_smem + (o ^ (((o >> 7) & 1u) << 4))) = make_uint4((i & 1u) ? 0u : one2, 0, 0, 0);
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   const uint32_t tmem_base = *tmem_holder;
   const int n_live = tilemap_total(tile_pre, p.map, p.total_tiles);
   const int my_tiles = ((int)blockIdx.x < n_live) ? (n_live - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int n_iters = (my_tiles + 1) / 2;                        // two tiles (streams) per iteration
+  const int n_iters = (my_tiles + NS - 1) / NS;                  // NS tiles (streams) per iteration
 
   if (warp == kWarpW) {
     // ===== weight producer: the stages of conv c, once per iteration (both streams read them) =====
@@ -171,79 +180,103 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       }
   } else if (warp == kWarpMma) {
     // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    // The first version walked the slices with a runtime count and per-MMA predicates: 16 issued instructions per MMA
+    // and ~100 cycles per MMA on this single warp (ncu source view, profiles/r2_group_v1_*).  The slice count is a
+    // compile-time constant per filter length now: one conv of one stream is straight-line code whose descriptors
+    // differ by constant adds.
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(64, bf16);
     constexpr uint32_t hiA = ((8u * 128u) >> 4) | (1u << 14) | (2u << 29);     // SWIZZLE_128B, 8-row groups 1024 B apart
     constexpr uint32_t hiB = ((8u * 32u) >> 4) | (1u << 14) | (6u << 29);      // SWIZZLE_32B, 8-row groups 256 B apart
     const uint32_t b_lo0 = desc_lo(smem_u32(w_smem));
-    const int pad_pos = (p.n_slices / kGroupsPerPos - G) / 2;                  // (k - 1) / 2 positions
-    const int n_sl = p.n_slices, n_stg = p.stages_per_conv;
-    int slot0 = 0;
-    uint32_t par0 = 0;
+    const uint64_t ones_desc = desc64(desc_lo(smem_u32(ones_smem)), hiB);
+    const int n_wst = p.n_wstages;
+    int slot = 0;
+    uint32_t par = 0;
     bool ok = true;
+#ifdef SA_DIAG
     const bool timing = p.timing != nullptr;
+#else
+    constexpr bool timing = false;                                             // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
     long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
-    for (int it = 0; it < n_iters && ok; ++it) {
-      for (int c = 0; c < p.n_convs && ok; ++c) {
-        const int t_in = c & 1;                                                // conv1 reads A, conv2 reads T
-        const uint32_t rdy_parity = ((uint32_t)it * (uint32_t)n_pairs + (uint32_t)(c >> 1)) & 1u;
-        int slot = slot0;
-        uint32_t par = par0;
+    // one conv (NSL Toeplitz slices + the bias slice) of both streams
+    auto conv = [&](auto nsl_c, auto conv2_c, int it, int c) {
+      constexpr int NSL = decltype(nsl_c)::value;
+      constexpr bool CONV2 = decltype(conv2_c)::value;                         // accumulates onto the residual
+      constexpr int NTOT = NSL + 1;
+      constexpr int NSTG = (NTOT + kGrpSlicesPerStage - 1) / kGrpSlicesPerStage;
+      constexpr int pad_pos = (NSL / kGroupsPerPos - G) / 2;                   // (k - 1) / 2 positions
+      constexpr int t_in = CONV2 ? 1 : 0;                                      // conv1 reads A, conv2 reads T
+      const uint32_t rdy_parity = ((uint32_t)it * (uint32_t)n_pairs + (uint32_t)(c >> 1)) & 1u;
+      const int slot0 = slot;
+      const uint32_t par0 = par;
 #pragma unroll 1
-        for (int st = 0; st < kGrpStreams && ok; ++st) {
-          const long long tr0 = timing ? clock64() : 0;
-          ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
-          if (timing) t_ready += clock64() - tr0;
-          if (!ok) break;
-          tc_fence_after();
-          // first slice of the first row: kPadBytes - pad_pos positions
-          const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - (uint32_t)pad_pos * PB);
-          const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + t_in) * kGrpMS * 64);
-          slot = slot0; par = par0;
-          int q0 = 0;
-#pragma unroll 1
-          for (int i = 0; i < n_stg; ++i, q0 += kGrpSlicesPerStage) {
-            if (st == 0) {
-              const long long tw0 = timing ? clock64() : 0;
-              ok = mbar_wait(bar_w_full(slot), par, p.error_flag);
-              if (timing) t_w += clock64() - tw0;
-              if (!ok) break;
-              tc_fence_after();
-            }
-            const uint32_t b_lo = b_lo0 + (uint32_t)slot * (kGrpStageBytes >> 4);
-            const uint32_t a_lo = a_lo0 + 2u * (uint32_t)q0;                   // 32 bytes per slice
+      for (int st = 0; st < kGrpStreams && ok; ++st) {
+        const long long tr0 = timing ? clock64() : 0;
+        ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
+        if (timing) t_ready += clock64() - tr0;
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - (uint32_t)pad_pos * PB);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + t_in) * kGrpMS * 64);
+        slot = slot0; par = par0;
 #pragma unroll
-            for (int s = 0; s < kGrpMS; ++s) {
+        for (int i = 0; i < NSTG; ++i) {
+          if (st == 0) {
+            const long long tw0 = timing ? clock64() : 0;
+            ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);
+            if (timing) t_w += clock64() - tw0;
+            tc_fence_after();
+          }
+          const uint32_t b_lo = b_lo0 + (uint32_t)slot * (kGrpStageBytes >> 4);
 #pragma unroll
-              for (int qq = 0; qq < kGrpSlicesPerStage; ++qq) {
-                if (q0 + qq < n_sl) {
-                  const uint32_t accum = (t_in == 1 || q0 + qq > 0) ? 1u : 0u;  // conv2 accumulates onto the residual
-                  if (leader)
-                    umma_f16(d_tmem + (uint32_t)(s * 64), desc64(a_lo + (uint32_t)(s * 128 * 8) + 2u * qq, hiA),
-                             desc64(b_lo + (uint32_t)qq * (kGrpSliceBytes >> 4), hiB), idesc, accum);
-                }
+          for (int s = 0; s < kGrpMS; ++s) {
+#pragma unroll
+            for (int qq = 0; qq < kGrpSlicesPerStage; ++qq) {
+              const int q = i * kGrpSlicesPerStage + qq;
+              if (q < NTOT) {
+                const uint64_t adesc = (q < NSL) ? desc64(a_lo0 + (uint32_t)(s * 128 * 8 + 2 * q), hiA) : ones_desc;
+                if (leader)
+                  umma_f16(d_tmem + (uint32_t)(s * 64), adesc, desc64(b_lo + (uint32_t)qq * (kGrpSliceBytes >> 4), hiB), idesc,
+                           (CONV2 || q > 0) ? 1u : 0u);
               }
             }
-            if (st == kGrpStreams - 1 && leader) umma_commit(bar_w_empty(slot));   // both streams have read the stage
-            __syncwarp();
-            if (++slot == p.n_wstages) { slot = 0; par ^= 1u; }
           }
-          if (!ok) break;
-          if (leader) umma_commit(bar_acc_full(st));
+          if (st == kGrpStreams - 1 && leader) umma_commit(bar_w_empty(slot));     // both streams have read the stage
           __syncwarp();
+          if (++slot == n_wst) { slot = 0; par ^= 1u; }
         }
-        slot0 = slot; par0 = par;
+        if (leader) umma_commit(bar_acc_full(st));
+        __syncwarp();
       }
-    }
+    };
+    auto run = [&](auto nsl_c) {
+      for (int it = 0; it < n_iters && ok; ++it)
+        for (int c = 0; c < p.n_convs && ok; c += 2) {
+          conv(nsl_c, std::false_type{}, it, c);
+          if (ok) conv(nsl_c, std::true_type{}, it, c + 1);
+        }
+    };
+    constexpr int CPP = kGroupsPerPos;
+    if (p.n_slices == (G + 2) * CPP) run(std::integral_constant<int, (G + 2) * CPP>{});           // k = 3
+    else if (p.n_slices == (G + 6) * CPP) run(std::integral_constant<int, (G + 6) * CPP>{});      // k = 7
+    else if (p.n_slices == (G + 10) * CPP) run(std::integral_constant<int, (G + 10) * CPP>{});    // k = 11
+    else if (p.error_flag) atomicExch(p.error_flag, 1);                                            // not instantiated (the host checks)
     if (timing && lane == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 0), (unsigned long long)(clock64() - t_begin));
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_ready);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 2), (unsigned long long)t_w);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 3), (unsigned long long)(clock64() - t_begin - t_ready - t_w));
     }
   } else {
     // ===== epilogue warps: one thread = one 128-byte row (G positions x C channels) of its stream's tile =====
-    const int st = warp >> 3;
-    const int s = (warp >> 2) & (kGrpMS - 1);
+    // Instruction diet (ncu source view of the first versions: ~300 issued instructions per conv and thread at ~5.6
+    // cycles each = the 1.7k-cycle epilogue latency that the MMA warp waited for): no bias add (it is in the MMA), one
+    // branch per row for the zero padding instead of per-store selects, tile-invariant swizzled store offsets, TMEM loads
+    // one group ahead of the conversion, diagnostics compiled out unless SA_DIAG.
+    const int st = warp / (4 * MS);
+    const int s = (warp >> 2) % MS;
     const int lg = warp & 3;
     const int r = s * 128 + lg * 32 + lane;                      // row within the stream tile
     constexpr int cchunks = C / 8;
@@ -251,10 +284,11 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     uint8_t* const bufT = buf(st, 1);
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 0) * kGrpMS + s) * 64);
     const uint32_t t_res = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 1) * kGrpMS + s) * 64);
-    // tile-invariant d-major maps of this row's G positions, for every pair with a dilated conv1:
-    //   posP[m][g] = position of time (G r + g) in the d_m-major input tile of pair m's conv1
-    //   tauI(m, g) = time whose conv1 output this row holds at column group g in pair m (>= R: none)
-    uint32_t pmap[kGrpMaxPairs][G];                               // posP | tauI << 16 (both < 2^16)
+    auto swz128 = [](uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); };
+    // tile-invariant d-major maps of this row's G positions, for every pair with a dilated conv1 (16 bits each):
+    //   physP(m, g) = swizzled byte offset of time (G r + g) in the d_m-major input tile of pair m's conv1
+    //   tauI(m, g)  = time whose conv1 output this row holds at position g in pair m (>= R: none)
+    uint32_t pmap[kGrpMaxPairs][G];
 #pragma unroll
     for (int m = 0; m < kGrpMaxPairs; ++m) {
       const int d = (m < n_pairs) ? p.dil[m] : 1;
@@ -264,52 +298,105 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         const int tau = G * r + g;
         const int pp = (d == 1) ? tau : (tau % d) * Q + tau / d;
         const int ti = (d == 1) ? tau : d * (tau % Q) + tau / Q;
-        pmap[m][g] = (uint32_t)pp | ((uint32_t)ti << 16);
+        pmap[m][g] = swz128(kPadBytes + (uint32_t)pp * PB) | ((uint32_t)ti << 16);
       }
     }
-    auto posP = [&](int m, int g) { return (int)(pmap[m][g] & 0xFFFFu); };
+    auto physP = [&](int m, int g) { return pmap[m][g] & 0xFFFFu; };
     auto tauI = [&](int m, int g) { return (int)(pmap[m][g] >> 16); };
-    // swizzled byte offset (within a staged tile) of the 16-byte chunk at byte `ch` of position `pos`, and of its neighbour
-    auto store_pos = [&](uint8_t* b, int pos, uint32_t ch, const uint4& lo, const uint4& hi8) {
-      const uint32_t lin = kPadBytes + (uint32_t)pos * PB + ch;
-      const uint32_t x = ((lin >> 7) & 7u) << 4;
-      *reinterpret_cast<uint4*>(b + (lin ^ x)) = lo;
-      *reinterpret_cast<uint4*>(b + ((lin + 16u) ^ x)) = hi8;
+    const uint32_t lin_row = kPadBytes + (uint32_t)r * 128u;     // this row in natural order
+    const uint32_t xrow = (uint32_t)(r & 7) << 4;                // its swizzle XOR (kPadBytes is a multiple of 1024)
+    // 16-column group gi of this row, natural order: chunks 2 gi and 2 gi + 1 of the 128-byte row
+    auto st_nat = [&](uint8_t* b, int gi, const uint4& lo, const uint4& hi8) {
+      *reinterpret_cast<uint4*>(b + lin_row + (((uint32_t)(2 * gi) * 16u) ^ xrow)) = lo;
+      *reinterpret_cast<uint4*>(b + lin_row + (((uint32_t)(2 * gi + 1) * 16u) ^ xrow)) = hi8;
+    };
+    // 16-column group gi at a position whose chunk 0 lives at the swizzled offset phys0: its chunk cc is at phys0 ^ 16 cc
+    auto st_at = [&](uint8_t* b, uint32_t phys0, int gi, const uint4& lo, const uint4& hi8) {
+      const uint32_t o = phys0 ^ ((uint32_t)(gi % kGroupsPerPos) * 32u);
+      *reinterpret_cast<uint4*>(b + o) = lo;
+      *reinterpret_cast<uint4*>(b + (o ^ 16u)) = hi8;
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    auto pack16 = [&](const uint32_t (&rr)[16], uint4& lo, uint4& hi8, float slope) {
+      float a[8], c8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] = __uint_as_float(rr[e]); c8[e] = __uint_as_float(rr[8 + e]); }
+      lo = pack8_lrelu(a, slope, true, bf16);
+      hi8 = pack8_lrelu(c8, slope, true, bf16);
+    };
+    // TMEM -> registers one 16-column group ahead of its use: f(gi, regs) for gi = 0..3
+    // (tcgen05.ld / wait are .sync.aligned: the whole warp must execute them converged, so every caller branches on
+    // warp-uniform conditions only and f may diverge inside)
+    auto for_groups = [&](uint32_t taddr, auto&& f) {
+      uint32_t ra[16], rb[16];
+      __syncwarp();
+      tmem_ld16(taddr, ra);
+      tmem_ld_wait();
+      tmem_ld16(taddr + 16u, rb);
+      f(0, ra);
+      __syncwarp();
+      tmem_ld_wait();
+      tmem_ld16(taddr + 32u, ra);
+      f(1, rb);
+      __syncwarp();
+      tmem_ld_wait();
+      tmem_ld16(taddr + 48u, rb);
+      f(2, ra);
+      __syncwarp();
+      tmem_ld_wait();
+      f(3, rb);
+      __syncwarp();
     };
     bool ok = true;
+#ifdef SA_DIAG
+    const bool timing = p.timing != nullptr && warp == 0;
+    long long t_x = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
+#define GRP_T0(v) const long long v = timing ? clock64() : 0
+#define GRP_ADD(acc, v) if (timing) acc += clock64() - v
+#else
+#define GRP_T0(v)
+#define GRP_ADD(acc, v)
+#endif
     for (int it = 0; it < n_iters && ok; ++it) {
-      const int tile = (int)blockIdx.x + (2 * it + st) * (int)gridDim.x;
-      const bool live = tile < n_live;                            // the last iteration may have one stream without a tile
+      GRP_T0(tx0);
+      const int tile = (int)blockIdx.x + (NS * it + st) * (int)gridDim.x;
+      const bool live = tile < n_live;                            // the last iteration may have streams without a tile
       int b = 0, mt = 0;
       if (live) tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
       const int t0 = mt * valid - p.halo;                         // time of the tile's first position
       const int t_row = t0 + G * r;
       const bool inside = live && t_row >= 0 && t_row < p.L;      // L, halo, valid are multiples of G: whole rows
       const bool keep = inside && G * r >= p.halo && G * r < R - p.halo;
+      const bool interior = live && t0 >= 0 && t0 + R <= p.L;     // no position of the tile is outside the utterance
+      const bool w_all = __all_sync(0xffffffffu, inside), w_any = __any_sync(0xffffffffu, inside);   // warp-uniform
       // ---- x: residual stream -> tensor memory, lrelu(x) -> input tile of pair 0's conv1 ----
       {
         const int d0 = p.dil[0];
+        float4 xq[4][4];                                          // all loads in flight before the first use
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
           const int g = gi / kGroupsPerPos;
           const int ch0 = (gi % kGroupsPerPos) * 16;
-          float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+          xq[gi][0] = xq[gi][1] = xq[gi][2] = xq[gi][3] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (inside) {
             const float* src = p.x32 + (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
-            ldg_f8(src, q0, q1);
-            ldg_f8(src + (size_t)p.L * 8, q2, q3);
+            ldg_f8(src, xq[gi][0], xq[gi][1]);
+            ldg_f8(src + (size_t)p.L * 8, xq[gi][2], xq[gi][3]);
           }
-          const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-          uint32_t rr[16];
+        }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) rr[e] = __float_as_uint(v[e]);
+        for (int gi = 0; gi < 4; ++gi) {
+          const int g = gi / kGroupsPerPos;
+          const float4 q0 = xq[gi][0], q1 = xq[gi][1], q2 = xq[gi][2], q3 = xq[gi][3];
+          const uint32_t rr[16] = {__float_as_uint(q0.x), __float_as_uint(q0.y), __float_as_uint(q0.z), __float_as_uint(q0.w),
+                                   __float_as_uint(q1.x), __float_as_uint(q1.y), __float_as_uint(q1.z), __float_as_uint(q1.w),
+                                   __float_as_uint(q2.x), __float_as_uint(q2.y), __float_as_uint(q2.z), __float_as_uint(q2.w),
+                                   __float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z), __float_as_uint(q3.w)};
           __syncwarp();
           tmem_st16(t_res + (uint32_t)(gi * 16), rr);
-          float lo[8], hi8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
-          store_pos(bufA, d0 == 1 ? G * r + g : posP(0, g), (uint32_t)ch0 * 2u, pack8_lrelu(lo, 0.1f, true, bf16),
-                    pack8_lrelu(hi8, 0.1f, true, bf16));
+          uint4 lo, hi8;
+          pack16(rr, lo, hi8, 0.1f);                              // rows outside the utterance were loaded as zeros
+          if (d0 == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(0, g), gi, lo, hi8);
         }
         tmem_st_wait();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -317,6 +404,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ready(st, 0));
       }
+      GRP_ADD(t_x, tx0);
       // the next tile of this stream and this tile's running sum: have them in L2 when they are needed
       if (keep && (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
 #pragma unroll
@@ -326,7 +414,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sum32 + (((size_t)b * cchunks + q) * (size_t)p.L + (size_t)(t_row + g)) * 8));
       }
       {
-        const int tile_n = tile + 2 * (int)gridDim.x;
+        const int tile_n = tile + NS * (int)gridDim.x;
         if (tile_n < n_live) {
           int bn, mtn;
           tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile_n, bn, mtn);
@@ -345,64 +433,82 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       for (int m = 0; m < kGrpMaxPairs; ++m) {
         if (m < n_pairs && ok) {
           const int d = p.dil[m];
-          // conv1: TMEM -> + bias -> lrelu -> conv2's input tile in natural order
-          ok = mbar_wait_relaxed(bar_acc_full(st), 0u, p.error_flag);     // phases alternate conv1 (0) / conv2 (1): n_convs is even
-          tc_fence_after();
+          // conv1: TMEM -> lrelu -> conv2's input tile in natural order
+          {
+            GRP_T0(ta0);
+            ok = mbar_wait_relaxed(bar_acc_full(st), 0u, p.error_flag);   // phases alternate conv1 (0) / conv2 (1): n_convs is even
+            tc_fence_after();
+            GRP_ADD(t_acc, ta0);
+          }
           if (ok) {
-            const float* bias_c = bias_s + (2 * m) * C;
+            if (d == 1) {
+              if (w_all) {
+                for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[16]) {
+                  uint4 lo, hi8;
+                  pack16(rr, lo, hi8, 0.1f);
+                  st_nat(bufT, gi, lo, hi8);
+                });
+              } else if (!w_any) {
 #pragma unroll
-            for (int gh = 0; gh < 2; ++gh) {
-            uint32_t rr[2][16];
-            __syncwarp();
-            tmem_ld16(t_acc1 + (uint32_t)(gh * 32), rr[0]);
-            tmem_ld16(t_acc1 + (uint32_t)(gh * 32 + 16), rr[1]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int gi = 2 * gh; gi < 2 * gh + 2; ++gi) {
-              const int g = gi / kGroupsPerPos;
-              const int ch0 = (gi % kGroupsPerPos) * 16;
-              const int tau = (d == 1) ? G * r + g : tauI(m, g);
-              const int tt = t0 + tau;
-              const bool ins = live && tau < R && tt >= 0 && tt < p.L;
-              float lo[8], hi8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                lo[e] = __uint_as_float(rr[gi - 2 * gh][e]) + bias_c[ch0 + e];
-                hi8[e] = __uint_as_float(rr[gi - 2 * gh][8 + e]) + bias_c[ch0 + 8 + e];
+                for (int gi = 0; gi < 4; ++gi) st_nat(bufT, gi, zero4, zero4);
+              } else {                                            // the utterance ends inside this warp's rows
+                for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[16]) {
+                  uint4 lo, hi8;
+                  pack16(rr, lo, hi8, 0.1f);
+                  st_nat(bufT, gi, inside ? lo : zero4, inside ? hi8 : zero4);
+                });
               }
-              if (tau < R)
-                store_pos(bufT, tau, (uint32_t)ch0 * 2u, pack8_lrelu(lo, 0.1f, ins, bf16), pack8_lrelu(hi8, 0.1f, ins, bf16));
-            }
+            } else if (interior) {
+              for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[16]) {
+                uint4 lo, hi8;
+                pack16(rr, lo, hi8, 0.1f);
+                const int tau = tauI(m, gi / kGroupsPerPos);
+                if (tau < R) st_at(bufT, swz128(kPadBytes + (uint32_t)tau * PB), gi, lo, hi8);
+              });
+            } else {
+              for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[16]) {
+                uint4 lo, hi8;
+                pack16(rr, lo, hi8, 0.1f);
+                const int tau = tauI(m, gi / kGroupsPerPos);
+                const int tt = t0 + tau;
+                const bool ins = live && tt >= 0 && tt < p.L;
+                if (tau < R) st_at(bufT, swz128(kPadBytes + (uint32_t)tau * PB), gi, ins ? lo : zero4, ins ? hi8 : zero4);
+              });
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready(st, 1));
           }
-          // conv2: the accumulator IS the residual stream x_{m+1} (minus the biases added here)
-          ok = ok && mbar_wait_relaxed(bar_acc_full(st), 1u, p.error_flag);
-          tc_fence_after();
+          // conv2: the accumulator IS the residual stream x_{m+1}
+          {
+            GRP_T0(ta0);
+            ok = ok && mbar_wait_relaxed(bar_acc_full(st), 1u, p.error_flag);
+            tc_fence_after();
+            GRP_ADD(t_acc, ta0);
+          }
           if (ok) {
-            const float* cb = cbias_s + m * C;
-            uint32_t rr[4][16];
-            __syncwarp();
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) tmem_ld16(t_res + (uint32_t)(gi * 16), rr[gi]);
-            tmem_ld_wait();
             if (m + 1 < n_pairs) {
-              const int dn = p.dil[m + 1 < kGrpMaxPairs ? m + 1 : 0];
+              const int mn = m + 1 < kGrpMaxPairs ? m + 1 : 0;
+              const int dn = p.dil[mn];
+              if (w_all) {
+                for_groups(t_res, [&](int gi, const uint32_t (&rr)[16]) {
+                  uint4 lo, hi8;
+                  pack16(rr, lo, hi8, 0.1f);
+                  if (dn == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(mn, gi / kGroupsPerPos), gi, lo, hi8);
+                });
+              } else if (!w_any) {
 #pragma unroll
-              for (int gi = 0; gi < 4; ++gi) {
-                const int g = gi / kGroupsPerPos;
-                const int ch0 = (gi % kGroupsPerPos) * 16;
-                float lo[8], hi8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  lo[e] = __uint_as_float(rr[gi][e]) + cb[ch0 + e];
-                  hi8[e] = __uint_as_float(rr[gi][8 + e]) + cb[ch0 + 8 + e];
+                for (int gi = 0; gi < 4; ++gi) {
+                  if (dn == 1) st_nat(bufA, gi, zero4, zero4); else st_at(bufA, physP(mn, gi / kGroupsPerPos), gi, zero4, zero4);
                 }
-                store_pos(bufA, dn == 1 ? G * r + g : posP(m + 1 < kGrpMaxPairs ? m + 1 : 0, g), (uint32_t)ch0 * 2u,
-                          pack8_lrelu(lo, 0.1f, inside, bf16), pack8_lrelu(hi8, 0.1f, inside, bf16));
+              } else {
+                for_groups(t_res, [&](int gi, const uint32_t (&rr)[16]) {
+                  uint4 lo, hi8;
+                  pack16(rr, lo, hi8, 0.1f);
+                  if (!inside) { lo = zero4; hi8 = zero4; }
+                  if (dn == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(mn, gi / kGroupsPerPos), gi, lo, hi8);
+                });
               }
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               tc_fence_before();
@@ -410,28 +516,24 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
               if (lane == 0) mbar_arrive(bar_ready(st, 0));
             } else {
               // final epilogue: multi-receptive-field combine (archi.py:82-86) + output streams
-              if (keep) {
-#pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
+              if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {        // the running sum was prefetched into L2 at tile start
+                for_groups(t_res, [&](int gi, const uint32_t (&rr)[16]) {
+                  if (!keep) return;
                   const int g = gi / kGroupsPerPos;
                   const int ch0 = (gi % kGroupsPerPos) * 16;
-                  float v[16];
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[gi][e]) + cb[ch0 + e];
                   const size_t i0 = (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
                   const size_t i1 = i0 + (size_t)p.L * 8;
-                  if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
-                    float4 s0, s1, s2, s3;
-                    ldg_f8(p.sum32 + i0, s0, s1);
-                    ldg_f8(p.sum32 + i1, s2, s3);
-                    v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-                    v[8] += s2.x; v[9] += s2.y; v[10] += s2.z; v[11] += s2.w; v[12] += s3.x; v[13] += s3.y; v[14] += s3.z; v[15] += s3.w;
-                  }
+                  float4 s0, s1, s2, s3;
+                  ldg_f8(p.sum32 + i0, s0, s1);
+                  ldg_f8(p.sum32 + i1, s2, s3);
+                  float v[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]) + v[e];
                   if (p.flags & EPI_SUM_FIN) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;
                   }
-                  if (p.flags & (EPI_SUM_SET | EPI_SUM_ADD)) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
+                  if (p.flags & EPI_SUM_ADD) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
                   if (p.flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
                   if (p.flags & EPI_OUT16) {
                     float lo[8], hi8[8];
@@ -440,7 +542,26 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
                     uint8_t* o = static_cast<uint8_t*>(p.out16) + (((size_t)b * (size_t)p.L + (size_t)(t_row + g)) * C + ch0) * 2;
                     stg_u8(o, pack8_lrelu(lo, p.slope_out, true, bf16), pack8_lrelu(hi8, p.slope_out, true, bf16));
                   }
-                }
+                });
+              } else {
+                for_groups(t_res, [&](int gi, const uint32_t (&rr)[16]) {
+                  if (!keep) return;
+                  const int g = gi / kGroupsPerPos;
+                  const int ch0 = (gi % kGroupsPerPos) * 16;
+                  const size_t i0 = (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
+                  const size_t i1 = i0 + (size_t)p.L * 8;
+                  float v[16];
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
+                  if (p.flags & EPI_SUM_SET) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
+                  if (p.flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
+                  if (p.flags & EPI_OUT16) {
+                    uint4 lo, hi8;
+                    pack16(rr, lo, hi8, p.slope_out);
+                    uint8_t* o = static_cast<uint8_t*>(p.out16) + (((size_t)b * (size_t)p.L + (size_t)(t_row + g)) * C + ch0) * 2;
+                    stg_u8(o, lo, hi8);
+                  }
+                });
               }
               tc_fence_before();                                 // TMEM reads done before the next tile overwrites the residual
             }
@@ -448,6 +569,17 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         }
       }
     }
+#ifdef SA_DIAG
+    if (timing && lane == 0) {
+      const long long tot = clock64() - t_begin;
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 4), (unsigned long long)tot);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 5), (unsigned long long)t_x);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 6), (unsigned long long)t_acc);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 7), (unsigned long long)(tot - t_x - t_acc));
+    }
+#endif
+#undef GRP_T0
+#undef GRP_ADD
   }
   tc_fence_before();
   __syncthreads();

@@ -408,19 +408,19 @@ cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cuda
 // ---- grouped (block-Toeplitz) fused ResBlock for C <= 32 (chain_group_tc.cuh) -------------------
 int g_use_group = 1;            // SATOOLS_B200_GROUP=0: C <= 32 on the per-tap kernels (chain_tc / chain3_tc)
 
-template <int C, bool BF16>
+template <int C, bool BF16, int NS, int MS>
 cudaError_t launch_group(const tc::GroupParams& p, size_t smem, int n_sm, cudaStream_t st) {
   static bool attr_set[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::group_chain_kernel<C, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
+    cudaError_t e = cudaFuncSetAttribute(tc::group_chain_kernel<C, BF16, NS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  const int ctas = std::max(1, std::min((p.total_tiles + 1) / 2, n_sm));     // two tiles in flight per CTA
-  tc::group_chain_kernel<C, BF16><<<ctas, tc::kGrpThreads, smem, st>>>(p);
+  const int ctas = std::max(1, std::min((p.total_tiles + NS - 1) / NS, n_sm));     // NS tiles in flight per CTA
+  tc::group_chain_kernel<C, BF16, NS, MS><<<ctas, tc::kGrpThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -662,17 +662,23 @@ struct Runner {
   }
 
   // Grouped kernel geometry for convs [c0, c1) of a block: halo (multiple of G), valid positions per tile, ring depth.
-  struct GroupPlan { int halo, valid, n_wstages; size_t smem; };
+  struct GroupPlan { int halo, valid, n_wstages, ns, ms; size_t smem; };
   bool group_plan(GroupPlan& pl, const tc_chain& ch, int L, int c0, int c1) const {
     if (!g_use_group || !ch.d_wg || (c0 & 1) || ((c1 - c0) & 1) || c1 <= c0) return false;
-    const int G = 64 / ch.c, R = tc::kGrpRows * G;
+    if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;                  // slice counts the MMA issue loop is instantiated for
+    // C = 16: four streams of one sub-tile (512 positions each); C = 32: two streams of two sub-tiles (512 positions each)
+    static const int ns16 = getenv("SATOOLS_B200_GROUP_NS16") ? atoi(getenv("SATOOLS_B200_GROUP_NS16")) : 4;
+    pl.ns = (ch.c == 16 && ns16 == 4) ? 4 : 2;
+    pl.ms = 4 / pl.ns;
+    const int G = 64 / ch.c, R = tc::grp_tile_positions(ch.c, pl.ms);
     int halo = 0;
     for (int c = c0; c < c1; ++c) halo += ch.pad[c];
     halo = (halo + G - 1) / G * G;
     pl.halo = halo;
     pl.valid = R - 2 * halo;
     if (L % G != 0 || pl.valid < R / 2 || L < 2 * pl.valid) return false;    // short sequences: the per-layer path wastes less
-    const size_t fixed = 4 * (size_t)tc::kGrpBufBytes + 3 * (size_t)tc::kGrpMaxPairs * ch.c * 4 + (6 + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
+    const size_t fixed = 2 * (size_t)pl.ns * tc::grp_buf_bytes(pl.ms) + tc::kGrpOnesBytes +
+                         (3 * tc::kGrpMaxStreams + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
     int stages = std::min(tc::kGrpMaxStages, 2 * ch.g_stages);              // two convs deep: the next conv streams in behind
     while (stages > ch.g_stages && fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) --stages;
     if (stages < ch.g_stages + 1 || fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) return false;
@@ -691,7 +697,6 @@ struct Runner {
     memset(&p, 0, sizeof(p));
     p.x32 = x32; p.sum32 = e.sum32; p.out32 = e.out32; p.out16 = e.out16;
     p.w = static_cast<const uint8_t*>(ch.d_wg) + (size_t)c0 * ch.g_stages * tc::kGrpStageBytes;
-    p.bias = ch.d_bias + (size_t)c0 * ch.c;
     p.error_flag = ctx.d_error;
     p.timing = (ctx.d_timing && ctx.timing_launches < 64) ? ctx.d_timing + 16 * ctx.timing_launches++ : nullptr;
     p.L = L; p.n_convs = c1 - c0;
@@ -704,8 +709,12 @@ struct Runner {
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
-    const cudaError_t ce = ch.c == 16 ? (a.bf16 ? launch_group<16, true>(p, pl.smem, a.n_sm, a.stream) : launch_group<16, false>(p, pl.smem, a.n_sm, a.stream))
-                                      : (a.bf16 ? launch_group<32, true>(p, pl.smem, a.n_sm, a.stream) : launch_group<32, false>(p, pl.smem, a.n_sm, a.stream));
+    cudaError_t ce = cudaErrorInvalidValue;
+#define SA_GROUP(CC, NN, MM)                                                                                          \
+    if (ch.c == CC && pl.ns == NN)                                                                                    \
+      ce = a.bf16 ? launch_group<CC, true, NN, MM>(p, pl.smem, a.n_sm, a.stream) : launch_group<CC, false, NN, MM>(p, pl.smem, a.n_sm, a.stream);
+    SA_GROUP(16, 4, 1) SA_GROUP(16, 2, 2) SA_GROUP(32, 2, 2)
+#undef SA_GROUP
     if (ce != cudaSuccess) return msgf("group_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
     *done = true;
@@ -882,7 +891,7 @@ const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* 
   if (grouped) {
     const int G = 64 / c, cpp = c / 16;
     ch.g_slices = (G + k - 1) * cpp;
-    ch.g_stages = (ch.g_slices + tc::kGrpSlicesPerStage - 1) / tc::kGrpSlicesPerStage;
+    ch.g_stages = (ch.g_slices + 1 + tc::kGrpSlicesPerStage - 1) / tc::kGrpSlicesPerStage;     // + the bias slice
     const size_t conv_g = (size_t)ch.g_stages * tc::kGrpStageBytes;
     std::vector<uint8_t> hg(conv_g * n_convs, 0);
     for (int cv = 0; cv < n_convs; ++cv)
@@ -899,6 +908,19 @@ const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* 
             }
         }
       }
+    // the bias slice (its A operand is the kernel's ones tile: 1.0 in K columns 0 and 1): bias = hi + lo in 16 bits each
+    for (int cv = 0; cv < n_convs; ++cv) {
+      uint8_t* blk = hg.data() + cv * conv_g + (size_t)ch.g_slices * tc::kGrpSliceBytes;
+      for (int n = 0; n < 64; ++n) {
+        const float bv = bias[cv][n % c];
+        const uint16_t hi = to16(bv, bf16);
+        float hif;
+        if (bf16) { __nv_bfloat16 t; memcpy(&t, &hi, 2); hif = __bfloat162float(t); } else { __half t; memcpy(&t, &hi, 2); hif = __half2float(t); }
+        const uint16_t lo = to16(bv - hif, bf16);
+        memcpy(blk + swizzle_offset((uint32_t)n * 32u, 32), &hi, 2);
+        memcpy(blk + swizzle_offset((uint32_t)n * 32u + 2u, 32), &lo, 2);
+      }
+    }
     TC_CUDA(cudaMalloc(&ch.d_wg, hg.size()));
     TC_CUDA(cudaMemcpy(ch.d_wg, hg.data(), hg.size(), cudaMemcpyHostToDevice));
   }
