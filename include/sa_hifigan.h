@@ -176,6 +176,37 @@ int sa_hifigan_synthesize_host_parts_async(sa_hifigan* h, const float* bn_host, 
                                            int32_t y_dtype, void* dev_scratch,
                                            size_t dev_scratch_bytes, void* stream);
 
+/* Compact conditioning.  What Net._forward concatenates is highly redundant: the ASR bottleneck
+ * features are rows of the extractor's VQ codebook (48 codewords, satools/satools/chain/nn.py:427-459, selected in
+ * egs/asr/librispeech/local/chain/tuning/tdnnf_wav2vec2_vq.py:290-314) and the speaker block is a one-hot that is constant
+ * in time (egs/vc/libritts/local/tuning/hifigan.py:94-97).  sa_hifigan_set_codebook uploads the codebook [n_codes, dim]
+ * (host or device pointer, fp32, n_codes <= 255, dim + 1 + n_speakers == input_dim); sa_hifigan_forward_vq then takes
+ *   vq_idx  uint8 [B, T]   code index per frame (>= n_codes: a zero vector, the pipeline's padding frames)
+ *   f0      fp32  [B, T]   normalised / transformed F0 at T frames (channel `dim`)
+ *   spk_ids int32 [B]      target speaker per item (channel dim + 1 + id is 1, constant in time)
+ * all on the device: 5 bytes per frame + 4 per item instead of 4 * input_dim bytes per frame.  Bit-identical to
+ * sa_hifigan_forward on the assembled tensor when its BN rows are exact codewords.  Tensor-core modes only. */
+int sa_hifigan_set_codebook(sa_hifigan* h, const float* codebook, int32_t n_codes, int32_t dim);
+int sa_hifigan_forward_vq(sa_hifigan* h, const uint8_t* vq_idx, const float* f0, const int32_t* spk_ids,
+                          int32_t B, int32_t T, const int32_t* frames_per_item, void* y, int32_t y_dtype,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stream-ordered host entries with TRIMMED output (the reference copies the whole padded batch back and
+ * trims on the host, bin/pipeline.py:148-156): frames_per_item is required; after the forward only the kept samples of
+ * every item, 320 * frames_per_item[b] + 1, are copied to y_host, packed one item after the other (item b starts at
+ * sample sum_{i<b} (320 * frames_per_item[i] + 1)).  With y_dtype = SA_DTYPE_PCM16 that is what torchaudio.save(...,
+ * encoding="PCM_S", bits_per_sample=16) writes (pipeline.py:160).  Same dev_scratch size as the untrimmed entries.
+ * The _vq_ form takes the compact conditioning from host memory (pinned for overlap). */
+int sa_hifigan_synthesize_host_trimmed_async(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
+                                             const int32_t* frames_per_item, void* y_host,
+                                             int32_t y_dtype, void* dev_scratch,
+                                             size_t dev_scratch_bytes, void* stream);
+int sa_hifigan_synthesize_host_vq_trimmed_async(sa_hifigan* h, const uint8_t* vq_host,
+                                                const float* f0_host, const int32_t* spk_ids_host,
+                                                int32_t B, int32_t T, const int32_t* frames_per_item,
+                                                void* y_host, int32_t y_dtype, void* dev_scratch,
+                                                size_t dev_scratch_bytes, void* stream);
+
 /* Debug tap: while `out` is non-NULL every following forward also writes activation `tap`
  * as fp32 [B,C,L] to `out` (device memory, caller sized: conv_pre B*initial_channels*T,
  * stage i B*C_i*L_i floats).  out = NULL switches it off. */

@@ -73,6 +73,8 @@ struct sa_hifigan {
   int n_sm = 148;
   sa::tc_context tc;
   std::vector<sa::tc_chain> chains;     // [n_stages * n_resblocks], fused narrow-stage ResBlocks
+  float* d_codebook = nullptr;          // [n_codes][code_dim] VQ codebook of the compact conditioning (sa_hifigan_set_codebook)
+  int n_codes = 0, code_dim = 0;
   cudaStream_t side_stream = nullptr;   // second stream of sa_hifigan_synthesize_host
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // sa_hifigan_synthesize_host_async: the forwards of all in-flight calls run on ONE compute stream (in submission
@@ -222,6 +224,7 @@ void sa_hifigan_destroy(sa_hifigan* h) {
   if (cudaGetDevice(&cur) == cudaSuccess) {
     cudaSetDevice(h->device);
     free_device_weights(h);
+    if (h->d_codebook) cudaFree(h->d_codebook);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -538,9 +541,21 @@ extern "C" {
 // x, or (x == nullptr) the conditioning parts bn / f0 / spk
 static int forward_impl(sa_hifigan* h, const float* x, const float* bn, const float* f0, const float* spk, int32_t n_bn,
                         int32_t n_spk, int32_t B, int32_t T, const int32_t* frames_per_item, void* y, int32_t y_dtype,
-                        void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h || !y || !workspace || (!x && (!bn || !f0 || !spk))) return fail(SA_ERR_INVALID_ARG, "NULL argument");
-  if (!x) {
+                        void* workspace, size_t workspace_bytes, void* stream, const uint8_t* vq_idx = nullptr,
+                        const int32_t* spk_ids = nullptr) {
+  if (!h || !y || !workspace) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (vq_idx) {                                     // compact conditioning: code index + F0 per frame, speaker id per item
+    if (!f0 || !spk_ids) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+    if (!h->d_codebook) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_set_codebook first");
+    if (h->finalized && h->precision == SA_PRECISION_FP32)
+      return fail(SA_ERR_UNSUPPORTED, "the fp32 parity mode takes the assembled x (sa_hifigan_forward)");
+    n_bn = h->code_dim; n_spk = h->cfg.input_dim - 1 - h->code_dim;
+    if (n_spk < 0) return fail(SA_ERR_INVALID_ARG, "codebook dimension %d + 1 exceeds input_dim %d", h->code_dim, h->cfg.input_dim);
+    x = nullptr; bn = nullptr;
+  } else if (!x && (!bn || !f0 || !spk)) {
+    return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  }
+  if (!x && !vq_idx) {
     if (n_bn < 1 || n_spk < 0 || n_bn + 1 + n_spk != h->cfg.input_dim)
       return fail(SA_ERR_INVALID_ARG, "n_bn + 1 + n_spk = %d + 1 + %d != input_dim %d", n_bn, n_spk, h->cfg.input_dim);
     if (h->finalized && h->precision == SA_PRECISION_FP32)
@@ -577,6 +592,7 @@ static int forward_impl(sa_hifigan* h, const float* x, const float* bn, const fl
     sa::tc_forward_args a;
     a.cfg = &h->cfg; a.x = x; a.B = B; a.T = T; a.frames_per_item = frames_per_item; a.y = y; a.y_dtype = y_dtype;
     a.bn = bn; a.f0 = f0; a.spk = spk; a.n_bn = n_bn; a.n_spk = n_spk;
+    a.vq_idx = vq_idx; a.spk_ids = spk_ids; a.codebook = h->d_codebook; a.n_codes = h->n_codes;
     a.workspace = workspace; a.stream = st; a.debug_tap = h->debug_tap; a.debug_out = h->debug_out;
     a.bf16 = h->precision == SA_PRECISION_BF16; a.n_sm = h->n_sm;
     std::vector<sa::tc_layer> layers(h->convs.size());
@@ -611,6 +627,133 @@ int sa_hifigan_forward_parts(sa_hifigan* h, const float* bn, int32_t n_bn, const
   if (!bn || !f0 || !spk) return fail(SA_ERR_INVALID_ARG, "NULL argument");
   return forward_impl(h, nullptr, bn, f0, spk, n_bn, n_spk, B, T, frames_per_item, y, y_dtype, workspace, workspace_bytes,
                       stream);
+}
+
+int sa_hifigan_set_codebook(sa_hifigan* h, const float* codebook, int32_t n_codes, int32_t dim) {
+  if (!h || !codebook) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (n_codes < 1 || n_codes > 255 || dim < 1 || dim + 1 > h->cfg.input_dim)
+    return fail(SA_ERR_INVALID_ARG, "need 1 <= n_codes <= 255 and dim + 1 <= input_dim (got %d codes of %d)", n_codes, dim);
+  SA_CUDA(cudaSetDevice(h->device));
+  if (h->d_codebook) cudaFree(h->d_codebook);
+  h->d_codebook = nullptr;
+  SA_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_codebook), (size_t)n_codes * dim * sizeof(float)));
+  SA_CUDA(cudaMemcpy(h->d_codebook, codebook, (size_t)n_codes * dim * sizeof(float), cudaMemcpyDefault));
+  h->n_codes = n_codes; h->code_dim = dim;
+  return SA_OK;
+}
+
+int sa_hifigan_forward_vq(sa_hifigan* h, const uint8_t* vq_idx, const float* f0, const int32_t* spk_ids, int32_t B, int32_t T,
+                          const int32_t* frames_per_item, void* y, int32_t y_dtype, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (!vq_idx || !f0 || !spk_ids) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  return forward_impl(h, nullptr, nullptr, f0, nullptr, 0, 0, B, T, frames_per_item, y, y_dtype, workspace, workspace_bytes,
+                      stream, vq_idx, spk_ids);
+}
+
+// Shared tail of the stream-ordered host entries with TRIMMED output: after the forward, only the kept
+// samples of every item, 320 * frames_per_item[b] + 1, go back to the host, packed one item after the other
+// (pipeline.py:156 trims to the original length on the host after copying the whole padded batch).
+static int d2h_trimmed(sa_hifigan* h, const void* yd, void* y_host, int32_t B, int32_t T, const int32_t* frames, size_t esz,
+                       cudaStream_t st) {
+  const int64_t Lout = sa_hifigan_output_length(h, T);
+  size_t off = 0;
+  for (int b = 0; b < B; ++b) {
+    const size_t n = (size_t)sa_hifigan_output_length(h, frames[b]) * esz;
+    SA_CUDA(cudaMemcpyAsync(static_cast<char*>(y_host) + off, static_cast<const char*>(yd) + (size_t)b * Lout * esz, n,
+                            cudaMemcpyDeviceToHost, st));
+    off += n;
+  }
+  return SA_OK;
+}
+
+static int host_async_common_checks(sa_hifigan* h, int32_t B, int32_t T, const int32_t* frames, int32_t y_dtype, void* dev_scratch,
+                                    size_t dev_scratch_bytes) {
+  if (!h->finalized) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_finalize first");
+  if (B < 1 || T < 1) return fail(SA_ERR_INVALID_ARG, "need B >= 1 and T >= 1");
+  if (!frames) return fail(SA_ERR_INVALID_ARG, "the trimmed entries need frames_per_item");
+  for (int b = 0; b < B; ++b)
+    if (frames[b] < 1 || frames[b] > T) return fail(SA_ERR_INVALID_ARG, "frames_per_item[%d]=%d outside [1,%d]", b, frames[b], T);
+  if (y_dtype != SA_DTYPE_F32 && y_dtype != SA_DTYPE_F16 && y_dtype != SA_DTYPE_PCM16)
+    return fail(SA_ERR_INVALID_ARG, "y_dtype must be F32, F16 or PCM16");
+  const size_t need = sa_hifigan_host_scratch_bytes(h, B, T, y_dtype);
+  if (dev_scratch_bytes < need) return fail(SA_ERR_WORKSPACE, "dev_scratch too small: %zu < %zu", dev_scratch_bytes, need);
+  if (reinterpret_cast<uintptr_t>(dev_scratch) & 255) return fail(SA_ERR_INVALID_ARG, "dev_scratch must be 256-byte aligned");
+  return SA_OK;
+}
+
+int sa_hifigan_synthesize_host_trimmed_async(sa_hifigan* h, const float* x_host, int32_t B, int32_t T,
+                                             const int32_t* frames_per_item, void* y_host, int32_t y_dtype, void* dev_scratch,
+                                             size_t dev_scratch_bytes, void* stream) {
+  if (!h || !x_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  int rc = host_async_common_checks(h, B, T, frames_per_item, y_dtype, dev_scratch, dev_scratch_bytes);
+  if (rc != SA_OK) return rc;
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cur = -1;
+  SA_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
+  char* base = static_cast<char*>(dev_scratch);
+  const size_t x_bytes = (size_t)B * h->cfg.input_dim * T * sizeof(float);
+  const size_t y_bytes = (size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz;
+  float* xd = reinterpret_cast<float*>(base);
+  void* yd = base + align_up(x_bytes, 256);
+  void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+  if (!h->compute_stream) {
+    SA_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  }
+  SA_CUDA(cudaMemcpyAsync(xd, x_host, x_bytes, cudaMemcpyHostToDevice, st));
+  SA_CUDA(cudaEventRecord(h->ev_in, st));
+  SA_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_in, 0));
+  rc = sa_hifigan_forward(h, xd, B, T, frames_per_item, yd, y_dtype, ws, sa_hifigan_workspace_bytes(h, B, T), h->compute_stream);
+  SA_CUDA(cudaEventRecord(h->ev_done, h->compute_stream));
+  SA_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+  if (rc == SA_OK) rc = d2h_trimmed(h, yd, y_host, B, T, frames_per_item, esz, st);
+  if (cur != h->device) cudaSetDevice(cur);
+  return rc;
+}
+
+int sa_hifigan_synthesize_host_vq_trimmed_async(sa_hifigan* h, const uint8_t* vq_host, const float* f0_host,
+                                                const int32_t* spk_ids_host, int32_t B, int32_t T,
+                                                const int32_t* frames_per_item, void* y_host, int32_t y_dtype,
+                                                void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  if (!h || !vq_host || !f0_host || !spk_ids_host || !y_host || !dev_scratch) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  int rc = host_async_common_checks(h, B, T, frames_per_item, y_dtype, dev_scratch, dev_scratch_bytes);
+  if (rc != SA_OK) return rc;
+  const size_t esz = (y_dtype == SA_DTYPE_F32) ? 4 : 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cur = -1;
+  SA_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) SA_CUDA(cudaSetDevice(h->device));
+  char* base = static_cast<char*>(dev_scratch);
+  const size_t x_bytes = (size_t)B * h->cfg.input_dim * T * sizeof(float);      // the staging region of the dense entry
+  const size_t y_bytes = (size_t)B * (size_t)sa_hifigan_output_length(h, T) * esz;
+  const size_t f0_bytes = (size_t)B * T * sizeof(float), idx_bytes = (size_t)B * T, spk_bytes = (size_t)B * sizeof(int32_t);
+  float* f0d = reinterpret_cast<float*>(base);
+  int32_t* spkd = reinterpret_cast<int32_t*>(base + align_up(f0_bytes, 256));
+  uint8_t* idxd = reinterpret_cast<uint8_t*>(base + align_up(f0_bytes, 256) + align_up(spk_bytes, 256));
+  if (align_up(f0_bytes, 256) + align_up(spk_bytes, 256) + idx_bytes > align_up(x_bytes, 256))
+    return fail(SA_ERR_WORKSPACE, "compact conditioning does not fit the x staging region");
+  void* yd = base + align_up(x_bytes, 256);
+  void* ws = base + align_up(x_bytes, 256) + align_up(y_bytes, 256);
+  if (!h->compute_stream) {
+    SA_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    SA_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  }
+  SA_CUDA(cudaMemcpyAsync(f0d, f0_host, f0_bytes, cudaMemcpyHostToDevice, st));
+  SA_CUDA(cudaMemcpyAsync(spkd, spk_ids_host, spk_bytes, cudaMemcpyHostToDevice, st));
+  SA_CUDA(cudaMemcpyAsync(idxd, vq_host, idx_bytes, cudaMemcpyHostToDevice, st));
+  SA_CUDA(cudaEventRecord(h->ev_in, st));
+  SA_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_in, 0));
+  rc = sa_hifigan_forward_vq(h, idxd, f0d, spkd, B, T, frames_per_item, yd, y_dtype, ws, sa_hifigan_workspace_bytes(h, B, T),
+                             h->compute_stream);
+  SA_CUDA(cudaEventRecord(h->ev_done, h->compute_stream));
+  SA_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+  if (rc == SA_OK) rc = d2h_trimmed(h, yd, y_host, B, T, frames_per_item, esz, st);
+  if (cur != h->device) cudaSetDevice(cur);
+  return rc;
 }
 
 int sa_hifigan_check(sa_hifigan* h, void* stream) {

@@ -102,6 +102,32 @@ __global__ void pack_parts_kernel(const float* __restrict__ bn, const float* __r
   out[(((size_t)b * (chunks / cpp) + c8 / cpp) * T + t) * cpp + c8 % cpp] = tc::pack8(v, bf16 != 0);
 }
 
+// The same packed input from the COMPACT conditioning: the ASR bottleneck features are rows of a
+// VQ codebook (48 codewords, /root/reference/satools/satools/chain/nn.py:427-459), the speaker block is a one-hot that is
+// constant in time (hifigan.py:94-97): 1 + 4 bytes per frame + 4 bytes per item cross PCIe instead of 2016 bytes per
+// frame.  Bit-identical to packing x when its BN rows are exact codewords (index >= n_codes: the zero padding frames).
+__global__ void pack_vq_kernel(const uint8_t* __restrict__ idx, const float* __restrict__ codebook, const float* __restrict__ f0,
+                               const int32_t* __restrict__ spk, uint4* __restrict__ out, int n_codes, int n_bn, int n_spk,
+                               int chunks, int T, int bf16, int pw) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const int code = idx[(size_t)b * T + t];
+  const int sp = spk[b];
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c8 * 8 + e;
+    float x = 0.f;
+    if (c < n_bn) x = code < n_codes ? __ldg(codebook + (size_t)code * n_bn + c) : 0.f;
+    else if (c == n_bn) x = __ldg(f0 + (size_t)b * T + t);
+    else if (c < n_bn + 1 + n_spk) x = (c - n_bn - 1 == sp) ? 1.f : 0.f;
+    v[e] = x;
+  }
+  const int cpp = pw >> 3;
+  out[(((size_t)b * (chunks / cpp) + c8 / cpp) * T + t) * cpp + c8 % cpp] = tc::pack8(v, bf16 != 0);
+}
+
 // fp32 blocked [B][C/8][L][8] -> fp32 [B][C][L]  (debug taps only)
 __global__ void unblock_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int L) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1056,9 +1082,12 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     if (a.x)
       pack_input_kernel<<<g, 128, 0, st>>>(a.x, reinterpret_cast<uint4*>(XIN16), cfg.input_dim, cpad / 8, a.T, a.bf16 ? 1 : 0,
                                            panel_width(cpad));
-    else
+    else if (a.bn)
       pack_parts_kernel<<<g, 128, 0, st>>>(a.bn, a.f0, a.spk, reinterpret_cast<uint4*>(XIN16), a.n_bn, a.n_spk, cpad / 8, a.T,
                                            a.bf16 ? 1 : 0, panel_width(cpad));
+    else
+      pack_vq_kernel<<<g, 128, 0, st>>>(a.vq_idx, a.codebook, a.f0, a.spk_ids, reinterpret_cast<uint4*>(XIN16), a.n_codes, a.n_bn,
+                                        a.n_spk, cpad / 8, a.T, a.bf16 ? 1 : 0, panel_width(cpad));
     ++*launches;
     TC_CUDA(cudaGetLastError());
   }

@@ -65,6 +65,11 @@ struct tc_forward_args {
   const float* f0 = nullptr;                                  // [B, 1, T]      channel n_bn
   const float* spk = nullptr;                                 // [B, n_spk]     channels n_bn+1 .., constant in time (hifigan.py:94-97)
   int n_bn = 0, n_spk = 0;
+  // or (x == nullptr && bn == nullptr) the compact conditioning: VQ code index per frame, F0, speaker id per item
+  const uint8_t* vq_idx = nullptr;                            // [B, T]; index >= n_codes: zero vector (padding frames)
+  const float* codebook = nullptr;                            // [n_codes, n_bn] device
+  const int32_t* spk_ids = nullptr;                           // [B] device; < 0 or >= n_spk: no speaker channel set
+  int n_codes = 0;
   int B, T;
   const int32_t* frames_per_item;
   void* y;

@@ -200,6 +200,53 @@ class CoreHifiGan(nn.Module):
             self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
         return (y, torch.empty((1)))
 
+    # ---- compact conditioning: VQ code index + F0 per frame, speaker id per item ----
+    def set_codebook(self, codebook: torch.Tensor) -> None:
+        """codebook [n_codes, n_bn] (the ASR-BN extractor's VectorQuantizerEMA embedding, chain/nn.py:427-459).  Kept on the
+        module (not a parameter: the generator's state dict stays the reference's) and uploaded with the weights."""
+        cb = codebook.detach().to("cpu", torch.float32).contiguous()
+        if cb.dim() != 2 or cb.shape[0] > 255 or cb.shape[1] + 1 > self.imput_dim:
+            raise ValueError(f"codebook must be [n_codes <= 255, n_bn < imput_dim], got {tuple(cb.shape)}")
+        self._codebook = cb
+        self._codebook_handle = None                   # re-upload on the next call
+
+    def _ensure_codebook(self) -> None:
+        cb = getattr(self, "_codebook", None)
+        if cb is None:
+            raise RuntimeError("call set_codebook(codebook) before the compact (VQ index) entries")
+        if getattr(self, "_codebook_handle", None) != self._handle:
+            _lib.check(_lib.load().sa_hifigan_set_codebook(self._handle, cb.data_ptr(), cb.shape[0], cb.shape[1]))
+            self._codebook_handle = self._handle
+
+    @torch.no_grad()
+    def forward_vq(self, vq_idx: torch.Tensor, f0: torch.Tensor, spk_ids: torch.Tensor,
+                   frames_per_item: Optional[Sequence[int]] = None,
+                   out_dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+        """vq_idx uint8 [B, T], f0 fp32 [B, T] (or [B, 1, T]), spk_ids int [B], on a CUDA device.  Equals forward(x) on
+        x = cat(codebook[vq_idx], f0, one_hot(spk_ids)) bit for bit (index >= n_codes: zero BN vector)."""
+        if not (vq_idx.is_cuda and f0.is_cuda and spk_ids.is_cuda):
+            raise RuntimeError("satools_b200.CoreHifiGan runs on CUDA (sm_100a) only; there is no CPU fallback.")
+        lib = _lib.load()
+        idx = vq_idx.detach().to(torch.uint8).contiguous()
+        B, T = idx.shape
+        f0 = f0.detach().to(torch.float32).reshape(B, -1).contiguous()
+        spk = spk_ids.detach().to(torch.int32).reshape(B).contiguous()
+        if f0.shape[1] != T:
+            raise ValueError(f"f0 has {f0.shape[1]} frames, vq_idx {T}")
+        with torch.cuda.device(idx.device):
+            self._ensure_ready(idx.device)
+            self._ensure_codebook()
+            ws = self._get_workspace(lib.sa_hifigan_workspace_bytes(self._handle, B, T), idx.device)
+            y = torch.empty((B, 1, self.output_length(T)), dtype=out_dtype, device=idx.device)
+            fpi = None
+            if frames_per_item is not None:
+                fpi = (C.c_int32 * B)(*[int(v) for v in frames_per_item])
+            stream = torch.cuda.current_stream(idx.device).cuda_stream
+            _lib.check(lib.sa_hifigan_forward_vq(self._handle, idx.data_ptr(), f0.data_ptr(), spk.data_ptr(), B, T, fpi,
+                                                 y.data_ptr(), _OUT_DTYPE[out_dtype], ws.data_ptr(), ws.numel(), stream))
+            self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
+        return (y, torch.empty((1)))
+
     # ---- latency path: one CUDA graph launch instead of ~50 kernel launches ---------------------
     def graphed(self, B: int, T: int, device=None, out_dtype: torch.dtype = torch.float32) -> "GraphedForward":
         """Capture forward() for one fixed input shape [B, imput_dim, T] into a CUDA graph (single utterances,
@@ -328,6 +375,7 @@ class CoreHifiGan(nn.Module):
             _lib.check(lib.sa_hifigan_create(C.byref(cfg), C.byref(out)))
             self._handle, self._handle_pid, self._handle_device = out.value, os.getpid(), idx
             self._weights_sig = None
+            self._codebook_handle = None
         if self.precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}")
         sig = self._signature()
@@ -360,6 +408,7 @@ class CoreHifiGan(nn.Module):
         self._workspace = None
         self._host_scratch = None
         self._weights_sig = None
+        self._codebook_handle = None
 
     def __del__(self):
         try:
@@ -372,7 +421,8 @@ class CoreHifiGan(nn.Module):
         # Pickling / deepcopy (DataLoader workers capture the model, pipeline.py:175): the native
         # handle and device scratch stay behind.
         state = self.__dict__.copy()
-        for k in ("_handle", "_workspace", "_host_scratch", "_weights_sig", "_finalized_precision", "_debug_buf"):
+        for k in ("_handle", "_workspace", "_host_scratch", "_weights_sig", "_finalized_precision", "_debug_buf",
+                  "_codebook_handle"):
             state[k] = None
         state["_handle_pid"] = -1
         return state

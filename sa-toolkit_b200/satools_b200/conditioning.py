@@ -21,10 +21,8 @@ def codebook(seed: int = 1234) -> np.ndarray:
     return np.random.default_rng(seed).standard_normal((N_CODEWORDS, N_BN)).astype(np.float32)
 
 
-def utterance(rng: np.random.Generator, frames: int, n_spk: int = N_SPEAKERS,
-              cb: Optional[np.ndarray] = None, voiced_fraction: float = 0.6) -> np.ndarray:
-    """One utterance: float32 [256+1+n_spk, frames]."""
-    cb = codebook() if cb is None else cb
+def utterance_parts(rng: np.random.Generator, frames: int, n_spk: int = N_SPEAKERS, voiced_fraction: float = 0.6):
+    """One utterance in the compact form: (idx uint8 [frames] VQ codeword per frame, f0 float32 [frames], spk int)."""
     idx = np.empty(frames, dtype=np.int64)
     f0 = np.zeros(frames, dtype=np.float32)
     t = 0
@@ -38,11 +36,25 @@ def utterance(rng: np.random.Generator, frames: int, n_spk: int = N_SPEAKERS,
         if rng.random() < voiced_fraction:
             f0[t:t + seg] = rng.standard_normal(min(seg, frames - t)).astype(np.float32)
         t += seg
+    return idx.astype(np.uint8), f0, int(rng.integers(n_spk))
+
+
+def assemble(idx: np.ndarray, f0: np.ndarray, spk: int, n_spk: int = N_SPEAKERS, cb: Optional[np.ndarray] = None) -> np.ndarray:
+    """x = [codebook[idx] | f0 | one_hot(spk)] as float32 [256+1+n_spk, frames] (hifigan.py:83-97)."""
+    cb = codebook() if cb is None else cb
+    frames = idx.shape[0]
     x = np.zeros((N_BN + 1 + n_spk, frames), dtype=np.float32)
-    x[:N_BN] = cb[idx].T
+    x[:N_BN] = cb[idx.astype(np.int64)].T
     x[N_BN] = f0
-    x[N_BN + 1 + int(rng.integers(n_spk))] = 1.0
+    x[N_BN + 1 + spk] = 1.0
     return x
+
+
+def utterance(rng: np.random.Generator, frames: int, n_spk: int = N_SPEAKERS,
+              cb: Optional[np.ndarray] = None, voiced_fraction: float = 0.6) -> np.ndarray:
+    """One utterance: float32 [256+1+n_spk, frames]."""
+    idx, f0, spk = utterance_parts(rng, frames, n_spk, voiced_fraction)
+    return assemble(idx, f0, spk, n_spk, cb)
 
 
 def quant_awgn_f0(f0: np.ndarray, rng: np.random.Generator, bins: int = 16, noise_db: float = 2.0) -> np.ndarray:

@@ -266,7 +266,7 @@ def test_config4_long_utterance_chunked_latency_path():
     gen = dev_gen(0, "fp16")
     x = conditioning.batch(31, [3000])[0]
     full = run(gen, x[None])[0, 0]
-    got = synth.synthesize_corpus(gen, {"long": x}, chunk_frames=512)["long"]
+    got = synth.synthesize_corpus(gen, {"long": x}, chunk_frames=512, out_dtype=torch.float32)["long"]
     assert got.shape == full.shape == (960001,)
     snr = helpers.snr_db(full, got)
     print(f"60 s chunked vs unchunked SNR {snr:.1f} dB")
@@ -284,7 +284,7 @@ def test_config5_corpus_sharding_covers_and_matches_single_item_runs():
     feats = {f"utt{i}": conditioning.batch(500 + i, [n])[0] for i, n in enumerate(frames)}
     got = {}
     for rank in range(2):
-        part = synth.synthesize_corpus(gen, feats, rank=rank, world_size=2, max_items=4)
+        part = synth.synthesize_corpus(gen, feats, rank=rank, world_size=2, max_items=4, out_dtype=torch.float32)
         assert not (set(part) & set(got))
         got.update(part)
     assert sorted(got) == sorted(feats)
@@ -521,3 +521,120 @@ def test_forward_parts_equals_forward_on_the_reference_concatenation(precision):
     gen.precision = "fp32"
     with pytest.raises(_lib.SaHifiganError, match="assembled x"):
         gen.forward_parts(xd[:, :256].contiguous(), xd[:, 256].contiguous(), xd[:, 257:, 0].contiguous())
+
+
+# ---- widening steps of SURVEY 8f: N1 (compact conditioning) and N4 (trimmed PCM16 output), and the corpus driver ----
+
+def _vq_batch(seed, frames):
+    """Compact conditioning of a ragged batch + the assembled, pipeline-padded tensor it stands for."""
+    rng = np.random.default_rng(seed)
+    cb = conditioning.codebook()
+    T = max(frames)
+    idx = np.full((len(frames), T), 255, dtype=np.uint8)          # 255 = padding frame (zero BN vector)
+    f0 = np.zeros((len(frames), T), dtype=np.float32)
+    spk = np.zeros(len(frames), dtype=np.int32)
+    x = np.zeros((len(frames), 504, T), dtype=np.float32)
+    for b, n in enumerate(frames):
+        i, f, s_ = conditioning.utterance_parts(rng, n)
+        idx[b, :n], f0[b, :n], spk[b] = i, f, s_
+        u = conditioning.assemble(i, f, s_, cb=cb)
+        x[b, :, :n] = u
+        x[b, 257:, n:] = u[257:, :1]
+    return idx, f0, spk, x, cb
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_vq_index_conditioning_equals_the_assembled_tensor(precision):
+    """N1: (VQ code index uint8, F0, speaker id) -- 5 bytes per frame instead of 2016 -- gives bit for bit the waveform of
+    the assembled [B, 504, T] tensor, padded and ragged, device and host entry."""
+    from satools_b200 import HostPipeline
+    from satools_b200.pipeline import trimmed_offsets
+    gen = dev_gen(2, precision)
+    frames = [130, 57, 96, 1, 130, 12]
+    idx, f0, spk, x, cb = _vq_batch(77, frames)
+    gen.set_codebook(torch.from_numpy(cb))
+    y_x = run(gen, x)
+    y_v, aux = gen.forward_vq(torch.from_numpy(idx).cuda(), torch.from_numpy(f0).cuda(), torch.from_numpy(spk).cuda())
+    gen.check()
+    assert tuple(aux.shape) == (1,)
+    np.testing.assert_array_equal(y_v.cpu().numpy(), y_x)
+    y_r = gen.forward_vq(torch.from_numpy(idx).cuda(), torch.from_numpy(f0).cuda(), torch.from_numpy(spk).cuda(),
+                         frames_per_item=frames)[0].cpu().numpy()
+    for b, f in enumerate(frames):
+        np.testing.assert_array_equal(y_r[b, 0, :320 * f + 1], y_x[b, 0, :320 * f + 1])
+    # host entry: trimmed PCM16 of the compact conditioning == clip(rint(y * 32767)) of the fp32 result (N4)
+    pipe = HostPipeline(gen)
+    t = pipe.submit_vq(torch.from_numpy(idx).pin_memory(), torch.from_numpy(f0).pin_memory(), torch.from_numpy(spk).pin_memory(), frames)
+    pcm = pipe.result(t).numpy()
+    off = trimmed_offsets(gen, frames)
+    assert pcm.dtype == np.int16 and pcm.shape == (off[-1],)
+    for b, f in enumerate(frames):
+        want = np.clip(np.rint(y_x[b, 0, :320 * f + 1] * 32767.0), -32768, 32767).astype(np.int16)
+        np.testing.assert_array_equal(pcm[off[b]:off[b + 1]], want)
+    assert pipe.h2d_bytes == idx.size + 4 * f0.size + 4 * spk.size and pipe.d2h_bytes == 2 * off[-1]
+    with pytest.raises(RuntimeError, match="set_codebook"):
+        copy.deepcopy(helpers.seeded_generator(2)).to("cuda:0").forward_vq(torch.from_numpy(idx).cuda(), torch.from_numpy(f0).cuda(),
+                                                                           torch.from_numpy(spk).cuda())
+
+
+def test_trimmed_host_entry_returns_exactly_the_kept_samples():
+    """N4: sa_hifigan_synthesize_host_trimmed_async copies back 320 * frames + 1 samples per item, packed; fp32 and PCM16."""
+    from satools_b200 import HostPipeline
+    from satools_b200.pipeline import trimmed_offsets
+    gen = dev_gen(0, "fp16")
+    frames = [64, 9, 33, 64, 2]
+    x = conditioning.batch(55, frames)
+    y = run(gen, x, frames_per_item=frames)
+    pipe = HostPipeline(gen)
+    xh = torch.from_numpy(x).pin_memory()
+    off = trimmed_offsets(gen, frames)
+    got = pipe.result(pipe.submit(xh, frames_per_item=frames, trimmed=True)).numpy()
+    pcm = pipe.result(pipe.submit(xh, frames_per_item=frames, trimmed=True, out_dtype=torch.int16)).numpy()
+    assert got.shape == pcm.shape == (off[-1],)
+    for b, f in enumerate(frames):
+        np.testing.assert_array_equal(got[off[b]:off[b + 1]], y[b, 0, :320 * f + 1])
+        np.testing.assert_array_equal(pcm[off[b]:off[b + 1]], np.clip(np.rint(y[b, 0, :320 * f + 1] * 32767.0), -32768, 32767).astype(np.int16))
+    with pytest.raises(ValueError, match="frames_per_item"):
+        pipe.submit(xh, trimmed=True)
+
+
+def test_corpus_driver_dense_and_compact_inputs_agree_and_stream_to_a_sink():
+    """A11 + N1 + N4: the corpus driver (LPT shard -> length buckets -> pinned slabs staged on worker threads -> two-slot
+    pipeline -> trimmed PCM16) gives the same samples for the assembled and the compact conditioning, equals single-batch
+    runs, honours original_len and chunk windows, and can stream into a sink instead of collecting."""
+    from satools_b200 import synth
+    gen = dev_gen(1, "fp16")
+    cb = conditioning.codebook()
+    gen.set_codebook(torch.from_numpy(cb))
+    rng = np.random.default_rng(8)
+    frames = [int(v) for v in rng.integers(20, 140, size=13)] + [700]        # one utterance long enough to be chunked
+    dense, compact = {}, {}
+    for i, n in enumerate(frames):
+        idx, f0, spk = conditioning.utterance_parts(rng, n)
+        compact[f"utt{i:02d}"] = synth.VQFeatures(idx, f0, spk)
+        dense[f"utt{i:02d}"] = conditioning.assemble(idx, f0, spk, cb=cb)
+    orig = {"utt03": 320 * frames[3] - 57}
+    stats = {}
+    a = synth.synthesize_corpus(gen, dense, max_items=4, chunk_frames=256, original_len=orig, stats=stats)
+    b = synth.synthesize_corpus(gen, compact, max_items=4, chunk_frames=256, original_len=orig)
+    assert sorted(a) == sorted(b) == sorted(dense)
+    for u in a:
+        assert a[u].dtype == np.int16
+        np.testing.assert_array_equal(a[u], b[u], err_msg=u)
+    assert a["utt03"].shape == (orig["utt03"],)
+    assert stats["batches"] >= 5 and stats["utterances"] == 14 and stats["d2h_bytes"] < 0.5 * stats["padded_frames"] * 320 * 4
+    # the chunked long utterance equals its unchunked synthesis (halo-20 windows), in PCM16
+    full = run(gen, dense["utt13"][None])[0, 0]
+    np.testing.assert_array_equal(a["utt13"], np.clip(np.rint(full * 32767.0), -32768, 32767).astype(np.int16))
+    # sharded over two ranks + streamed into a sink: same samples, nothing collected
+    seen = {}
+    for rank in range(2):
+        ret = synth.synthesize_corpus(gen, compact, rank=rank, world_size=2, max_items=4, chunk_frames=256,
+                                      sink=lambda u, w: seen.__setitem__(u, w.copy()))
+        assert ret == {}
+    assert sorted(seen) == sorted(dense)
+    for i, u in enumerate(sorted(seen)):
+        # other batch mates = other padded length: the last 20 frames of an item see the padding (reference behaviour,
+        # SURVEY Appendix B), everything before is independent of the batching
+        keep = 320 * (frames[i] - 20)
+        np.testing.assert_array_equal(seen[u][:keep], a[u][:keep], err_msg=u)
