@@ -10,14 +10,25 @@ utterances of 10-15 s, padded to the longest item exactly as the reference pipel
 (/root/reference/satools/satools/bin/pipeline.py:43-66).  One step = one generator forward over
 the batch.  `value` counts the TRUE audio seconds of the 64 items (not the padding).
 
-  value     forward with x resident in HBM, CUDA events on the launching stream
-  e2e       the same batch through the host-buffer C ABI as the corpus driver calls it (HostPipeline: two
-            slots over sa_hifigan_synthesize_host_async): pinned host x -> H2D -> forward -> D2H of the
-            fp32 waveform, every step; the blocking one-call-per-step form is reported beside it
+  value     forward with x resident in HBM (padded semantics: every item computed to 750 frames, as the reference does),
+            CUDA events on the launching stream, exactly K steps; `sustained` = the same loop run for >= 5 s (the chip
+            is power capped: the longer the run, the lower the clock)
+  e2e       the same padded batch through the host-buffer C ABI (HostPipeline: two slots over
+            sa_hifigan_synthesize_host_async): pinned host x -> H2D -> forward -> D2H of the fp32 waveform, every step.
+            Same semantics as `value`.  Beside it: the ragged form (frames_per_item), the corpus driver's default form
+            (ragged + trimmed PCM16 output) and the compact-conditioning form (VQ index input, 5 bytes per frame)
   roofline  tensor-pipe roofline of the whole conv chain + per-stage breakdown from a per-launch
             CUDA-event profile (sa_hifigan_get_profile)
-  cpu_baseline  the torch-CPU port of the reference (oracle/hifigan_torch_cpu.py) on the same
-            weights, all host threads, on a bounded sample of the same batch
+  cpu_baseline  the torch-CPU port of the reference (oracle/hifigan_torch_cpu.py) on the same weights on a bounded
+            sample of the same batch: all host threads, and 1 thread ("as shipped": importing satools sets
+            torch.set_num_threads(1), /root/reference/satools/satools/hifigan/yaapt.py:27)
+  gpu_eager_reference  the reference's op sequence on THIS GPU the way the reference runs it there: torch eager
+            (cuDNN) under torch.autocast('cuda') (egs/vc/libritts/local/tuning/hifigan.py:99), same weights and batch
+  extra     the other BASELINE.json configs: [2] bf16 + quant_16_awgn_2 batch 64, [3] one 60 s utterance (chunked,
+            halo 20), [0] one 5 s utterance (latency: direct, CUDA graph, host entry)
+  corpus    configs[4]: a synthetic LibriSpeech-length corpus through satools_b200.synth.synthesize_corpus (LPT
+            sharding over the ranks, length buckets, pinned-slab staging threads, two-slot pipeline, trimmed PCM16):
+            STRONG scaling (the corpus is fixed, ranks split it), time = max over ranks
 
 Multi-GPU: launched under torchrun, one rank per GPU; every rank synthesizes its own batch of 64
 (weak scaling, utterances sharded, no collective on the data path); a barrier and a max over
@@ -176,6 +187,52 @@ def workload_config(args, where):
             "parallelism": f"utterance sharding x{args.gpus}, no collective", "where": where}
 
 
+def corpus_lengths(hours: float, seed: int = 20240):
+    """LibriSpeech-like utterance lengths: log-normal, mean 12.3 s, clipped to 1-35 s; in frames."""
+    rng = np.random.default_rng(seed)
+    n = max(8, int(round(hours * 3600.0 / 12.3)))
+    sec = np.clip(rng.lognormal(np.log(12.3) - 0.18, 0.6, n), 1.0, 35.0)
+    return np.maximum(1, np.round(sec * FRAMES_PER_SEC)).astype(int).tolist()
+
+
+def run_corpus(gen, dev, rank, world, hours, compact):
+    """One pass of the corpus driver over this rank's shard.  The corpus references a pool of 192 distinct synthetic
+    utterances (cut to length), so host memory stays small while every utterance is staged, copied, synthesized, copied
+    back and handed to a sink like a real one."""
+    from satools_b200 import conditioning, synth
+    lengths = corpus_lengths(hours)
+    rng = np.random.default_rng(99)
+    cb = conditioning.codebook()
+    pool = []
+    for k in range(192):
+        idx, f0, spk = conditioning.utterance_parts(rng, 35 * FRAMES_PER_SEC)
+        pool.append((idx, f0, spk, None if compact else conditioning.assemble(idx, f0, spk, cb=cb)))
+    feats = {}
+    for i, n in enumerate(lengths):
+        idx, f0, spk, x = pool[i % len(pool)]
+        feats[f"utt{i:06d}"] = synth.VQFeatures(idx[:n], f0[:n], spk) if compact else x[:, :n]
+    if compact:
+        gen.set_codebook(torch.from_numpy(cb))
+    acc = [0, 0]
+
+    def sink(u, w):
+        acc[0] += int(w[w.shape[0] // 2])
+        acc[1] += w.shape[0]
+
+    warm = {u: feats[u] for u in sorted(feats, key=lambda u: -synth._frames(feats[u]))[:96 * world]}   # the longest: sizes every slab
+    synth.synthesize_corpus(gen, warm, rank=rank, world_size=world, sink=sink, device=dev)
+    torch.cuda.synchronize()
+    stats = {}
+    t0 = time.perf_counter()
+    synth.synthesize_corpus(gen, feats, rank=rank, world_size=world, sink=sink, stats=stats, device=dev)
+    torch.cuda.synchronize()
+    stats["seconds"] = time.perf_counter() - t0
+    stats["samples"] = acc[1] // 2
+    stats["audio_s_total"] = sum(lengths) / FRAMES_PER_SEC
+    stats["n_utts_total"] = len(lengths)
+    return stats
+
+
 def main():
     # Only the final JSON line may reach stdout: NCCL / torch print banners from C code, so fd 1 is
     # pointed at stderr until the result is printed.
@@ -195,6 +252,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SATOOLS_B200_PRECISION", "fp16"))
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra configs, the eager-GPU leg and the corpus leg")
+    ap.add_argument("--sustain-seconds", type=float, default=5.0)
+    ap.add_argument("--corpus-hours", type=float, default=100.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -206,7 +266,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from satools_b200 import CoreHifiGan
+    from satools_b200 import CoreHifiGan, HostPipeline, conditioning
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -230,39 +290,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput -------------------------------------------------------
+    def max_over_ranks(v):
+        t = torch.tensor([float(v)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_forward(n, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            gen(x_dev, **kw)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n
+
+    # ---- device-resident throughput: exactly K steps, then the same loop for >= sustain seconds ----------
     for _ in range(args.warmup):
         gen(x_dev)
     launches_per_step = gen.last_launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            gen(x_dev)
-        e1.record()
-        barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    ms_per_step = total_ms / args.steps
+        ms_per_step = timed_forward(args.steps)
+    n_sustain = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / ms_per_step)))
+    with ClockSampler(local) as clk_sustain:
+        sustain_ms = timed_forward(n_sustain)
+    ragged_ms_per_step = timed_forward(args.steps, frames_per_item=frames)
 
-    # ---- the same forward told the true lengths (frames_per_item): tiles past an item's kept samples are skipped ----
-    for _ in range(2):
-        gen(x_dev, frames_per_item=frames)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        gen(x_dev, frames_per_item=frames)
-    e1.record()
-    barrier()
-    rms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(rms, op=dist.ReduceOp.MAX)
-    ragged_ms_per_step = float(rms.item()) / args.steps
-
-    # ---- end to end through the host-buffer C-ABI entry --------------------------------------
+    # ---- end to end through the host-buffer C-ABI entries -----------------------------------------------
     y_host = torch.empty((args.batch, 1, gen.output_length(x_np.shape[2])), dtype=torch.float32, pin_memory=True)
     gen.synthesize_host(x_host, out=y_host, device=dev)
     barrier()
@@ -270,43 +325,54 @@ def main():
     for _ in range(args.steps):
         gen.synthesize_host(x_host, out=y_host, device=dev)       # returns after the D2H completed
     torch.cuda.synchronize()
-    sync_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(sync_s, op=dist.ReduceOp.MAX)
-    sync_ms_per_step = 1e3 * float(sync_s.item()) / args.steps
+    sync_ms_per_step = 1e3 * max_over_ranks(time.perf_counter() - t0) / args.steps
 
-    # The corpus driver's call pattern (satools_b200/synth.py): batches go through HostPipeline, two slots over
-    # sa_hifigan_synthesize_host_async, so the H2D / D2H copies of one batch run under the kernels of its neighbour.
-    # Every step still copies its own input from pinned host memory and reads its own waveform back on the host.
-    from satools_b200 import HostPipeline
     pipe = HostPipeline(gen, depth=2, device=dev)
     xs = [x_host, x_host.clone().pin_memory()]
     ys = [y_host, torch.empty_like(y_host).pin_memory()]
+    n_trim = sum(gen.output_length(f) for f in frames)
+    ys_pcm = [torch.empty(n_trim, dtype=torch.int16).pin_memory() for _ in range(2)]
+    # compact conditioning of the same 64 utterances (regenerated with the same seeds: identical content)
+    rngw = np.random.default_rng(1234 + 1 + 1000 * rank)
+    T_pad = x_np.shape[2]
+    idx_np = np.full((args.batch, T_pad), 255, dtype=np.uint8)
+    f0_np = np.zeros((args.batch, T_pad), dtype=np.float32)
+    spk_np = np.zeros(args.batch, dtype=np.int32)
+    for b, n in enumerate(frames):
+        i_, f_, s_ = conditioning.utterance_parts(rngw, n)
+        idx_np[b, :n], f0_np[b, :n], spk_np[b] = i_, f_, s_
+    gen.set_codebook(torch.from_numpy(conditioning.codebook()))
+    vq_in = [tuple(torch.from_numpy(a.copy()).pin_memory() for a in (idx_np, f0_np, spk_np)) for _ in range(2)]
     checksum = 0.0
 
-    def run_pipelined(n, fpi):
+    def run_pipelined(n, mode):
         nonlocal checksum
         prev = None
         for k in range(n):
-            t = pipe.submit(xs[k & 1], out=ys[k & 1], frames_per_item=fpi)
+            if mode == "padded":
+                t = pipe.submit(xs[k & 1], out=ys[k & 1])
+            elif mode == "ragged":
+                t = pipe.submit(xs[k & 1], out=ys[k & 1], frames_per_item=frames)
+            elif mode == "trimmed_pcm16":
+                t = pipe.submit(xs[k & 1], out=ys_pcm[k & 1], frames_per_item=frames, trimmed=True)
+            else:
+                t = pipe.submit_vq(*vq_in[k & 1], frames, out=ys_pcm[k & 1])
             if prev is not None:
-                checksum += float(pipe.result(prev)[0, 0, 1000])   # host read of the previous step's result
+                checksum += float(pipe.result(prev).view(-1)[1000])   # host read of the previous step's result
             prev = t
-        checksum += float(pipe.result(prev)[0, 0, 1000])
+        checksum += float(pipe.result(prev).view(-1)[1000])
 
-    def timed_pipeline(fpi):
-        run_pipelined(max(2, args.warmup), fpi)
+    def timed_pipeline(mode):
+        run_pipelined(max(2, args.warmup), mode)
         barrier()
+        h0, d0 = pipe.h2d_bytes, pipe.d2h_bytes
         t0 = time.perf_counter()
-        run_pipelined(args.steps, fpi)
+        run_pipelined(args.steps, mode)
         torch.cuda.synchronize()
-        sec = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-        return 1e3 * float(sec.item()) / args.steps
+        ms = 1e3 * max_over_ranks(time.perf_counter() - t0) / args.steps
+        return ms, (pipe.h2d_bytes - h0) // args.steps, (pipe.d2h_bytes - d0) // args.steps
 
-    e2e_padded_ms_per_step = timed_pipeline(None)          # padded semantics: every item computed to 750 frames
-    e2e_ms_per_step = timed_pipeline(frames)               # what synth.synthesize_corpus does: true lengths passed along
+    e2e = {m: timed_pipeline(m) for m in ("padded", "ragged", "trimmed_pcm16", "vq_trimmed_pcm16")}
 
     # ---- per-launch profile -> per-section roofline --------------------------------------
     peaks = load_peaks()
@@ -329,29 +395,140 @@ def main():
                 "peak_source": peaks["source"] + ", sustained bf16 (kernels timed inside a long step)",
                 "kernel": "whole conv chain of one forward (conv_pre + 5 x (upsampler + 18 ResBlock convs) + tail)",
                 "algorithmic_gflop_per_step": round(flops_step, 1), "profiled_ms_per_step": round(conv_ms, 3),
+                "sustained_frac": round(flops_step / sustain_ms / peaks["tflops"], 4),
                 "dominant_section": SECTION_NAMES[dominant], "sections": stages}
 
+    extras, eager, cpu, corpus = None, None, None, None
+    single = rank == 0 and world == 1
+
+    # ---- the reference's own GPU path on this GPU: torch eager + cuDNN under autocast(fp16) ----------------
+    if single and not args.no_extras:
+        from oracle import hifigan_torch_cpu as otc
+        p_cuda = {k: (w.to(dev), b.to(dev)) for k, (w, b) in otc.fold(state_cpu, torch.float32).items()}
+        with torch.autocast("cuda", dtype=torch.float16):
+            otc.generator_forward(p_cuda, x_dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                otc.generator_forward(p_cuda, x_dev)
+            e1.record()
+            torch.cuda.synchronize()
+        eg_ms = e0.elapsed_time(e1) / 3
+        eager = {"value": audio_s / (eg_ms / 1e3), "unit": "audio-s/s", "ms_per_step": eg_ms,
+                 "what": "reference op sequence (torch eager, cuDNN convs, weight-norm folded once) under torch.autocast('cuda', fp16) "
+                         "as hifigan.py:99 runs it; same weights, same padded batch, device-resident", "steps": 3}
+        del p_cuda
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs ------------------------------------------------------------------
+    if single and not args.no_extras:
+        from satools_b200 import synth
+        extras = {}
+        # configs[2]: bf16 operands, fp32 accumulate, quant_16_awgn_2 conditioning, batch 64
+        x3 = torch.from_numpy(conditioning.batch(4343, frames, pad_to=x_np.shape[2], f0_transformation="quant_16_awgn_2")).to(dev)
+        gen.precision = "bf16"
+        for _ in range(3):
+            gen(x3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            gen(x3)
+        e1.record()
+        torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1) / args.steps
+        extras["config2_bf16_quant_awgn_b64"] = {"value": audio_s / (ms3 / 1e3), "unit": "audio-s/s", "ms_per_step": ms3,
+                                                 "precision": "bf16 operands, fp32 accumulate", "steps": args.steps}
+        gen.precision = args.precision
+        del x3
+        # configs[0]: one 5 s utterance (latency path)
+        x5 = torch.from_numpy(conditioning.batch(21, [250])).to(dev)
+        x5h = torch.from_numpy(conditioning.batch(21, [250])).pin_memory()
+        g5 = gen.graphed(1, 250)
+
+        def lat(fn, n=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            return 1e3 * float(np.median(ts))
+        extras["config0_5s_latency"] = {"direct_ms": lat(lambda: gen(x5)), "cuda_graph_ms": lat(lambda: g5(x5)),
+                                        "host_entry_ms": lat(lambda: gen.synthesize_host(x5h, device=dev)),
+                                        "launches": g5.launches, "unit": "ms per 5 s utterance (median of 50)"}
+        # configs[3]: one 60 s utterance, chunked synthesis with halo overlap vs one unchunked forward
+        x60 = conditioning.batch(31, [3000])[0]
+        x60d = torch.from_numpy(x60[None]).to(dev)
+        chunked = lat(lambda: synth.synthesize_corpus(gen, {"long": x60}, chunk_frames=512, device=dev), n=7)
+        extras["config3_60s_latency"] = {"chunked_host_ms": chunked, "unchunked_device_ms": lat(lambda: gen(x60d), n=10),
+                                         "chunks": "6 windows of 512 + 2 x 20 halo frames in one batch, host features in, PCM16 out",
+                                         "unit": "ms per 60 s utterance (median)"}
+        del x60d
+
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if single and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
         fwd = cpu_port_runner(state_cpu)
         sample = torch.from_numpy(np.ascontiguousarray(x_np[:2, :, :max(frames[:2])]))
-        fwd(sample[:, :, :100])
-        t0 = time.perf_counter()
-        n = 0
-        while True:
-            fwd(sample)
-            n += 1
-            if time.perf_counter() - t0 > 10.0 or n >= 8:
-                break
-        dt = time.perf_counter() - t0
-        cpu = {"value": n * sum(frames[:2]) / FRAMES_PER_SEC / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": f"first 2 utterances of the batch x {n} runs ({dt:.1f} s), torch-CPU fp32 port of the reference"}
+
+        def cpu_rate(threads, budget_s, max_runs):
+            torch.set_num_threads(threads)
+            x_s = sample if threads > 1 else sample[:1, :, :frames[0]]
+            sec = (sum(frames[:2]) if threads > 1 else frames[0]) / FRAMES_PER_SEC
+            fwd(x_s[:, :, :100])
+            t0 = time.perf_counter()
+            n = 0
+            while True:
+                fwd(x_s)
+                n += 1
+                if time.perf_counter() - t0 > budget_s or n >= max_runs:
+                    break
+            dt = time.perf_counter() - t0
+            return n * sec / dt, n, dt
+        v, n, dt = cpu_rate(cores, 10.0, 8)
+        v1, n1, dt1 = cpu_rate(1, 8.0, 2)
+        torch.set_num_threads(cores)
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": f"first 2 utterances of the batch x {n} runs ({dt:.1f} s), torch-CPU fp32 port of the reference",
+               "as_shipped_1thread": {"value": v1, "cores": 1,
+                                      "sample": f"first utterance of the batch x {n1} runs ({dt1:.1f} s); importing satools sets "
+                                                "torch.set_num_threads(1) (hifigan/yaapt.py:27)"}}
+
+    # ---- configs[4]: the corpus driver, strong scaling over the ranks ---------------------------------------
+    if not args.no_extras:
+        out_c = {}
+        for name, compact in (("dense_x", False), ("vq_index", True)):
+            st = run_corpus(gen, dev, rank, world, args.corpus_hours, compact)
+            sec = max_over_ranks(st["seconds"])
+            per_rank = [st["seconds"]]
+            loads = [st["frames"]]
+            if world > 1:
+                g = [None] * world
+                dist.all_gather_object(g, (st["seconds"], st["frames"]))
+                per_rank, loads = [a for a, _ in g], [b for _, b in g]
+            out_c[name] = {"value": st["audio_s_total"] / sec, "unit": "audio-s/s", "seconds": sec, "scaling": "strong",
+                           "corpus_hours": st["audio_s_total"] / 3600.0, "utterances": st["n_utts_total"],
+                           "per_rank_seconds": [round(v, 3) for v in per_rank],
+                           "load_imbalance": round(max(loads) / (sum(loads) / len(loads)) - 1.0, 5),
+                           "rank0": {"batches": st["batches"], "padding_waste": round(1.0 - st["frames"] / st["padded_frames"], 4),
+                                     "host_stage_ms_per_batch": round(1e3 * st["stage_s"] / st["batches"], 3),
+                                     "exposed_stage_wait_ms_per_batch": round(1e3 * st["stage_wait_s"] / st["batches"], 3),
+                                     "collect_ms_per_batch": round(1e3 * st["collect_s"] / st["batches"], 3),
+                                     "gpu_wait_ms_per_batch": round(1e3 * st["gpu_wait_s"] / st["batches"], 3),
+                                     "h2d_bytes_per_audio_s": round(st["h2d_bytes"] * FRAMES_PER_SEC / st["frames"], 1),
+                                     "d2h_bytes_per_audio_s": round(st["d2h_bytes"] * FRAMES_PER_SEC / st["frames"], 1)}}
+        corpus = dict(out_c, api="satools_b200.synth.synthesize_corpus: scheduler.shard (LPT) -> scheduler.batches -> pinned-slab "
+                                 "staging threads -> HostPipeline (trimmed PCM16 D2H) -> sink; host features in, host waveforms out",
+                      length_law="log-normal, mean 12.3 s, clipped to 1-35 s")
 
     if rank == 0:
         value = world * audio_s / (ms_per_step / 1e3)
+        pad_ms, pad_h2d, pad_d2h = e2e["padded"]
         out = {
             "metric": "hifigan_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -360,13 +537,24 @@ def main():
             "config": dict(workload_config(args, "B200"), precision=args.precision,
                            accumulate="fp32", audio_s_per_step_per_gpu=audio_s, padded_audio_s_per_step_per_gpu=padded_audio_s),
             "clocks": clk.summary(),
-            "e2e": {"value": world * audio_s / (e2e_ms_per_step / 1e3), "unit": "audio-s/s",
-                    "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": int(x_host.numel() * 4),
-                    "d2h_bytes_per_step": int(y_host.numel() * 4), "api": "HostPipeline over sa_hifigan_synthesize_host_async (pinned host buffers, two slots), frames_per_item "
-                           "passed as satools_b200.synth does: tiles past an item's true length + 24 frames are skipped, the "
-                           "kept samples are bit-identical to the padded run (test_ragged_batch_*)",
-                    "padded_value": world * audio_s / (e2e_padded_ms_per_step / 1e3),
-                    "padded_ms_per_step": e2e_padded_ms_per_step,
+            "sustained": {"value": world * audio_s / (sustain_ms / 1e3), "unit": "audio-s/s", "steps": n_sustain,
+                          "ms_per_step": sustain_ms, "seconds": n_sustain * sustain_ms / 1e3, "clocks": clk_sustain.summary(),
+                          "note": "the same padded forward loop run for >= 5 s: the power-capped steady state"},
+            "e2e": {"value": world * audio_s / (pad_ms / 1e3), "unit": "audio-s/s", "ms_per_step": pad_ms,
+                    "h2d_bytes_per_step": int(pad_h2d), "d2h_bytes_per_step": int(pad_d2h),
+                    "api": "HostPipeline over sa_hifigan_synthesize_host_async (pinned host buffers, two slots): padded semantics, "
+                           "fp32 [64,504,750] in, fp32 [64,1,240001] out -- the same work as `value`",
+                    "ragged_value": world * audio_s / (e2e["ragged"][0] / 1e3), "ragged_ms_per_step": e2e["ragged"][0],
+                    "trimmed_pcm16_value": world * audio_s / (e2e["trimmed_pcm16"][0] / 1e3),
+                    "trimmed_pcm16_ms_per_step": e2e["trimmed_pcm16"][0],
+                    "trimmed_pcm16_d2h_bytes_per_step": int(e2e["trimmed_pcm16"][2]),
+                    "vq_trimmed_pcm16_value": world * audio_s / (e2e["vq_trimmed_pcm16"][0] / 1e3),
+                    "vq_trimmed_pcm16_ms_per_step": e2e["vq_trimmed_pcm16"][0],
+                    "vq_trimmed_pcm16_h2d_bytes_per_step": int(e2e["vq_trimmed_pcm16"][1]),
+                    "vq_trimmed_pcm16_d2h_bytes_per_step": int(e2e["vq_trimmed_pcm16"][2]),
+                    "variants": "ragged: frames_per_item passed (tiles past an item's true length + 24 frames are skipped; kept samples "
+                                "bit-identical, test_ragged_batch_*); trimmed_pcm16: + only the kept samples come back, as int16 "
+                                "(the corpus driver's default, pipeline.py:156-160); vq: + VQ index / F0 / speaker id in (N1)",
                     "single_call_value": world * audio_s / (sync_ms_per_step / 1e3),
                     "single_call_ms_per_step": sync_ms_per_step,
                     "single_call_api": "sa_hifigan_synthesize_host (one blocking call per step)"},
@@ -377,6 +565,9 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_eager_reference": eager,
+            "extra": extras,
+            "corpus": corpus,
         }
         emit(out)
     if world > 1:

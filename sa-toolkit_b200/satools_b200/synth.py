@@ -79,6 +79,19 @@ class _Slabs:
         self.out = [torch.empty(max_out_samples, dtype=out_dtype).pin_memory() for _ in range(n)]
 
 
+_SLAB_CACHE: dict = {}
+
+
+def _get_slabs(n, cin, max_items, max_padded_frames, max_out_samples, out_dtype, vq) -> _Slabs:
+    """Pinned allocations cost milliseconds each: keep the largest set per (input form, output type) for the next call."""
+    key = (vq, cin, out_dtype)
+    c = _SLAB_CACHE.get(key)
+    if c is None or c[0] < max_items or c[1] < max_padded_frames or c[2] < max_out_samples:
+        caps = (max(max_items, c[0] if c else 0), max(max_padded_frames, c[1] if c else 0), max(max_out_samples, c[2] if c else 0))
+        _SLAB_CACHE[key] = (*caps, _Slabs(n, cin, caps[0], caps[1], caps[2], out_dtype, vq))
+    return _SLAB_CACHE[key][3]
+
+
 @torch.no_grad()
 def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_size: int = 1,
                       max_items: int = 64, max_padded_frames: int = 64 * 750, chunk_frames: int = 3000,
@@ -127,7 +140,7 @@ def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_s
     max_pf = max(T * len(items) for T, items in plan)
     max_os = max(sum(gen.output_length(rhi - rlo) for (_, rlo, rhi, _, _) in items) for _, items in plan)
     n_slabs = 3
-    slabs = _Slabs(n_slabs, cin, max_b, max_pf, max_os, out_dtype, vq)
+    slabs = _get_slabs(n_slabs, cin, max_b, max_pf, max_os, out_dtype, vq)
     st = {"batches": len(plan), "utterances": len(mine), "frames": int(sum(lengths[i] for i in mine)),
           "padded_frames": int(sum(T * len(items) for T, items in plan)), "stage_s": 0.0, "stage_wait_s": 0.0,
           "collect_s": 0.0, "gpu_wait_s": 0.0}
