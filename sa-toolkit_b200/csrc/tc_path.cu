@@ -703,6 +703,12 @@ struct Runner {
     pl.halo = halo;
     pl.valid = R - 2 * halo;
     if (L % G != 0 || pl.valid < R / 2 || L < 2 * pl.valid) return false;    // short sequences: the per-layer path wastes less
+    // Little work (single short utterances, the latency path): every launch pays its fixed set-up (zeroing 140 KB of shared
+    // memory, barriers, TMEM) and a stage is three launches here instead of one stage_chain3 launch; measured on a 5 s
+    // utterance: 1.26 ms grouped vs 0.97 ms per-tap.  SATOOLS_B200_GROUP_MIN_TILES overrides the threshold (tests: 0).
+    static const int min_tiles_env = getenv("SATOOLS_B200_GROUP_MIN_TILES") ? atoi(getenv("SATOOLS_B200_GROUP_MIN_TILES")) : -1;
+    const int min_tiles = min_tiles_env >= 0 ? min_tiles_env : 2 * pl.ns * a.n_sm;
+    if (((L + pl.valid - 1) / pl.valid) * a.B < min_tiles) return false;
     const size_t fixed = 2 * (size_t)pl.ns * tc::grp_buf_bytes(pl.ms) + tc::kGrpOnesBytes +
                          (3 * tc::kGrpMaxStreams + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
     int stages = std::min(tc::kGrpMaxStages, 2 * ch.g_stages);              // two convs deep: the next conv streams in behind

@@ -10,6 +10,8 @@ for p in (ROOT, os.path.join(ROOT, "sa-toolkit_b200"), os.path.join(ROOT, "tests
 import numpy as np
 import torch
 
+os.environ.setdefault("SATOOLS_B200_GROUP_MIN_TILES", "0")     # small inputs here: dispatch the grouped kernels anyway
+
 import helpers
 from oracle import hifigan_numpy as onp
 from satools_b200 import CoreHifiGan, conditioning
