@@ -58,6 +58,7 @@ constexpr uint32_t kGrpSliceBytes = 64 * 32;               // one Toeplitz block
 constexpr int kGrpSlicesPerStage = 4;
 constexpr uint32_t kGrpStageBytes = kGrpSlicesPerStage * kGrpSliceBytes;   // 8 KB
 constexpr int kGrpMaxPairs = 3;
+constexpr int kGrpMaxChains = 3;
 __host__ __device__ constexpr uint32_t grp_buf_bytes(int ms) { return (uint32_t)(ms * 128 + 2 * kGrpPadRows) * 128u; }   // multiple of 1024
 __host__ __device__ constexpr int grp_tile_positions(int c, int ms) { return ms * 128 * (64 / c); }
 constexpr uint32_t kGrpOnesBytes = 128 * 32;                               // A operand of the bias slice
@@ -67,20 +68,24 @@ struct GroupParams {
   float* sum32;             // MRF running sum, fp32 blocked
   float* out32;             // EPI_OUT32
   void* out16;              // EPI_OUT16: lrelu(output), 16-bit [B][1][L][C]
-  const void* w;            // n_convs convs, each stages_per_conv stages of 8 KB (4 slices per stage: the n_slices
-                            // Toeplitz blocks, then the bias block, zero padded)
+  // One launch runs n_chains ResBlocks over every tile, one after the other (the three multi-receptive-field chains of a
+  // stage read the same input tile: x is re-read from L2 and the running sum stays in L2 between them, so a stage moves
+  // ~2.5 GB through DRAM instead of ~7.3 GB as three launches); n_chains = 1: a single ResBlock (or a part of one).
+  int n_chains;
+  const void* w[kGrpMaxChains];      // per chain: n_convs convs, each stages_per_conv stages of 8 KB (4 slices per stage: the
+                                     // n_slices Toeplitz blocks, then the bias block, zero padded)
+  int n_slices[kGrpMaxChains];       // (G + k - 1) * C / 16 Toeplitz slices (+ 1 bias slice)
+  int stages_per_conv[kGrpMaxChains];// ceil((n_slices + 1) / 4)
+  uint32_t flags[kGrpMaxChains];     // EPI_* of each chain's final epilogue (SUM_SET / SUM_ADD / SUM_FIN, OUT32, OUT16)
   int* error_flag;
   long long* timing;        // optional [16] cycle counters: MMA warp total / wait ready / wait weights
   int L;                    // positions per item (multiple of G)
   int n_convs;              // 2 * n_pairs
   int dil[kGrpMaxPairs];    // dilation of conv1 of each pair
   int halo;                 // recomputed positions per side (sum of all conv reaches), multiple of G
-  int n_slices;             // (G + k - 1) * C / 16 Toeplitz slices (+ 1 bias slice)
-  int stages_per_conv;      // ceil((n_slices + 1) / 4)
   int n_wstages;            // ring depth, >= stages_per_conv + 1
   int tiles_per_item, total_tiles;
   TileMapParams map;        // ragged batches (conv_tc.cuh); tile axis = valid positions per tile
-  uint32_t flags;           // EPI_* of the final epilogue
   float slope_out;
   float n_blocks;
 };
@@ -164,9 +169,10 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     uint32_t par = 1;                                            // parity of the previous use of `slot`
     bool wrapped = false, ok = true;
     for (int it = 0; it < n_iters && ok; ++it)
+     for (int j = 0; j < p.n_chains && ok; ++j)
       for (int c = 0; c < p.n_convs && ok; ++c) {
-        const uint8_t* src = static_cast<const uint8_t*>(p.w) + (size_t)c * p.stages_per_conv * kGrpStageBytes;
-        for (int i = 0; i < p.stages_per_conv; ++i) {
+        const uint8_t* src = static_cast<const uint8_t*>(p.w[j]) + (size_t)c * p.stages_per_conv[j] * kGrpStageBytes;
+        for (int i = 0; i < p.stages_per_conv[j]; ++i) {
           if (wrapped) ok = mbar_wait_relaxed(bar_w_empty(slot), par, p.error_flag);
           if (!ok) break;
           if (leader) {
@@ -201,14 +207,14 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
 #endif
     long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
     // one conv (NSL Toeplitz slices + the bias slice) of both streams
-    auto conv = [&](auto nsl_c, auto conv2_c, int it, int c) {
+    auto conv = [&](auto nsl_c, auto conv2_c, uint32_t ph0, int c) {
       constexpr int NSL = decltype(nsl_c)::value;
       constexpr bool CONV2 = decltype(conv2_c)::value;                         // accumulates onto the residual
       constexpr int NTOT = NSL + 1;
       constexpr int NSTG = (NTOT + kGrpSlicesPerStage - 1) / kGrpSlicesPerStage;
       constexpr int pad_pos = (NSL / kGroupsPerPos - G) / 2;                   // (k - 1) / 2 positions
       constexpr int t_in = CONV2 ? 1 : 0;                                      // conv1 reads A, conv2 reads T
-      const uint32_t rdy_parity = ((uint32_t)it * (uint32_t)n_pairs + (uint32_t)(c >> 1)) & 1u;
+      const uint32_t rdy_parity = (ph0 + (uint32_t)(c >> 1)) & 1u;            // ph0: pairs completed before this chain
       const int slot0 = slot;
       const uint32_t par0 = par;
 #pragma unroll 1
@@ -251,18 +257,22 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         __syncwarp();
       }
     };
-    auto run = [&](auto nsl_c) {
-      for (int it = 0; it < n_iters && ok; ++it)
-        for (int c = 0; c < p.n_convs && ok; c += 2) {
-          conv(nsl_c, std::false_type{}, it, c);
-          if (ok) conv(nsl_c, std::true_type{}, it, c + 1);
-        }
+    auto chain = [&](auto nsl_c, uint32_t ph0) {
+      for (int c = 0; c < p.n_convs && ok; c += 2) {
+        conv(nsl_c, std::false_type{}, ph0, c);
+        if (ok) conv(nsl_c, std::true_type{}, ph0, c + 1);
+      }
     };
     constexpr int CPP = kGroupsPerPos;
-    if (p.n_slices == (G + 2) * CPP) run(std::integral_constant<int, (G + 2) * CPP>{});           // k = 3
-    else if (p.n_slices == (G + 6) * CPP) run(std::integral_constant<int, (G + 6) * CPP>{});      // k = 7
-    else if (p.n_slices == (G + 10) * CPP) run(std::integral_constant<int, (G + 10) * CPP>{});    // k = 11
-    else if (p.error_flag) atomicExch(p.error_flag, 1);                                            // not instantiated (the host checks)
+    uint32_t ph0 = 0;
+    for (int it = 0; it < n_iters && ok; ++it)
+      for (int j = 0; j < p.n_chains && ok; ++j, ph0 += (uint32_t)n_pairs) {
+        const int nsl = p.n_slices[j];
+        if (nsl == (G + 2) * CPP) chain(std::integral_constant<int, (G + 2) * CPP>{}, ph0);           // k = 3
+        else if (nsl == (G + 6) * CPP) chain(std::integral_constant<int, (G + 6) * CPP>{}, ph0);      // k = 7
+        else if (nsl == (G + 10) * CPP) chain(std::integral_constant<int, (G + 10) * CPP>{}, ph0);    // k = 11
+        else { if (p.error_flag) atomicExch(p.error_flag, 1); ok = false; }                             // not instantiated (the host checks)
+      }
     if (timing && lane == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 0), (unsigned long long)(clock64() - t_begin));
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_ready);
@@ -358,7 +368,6 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
 #define GRP_ADD(acc, v)
 #endif
     for (int it = 0; it < n_iters && ok; ++it) {
-      GRP_T0(tx0);
       const int tile = (int)blockIdx.x + (NS * it + st) * (int)gridDim.x;
       const bool live = tile < n_live;                            // the last iteration may have streams without a tile
       int b = 0, mt = 0;
@@ -369,6 +378,26 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       const bool keep = inside && G * r >= p.halo && G * r < R - p.halo;
       const bool interior = live && t0 >= 0 && t0 + R <= p.L;     // no position of the tile is outside the utterance
       const bool w_all = __all_sync(0xffffffffu, inside), w_any = __any_sync(0xffffffffu, inside);   // warp-uniform
+      // The next tile of this stream: have its rows in L2 by the time they are needed.
+      {
+        const int tile_n = tile + NS * (int)gridDim.x;
+        if (tile_n < n_live) {
+          int bn, mtn;
+          tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile_n, bn, mtn);
+          const int tn = mtn * valid - p.halo + G * r;
+          if (tn >= 0 && tn < p.L) {
+#pragma unroll
+            for (int q = 0; q < cchunks; ++q)
+#pragma unroll
+              for (int g = 0; g < G; g += 4)                       // 32 B per position: one 128-byte line holds 4
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + q) * (size_t)p.L + (size_t)(tn + g)) * 8));
+          }
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < p.n_chains && ok; ++j) {
+      const uint32_t flags = p.flags[j];
+      GRP_T0(tx0);
       // ---- x: residual stream -> tensor memory, lrelu(x) -> input tile of pair 0's conv1 ----
       {
         const int d0 = p.dil[0];
@@ -405,28 +434,13 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         if (lane == 0) mbar_arrive(bar_ready(st, 0));
       }
       GRP_ADD(t_x, tx0);
-      // the next tile of this stream and this tile's running sum: have them in L2 when they are needed
-      if (keep && (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
+      // a running sum left in HBM by an earlier launch: have it in L2 when the final epilogue needs it
+      if (p.n_chains == 1 && keep && (flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
 #pragma unroll
         for (int q = 0; q < cchunks; ++q)
 #pragma unroll
-          for (int g = 0; g < G; g += 4)                           // 32 B per position: one 128-byte line holds 4
+          for (int g = 0; g < G; g += 4)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sum32 + (((size_t)b * cchunks + q) * (size_t)p.L + (size_t)(t_row + g)) * 8));
-      }
-      {
-        const int tile_n = tile + NS * (int)gridDim.x;
-        if (tile_n < n_live) {
-          int bn, mtn;
-          tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile_n, bn, mtn);
-          const int tn = mtn * valid - p.halo + G * r;
-          if (tn >= 0 && tn < p.L) {
-#pragma unroll
-            for (int q = 0; q < cchunks; ++q)
-#pragma unroll
-              for (int g = 0; g < G; g += 4)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + q) * (size_t)p.L + (size_t)(tn + g)) * 8));
-          }
-        }
       }
       // ---- the (conv1, conv2) pairs ----
 #pragma unroll
@@ -516,7 +530,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
               if (lane == 0) mbar_arrive(bar_ready(st, 0));
             } else {
               // final epilogue: multi-receptive-field combine (archi.py:82-86) + output streams
-              if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {        // the running sum was prefetched into L2 at tile start
+              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {          // the running sum is in L2 (prefetched, or just written)
                 for_groups(t_res, [&](int gi, const uint32_t (&rr)[16]) {
                   if (!keep) return;
                   const int g = gi / kGroupsPerPos;
@@ -529,13 +543,13 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
                   float v[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
 #pragma unroll
                   for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]) + v[e];
-                  if (p.flags & EPI_SUM_FIN) {
+                  if (flags & EPI_SUM_FIN) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;
                   }
-                  if (p.flags & EPI_SUM_ADD) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
-                  if (p.flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
-                  if (p.flags & EPI_OUT16) {
+                  if (flags & EPI_SUM_ADD) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
+                  if (flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
+                  if (flags & EPI_OUT16) {
                     float lo[8], hi8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
@@ -553,9 +567,9 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
                   float v[16];
 #pragma unroll
                   for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
-                  if (p.flags & EPI_SUM_SET) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
-                  if (p.flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
-                  if (p.flags & EPI_OUT16) {
+                  if (flags & EPI_SUM_SET) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
+                  if (flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
+                  if (flags & EPI_OUT16) {
                     uint4 lo, hi8;
                     pack16(rr, lo, hi8, p.slope_out);
                     uint8_t* o = static_cast<uint8_t*>(p.out16) + (((size_t)b * (size_t)p.L + (size_t)(t_row + g)) * C + ch0) * 2;
@@ -568,6 +582,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
           }
         }
       }
+      }   // chains
     }
 #ifdef SA_DIAG
     if (timing && lane == 0) {
