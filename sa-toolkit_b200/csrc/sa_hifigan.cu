@@ -216,6 +216,7 @@ static void free_device_weights(sa_hifigan* h) {
   }
   for (auto& ch : h->chains) sa::tc_free_chain(ch);
   h->chains.clear();
+  h->tc.tmaps.clear();                  // cached tensor maps point at the freed weight buffers
 }
 
 void sa_hifigan_destroy(sa_hifigan* h) {

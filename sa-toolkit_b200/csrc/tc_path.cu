@@ -537,6 +537,28 @@ struct Runner {
   tc_context& ctx;
   const tc_forward_args& a;
   int64_t* launches;
+  // cuTensorMapEncodeTiled through the per-handle cache (key: base pointer + dims + box + type + swizzle)
+  CUresult tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* gdim, const cuuint64_t* gstr,
+                const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    tc_tmap_entry k;
+    k.ptr = ptr; k.d0 = gdim[0]; k.d1 = gdim[1]; k.d2 = rank > 2 ? gdim[2] : 0; k.d3 = rank > 3 ? gdim[3] : 0;
+    k.b0 = box[0]; k.b1 = box[1]; k.dtype = (int)dt; k.swizzle = (int)swz; k.rank = rank;
+    for (const tc_tmap_entry& e : ctx.tmaps)
+      if (e.ptr == k.ptr && e.d0 == k.d0 && e.d1 == k.d1 && e.d2 == k.d2 && e.d3 == k.d3 && e.b0 == k.b0 && e.b1 == k.b1 &&
+          e.dtype == k.dtype && e.swizzle == k.swizzle && e.rank == k.rank) {
+        *out = e.map;
+        return CUDA_SUCCESS;
+      }
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = reinterpret_cast<encode_tiled_fn>(ctx.encode_fn)(&k.map, dt, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, box,
+                                                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return r;
+    if (ctx.tmaps.size() >= 512) ctx.tmaps.clear();          // many shapes in one process: start over rather than grow
+    ctx.tmaps.push_back(k);
+    *out = k.map;
+    return CUDA_SUCCESS;
+  }
   const int* d_frames = nullptr;                 // device copy of frames_per_item (ragged batches), else nullptr
   tc::TileMapParams tile_map(int rows) const {   // rows = rows per item on the kernel's tile axis
     tc::TileMapParams m;
@@ -576,11 +598,7 @@ struct Runner {
     const cuuint32_t box[4] = {(cuuint32_t)pw, (cuuint32_t)pl.box_rows, 1, 1};
     const CUtensorMapSwizzle swz = pw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = reinterpret_cast<encode_tiled_fn>(ctx.encode_fn)(
-        &p.tmap, a.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in16),
-        gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = tmap(&p.tmap, a.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in16, gdim, gstr, box, swz);
     if (r != CUDA_SUCCESS) {
       snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for L=%d panels=%d box_rows=%d", (int)r, l_in,
                w.cin_pad / pw, pl.box_rows);
@@ -590,10 +608,7 @@ struct Runner {
       const cuuint64_t wdim[2] = {64, (cuuint64_t)(w.bytes / 128)};
       const cuuint64_t wstr[1] = {128};
       const cuuint32_t wbox[2] = {64, (cuuint32_t)((pl.k16_per_stage / 4) * (w.n / 2))};
-      const cuuint32_t wes[2] = {1, 1};
-      r = reinterpret_cast<encode_tiled_fn>(ctx.encode_fn)(
-          &p.wmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w.d_w, wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      r = tmap(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w.d_w, wdim, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
       if (r != CUDA_SUCCESS) {
         snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for the weights (%zu rows, box %u)", (int)r,
                  w.bytes / 128, wbox[1]);

@@ -1,7 +1,9 @@
 // Tensor-core (tcgen05) path of the generator: interface used by sa_hifigan.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/sa_hifigan.h"
 
 namespace sa {
@@ -40,7 +42,15 @@ struct tc_chain {
   int g_slices = 0, g_stages = 0;
 };
 
+// Encoded tensor maps are cached per (buffer, geometry): a forward re-uses ~45 of them, and re-encoding them on the host
+// for every call showed up in the single-utterance latency path.
+struct tc_tmap_entry {
+  const void* ptr; uint64_t d0, d1, d2, d3; uint32_t b0, b1; int dtype, swizzle, rank;
+  CUtensorMap map;
+};
+
 struct tc_context {
+  std::vector<tc_tmap_entry> tmaps;
   bool ready = false;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   int* h_error = nullptr;     // mapped pinned flag raised by a kernel whose barrier wait timed out
