@@ -158,17 +158,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint, in ns, runs
+// out), so a waiting warp neither polls shared memory nor takes issue slots, and wakes on the completion itself.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t ticks = 0u) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+  if (ticks)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ticks)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
   return ok != 0;
 }
+// suspend-time hint (ns) of the relaxed waits, set once per process by tc_init (SATOOLS_B200_MBAR_NS; 0 = poll with
+// nanosleep(40) between plain try_waits, the round-1 behaviour)
+__device__ uint32_t g_mbar_suspend_ns = 20000;
 // Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
   if (mbar_try_wait(bar, parity)) return true;
@@ -187,8 +201,9 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
 __device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* error_flag) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
+  const uint32_t hint = g_mbar_suspend_ns;
+  while (!mbar_try_wait(bar, parity, hint)) {
+    if (hint == 0) __nanosleep(40);
     if (clock64() - t0 > 4000000000LL) {
       if (error_flag) atomicExch(error_flag, 1);
       return false;

@@ -707,8 +707,10 @@ struct Runner {
   bool group_plan(GroupPlan& pl, const tc_chain& ch, int L, int c0, int c1) const {
     if (!g_use_group || !ch.d_wg || (c0 & 1) || ((c1 - c0) & 1) || c1 <= c0) return false;
     if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;                  // slice counts the MMA issue loop is instantiated for
-    // C = 16: four streams of one sub-tile (512 positions each); C = 32: two streams of two sub-tiles (512 positions each)
-    static const int ns16 = getenv("SATOOLS_B200_GROUP_NS16") ? atoi(getenv("SATOOLS_B200_GROUP_NS16")) : 4;
+    // Two streams of two sub-tiles: 1024 positions per tile for C = 16, 512 for C = 32.  (Four streams of one sub-tile for
+    // C = 16, SATOOLS_B200_GROUP_NS16=4, measured slower: 4.67 vs 4.13 ms for stage 4 -- twice the halo share, and the streams
+    // run in lockstep on one shared weight ring, so more of them do not decouple anything.)
+    static const int ns16 = getenv("SATOOLS_B200_GROUP_NS16") ? atoi(getenv("SATOOLS_B200_GROUP_NS16")) : 2;
     pl.ns = (ch.c == 16 && ns16 == 4) ? 4 : 2;
     pl.ms = 4 / pl.ns;
     const int G = 64 / ch.c, R = tc::grp_tile_positions(ch.c, pl.ms);
@@ -1025,6 +1027,10 @@ const char* tc_init(tc_context& ctx, int device) {
   TC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx.d_error), ctx.h_error, 0));
   if (const char* env = getenv("SATOOLS_B200_CHAIN_TIMING")) {
     if (atoi(env) != 0) TC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx.d_timing), 64 * 16 * sizeof(long long)));
+  }
+  if (const char* env = getenv("SATOOLS_B200_MBAR_NS")) {
+    const uint32_t v = (uint32_t)atoi(env);
+    TC_CUDA(cudaMemcpyToSymbol(tc::g_mbar_suspend_ns, &v, sizeof(v)));
   }
   if (const char* env = getenv("SATOOLS_B200_CHAIN3")) g_use_chain3 = atoi(env);
   if (const char* env = getenv("SATOOLS_B200_GROUP")) g_use_group = atoi(env);
