@@ -71,6 +71,12 @@ struct GroupParams {
   // One launch runs n_chains ResBlocks over every tile, one after the other (the three multi-receptive-field chains of a
   // stage read the same input tile: x is re-read from L2 and the running sum stays in L2 between them, so a stage moves
   // ~2.5 GB through DRAM instead of ~7.3 GB as three launches); n_chains = 1: a single ResBlock (or a part of one).
+  // fuse_up: the stage's transposed conv (k = 4, stride 2; archi.py:80-81) runs inside this kernel, as one more
+  // block-Toeplitz conv from a TMA-staged tile of the previous stage's 16-bit output straight into the residual columns of
+  // tensor memory: the fp32 stage input never exists in HBM (no upsampler launch, no 4 B/element write + re-reads).
+  CUtensorMap up_map;                // previous stage's lrelu'd 16-bit output as [B][rows][64], SWIZZLE_128B, box {64, 136}
+  const void* up_w;                  // up_stages stages: the up_slices Toeplitz blocks of the transposed conv + its bias block
+  int fuse_up, up_stages;
   int n_chains;
   const void* w[kGrpMaxChains];      // per chain: n_convs convs, each stages_per_conv stages of 8 KB (4 slices per stage: the
                                      // n_slices Toeplitz blocks, then the bias block, zero padded)
@@ -113,6 +119,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 template <int C, bool BF16, int NS, int MS>
 __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __grid_constant__ GroupParams p) {
   static_assert(C == 16 || C == 32, "grouped formulation: C = 16 (G = 4) or C = 32 (G = 2)");
@@ -138,7 +150,12 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   auto bar_acc_full = [&](int st) { return smem_u32(&bars[2 * kGrpMaxStreams + st]); };
   auto bar_w_full = [&](int i) { return smem_u32(&bars[3 * kGrpMaxStreams + i]); };
   auto bar_w_empty = [&](int i) { return smem_u32(&bars[3 * kGrpMaxStreams + kGrpMaxStages + i]); };
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3 * kGrpMaxStreams + 2 * kGrpMaxStages);
+  // fuse_up: up_full[stream] (input tile landed), up_empty[stream] (buffer A free for the next tile), res_free[stream]
+  // (the final epilogue has read the residual columns)
+  auto bar_up_full = [&](int st) { return smem_u32(&bars[3 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
+  auto bar_up_empty = [&](int st) { return smem_u32(&bars[4 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
+  auto bar_res_free = [&](int st) { return smem_u32(&bars[5 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6 * kGrpMaxStreams + 2 * kGrpMaxStages);
 
   const int valid = R - 2 * p.halo;
   __shared__ int tile_pre[kMaxMapItems + 1];
@@ -151,7 +168,11 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       mbar_init(bar_ready(st, 0), kGrpMS * 4);                   // the warps of the stream
       mbar_init(bar_ready(st, 1), kGrpMS * 4);
       mbar_init(bar_acc_full(st), 1);
+      mbar_init(bar_up_full(st), 1);
+      mbar_init(bar_up_empty(st), 1);
+      mbar_init(bar_res_free(st), kGrpMS * 4);
     }
+    if (p.fuse_up) prefetch_tmap(&p.up_map);
     for (int i = 0; i < kGrpMaxStages; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
     fence_barrier_init();
   }
@@ -182,11 +203,37 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     int slot = 0;
     uint32_t par = 1;                                            // parity of the previous use of `slot`
     bool wrapped = false, ok = true;
+    uint32_t n = 0;                                              // (iteration, chain) counter
     for (int it = 0; it < n_iters && ok; ++it)
-     for (int j = 0; j < p.n_chains && ok; ++j)
-      for (int c = 0; c < p.n_convs && ok; ++c) {
-        const uint8_t* src = static_cast<const uint8_t*>(p.w[j]) + (size_t)c * p.stages_per_conv[j] * kGrpStageBytes;
-        for (int i = 0; i < p.stages_per_conv[j]; ++i) {
+     for (int j = 0; j < p.n_chains && ok; ++j, ++n) {
+      if (p.fuse_up) {
+        // the input tile of every stream: rows [t0 / G - 8, t0 / G + 264) of the item (out-of-range rows arrive as zeros:
+        // the zero padding of the transposed conv), into buffer A once conv1 of the previous chain's last pair has read it
+        for (int st = 0; st < NS && ok; ++st) {
+          if (n > 0) ok = mbar_wait_relaxed(bar_up_empty(st), (n - 1) & 1u, p.error_flag);
+          if (!ok) break;
+          const int tile = (int)blockIdx.x + (NS * it + st) * (int)gridDim.x;
+          if (tile < n_live) {
+            int b, mt;
+            tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
+            const int row0 = (mt * valid - p.halo) / G - kGrpPadRows;
+            if (leader) {
+              mbar_arrive_expect_tx(bar_up_full(st), kGrpBufBytes);
+              const uint32_t dst = smem_u32(buf(st, 0));
+              tma_load_3d(dst, &p.up_map, bar_up_full(st), 0, row0, b);
+              tma_load_3d(dst + kGrpBufBytes / 2, &p.up_map, bar_up_full(st), 0, row0 + (int)(kGrpBufBytes / 256), b);
+            }
+          } else if (leader) {
+            mbar_arrive(bar_up_full(st));                          // a stream without a tile: nothing to load
+          }
+          __syncwarp();
+        }
+      }
+      for (int c = p.fuse_up ? -1 : 0; c < p.n_convs && ok; ++c) {
+        const int n_stg = c < 0 ? p.up_stages : p.stages_per_conv[j];
+        const uint8_t* src = c < 0 ? static_cast<const uint8_t*>(p.up_w)
+                                   : static_cast<const uint8_t*>(p.w[j]) + (size_t)c * p.stages_per_conv[j] * kGrpStageBytes;
+        for (int i = 0; i < n_stg; ++i) {
           if (wrapped) ok = mbar_wait_relaxed(bar_w_empty(slot), par, p.error_flag);
           if (!ok) break;
           if (leader) {
@@ -198,6 +245,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
           if (++slot == p.n_wstages) { slot = 0; par ^= 1u; wrapped = true; }
         }
       }
+     }
   } else if (warp == kWarpMma) {
     // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
     // The first version walked the slices with a runtime count and per-MMA predicates: 16 issued instructions per MMA
@@ -221,25 +269,36 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
 #endif
     long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
     // one conv (NSL Toeplitz slices + the bias slice) of both streams
-    auto conv = [&](auto nsl_c, auto conv2_c, uint32_t ph0, int c) {
+    // kind 0: conv1 (reads A, fresh accumulator), 1: conv2 (reads T, accumulates onto the residual), 2: the fused
+    // transposed conv (reads the TMA-staged input tile in A, writes the residual columns)
+    auto conv = [&](auto nsl_c, auto kind_c, uint32_t ph0, int c, uint32_t n) {
       constexpr int NSL = decltype(nsl_c)::value;
-      constexpr bool CONV2 = decltype(conv2_c)::value;                         // accumulates onto the residual
+      constexpr int KIND = decltype(kind_c)::value;
+      constexpr bool CONV2 = KIND == 1;                                        // accumulates onto the residual
       constexpr int NTOT = NSL + 1;
       constexpr int NSTG = (NTOT + kGrpSlicesPerStage - 1) / kGrpSlicesPerStage;
-      constexpr int pad_pos = (NSL / kGroupsPerPos - G) / 2;                   // (k - 1) / 2 positions
-      constexpr int t_in = CONV2 ? 1 : 0;                                      // conv1 reads A, conv2 reads T
+      // bytes before the row's first position that the first slice starts at: (k - 1) / 2 positions, or one INPUT position
+      // (= 2 output positions' worth of bytes: twice the channels) for the transposed conv
+      constexpr uint32_t lead = KIND == 2 ? 2u * PB : (uint32_t)((NSL / kGroupsPerPos - G) / 2) * PB;
+      constexpr int t_in = KIND == 1 ? 1 : 0;                                  // conv1 / up read A, conv2 reads T
+      constexpr int d_idx = KIND == 0 ? 0 : 1;                                 // conv1 -> accumulator, conv2 / up -> residual
       const uint32_t rdy_parity = (ph0 + (uint32_t)(c >> 1)) & 1u;            // ph0: pairs completed before this chain
       const int slot0 = slot;
       const uint32_t par0 = par;
 #pragma unroll 1
       for (int st = 0; st < kGrpStreams && ok; ++st) {
         const long long tr0 = timing ? clock64() : 0;
-        ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
+        if (KIND == 2) {
+          ok = mbar_wait(bar_up_full(st), n & 1u, p.error_flag);               // input tile landed
+          if (ok && n > 0) ok = mbar_wait(bar_res_free(st), (n - 1) & 1u, p.error_flag);   // previous residual consumed
+        } else {
+          ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
+        }
         if (timing) t_ready += clock64() - tr0;
         if (!ok) break;
         tc_fence_after();
-        const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - (uint32_t)pad_pos * PB);
-        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + t_in) * kGrpMS * 64);
+        const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - lead);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + d_idx) * kGrpMS * 64);
         slot = slot0; par = par0;
 #pragma unroll
         for (int i = 0; i < NSTG; ++i) {
@@ -267,24 +326,33 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
           __syncwarp();
           if (++slot == n_wst) { slot = 0; par ^= 1u; }
         }
-        if (leader) umma_commit(bar_acc_full(st));
+        if (leader) {
+          umma_commit(bar_acc_full(st));
+          if (KIND == 0 && c == p.n_convs - 2 && p.fuse_up) umma_commit(bar_up_empty(st));   // buffer A read for the last time
+        }
         __syncwarp();
       }
     };
-    auto chain = [&](auto nsl_c, uint32_t ph0) {
+    using K0 = std::integral_constant<int, 0>;
+    using K1 = std::integral_constant<int, 1>;
+    using K2 = std::integral_constant<int, 2>;
+    auto chain = [&](auto nsl_c, uint32_t ph0, uint32_t n) {
       for (int c = 0; c < p.n_convs && ok; c += 2) {
-        conv(nsl_c, std::false_type{}, ph0, c);
-        if (ok) conv(nsl_c, std::true_type{}, ph0, c + 1);
+        conv(nsl_c, K0{}, ph0, c, n);
+        if (ok) conv(nsl_c, K1{}, ph0, c + 1, n);
       }
     };
     constexpr int CPP = kGroupsPerPos;
-    uint32_t ph0 = 0;
+    constexpr int NSL_UP = (G / 2 + 2) * 2 * CPP;                 // (own + 2 halo) input positions x (2 C / 16) channel blocks
+    uint32_t ph0 = 0, n = 0;
     for (int it = 0; it < n_iters && ok; ++it)
-      for (int j = 0; j < p.n_chains && ok; ++j, ph0 += (uint32_t)n_pairs) {
+      for (int j = 0; j < p.n_chains && ok; ++j, ph0 += (uint32_t)n_pairs, ++n) {
+        if (p.fuse_up) conv(std::integral_constant<int, NSL_UP>{}, K2{}, 0u, 0, n);
+        if (!ok) break;
         const int nsl = p.n_slices[j];
-        if (nsl == (G + 2) * CPP) chain(std::integral_constant<int, (G + 2) * CPP>{}, ph0);           // k = 3
-        else if (nsl == (G + 6) * CPP) chain(std::integral_constant<int, (G + 6) * CPP>{}, ph0);      // k = 7
-        else if (nsl == (G + 10) * CPP) chain(std::integral_constant<int, (G + 10) * CPP>{}, ph0);    // k = 11
+        if (nsl == (G + 2) * CPP) chain(std::integral_constant<int, (G + 2) * CPP>{}, ph0, n);           // k = 3
+        else if (nsl == (G + 6) * CPP) chain(std::integral_constant<int, (G + 6) * CPP>{}, ph0, n);      // k = 7
+        else if (nsl == (G + 10) * CPP) chain(std::integral_constant<int, (G + 10) * CPP>{}, ph0, n);    // k = 11
         else { if (p.error_flag) atomicExch(p.error_flag, 1); ok = false; }                             // not instantiated (the host checks)
       }
     if (timing && lane == 0) {
@@ -366,6 +434,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       __syncwarp();
     };
     bool ok = true;
+    uint32_t aph = 0;                                            // completed phases of this stream's acc_full barrier
 #ifdef SA_DIAG
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_x = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
@@ -407,6 +476,33 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       const uint32_t flags = p.flags[j];
       GRP_T0(tx0);
       // ---- x: residual stream -> tensor memory, lrelu(x) -> input tile of pair 0's conv1 ----
+      if (p.fuse_up) {
+        // x = the stage's transposed conv, computed by the MMA warp from the staged input tile into the residual
+        // columns: read it back once to stage lrelu(x); rows outside the utterance are the zero padding of conv1
+        ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
+        ++aph;
+        tc_fence_after();
+        if (ok) {
+          const int d0 = p.dil[0];
+          if (w_any) {
+            for_groups(t_res, [&](int gi, const uint32_t (&rr)[32], int o) {
+              uint4 lo, hi8;
+              pack16(rr, o, lo, hi8, 0.1f);
+              if (!inside) { lo = zero4; hi8 = zero4; }
+              if (d0 == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(0, gi / kGroupsPerPos), gi, lo, hi8);
+            });
+          } else {
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              if (d0 == 1) st_nat(bufA, gi, zero4, zero4); else st_at(bufA, physP(0, gi / kGroupsPerPos), gi, zero4, zero4);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_ready(st, 0));
+        }
+      } else
       {
         const int d0 = p.dil[0];
         float4 xq[4][4];                                          // all loads in flight before the first use
@@ -458,7 +554,8 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
           // conv1: TMEM -> lrelu -> conv2's input tile in natural order
           {
             GRP_T0(ta0);
-            ok = mbar_wait_relaxed(bar_acc_full(st), 0u, p.error_flag);   // phases alternate conv1 (0) / conv2 (1): n_convs is even
+            ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
+            ++aph;
             tc_fence_after();
             GRP_ADD(t_acc, ta0);
           }
@@ -505,7 +602,8 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
           // conv2: the accumulator IS the residual stream x_{m+1}
           {
             GRP_T0(ta0);
-            ok = ok && mbar_wait_relaxed(bar_acc_full(st), 1u, p.error_flag);
+            ok = ok && mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
+            ++aph;
             tc_fence_after();
             GRP_ADD(t_acc, ta0);
           }
@@ -586,6 +684,10 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
                 });
               }
               tc_fence_before();                                 // TMEM reads done before the next tile overwrites the residual
+              if (p.fuse_up) {                                   // ... which the MMA warp does itself when the upsampler is fused
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_res_free(st));
+              }
             }
           }
         }

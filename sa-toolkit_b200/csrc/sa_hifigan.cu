@@ -73,6 +73,7 @@ struct sa_hifigan {
   int n_sm = 148;
   sa::tc_context tc;
   std::vector<sa::tc_chain> chains;     // [n_stages * n_resblocks], fused narrow-stage ResBlocks
+  std::vector<sa::tc_upgroup> upg;      // [n_stages], transposed convs packed for fusion into the grouped kernel
   float* d_codebook = nullptr;          // [n_codes][code_dim] VQ codebook of the compact conditioning (sa_hifigan_set_codebook)
   int n_codes = 0, code_dim = 0;
   cudaStream_t side_stream = nullptr;   // second stream of sa_hifigan_synthesize_host
@@ -216,6 +217,8 @@ static void free_device_weights(sa_hifigan* h) {
   }
   for (auto& ch : h->chains) sa::tc_free_chain(ch);
   h->chains.clear();
+  for (auto& u : h->upg) sa::tc_free_upgroup(u);
+  h->upg.clear();
   h->tc.tmaps.clear();                  // cached tensor maps point at the freed weight buffers
 }
 
@@ -377,6 +380,13 @@ int sa_hifigan_finalize(sa_hifigan* h, int32_t precision) {
                                             precision == SA_PRECISION_BF16);
         if (err) return fail(SA_ERR_CUDA, "resblocks.%d: %s", i * cfg.n_resblocks + j, err);
       }
+    h->upg.assign((size_t)cfg.n_stages, sa::tc_upgroup());
+    for (int i = 0; i < cfg.n_stages; ++i) {
+      const sa_conv& c = h->convs[h->up(i)];
+      const char* uerr = sa::tc_pack_upgroup(h->upg[i], c.w.data(), c.bias.data(), c.cin, c.cout, c.k, c.stride, c.pad,
+                                             precision == SA_PRECISION_BF16);
+      if (uerr) return fail(SA_ERR_CUDA, "ups.%d: %s", i, uerr);
+    }
     const char* err = sa::tc_init(h->tc, h->device);
     if (err) return fail(SA_ERR_CUDA, "tensor-core path init: %s", err);
   }
@@ -604,6 +614,7 @@ static int forward_impl(sa_hifigan* h, const float* x, const float* bn, const fl
     a.layers = layers.data();
     a.n_layers = (int)layers.size();
     a.chains = (h->use_fused && !h->chains.empty()) ? h->chains.data() : nullptr;
+    a.upg = (h->use_fused && !h->upg.empty()) ? h->upg.data() : nullptr;
     a.mark_ctx = h;
     a.mark = h->prof_on ? +[](void* ctx, int tag, cudaStream_t s) { static_cast<sa_hifigan*>(ctx)->mark(tag, s); }
                         : nullptr;

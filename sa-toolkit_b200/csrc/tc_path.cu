@@ -739,7 +739,7 @@ struct Runner {
   // One grouped launch over n_ch ResBlocks of the same stage (n_ch = 1: convs [c0, c1) of one block).  fl[j]: the EPI_*
   // flags of chain j's final epilogue.  *done = false: not applicable, use the per-tap kernels.
   const char* group(const tc_chain* chs, int n_ch, const float* x32, int L, const Epi& e, const uint32_t* fl, int tag, bool* done,
-                    int c0 = 0, int c1 = -1) {
+                    int c0 = 0, int c1 = -1, const tc_upgroup* up = nullptr, const void* up_in16 = nullptr) {
     *done = false;
     if (n_ch < 1 || n_ch > tc::kGrpMaxChains) return nullptr;
     if (c1 < 0) c1 = chs[0].n_convs;
@@ -776,6 +776,18 @@ struct Runner {
     p.L = L; p.n_convs = c1 - c0;
     for (int c = c0; c < c1; c += 2) p.dil[(c - c0) / 2] = ch.dil[c];
     p.halo = pl.halo;
+    if (up && up->d_w && up_in16) {                               // the stage's transposed conv inside this launch
+      if (pl.ms != 2 || c0 != 0 || up->stages + 1 > pl.n_wstages) return nullptr;
+      // previous stage's output [B][1][L/2][2 C] 16-bit, seen as rows of 128 bytes: L * C * 2 / 128 = L / G rows per item
+      const cuuint64_t rows = (cuuint64_t)L / (64 / ch.c);
+      const cuuint64_t gdim[3] = {64, rows, (cuuint64_t)a.B};
+      const cuuint64_t gstr[2] = {128, rows * 128};
+      const cuuint32_t box[3] = {64, (cuuint32_t)(tc::grp_buf_bytes(pl.ms) / 256), 1};
+      if (tmap(&p.up_map, a.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, up_in16, gdim, gstr, box,
+               CU_TENSOR_MAP_SWIZZLE_128B) != CUDA_SUCCESS)
+        return "cuTensorMapEncodeTiled failed for the fused upsampler input";
+      p.up_w = up->d_w; p.up_stages = up->stages; p.fuse_up = 1;
+    }
     p.n_wstages = pl.n_wstages;
     p.tiles_per_item = (L + pl.valid - 1) / pl.valid;
     p.total_tiles = p.tiles_per_item * a.B;
@@ -1007,6 +1019,50 @@ void tc_free_chain(tc_chain& ch) {
   ch = tc_chain();
 }
 
+// Transposed conv (weight [Cin][Cout][k], k = 4, stride u = 2, pad p = 1, Cin = 2 C) as block-Toeplitz slices for the grouped
+// kernel.  A 128-byte output row holds G = 64 / C output positions n0 + g'; it reads the input positions i0 - 1 + c,
+// c = 0 .. G/2 + 1 (i0 = n0 / 2), each 2 C channels = 2 C / 16 slices; tap j = (n0 + g') + p - u (i0 - 1 + c) = g' + 3 - 2 c.
+const char* tc_pack_upgroup(tc_upgroup& u, const float* folded, const float* bias, int cin, int cout, int k, int stride, int pad,
+                            bool bf16) {
+  tc_free_upgroup(u);
+  if ((cout != 16 && cout != 32) || cin != 2 * cout || k != 4 || stride != 2 || pad != 1) return nullptr;
+  const int C = cout, G = 64 / C, blocks = cin / 16, n_pos = G / 2 + 2;
+  u.slices = n_pos * blocks;
+  u.stages = (u.slices + 1 + tc::kGrpSlicesPerStage - 1) / tc::kGrpSlicesPerStage;
+  std::vector<uint8_t> h((size_t)u.stages * tc::kGrpStageBytes, 0);
+  auto put = [&](uint8_t* blk, int n, int kk, float v) {
+    const uint16_t hv = to16(v, bf16);
+    memcpy(blk + swizzle_offset((uint32_t)n * 32u + (uint32_t)kk * 2u, 32), &hv, 2);
+  };
+  for (int q = 0; q < u.slices; ++q) {
+    uint8_t* blk = h.data() + (size_t)q * tc::kGrpSliceBytes;
+    const int c = q / blocks, hb = q % blocks;
+    for (int g = 0; g < G; ++g) {
+      const int j = g + pad + stride - stride * c;               // g' + p - u (c - 1)
+      if (j < 0 || j >= k) continue;
+      for (int co = 0; co < C; ++co)
+        for (int kk = 0; kk < 16; ++kk) put(blk, g * C + co, kk, folded[((size_t)(hb * 16 + kk) * cout + co) * k + j]);
+    }
+  }
+  uint8_t* bb = h.data() + (size_t)u.slices * tc::kGrpSliceBytes;  // bias block: hi + lo halves against the kernel's ones tile
+  for (int n = 0; n < 64; ++n) {
+    const float bv = bias[n % C];
+    const uint16_t hi = to16(bv, bf16);
+    float hif;
+    if (bf16) { __nv_bfloat16 t; memcpy(&t, &hi, 2); hif = __bfloat162float(t); } else { __half t; memcpy(&t, &hi, 2); hif = __half2float(t); }
+    put(bb, n, 0, hif);
+    put(bb, n, 1, bv - hif);
+  }
+  TC_CUDA(cudaMalloc(&u.d_w, h.size()));
+  TC_CUDA(cudaMemcpy(u.d_w, h.data(), h.size(), cudaMemcpyHostToDevice));
+  return nullptr;
+}
+
+void tc_free_upgroup(tc_upgroup& u) {
+  if (u.d_w) cudaFree(u.d_w);
+  u = tc_upgroup();
+}
+
 void tc_free_weights(tc_weights& w) {
   if (w.d_w) cudaFree(w.d_w);
   w = tc_weights();
@@ -1151,6 +1207,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     if ((err = unblock_tap(SA_TAP_CONV_PRE, cfg.initial_channels, a.T))) return err;
   }
   int L = a.T;
+  void* Pcur = P16;                                 // where the 16-bit output of the previous section lives
   // The last stage hands conv_post its lrelu(0.01)-activated output in the 16-bit blocked layout (half the bytes of
   // the fp32 stream, read once); other filter lengths keep the fp32 hand-off.
   const bool post16 = a.layers[L_post].k == 7 && a.layers[L_post].cin % 16 == 0;
@@ -1162,14 +1219,28 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       Runner::GroupPlan gp;
       stage_grouped = run.group_plan(gp, a.chains[i * nrb + j], L * up.stride, 0, a.chains[i * nrb + j].n_convs);
     }
-    {                                               // archi.py:80-81
+    // Grouped stages with a k = 4 / stride 2 upsampler run the transposed conv inside the grouped kernel (fuse_up): no
+    // upsampler launch and no fp32 stage input in HBM.  The stage then reads Pcur while it writes its own 16-bit output, so
+    // that goes to the other buffer.  SATOOLS_B200_GROUP_UP=0 keeps the separate upsampler launch.
+    static const int group_up = getenv("SATOOLS_B200_GROUP_UP") ? atoi(getenv("SATOOLS_B200_GROUP_UP")) : 1;
+    bool fuse_up = false;
+    if (stage_grouped && group_up && a.upg && a.upg[i].d_w) {
+      Runner::GroupPlan gp;
+      fuse_up = run.group_plan(gp, a.chains[i * nrb], L * up.stride, 0, a.chains[i * nrb].n_convs) && gp.ms == 2 &&
+                a.upg[i].stages + 1 <= gp.n_wstages;
+    }
+    void* const Pin = Pcur;
+    void* const Pout = (fuse_up && Pcur == P16) ? T16 : P16;
+    if (!fuse_up) {                                 // archi.py:80-81
       // The fused ResBlock kernels read the fp32 stage input only; lrelu(x) in 16 bits is for the per-layer convs.
       for (int j = 0; j < nrb && all_fused && !stage_grouped; ++j) all_fused = run.chain_usable(a.chains[i * nrb + j], L * up.stride);
       Epi e;
       e.flags = tc::EPI_OUT32 | (all_fused ? 0u : tc::EPI_OUT16);
       e.out32 = X32; e.out16 = AX16; e.slope_out = 0.1f;
-      if ((err = run.conv(up, P16, L, e, 16 * (1 + i)))) return err;
+      if ((err = run.conv(up, Pin, L, e, 16 * (1 + i)))) return err;
     }
+    Pcur = Pout;
+    const tc_upgroup* upg_i = fuse_up ? &a.upg[i] : nullptr;
     L *= up.stride;
     const bool last_stage = (i == nst - 1);
     const bool tap_here = a.debug_out && a.debug_tap == SA_TAP_STAGE0 + i;
@@ -1189,9 +1260,9 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       uint32_t fl[tc::kGrpMaxChains];
       for (int j = 0; j < nrb; ++j) fl[j] = (j == 0) ? tc::EPI_SUM_SET : (j == nrb - 1 ? tc::EPI_SUM_FIN : tc::EPI_SUM_ADD);
       if ((last_stage && !post16) || tap_here) { fl[nrb - 1] |= tc::EPI_OUT32; fin.out32 = H32; }
-      if (!last_stage || post16) { fl[nrb - 1] |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = last_stage ? 0.01f : 0.1f; }
+      if (!last_stage || post16) { fl[nrb - 1] |= tc::EPI_OUT16; fin.out16 = Pout; fin.slope_out = last_stage ? 0.01f : 0.1f; }
       bool done = false;
-      if ((err = run.group(a.chains + i * nrb, nrb, X32, L, fin, fl, 16 * (1 + i) + 1, &done))) return err;
+      if ((err = run.group(a.chains + i * nrb, nrb, X32, L, fin, fl, 16 * (1 + i) + 1, &done, 0, -1, upg_i, Pin))) return err;
       if (done) {
         if ((err = unblock_tap(SA_TAP_STAGE0 + i, up.cout, L))) return err;
         continue;
@@ -1200,7 +1271,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     if (a.chains && !stage_grouped) {               // narrowest stages on the per-tap kernels: the whole stage in one kernel
       Epi fin;
       if ((last_stage && !post16) || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = R32; }
-      if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = last_stage ? 0.01f : 0.1f; }
+      if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = Pout; fin.slope_out = last_stage ? 0.01f : 0.1f; }
       bool done = false;
       if ((err = run.chain3(a.chains + i * nrb, nrb, X32, L, fin, 16 * (1 + i) + 1, &done))) return err;
       if (done) {
@@ -1217,14 +1288,14 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       if (nrb > 1) fin.flags |= (j == 0) ? tc::EPI_SUM_SET : (j == nrb - 1 ? tc::EPI_SUM_FIN : tc::EPI_SUM_ADD);
       if (j == nrb - 1) {
         if ((last_stage && !post16) || tap_here) { fin.flags |= tc::EPI_OUT32; fin.out32 = H32; }
-        if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = P16; fin.slope_out = last_stage ? 0.01f : 0.1f; }
+        if (!last_stage || post16) { fin.flags |= tc::EPI_OUT16; fin.out16 = Pout; fin.slope_out = last_stage ? 0.01f : 0.1f; }
       }
       if (a.chains) {                               // narrow stages: the whole ResBlock in one kernel
         bool done = false;
         const tc_chain& ch = a.chains[i * nrb + j];
         if (stage_grouped) {                        // C <= 32: grouped (block-Toeplitz) kernel, one launch per ResBlock
           const uint32_t fl1[1] = {fin.flags};
-          if ((err = run.group(&ch, 1, X32, L, fin, fl1, tag, &done))) return err;
+          if ((err = run.group(&ch, 1, X32, L, fin, fl1, tag, &done, 0, -1, upg_i, Pin))) return err;
           if (done) continue;
           return "grouped ResBlock launch failed";
         }
@@ -1269,10 +1340,10 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
       const size_t sm = (size_t)post.cin * 32 + 7 * 256 * sizeof(float);
       const int pw = panel_width(post.cin);
       if (a.bf16)
-        conv_post16_k7_kernel<true><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(P16), post.d_w32, post.d_bias, a.y,
+        conv_post16_k7_kernel<true><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(Pcur), post.d_w32, post.d_bias, a.y,
                                                           post.cin, pw, L, a.y_dtype, d_frames, kRaggedMarginFrames, L / a.T);
       else
-        conv_post16_k7_kernel<false><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(P16), post.d_w32, post.d_bias, a.y,
+        conv_post16_k7_kernel<false><<<g16, 256, sm, st>>>(reinterpret_cast<const uint4*>(Pcur), post.d_w32, post.d_bias, a.y,
                                                            post.cin, pw, L, a.y_dtype, d_frames, kRaggedMarginFrames, L / a.T);
     } else
     conv_post_blocked_kernel<<<g, threads, post.cin * post.k * sizeof(float), st>>>(Hout, post.d_w32, post.d_bias, a.y,

@@ -49,6 +49,13 @@ struct tc_tmap_entry {
   CUtensorMap map;
 };
 
+// The stage's transposed conv packed for the grouped kernel (chain_group_tc.cuh, fuse_up): block-Toeplitz slices over the
+// input positions a 128-byte output row needs + the bias block, in 8 KB stages.  Only k = 4, stride 2, pad 1, Cin = 2 Cout.
+struct tc_upgroup {
+  void* d_w = nullptr;
+  int slices = 0, stages = 0;
+};
+
 struct tc_context {
   std::vector<tc_tmap_entry> tmaps;
   bool ready = false;
@@ -93,6 +100,7 @@ struct tc_forward_args {
   const tc_layer* layers;
   int n_layers;
   const tc_chain* chains = nullptr;                           // [n_stages * n_resblocks]; d_w == NULL: not packed
+  const tc_upgroup* upg = nullptr;                            // [n_stages]; d_w == NULL: the upsampler is not fusable
   void* mark_ctx = nullptr;                                   // per-launch profiling hook
   void (*mark)(void* ctx, int tag, cudaStream_t s) = nullptr;
 };
@@ -106,6 +114,9 @@ bool tc_chain_supported(int c, int k, int n_convs);
 const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* const* folded, const float* const* bias,
                           const int* dil, const int* pad, bool bf16);
 void tc_free_chain(tc_chain& ch);
+const char* tc_pack_upgroup(tc_upgroup& u, const float* folded, const float* bias, int cin, int cout, int k, int stride, int pad,
+                            bool bf16);
+void tc_free_upgroup(tc_upgroup& u);
 const char* tc_init(tc_context& ctx, int device);
 bool tc_error_raised(const tc_context& ctx);
 int tc_read_chain_timing(tc_context& ctx, long long* out, int max_launches);
