@@ -150,11 +150,12 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   auto bar_acc_full = [&](int st) { return smem_u32(&bars[2 * kGrpMaxStreams + st]); };
   auto bar_w_full = [&](int i) { return smem_u32(&bars[3 * kGrpMaxStreams + i]); };
   auto bar_w_empty = [&](int i) { return smem_u32(&bars[3 * kGrpMaxStreams + kGrpMaxStages + i]); };
-  // fuse_up: up_full[stream] (input tile landed), up_empty[stream] (buffer A free for the next tile), res_free[stream]
-  // (the final epilogue has read the residual columns)
+  // fuse_up: up_full[stream] (input tile landed), up_empty[stream] (buffer A free for the next tile), up_done[stream] (the
+  // transposed conv's accumulator is complete: a barrier of its own, because the MMA warp issues it right behind the previous
+  // chain's last conv2 -- two completions of acc_full ahead of the epilogue would alias its parity)
   auto bar_up_full = [&](int st) { return smem_u32(&bars[3 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
   auto bar_up_empty = [&](int st) { return smem_u32(&bars[4 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
-  auto bar_res_free = [&](int st) { return smem_u32(&bars[5 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
+  auto bar_up_done = [&](int st) { return smem_u32(&bars[5 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6 * kGrpMaxStreams + 2 * kGrpMaxStages);
 
   const int valid = R - 2 * p.halo;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       mbar_init(bar_acc_full(st), 1);
       mbar_init(bar_up_full(st), 1);
       mbar_init(bar_up_empty(st), 1);
-      mbar_init(bar_res_free(st), kGrpMS * 4);
+      mbar_init(bar_up_done(st), 1);
     }
     if (p.fuse_up) prefetch_tmap(&p.up_map);
     for (int i = 0; i < kGrpMaxStages; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     constexpr bool timing = false;                                             // in-kernel cycle counters: -DSA_DIAG builds only
 #endif
     long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
+    long long t_kind[4] = {0, 0, 0, 0};                                        // wait by kind: conv1 ready, conv2 ready, up_full, res_free
     // one conv (NSL Toeplitz slices + the bias slice) of both streams
     // kind 0: conv1 (reads A, fresh accumulator), 1: conv2 (reads T, accumulates onto the residual), 2: the fused
     // transposed conv (reads the TMA-staged input tile in A, writes the residual columns)
@@ -290,15 +292,18 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         const long long tr0 = timing ? clock64() : 0;
         if (KIND == 2) {
           ok = mbar_wait(bar_up_full(st), n & 1u, p.error_flag);               // input tile landed
-          if (ok && n > 0) ok = mbar_wait(bar_res_free(st), (n - 1) & 1u, p.error_flag);   // previous residual consumed
+          if (timing) t_kind[2] += clock64() - tr0;
         } else {
           ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
+          if (timing) t_kind[KIND] += clock64() - tr0;
         }
         if (timing) t_ready += clock64() - tr0;
         if (!ok) break;
         tc_fence_after();
         const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - lead);
-        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + d_idx) * kGrpMS * 64);
+        // fuse_up: the column halves swap roles from chain to chain (see the epilogue): the transposed conv of chain n writes
+        // the half that was conv1's accumulator in chain n - 1 (drained long ago), never the residual still being read
+        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + (d_idx ^ (int)(p.fuse_up ? (n & 1u) : 0u))) * kGrpMS * 64);
         slot = slot0; par = par0;
 #pragma unroll
         for (int i = 0; i < NSTG; ++i) {
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
           if (++slot == n_wst) { slot = 0; par ^= 1u; }
         }
         if (leader) {
-          umma_commit(bar_acc_full(st));
+          umma_commit(KIND == 2 ? bar_up_done(st) : bar_acc_full(st));
           if (KIND == 0 && c == p.n_convs - 2 && p.fuse_up) umma_commit(bar_up_empty(st));   // buffer A read for the last time
         }
         __syncwarp();
@@ -360,6 +365,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_ready);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 2), (unsigned long long)t_w);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 3), (unsigned long long)(clock64() - t_begin - t_ready - t_w));
+      for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 10 + i), (unsigned long long)t_kind[i]);
     }
   } else {
     // ===== epilogue warps: one thread = one 128-byte row (G positions x C channels) of its stream's tile =====
@@ -374,8 +380,14 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     constexpr int cchunks = C / 8;
     uint8_t* const bufA = buf(st, 0);
     uint8_t* const bufT = buf(st, 1);
-    const uint32_t t_acc1 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 0) * kGrpMS + s) * 64);
-    const uint32_t t_res = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 1) * kGrpMS + s) * 64);
+    // fuse_up: the two 64-column halves of this sub-tile swap roles from chain to chain -- the next tile's transposed conv
+    // lands in the columns that held conv1's accumulator while the final epilogue still reads the old residual, so the
+    // MMA warp never waits for the global-memory part of a tile's last epilogue.
+    const uint32_t t_col0 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 0) * kGrpMS + s) * 64);
+    const uint32_t t_col1 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 1) * kGrpMS + s) * 64);
+    uint32_t t_acc1 = t_col0, t_res = t_col1;
+    uint32_t n_chain = 0;                                        // chains this thread has started
+    const float inv_n = 1.0f / p.n_blocks;
     auto swz128 = [](uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); };
     // tile-invariant d-major maps of this row's G positions, for every pair with a dilated conv1 (16 bits each):
     //   physP(m, g) = swizzled byte offset of time (G r + g) in the d_m-major input tile of pair m's conv1
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     uint32_t aph = 0;                                            // completed phases of this stream's acc_full barrier
 #ifdef SA_DIAG
     const bool timing = p.timing != nullptr && warp == 0;
-    long long t_x = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
+    long long t_x = 0, t_acc = 0, t_fin = 0, t_begin = timing ? clock64() : 0;
 #define GRP_T0(v) const long long v = timing ? clock64() : 0
 #define GRP_ADD(acc, v) if (timing) acc += clock64() - v
 #else
@@ -472,15 +484,27 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         }
       }
 #pragma unroll 1
-      for (int j = 0; j < p.n_chains && ok; ++j) {
+      for (int j = 0; j < p.n_chains && ok; ++j, ++n_chain) {
       const uint32_t flags = p.flags[j];
+      if (p.fuse_up) { t_acc1 = (n_chain & 1u) ? t_col1 : t_col0; t_res = (n_chain & 1u) ? t_col0 : t_col1; }
+      // The running multi-receptive-field sum lives in a layout private to the grouped kernels: 32-row blocks, inside a
+      // block [piece 0..7][row][8 floats], so that lane l of a warp store writes 32 bytes right behind lane l - 1 (a
+      // thread-per-row store into the channel-blocked [C/8][L][8] layout put the 32 lanes into 32 different lines:
+      // 32 LSU wavefronts per instruction, the final epilogues took a quarter of the kernel).
+      const int grow = b * (p.L / G) + t_row / G;                 // row of this thread in the whole batch (used under `keep`)
+      float* const sp = p.sum32 + (size_t)(grow >> 5) * 2048 + (size_t)(grow & 31) * 8;   // piece i at + 256 i floats
+      const bool add = (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) != 0;
+      float4 sq[8];                                               // 32 floats of the running sum
+      auto load_half = [&](int h) {
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) ldg_f8(sp + (4 * h + pc) * 256, sq[2 * pc], sq[2 * pc + 1]);
+      };
       GRP_T0(tx0);
       // ---- x: residual stream -> tensor memory, lrelu(x) -> input tile of pair 0's conv1 ----
       if (p.fuse_up) {
         // x = the stage's transposed conv, computed by the MMA warp from the staged input tile into the residual
         // columns: read it back once to stage lrelu(x); rows outside the utterance are the zero padding of conv1
-        ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
-        ++aph;
+        ok = mbar_wait_relaxed(bar_up_done(st), n_chain & 1u, p.error_flag);
         tc_fence_after();
         if (ok) {
           const int d0 = p.dil[0];
@@ -539,12 +563,9 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       }
       GRP_ADD(t_x, tx0);
       // a running sum left in HBM by an earlier launch: have it in L2 when the final epilogue needs it
-      if (p.n_chains == 1 && keep && (flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
+      if (p.n_chains == 1 && keep && add) {
 #pragma unroll
-        for (int q = 0; q < cchunks; ++q)
-#pragma unroll
-          for (int g = 0; g < G; g += 4)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sum32 + (((size_t)b * cchunks + q) * (size_t)p.L + (size_t)(t_row + g)) * 8));
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + i * 256));
       }
       // ---- the (conv1, conv2) pairs ----
 #pragma unroll
@@ -600,15 +621,17 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
             if (lane == 0) mbar_arrive(bar_ready(st, 1));
           }
           // conv2: the accumulator IS the residual stream x_{m+1}
-          {
+          auto wait_conv2 = [&]() {
             GRP_T0(ta0);
             ok = ok && mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
             ++aph;
             tc_fence_after();
             GRP_ADD(t_acc, ta0);
-          }
+          };
           if (ok) {
             if (m + 1 < n_pairs) {
+              wait_conv2();
+              if (!ok) break;
               const int mn = m + 1 < kGrpMaxPairs ? m + 1 : 0;
               const int dn = p.dil[mn];
               if (w_all) {
@@ -636,58 +659,86 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
               if (lane == 0) mbar_arrive(bar_ready(st, 0));
             } else {
               // final epilogue: multi-receptive-field combine (archi.py:82-86) + output streams
-              if (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {          // the running sum is in L2 (prefetched, or just written)
-                for_groups(t_res, [&](int gi, const uint32_t (&rr)[32], int o) {
-                  if (!keep) return;
-                  const int g = gi / kGroupsPerPos;
-                  const int ch0 = (gi % kGroupsPerPos) * 16;
-                  const size_t i0 = (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
-                  const size_t i1 = i0 + (size_t)p.L * 8;
-                  float4 s0, s1, s2, s3;
-                  ldg_f8(p.sum32 + i0, s0, s1);
-                  ldg_f8(p.sum32 + i1, s2, s3);
-                  float v[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+              if (keep && add) load_half(0);                     // the first sum loads fly under the wait for conv2
+              __syncwarp();
+              wait_conv2();
+              if (!ok) break;
+              GRP_T0(tf0);
+              // One half row (32 columns) at a time: TMEM -> registers, + running sum, stores.  The 16-bit output row
+              // (128 contiguous bytes per thread, [B][L][C]) is transposed inside lane quads first, so a store instruction
+              // writes whole 128-byte lines (8 per warp) instead of 32 bytes into each of 32 lines.
+              {
+                const bool o16 = (flags & EPI_OUT16) != 0;
+                uint4 pkl[4], pkh[4];
+                auto do_half = [&](int h, const uint32_t (&rr)[32]) {
 #pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[o + e]) + v[e];
-                  if (flags & EPI_SUM_FIN) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = v[e] / p.n_blocks;
-                  }
-                  if (flags & EPI_SUM_ADD) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
-                  if (flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
-                  if (flags & EPI_OUT16) {
+                  for (int u = 0; u < 2; ++u) {
+                    const int gi = 2 * h + u;
                     float lo[8], hi8[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { lo[e] = v[e]; hi8[e] = v[8 + e]; }
-                    uint8_t* o = static_cast<uint8_t*>(p.out16) + (((size_t)b * (size_t)p.L + (size_t)(t_row + g)) * C + ch0) * 2;
-                    stg_u8(o, pack8_lrelu(lo, p.slope_out, true, bf16), pack8_lrelu(hi8, p.slope_out, true, bf16));
-                  }
-                });
-              } else {
-                for_groups(t_res, [&](int gi, const uint32_t (&rr)[32], int o) {
-                  if (!keep) return;
-                  const int g = gi / kGroupsPerPos;
-                  const int ch0 = (gi % kGroupsPerPos) * 16;
-                  const size_t i0 = (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
-                  const size_t i1 = i0 + (size_t)p.L * 8;
-                  float v[16];
+                    for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(rr[16 * u + e]); hi8[e] = __uint_as_float(rr[16 * u + 8 + e]); }
+                    if (add) {
+                      const float4 s0 = sq[4 * u + 0], s1 = sq[4 * u + 1], s2 = sq[4 * u + 2], s3 = sq[4 * u + 3];
+                      const float sl[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                      const float sh[8] = {s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
 #pragma unroll
-                  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[o + e]);
-                  if (flags & EPI_SUM_SET) { stg_f8(p.sum32 + i0, v); stg_f8(p.sum32 + i1, v + 8); }
-                  if (flags & EPI_OUT32) { stg_f8(p.out32 + i0, v); stg_f8(p.out32 + i1, v + 8); }
-                  if (flags & EPI_OUT16) {
-                    uint4 lo, hi8;
-                    pack16(rr, o, lo, hi8, p.slope_out);
-                    uint8_t* o = static_cast<uint8_t*>(p.out16) + (((size_t)b * (size_t)p.L + (size_t)(t_row + g)) * C + ch0) * 2;
-                    stg_u8(o, lo, hi8);
+                      for (int e = 0; e < 8; ++e) { lo[e] = lo[e] + sl[e]; hi8[e] = hi8[e] + sh[e]; }
+                      if (flags & EPI_SUM_FIN) {
+                        // x / n as q = x * (1/n) plus one residual correction (q + (x - n q) * (1/n)): the correctly rounded
+                        // quotient for normal operands without the division's slow-path call (64 calls per row made ptxas
+                        // spill the whole epilogue around them)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                          const float ql = lo[e] * inv_n, qh = hi8[e] * inv_n;
+                          lo[e] = fmaf(fmaf(-p.n_blocks, ql, lo[e]), inv_n, ql);
+                          hi8[e] = fmaf(fmaf(-p.n_blocks, qh, hi8[e]), inv_n, qh);
+                        }
+                      }
+                    }
+                    if (keep) {
+                      if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) { stg_f8(sp + (2 * gi) * 256, lo); stg_f8(sp + (2 * gi + 1) * 256, hi8); }
+                      if (flags & EPI_OUT32) {                   // debug taps / fp32 hand-off: the channel-blocked layout
+                        const int g = gi / kGroupsPerPos;
+                        const int ch0 = (gi % kGroupsPerPos) * 16;
+                        const size_t i0 = (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
+                        stg_f8(p.out32 + i0, lo);
+                        stg_f8(p.out32 + i0 + (size_t)p.L * 8, hi8);
+                      }
+                    }
+                    if (o16) { pkl[gi] = pack8_lrelu(lo, p.slope_out, true, bf16); pkh[gi] = pack8_lrelu(hi8, p.slope_out, true, bf16); }
                   }
-                });
+                };
+                {
+                  uint32_t ra[32];
+                  __syncwarp();
+                  tmem_ld32(t_res, ra);
+                  tmem_ld_wait();
+                  do_half(0, ra);
+                }
+                if (keep && add) load_half(1);
+                {
+                  uint32_t rb[32];
+                  __syncwarp();
+                  tmem_ld32(t_res + 32u, rb);
+                  tmem_ld_wait();
+                  do_half(1, rb);
+                }
+                if (o16) {                                       // warp-uniform
+                  __syncwarp();
+                  const int j4 = lane & 3;
+                  quad_transpose(pkl, j4);                       // now [k] = 32-byte piece j4 of the row of the quad's lane k
+                  quad_transpose(pkh, j4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int rk = r - j4 + k;
+                    const int tk = t0 + G * rk;
+                    if (live && tk >= 0 && tk < p.L && G * rk >= p.halo && G * rk < R - p.halo)
+                      stg_u8(static_cast<uint8_t*>(p.out16) + ((size_t)b * (size_t)p.L + (size_t)tk) * (C * 2) + 32 * j4, pkl[k], pkh[k]);
+                  }
+                }
+                tc_fence_before();                               // TMEM reads done before the columns are written again
               }
-              tc_fence_before();                                 // TMEM reads done before the next tile overwrites the residual
-              if (p.fuse_up) {                                   // ... which the MMA warp does itself when the upsampler is fused
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_res_free(st));
-              }
+              GRP_ADD(t_fin, tf0);
             }
           }
         }
@@ -701,6 +752,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 5), (unsigned long long)t_x);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 6), (unsigned long long)t_acc);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 7), (unsigned long long)(tot - t_x - t_acc));
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 8), (unsigned long long)t_fin);
     }
 #endif
 #undef GRP_T0

@@ -727,7 +727,7 @@ struct Runner {
     const int min_tiles = min_tiles_env >= 0 ? min_tiles_env : 2 * pl.ns * a.n_sm;
     if (((L + pl.valid - 1) / pl.valid) * a.B < min_tiles) return false;
     const size_t fixed = 2 * (size_t)pl.ns * tc::grp_buf_bytes(pl.ms) + tc::kGrpOnesBytes +
-                         (3 * tc::kGrpMaxStreams + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
+                         (6 * tc::kGrpMaxStreams + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
     int stages = std::min(tc::kGrpMaxStages, 2 * ch.g_stages);              // two convs deep: the next conv streams in behind
     while (stages > ch.g_stages && fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) --stages;
     if (stages < ch.g_stages + 1 || fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) return false;
@@ -1121,7 +1121,7 @@ Sizes sizes(const sa_hifigan_cfg& cfg, int B, int T) {
   const size_t E = (size_t)B * T * per_frame;
   Sizes s;
   s.e16 = align_up(E * 2, 256);
-  s.e32 = align_up(E * 4, 256);
+  s.e32 = align_up(E * 4 + 8192, 256);          // + the last partial 32-row block of the grouped kernels' sum layout
   s.xin = align_up((size_t)B * T * tc_cin_pad(cfg.input_dim) * 2, 256);
   s.frames = align_up((size_t)B * sizeof(int32_t), 256);
   return s;

@@ -25,7 +25,7 @@ names = ["mma_total", "mma_wait_ready", "mma_wait_w", "mma_issue", "epi_total", 
 labels = []
 print("cycle counters per launch (timed launches in order: conv_tc launches = MMA warp [total, wait A, wait W, wait acc-empty], epilogue warp 0 [total, wait acc-full]; fused kernels as in sa_hifigan.h), summed over CTAs / 148")
 for i in range(n):
-    v = [buf[i * 16 + j] / 148.0 for j in range(10)]
+    v = [buf[i * 16 + j] / 148.0 for j in range(14)]
     tot = v[0] or 1.0
     print(f"launch {i:2d} " + " ".join(f"{val/1e3:7.0f}k({100*val/ (tot if j < 4 else (v[4] or 1)):3.0f}%)" for j, val in enumerate(v)))
 
