@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
 
   if (warp == kWarpW && lane == 0) {
     for (int st = 0; st < kGrpStreams; ++st) {
-      mbar_init(bar_ready(st, 0), kGrpMS * 4);                   // the warps of the stream
-      mbar_init(bar_ready(st, 1), kGrpMS * 4);
+      mbar_init(bar_ready(st, 0), kGrpEpiWarps);                 // every epilogue warp serves every stream
+      mbar_init(bar_ready(st, 1), kGrpEpiWarps);
       mbar_init(bar_acc_full(st), 1);
       mbar_init(bar_up_full(st), 1);
       mbar_init(bar_up_empty(st), 1);
@@ -368,57 +368,61 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 10 + i), (unsigned long long)t_kind[i]);
     }
   } else {
-    // ===== epilogue warps: one thread = one 128-byte row (G positions x C channels) of its stream's tile =====
-    // Instruction diet (ncu source view of the first versions: ~300 issued instructions per conv and thread at ~5.6
-    // cycles each = the 1.7k-cycle epilogue latency that the MMA warp waited for): no bias add (it is in the MMA), one
-    // branch per row for the zero padding instead of per-store selects, tile-invariant swizzled store offsets, TMEM loads
-    // one group ahead of the conversion, diagnostics compiled out unless SA_DIAG.
-    const int st = warp / (4 * MS);
-    const int s = (warp >> 2) % MS;
+    // ===== epilogue warps: one thread = HALF a 128-byte row (32 accumulator columns) of BOTH streams' tiles =====
+    // Every epilogue step (TMEM -> leaky-ReLU -> 16-bit -> shared memory -> fence -> arrive) sits on the dependency chain
+    // conv c -> conv c + 1 of its stream, and in-kernel counters put it at ~2000 cycles against 700-1400 cycles of MMAs per
+    // conv and stream: the MMA warp waited for it.  With one thread per row, half of the epilogue warps idled while the
+    // other stream's were the critical path; now all 16 warps drain each stream's accumulator (lane group lg = warp % 4 as
+    // the hardware requires, sub-tile s, column half h) and alternate between the streams in the MMA warp's issue order:
+    // a step touches 32 columns per thread -- one tcgen05.ld.x32, four 16-byte stores -- and twice as many warps hide the
+    // latencies.  Register pressure halves with it (no spills at 96 registers).
+    static_assert(NS == 2 && MS == 2, "epilogue mapping: 16 warps = 4 lane groups x 2 sub-tiles x 2 column halves, two streams");
+    const int h = warp >> 3;                                     // column half: columns [32 h, 32 h + 32) = row bytes [64 h, 64 h + 64)
+    const int s = (warp >> 2) & 1;
     const int lg = warp & 3;
-    const int r = s * 128 + lg * 32 + lane;                      // row within the stream tile
+    const int r = s * 128 + lg * 32 + lane;                      // row within a stream tile
     constexpr int cchunks = C / 8;
-    uint8_t* const bufA = buf(st, 0);
-    uint8_t* const bufT = buf(st, 1);
-    // fuse_up: the two 64-column halves of this sub-tile swap roles from chain to chain -- the next tile's transposed conv
-    // lands in the columns that held conv1's accumulator while the final epilogue still reads the old residual, so the
-    // MMA warp never waits for the global-memory part of a tile's last epilogue.
-    const uint32_t t_col0 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 0) * kGrpMS + s) * 64);
-    const uint32_t t_col1 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + 1) * kGrpMS + s) * 64);
-    uint32_t t_acc1 = t_col0, t_res = t_col1;
-    uint32_t n_chain = 0;                                        // chains this thread has started
+    constexpr int PP = G / 2;                                    // positions per half row
+    // TMEM address of this thread's 32 columns in column set idx (0 / 1) of stream st
+    auto t_cols = [&](int st, int idx) {
+      return tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((st * 2 + idx) * kGrpMS + s) * 64 + 32 * h);
+    };
+    uint32_t n_chain = 0;                                        // chains this thread has started (both streams)
     const float inv_n = 1.0f / p.n_blocks;
     auto swz128 = [](uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); };
-    // tile-invariant d-major maps of this row's G positions, for every pair with a dilated conv1 (16 bits each):
-    //   physP(m, g) = swizzled byte offset of time (G r + g) in the d_m-major input tile of pair m's conv1
-    //   tauI(m, g)  = time whose conv1 output this row holds at position g in pair m (>= R: none)
-    uint32_t pmap[kGrpMaxPairs][G];
+    // tile-invariant d-major maps of this thread's PP positions g = PP h + i, for every pair with a dilated conv1:
+    //   physP(m, i) = swizzled byte offset of time (G r + g) in the d_m-major input tile of pair m's conv1
+    //   tauI(m, i)  = time whose conv1 output this row holds at position g in pair m (>= R: none)
+    uint32_t pmap[kGrpMaxPairs][PP];
 #pragma unroll
     for (int m = 0; m < kGrpMaxPairs; ++m) {
       const int d = (m < n_pairs) ? p.dil[m] : 1;
       const int Q = (R + d - 1) / d;
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int tau = G * r + g;
+      for (int i = 0; i < PP; ++i) {
+        const int tau = G * r + PP * h + i;
         const int pp = (d == 1) ? tau : (tau % d) * Q + tau / d;
         const int ti = (d == 1) ? tau : d * (tau % Q) + tau / Q;
-        pmap[m][g] = swz128(kPadBytes + (uint32_t)pp * PB) | ((uint32_t)ti << 16);
+        pmap[m][i] = swz128(kPadBytes + (uint32_t)pp * PB) | ((uint32_t)ti << 16);
       }
     }
-    auto physP = [&](int m, int g) { return pmap[m][g] & 0xFFFFu; };
-    auto tauI = [&](int m, int g) { return (int)(pmap[m][g] >> 16); };
+    auto physP = [&](int m, int i) { return pmap[m][i] & 0xFFFFu; };
+    auto tauI = [&](int m, int i) { return (int)(pmap[m][i] >> 16); };
     const uint32_t lin_row = kPadBytes + (uint32_t)r * 128u;     // this row in natural order
     const uint32_t xrow = (uint32_t)(r & 7) << 4;                // its swizzle XOR (kPadBytes is a multiple of 1024)
-    // 16-column group gi of this row, natural order: chunks 2 gi and 2 gi + 1 of the 128-byte row
-    auto st_nat = [&](uint8_t* b, int gi, const uint4& lo, const uint4& hi8) {
-      *reinterpret_cast<uint4*>(b + lin_row + (((uint32_t)(2 * gi) * 16u) ^ xrow)) = lo;
-      *reinterpret_cast<uint4*>(b + lin_row + (((uint32_t)(2 * gi + 1) * 16u) ^ xrow)) = hi8;
+    // Local 16-column group u (0 / 1) of this thread = group gi = 2 h + u of the row = chunks 2 gi and 2 gi + 1.
+    auto st_nat = [&](uint8_t* bp, int u, const uint4& lo, const uint4& hi8) {
+      *reinterpret_cast<uint4*>(bp + lin_row + (((uint32_t)(4 * h + 2 * u) * 16u) ^ xrow)) = lo;
+      *reinterpret_cast<uint4*>(bp + lin_row + (((uint32_t)(4 * h + 2 * u + 1) * 16u) ^ xrow)) = hi8;
     };
-    // 16-column group gi at a position whose chunk 0 lives at the swizzled offset phys0: its chunk cc is at phys0 ^ 16 cc
-    auto st_at = [&](uint8_t* b, uint32_t phys0, int gi, const uint4& lo, const uint4& hi8) {
-      const uint32_t o = phys0 ^ ((uint32_t)(gi % kGroupsPerPos) * 32u);
-      *reinterpret_cast<uint4*>(b + o) = lo;
-      *reinterpret_cast<uint4*>(b + (o ^ 16u)) = hi8;
+    // local position index of group u, and its 16-channel block inside the position
+    auto pos_of = [&](int u) { return (kGroupsPerPos == 1) ? u : 0; };
+    auto blk_of = [&](int u) { return (kGroupsPerPos == 1) ? 0 : u; };
+    // group u at a position whose chunk 0 lives at the swizzled offset phys0: its chunk cc is at phys0 ^ 16 cc
+    auto st_at = [&](uint8_t* bp, uint32_t phys0, int u, const uint4& lo, const uint4& hi8) {
+      const uint32_t o = phys0 ^ ((uint32_t)blk_of(u) * 32u);
+      *reinterpret_cast<uint4*>(bp + o) = lo;
+      *reinterpret_cast<uint4*>(bp + (o ^ 16u)) = hi8;
     };
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     auto pack16 = [&](const auto& rr, int o, uint4& lo, uint4& hi8, float slope) {       // 16 columns from offset o of rr
@@ -428,25 +432,20 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       lo = pack8_lrelu(a, slope, true, bf16);
       hi8 = pack8_lrelu(c8, slope, true, bf16);
     };
-    // TMEM -> registers in two 32-column loads, the second in flight while the first is used: f(gi, regs, offset) for the
-    // 16-column groups gi = 0..3.  (tcgen05.ld / wait are .sync.aligned: the whole warp must execute them converged, so
-    // every caller branches on warp-uniform conditions only; f may diverge inside.)
+    // TMEM -> registers, this thread's 32 columns in one load: f(u, regs, offset) for its two 16-column groups.
+    // (tcgen05.ld / wait are .sync.aligned: the whole warp must execute them converged, so every caller branches on
+    // warp-uniform conditions only; f may diverge inside.)
     auto for_groups = [&](uint32_t taddr, auto&& f) {
-      uint32_t ra[32], rb[32];
+      uint32_t rr[32];
       __syncwarp();
-      tmem_ld32(taddr, ra);
+      tmem_ld32(taddr, rr);
       tmem_ld_wait();
-      tmem_ld32(taddr + 32u, rb);
-      f(0, ra, 0);
-      f(1, ra, 16);
-      __syncwarp();
-      tmem_ld_wait();
-      f(2, rb, 0);
-      f(3, rb, 16);
+      f(0, rr, 0);
+      f(1, rr, 16);
       __syncwarp();
     };
     bool ok = true;
-    uint32_t aph = 0;                                            // completed phases of this stream's acc_full barrier
+    uint32_t aph = 0;                                            // completed phases of the acc_full barriers (same for both streams)
 #ifdef SA_DIAG
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_x = 0, t_acc = 0, t_fin = 0, t_begin = timing ? clock64() : 0;
@@ -456,116 +455,122 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
 #define GRP_T0(v)
 #define GRP_ADD(acc, v)
 #endif
+    // per-stream tile state, packed: flag bits
+    constexpr uint32_t F_LIVE = 1u, F_INSIDE = 2u, F_KEEP = 4u, F_INTERIOR = 8u, F_WALL = 16u, F_WANY = 32u;
     for (int it = 0; it < n_iters && ok; ++it) {
-      const int tile = (int)blockIdx.x + (NS * it + st) * (int)gridDim.x;
-      const bool live = tile < n_live;                            // the last iteration may have streams without a tile
-      int b = 0, mt = 0;
-      if (live) tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
-      const int t0 = mt * valid - p.halo;                         // time of the tile's first position
-      const int t_row = t0 + G * r;
-      const bool inside = live && t_row >= 0 && t_row < p.L;      // L, halo, valid are multiples of G: whole rows
-      const bool keep = inside && G * r >= p.halo && G * r < R - p.halo;
-      const bool interior = live && t0 >= 0 && t0 + R <= p.L;     // no position of the tile is outside the utterance
-      const bool w_all = __all_sync(0xffffffffu, inside), w_any = __any_sync(0xffffffffu, inside);   // warp-uniform
-      // The next tile of this stream: have its rows in L2 by the time they are needed.
-      {
-        const int tile_n = tile + NS * (int)gridDim.x;
-        if (tile_n < n_live) {
-          int bn, mtn;
-          tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile_n, bn, mtn);
-          const int tn = mtn * valid - p.halo + G * r;
-          if (tn >= 0 && tn < p.L) {
+      int tb[NS], tt0[NS];                                        // item and time of the first position of each stream's tile
+      uint32_t tf[NS];
 #pragma unroll
-            for (int q = 0; q < cchunks; ++q)
+      for (int st = 0; st < NS; ++st) {
+        const int tile = (int)blockIdx.x + (NS * it + st) * (int)gridDim.x;
+        const bool live = tile < n_live;                          // the last iteration may have streams without a tile
+        int b = 0, mt = 0;
+        if (live) tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
+        const int t0 = mt * valid - p.halo;
+        const int t_row = t0 + G * r;
+        const bool inside = live && t_row >= 0 && t_row < p.L;    // L, halo, valid are multiples of G: whole rows
+        const bool keep = inside && G * r >= p.halo && G * r < R - p.halo;
+        const bool interior = live && t0 >= 0 && t0 + R <= p.L;   // no position of the tile is outside the utterance
+        const bool w_all = __all_sync(0xffffffffu, inside), w_any = __any_sync(0xffffffffu, inside);   // warp-uniform
+        tb[st] = b; tt0[st] = t0;
+        tf[st] = (live ? F_LIVE : 0u) | (inside ? F_INSIDE : 0u) | (keep ? F_KEEP : 0u) | (interior ? F_INTERIOR : 0u) |
+                 (w_all ? F_WALL : 0u) | (w_any ? F_WANY : 0u);
+        // The next tile of this stream: have its rows in L2 by the time they are needed (fp32 stage input only).
+        if (!p.fuse_up) {
+          const int tile_n = tile + NS * (int)gridDim.x;
+          if (tile_n < n_live) {
+            int bn, mtn;
+            tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile_n, bn, mtn);
+            const int tn = mtn * valid - p.halo + G * r + PP * h;
+            if (tn >= 0 && tn < p.L) {
 #pragma unroll
-              for (int g = 0; g < G; g += 4)                       // 32 B per position: one 128-byte line holds 4
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + q) * (size_t)p.L + (size_t)(tn + g)) * 8));
+              for (int q = 0; q < cchunks; ++q)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + q) * (size_t)p.L + (size_t)tn) * 8));
+            }
           }
         }
       }
 #pragma unroll 1
       for (int j = 0; j < p.n_chains && ok; ++j, ++n_chain) {
       const uint32_t flags = p.flags[j];
-      if (p.fuse_up) { t_acc1 = (n_chain & 1u) ? t_col1 : t_col0; t_res = (n_chain & 1u) ? t_col0 : t_col1; }
+      // fuse_up: the two 64-column sets of a sub-tile swap roles from chain to chain -- the next tile's transposed conv
+      // lands in the columns that held conv1's accumulator while the final epilogue still reads the old residual, so the
+      // MMA warp never waits for the global-memory part of a tile's last epilogue.
+      const int i_acc = (p.fuse_up && (n_chain & 1u)) ? 1 : 0, i_res = i_acc ^ 1;
+      const bool add = (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) != 0;
       // The running multi-receptive-field sum lives in a layout private to the grouped kernels: 32-row blocks, inside a
       // block [piece 0..7][row][8 floats], so that lane l of a warp store writes 32 bytes right behind lane l - 1 (a
       // thread-per-row store into the channel-blocked [C/8][L][8] layout put the 32 lanes into 32 different lines:
-      // 32 LSU wavefronts per instruction, the final epilogues took a quarter of the kernel).
-      const int grow = b * (p.L / G) + t_row / G;                 // row of this thread in the whole batch (used under `keep`)
-      float* const sp = p.sum32 + (size_t)(grow >> 5) * 2048 + (size_t)(grow & 31) * 8;   // piece i at + 256 i floats
-      const bool add = (flags & (EPI_SUM_ADD | EPI_SUM_FIN)) != 0;
-      float4 sq[8];                                               // 32 floats of the running sum
-      auto load_half = [&](int h) {
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) ldg_f8(sp + (4 * h + pc) * 256, sq[2 * pc], sq[2 * pc + 1]);
+      // 32 LSU wavefronts per instruction).  This thread owns pieces 4 h .. 4 h + 3 of its row.
+      auto sum_ptr = [&](int st) {
+        const int grow = tb[st] * (p.L / G) + (tt0[st] + G * r) / G;   // row in the whole batch (used under `keep` only)
+        return p.sum32 + (size_t)(grow >> 5) * 2048 + (size_t)(grow & 31) * 8 + (size_t)(4 * h) * 256;
       };
-      GRP_T0(tx0);
       // ---- x: residual stream -> tensor memory, lrelu(x) -> input tile of pair 0's conv1 ----
-      if (p.fuse_up) {
-        // x = the stage's transposed conv, computed by the MMA warp from the staged input tile into the residual
-        // columns: read it back once to stage lrelu(x); rows outside the utterance are the zero padding of conv1
-        ok = mbar_wait_relaxed(bar_up_done(st), n_chain & 1u, p.error_flag);
-        tc_fence_after();
-        if (ok) {
-          const int d0 = p.dil[0];
-          if (w_any) {
-            for_groups(t_res, [&](int gi, const uint32_t (&rr)[32], int o) {
+#pragma unroll
+      for (int st = 0; st < NS; ++st) {
+        if (!ok) break;
+        GRP_T0(tx0);
+        uint8_t* const bufA = buf(st, 0);
+        const bool inside = (tf[st] & F_INSIDE) != 0;
+        const int d0 = p.dil[0];
+        if (p.fuse_up) {
+          // x = the stage's transposed conv, computed by the MMA warp from the staged input tile into the residual
+          // columns: read it back once to stage lrelu(x); rows outside the utterance are the zero padding of conv1
+          ok = mbar_wait_relaxed(bar_up_done(st), n_chain & 1u, p.error_flag);
+          tc_fence_after();
+          if (!ok) break;
+          if (tf[st] & F_WANY) {
+            for_groups(t_cols(st, i_res), [&](int u, const uint32_t (&rr)[32], int o) {
               uint4 lo, hi8;
               pack16(rr, o, lo, hi8, 0.1f);
               if (!inside) { lo = zero4; hi8 = zero4; }
-              if (d0 == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(0, gi / kGroupsPerPos), gi, lo, hi8);
+              if (d0 == 1) st_nat(bufA, u, lo, hi8); else st_at(bufA, physP(0, pos_of(u)), u, lo, hi8);
             });
           } else {
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-              if (d0 == 1) st_nat(bufA, gi, zero4, zero4); else st_at(bufA, physP(0, gi / kGroupsPerPos), gi, zero4, zero4);
+            for (int u = 0; u < 2; ++u) {
+              if (d0 == 1) st_nat(bufA, u, zero4, zero4); else st_at(bufA, physP(0, pos_of(u)), u, zero4, zero4);
             }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_ready(st, 0));
-        }
-      } else
-      {
-        const int d0 = p.dil[0];
-        float4 xq[4][4];                                          // all loads in flight before the first use
+        } else {
+          const int t_pos = tt0[st] + G * r + PP * h;             // first position of this half row
+          float4 xq[2][4];                                        // all loads in flight before the first use
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const int g = gi / kGroupsPerPos;
-          const int ch0 = (gi % kGroupsPerPos) * 16;
-          xq[gi][0] = xq[gi][1] = xq[gi][2] = xq[gi][3] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (inside) {
-            const float* src = p.x32 + (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
-            ldg_f8(src, xq[gi][0], xq[gi][1]);
-            ldg_f8(src + (size_t)p.L * 8, xq[gi][2], xq[gi][3]);
+          for (int u = 0; u < 2; ++u) {
+            xq[u][0] = xq[u][1] = xq[u][2] = xq[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inside) {
+              const float* src = p.x32 + (((size_t)tb[st] * cchunks + 2 * blk_of(u)) * (size_t)p.L + (size_t)(t_pos + pos_of(u))) * 8;
+              ldg_f8(src, xq[u][0], xq[u][1]);
+              ldg_f8(src + (size_t)p.L * 8, xq[u][2], xq[u][3]);
+            }
           }
-        }
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const int g = gi / kGroupsPerPos;
-          const float4 q0 = xq[gi][0], q1 = xq[gi][1], q2 = xq[gi][2], q3 = xq[gi][3];
-          const uint32_t rr[16] = {__float_as_uint(q0.x), __float_as_uint(q0.y), __float_as_uint(q0.z), __float_as_uint(q0.w),
-                                   __float_as_uint(q1.x), __float_as_uint(q1.y), __float_as_uint(q1.z), __float_as_uint(q1.w),
-                                   __float_as_uint(q2.x), __float_as_uint(q2.y), __float_as_uint(q2.z), __float_as_uint(q2.w),
-                                   __float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z), __float_as_uint(q3.w)};
-          __syncwarp();
-          tmem_st16(t_res + (uint32_t)(gi * 16), rr);
-          uint4 lo, hi8;
-          pack16(rr, 0, lo, hi8, 0.1f);                           // rows outside the utterance were loaded as zeros
-          if (d0 == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(0, g), gi, lo, hi8);
+          for (int u = 0; u < 2; ++u) {
+            const float4 q0 = xq[u][0], q1 = xq[u][1], q2 = xq[u][2], q3 = xq[u][3];
+            const uint32_t rr[16] = {__float_as_uint(q0.x), __float_as_uint(q0.y), __float_as_uint(q0.z), __float_as_uint(q0.w),
+                                     __float_as_uint(q1.x), __float_as_uint(q1.y), __float_as_uint(q1.z), __float_as_uint(q1.w),
+                                     __float_as_uint(q2.x), __float_as_uint(q2.y), __float_as_uint(q2.z), __float_as_uint(q2.w),
+                                     __float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z), __float_as_uint(q3.w)};
+            __syncwarp();
+            tmem_st16(t_cols(st, i_res) + (uint32_t)(u * 16), rr);
+            uint4 lo, hi8;
+            pack16(rr, 0, lo, hi8, 0.1f);                         // rows outside the utterance were loaded as zeros
+            if (d0 == 1) st_nat(bufA, u, lo, hi8); else st_at(bufA, physP(0, pos_of(u)), u, lo, hi8);
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ready(st, 0));
-      }
-      GRP_ADD(t_x, tx0);
-      // a running sum left in HBM by an earlier launch: have it in L2 when the final epilogue needs it
-      if (p.n_chains == 1 && keep && add) {
+        GRP_ADD(t_x, tx0);
+        // a running sum left in HBM by an earlier launch: have it in L2 when the final epilogue needs it
+        if (p.n_chains == 1 && (tf[st] & F_KEEP) && add) {
+          const float* sp = sum_ptr(st);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + i * 256));
+          for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + i * 256));
+        }
       }
       // ---- the (conv1, conv2) pairs ----
 #pragma unroll
@@ -573,46 +578,54 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         if (m < n_pairs && ok) {
           const int d = p.dil[m];
           // conv1: TMEM -> lrelu -> conv2's input tile in natural order
-          {
-            GRP_T0(ta0);
-            ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
-            ++aph;
-            tc_fence_after();
-            GRP_ADD(t_acc, ta0);
-          }
-          if (ok) {
-            if (d == 1) {
-              if (w_all) {
-                for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[32], int o) {
-                  uint4 lo, hi8;
-                  pack16(rr, o, lo, hi8, 0.1f);
-                  st_nat(bufT, gi, lo, hi8);
-                });
-              } else if (!w_any) {
 #pragma unroll
-                for (int gi = 0; gi < 4; ++gi) st_nat(bufT, gi, zero4, zero4);
-              } else {                                            // the utterance ends inside this warp's rows
-                for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[32], int o) {
+          for (int st = 0; st < NS; ++st) {
+            if (!ok) break;
+            uint8_t* const bufT = buf(st, 1);
+            const uint32_t f = tf[st];
+            const bool inside = (f & F_INSIDE) != 0;
+            {
+              GRP_T0(ta0);
+              ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
+              tc_fence_after();
+              GRP_ADD(t_acc, ta0);
+            }
+            if (!ok) break;
+            const uint32_t t_acc1 = t_cols(st, i_acc);
+            if (d == 1) {
+              if (f & F_WALL) {
+                for_groups(t_acc1, [&](int u, const uint32_t (&rr)[32], int o) {
                   uint4 lo, hi8;
                   pack16(rr, o, lo, hi8, 0.1f);
-                  st_nat(bufT, gi, inside ? lo : zero4, inside ? hi8 : zero4);
+                  st_nat(bufT, u, lo, hi8);
+                });
+              } else if (!(f & F_WANY)) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) st_nat(bufT, u, zero4, zero4);
+              } else {                                            // the utterance ends inside this warp's rows
+                for_groups(t_acc1, [&](int u, const uint32_t (&rr)[32], int o) {
+                  uint4 lo, hi8;
+                  pack16(rr, o, lo, hi8, 0.1f);
+                  st_nat(bufT, u, inside ? lo : zero4, inside ? hi8 : zero4);
                 });
               }
-            } else if (interior) {
-              for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[32], int o) {
+            } else if (f & F_INTERIOR) {
+              for_groups(t_acc1, [&](int u, const uint32_t (&rr)[32], int o) {
                 uint4 lo, hi8;
                 pack16(rr, o, lo, hi8, 0.1f);
-                const int tau = tauI(m, gi / kGroupsPerPos);
-                if (tau < R) st_at(bufT, swz128(kPadBytes + (uint32_t)tau * PB), gi, lo, hi8);
+                const int tau = tauI(m, pos_of(u));
+                if (tau < R) st_at(bufT, swz128(kPadBytes + (uint32_t)tau * PB), u, lo, hi8);
               });
             } else {
-              for_groups(t_acc1, [&](int gi, const uint32_t (&rr)[32], int o) {
+              const bool live = (f & F_LIVE) != 0;
+              const int t0 = tt0[st];
+              for_groups(t_acc1, [&](int u, const uint32_t (&rr)[32], int o) {
                 uint4 lo, hi8;
                 pack16(rr, o, lo, hi8, 0.1f);
-                const int tau = tauI(m, gi / kGroupsPerPos);
+                const int tau = tauI(m, pos_of(u));
                 const int tt = t0 + tau;
                 const bool ins = live && tt >= 0 && tt < p.L;
-                if (tau < R) st_at(bufT, swz128(kPadBytes + (uint32_t)tau * PB), gi, ins ? lo : zero4, ins ? hi8 : zero4);
+                if (tau < R) st_at(bufT, swz128(kPadBytes + (uint32_t)tau * PB), u, ins ? lo : zero4, ins ? hi8 : zero4);
               });
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -620,37 +633,42 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready(st, 1));
           }
+          ++aph;
           // conv2: the accumulator IS the residual stream x_{m+1}
-          auto wait_conv2 = [&]() {
-            GRP_T0(ta0);
-            ok = ok && mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
-            ++aph;
-            tc_fence_after();
-            GRP_ADD(t_acc, ta0);
-          };
-          if (ok) {
+#pragma unroll
+          for (int st = 0; st < NS; ++st) {
+            if (!ok) break;
+            uint8_t* const bufA = buf(st, 0);
+            const uint32_t f = tf[st];
+            const bool inside = (f & F_INSIDE) != 0, keep = (f & F_KEEP) != 0;
+            const uint32_t t_res = t_cols(st, i_res);
             if (m + 1 < n_pairs) {
-              wait_conv2();
+              {
+                GRP_T0(ta0);
+                ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
+                tc_fence_after();
+                GRP_ADD(t_acc, ta0);
+              }
               if (!ok) break;
               const int mn = m + 1 < kGrpMaxPairs ? m + 1 : 0;
               const int dn = p.dil[mn];
-              if (w_all) {
-                for_groups(t_res, [&](int gi, const uint32_t (&rr)[32], int o) {
+              if (f & F_WALL) {
+                for_groups(t_res, [&](int u, const uint32_t (&rr)[32], int o) {
                   uint4 lo, hi8;
                   pack16(rr, o, lo, hi8, 0.1f);
-                  if (dn == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(mn, gi / kGroupsPerPos), gi, lo, hi8);
+                  if (dn == 1) st_nat(bufA, u, lo, hi8); else st_at(bufA, physP(mn, pos_of(u)), u, lo, hi8);
                 });
-              } else if (!w_any) {
+              } else if (!(f & F_WANY)) {
 #pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
-                  if (dn == 1) st_nat(bufA, gi, zero4, zero4); else st_at(bufA, physP(mn, gi / kGroupsPerPos), gi, zero4, zero4);
+                for (int u = 0; u < 2; ++u) {
+                  if (dn == 1) st_nat(bufA, u, zero4, zero4); else st_at(bufA, physP(mn, pos_of(u)), u, zero4, zero4);
                 }
               } else {
-                for_groups(t_res, [&](int gi, const uint32_t (&rr)[32], int o) {
+                for_groups(t_res, [&](int u, const uint32_t (&rr)[32], int o) {
                   uint4 lo, hi8;
                   pack16(rr, o, lo, hi8, 0.1f);
                   if (!inside) { lo = zero4; hi8 = zero4; }
-                  if (dn == 1) st_nat(bufA, gi, lo, hi8); else st_at(bufA, physP(mn, gi / kGroupsPerPos), gi, lo, hi8);
+                  if (dn == 1) st_nat(bufA, u, lo, hi8); else st_at(bufA, physP(mn, pos_of(u)), u, lo, hi8);
                 });
               }
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -658,89 +676,75 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_ready(st, 0));
             } else {
-              // final epilogue: multi-receptive-field combine (archi.py:82-86) + output streams
-              if (keep && add) load_half(0);                     // the first sum loads fly under the wait for conv2
+              // final epilogue: multi-receptive-field combine (archi.py:82-86) + output streams.  The 32 floats of the
+              // running sum are requested before the wait for conv2.  The 16-bit output row ([B][L][C]: 128 contiguous
+              // bytes per row, 64 per thread) is transposed inside lane quads, so one store instruction writes 64
+              // contiguous bytes of 8 rows instead of 16 bytes into each of 32 lines.
+              float* const sp = sum_ptr(st);
+              float4 sq[8];
+              if (keep && add) {
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc) ldg_f8(sp + pc * 256, sq[2 * pc], sq[2 * pc + 1]);
+              }
               __syncwarp();
-              wait_conv2();
+              {
+                GRP_T0(ta0);
+                ok = mbar_wait_relaxed(bar_acc_full(st), aph & 1u, p.error_flag);
+                tc_fence_after();
+                GRP_ADD(t_acc, ta0);
+              }
               if (!ok) break;
               GRP_T0(tf0);
-              // One half row (32 columns) at a time: TMEM -> registers, + running sum, stores.  The 16-bit output row
-              // (128 contiguous bytes per thread, [B][L][C]) is transposed inside lane quads first, so a store instruction
-              // writes whole 128-byte lines (8 per warp) instead of 32 bytes into each of 32 lines.
-              {
-                const bool o16 = (flags & EPI_OUT16) != 0;
-                uint4 pkl[4], pkh[4];
-                auto do_half = [&](int h, const uint32_t (&rr)[32]) {
+              const bool o16 = (flags & EPI_OUT16) != 0;
+              const int b = tb[st], t0 = tt0[st];
+              uint4 pk[4];
+              for_groups(t_res, [&](int u, const uint32_t (&rr)[32], int o) {
+                float lo[8], hi8[8];
 #pragma unroll
-                  for (int u = 0; u < 2; ++u) {
-                    const int gi = 2 * h + u;
-                    float lo[8], hi8[8];
+                for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(rr[o + e]); hi8[e] = __uint_as_float(rr[o + 8 + e]); }
+                if (add) {
+                  const float4 s0 = sq[4 * u + 0], s1 = sq[4 * u + 1], s2 = sq[4 * u + 2], s3 = sq[4 * u + 3];
+                  const float sl[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                  const float sh[8] = {s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(rr[16 * u + e]); hi8[e] = __uint_as_float(rr[16 * u + 8 + e]); }
-                    if (add) {
-                      const float4 s0 = sq[4 * u + 0], s1 = sq[4 * u + 1], s2 = sq[4 * u + 2], s3 = sq[4 * u + 3];
-                      const float sl[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                      const float sh[8] = {s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+                  for (int e = 0; e < 8; ++e) { lo[e] = lo[e] + sl[e]; hi8[e] = hi8[e] + sh[e]; }
+                  if (flags & EPI_SUM_FIN) {
+                    // x / n as q = x * (1/n) plus one residual correction (q + (x - n q) * (1/n)): the correctly rounded
+                    // quotient for normal operands without the division's slow-path calls
 #pragma unroll
-                      for (int e = 0; e < 8; ++e) { lo[e] = lo[e] + sl[e]; hi8[e] = hi8[e] + sh[e]; }
-                      if (flags & EPI_SUM_FIN) {
-                        // x / n as q = x * (1/n) plus one residual correction (q + (x - n q) * (1/n)): the correctly rounded
-                        // quotient for normal operands without the division's slow-path call (64 calls per row made ptxas
-                        // spill the whole epilogue around them)
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                          const float ql = lo[e] * inv_n, qh = hi8[e] * inv_n;
-                          lo[e] = fmaf(fmaf(-p.n_blocks, ql, lo[e]), inv_n, ql);
-                          hi8[e] = fmaf(fmaf(-p.n_blocks, qh, hi8[e]), inv_n, qh);
-                        }
-                      }
+                    for (int e = 0; e < 8; ++e) {
+                      const float ql = lo[e] * inv_n, qh = hi8[e] * inv_n;
+                      lo[e] = fmaf(fmaf(-p.n_blocks, ql, lo[e]), inv_n, ql);
+                      hi8[e] = fmaf(fmaf(-p.n_blocks, qh, hi8[e]), inv_n, qh);
                     }
-                    if (keep) {
-                      if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) { stg_f8(sp + (2 * gi) * 256, lo); stg_f8(sp + (2 * gi + 1) * 256, hi8); }
-                      if (flags & EPI_OUT32) {                   // debug taps / fp32 hand-off: the channel-blocked layout
-                        const int g = gi / kGroupsPerPos;
-                        const int ch0 = (gi % kGroupsPerPos) * 16;
-                        const size_t i0 = (((size_t)b * cchunks + (ch0 >> 3)) * (size_t)p.L + (size_t)(t_row + g)) * 8;
-                        stg_f8(p.out32 + i0, lo);
-                        stg_f8(p.out32 + i0 + (size_t)p.L * 8, hi8);
-                      }
-                    }
-                    if (o16) { pkl[gi] = pack8_lrelu(lo, p.slope_out, true, bf16); pkh[gi] = pack8_lrelu(hi8, p.slope_out, true, bf16); }
-                  }
-                };
-                {
-                  uint32_t ra[32];
-                  __syncwarp();
-                  tmem_ld32(t_res, ra);
-                  tmem_ld_wait();
-                  do_half(0, ra);
-                }
-                if (keep && add) load_half(1);
-                {
-                  uint32_t rb[32];
-                  __syncwarp();
-                  tmem_ld32(t_res + 32u, rb);
-                  tmem_ld_wait();
-                  do_half(1, rb);
-                }
-                if (o16) {                                       // warp-uniform
-                  __syncwarp();
-                  const int j4 = lane & 3;
-                  quad_transpose(pkl, j4);                       // now [k] = 32-byte piece j4 of the row of the quad's lane k
-                  quad_transpose(pkh, j4);
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const int rk = r - j4 + k;
-                    const int tk = t0 + G * rk;
-                    if (live && tk >= 0 && tk < p.L && G * rk >= p.halo && G * rk < R - p.halo)
-                      stg_u8(static_cast<uint8_t*>(p.out16) + ((size_t)b * (size_t)p.L + (size_t)tk) * (C * 2) + 32 * j4, pkl[k], pkh[k]);
                   }
                 }
-                tc_fence_before();                               // TMEM reads done before the columns are written again
+                if (keep) {
+                  if (flags & (EPI_SUM_SET | EPI_SUM_ADD)) { stg_f8(sp + (2 * u) * 256, lo); stg_f8(sp + (2 * u + 1) * 256, hi8); }
+                  if (flags & EPI_OUT32) {                       // debug taps / fp32 hand-off: the channel-blocked layout
+                    const size_t i0 = (((size_t)b * cchunks + 2 * blk_of(u)) * (size_t)p.L + (size_t)(t0 + G * r + PP * h + pos_of(u))) * 8;
+                    stg_f8(p.out32 + i0, lo);
+                    stg_f8(p.out32 + i0 + (size_t)p.L * 8, hi8);
+                  }
+                }
+                if (o16) { pk[2 * u] = pack8_lrelu(lo, p.slope_out, true, bf16); pk[2 * u + 1] = pack8_lrelu(hi8, p.slope_out, true, bf16); }
+              });
+              if (o16) {                                         // warp-uniform
+                const int j4 = lane & 3;
+                quad_transpose(pk, j4);                          // now pk[k] = 16-byte piece j4 of the half row of the quad's lane k
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int rk = r - j4 + k;
+                  const int tk = t0 + G * rk;
+                  if ((f & F_LIVE) && tk >= 0 && tk < p.L && G * rk >= p.halo && G * rk < R - p.halo)
+                    *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + ((size_t)b * (size_t)p.L + (size_t)tk) * (C * 2) + 64 * h + 16 * j4) = pk[k];
+                }
               }
+              tc_fence_before();                                 // TMEM reads done before the columns are written again
               GRP_ADD(t_fin, tf0);
             }
           }
+          ++aph;
         }
       }
       }   // chains

@@ -708,10 +708,9 @@ struct Runner {
     if (!g_use_group || !ch.d_wg || (c0 & 1) || ((c1 - c0) & 1) || c1 <= c0) return false;
     if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;                  // slice counts the MMA issue loop is instantiated for
     // Two streams of two sub-tiles: 1024 positions per tile for C = 16, 512 for C = 32.  (Four streams of one sub-tile for
-    // C = 16, SATOOLS_B200_GROUP_NS16=4, measured slower: 4.67 vs 4.13 ms for stage 4 -- twice the halo share, and the streams
-    // run in lockstep on one shared weight ring, so more of them do not decouple anything.)
-    static const int ns16 = getenv("SATOOLS_B200_GROUP_NS16") ? atoi(getenv("SATOOLS_B200_GROUP_NS16")) : 2;
-    pl.ns = (ch.c == 16 && ns16 == 4) ? 4 : 2;
+    // C = 16 measured slower, 4.67 vs 4.13 ms for stage 4 -- twice the halo share, and the streams run in lockstep on one
+    // shared weight ring, so more of them do not decouple anything; the epilogue mapping is now fixed to two streams.)
+    pl.ns = 2;
     pl.ms = 4 / pl.ns;
     const int G = 64 / ch.c, R = tc::grp_tile_positions(ch.c, pl.ms);
     int halo = 0;
@@ -798,7 +797,7 @@ struct Runner {
 #define SA_GROUP(CC, NN, MM)                                                                                          \
     if (ch.c == CC && pl.ns == NN)                                                                                    \
       ce = a.bf16 ? launch_group<CC, true, NN, MM>(p, pl.smem, a.n_sm, a.stream) : launch_group<CC, false, NN, MM>(p, pl.smem, a.n_sm, a.stream);
-    SA_GROUP(16, 4, 1) SA_GROUP(16, 2, 2) SA_GROUP(32, 2, 2)
+    SA_GROUP(16, 2, 2) SA_GROUP(32, 2, 2)
 #undef SA_GROUP
     if (ce != cudaSuccess) return msgf("group_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
