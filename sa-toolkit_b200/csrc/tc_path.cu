@@ -16,6 +16,7 @@
 #include "chain_tc.cuh"
 #include "chain3_tc.cuh"
 #include "chain_group_tc.cuh"
+#include "chain_group_v1_tc.cuh"
 
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -450,6 +451,23 @@ cudaError_t launch_group(const tc::GroupParams& p, size_t smem, int n_sm, cudaSt
   return cudaGetLastError();
 }
 
+// first epilogue mapping (chain_group_v1_tc.cuh): one thread per row and stream; used for C = 32
+template <int C, bool BF16, int NS, int MS>
+cudaError_t launch_group_v1(const tc::GroupParams& p, size_t smem, int n_sm, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::v1::group_chain_kernel<C, BF16, NS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int ctas = std::max(1, std::min((p.total_tiles + NS - 1) / NS, n_sm));
+  tc::v1::group_chain_kernel<C, BF16, NS, MS><<<ctas, tc::kGrpThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 // ---- CTA-pair kernel (conv_pair_tc.cuh): plan + launch ------------------------------------
 int use_pair() {              // SATOOLS_B200_PAIR=0: wide layers on the single-CTA kernel
   static const int v = getenv("SATOOLS_B200_PAIR") ? atoi(getenv("SATOOLS_B200_PAIR")) : 1;
@@ -794,9 +812,15 @@ struct Runner {
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
     cudaError_t ce = cudaErrorInvalidValue;
+    // Epilogue mapping per channel count (measured, see chain_group_v1_tc.cuh): bit 0: C = 16, bit 1: C = 32 on the first
+    // mapping (one thread per row and stream); default C = 32 only.  The two kernels lay the running sum out differently, but
+    // all ResBlocks of a stage share a channel count, so a stage never mixes them.
+    static const int v1_mask = getenv("SATOOLS_B200_GROUP_V1") ? atoi(getenv("SATOOLS_B200_GROUP_V1")) : 2;
+    const bool v1 = (v1_mask & (ch.c == 16 ? 1 : 2)) != 0;
 #define SA_GROUP(CC, NN, MM)                                                                                          \
     if (ch.c == CC && pl.ns == NN)                                                                                    \
-      ce = a.bf16 ? launch_group<CC, true, NN, MM>(p, pl.smem, a.n_sm, a.stream) : launch_group<CC, false, NN, MM>(p, pl.smem, a.n_sm, a.stream);
+      ce = v1 ? (a.bf16 ? launch_group_v1<CC, true, NN, MM>(p, pl.smem, a.n_sm, a.stream) : launch_group_v1<CC, false, NN, MM>(p, pl.smem, a.n_sm, a.stream)) \
+              : (a.bf16 ? launch_group<CC, true, NN, MM>(p, pl.smem, a.n_sm, a.stream) : launch_group<CC, false, NN, MM>(p, pl.smem, a.n_sm, a.stream));
     SA_GROUP(16, 2, 2) SA_GROUP(32, 2, 2)
 #undef SA_GROUP
     if (ce != cudaSuccess) return msgf("group_chain launch: %s", cudaGetErrorString(ce));
