@@ -52,7 +52,8 @@ namespace tc {
 constexpr int kGrpMaxStreams = 4;
 constexpr int kGrpPadRows = 8;                             // slack rows on both sides (one 1024-byte swizzle atom)
 constexpr int kGrpEpiWarps = 16;                           // NS * MS * 4
-constexpr int kGrpThreads = 32 * (kGrpEpiWarps + 2);       // 576
+constexpr int kGrpMmaWarps = 2;                            // one MMA-issuing warp per stream
+constexpr int kGrpThreads = 32 * (kGrpEpiWarps + 1 + kGrpMmaWarps);   // 608
 constexpr int kGrpMaxStages = 12;                          // weight ring depth (runtime n_wstages <= this)
 constexpr uint32_t kGrpSliceBytes = 64 * 32;               // one Toeplitz block: [64 rows (g', co)][16 ci] 16-bit
 constexpr int kGrpSlicesPerStage = 4;
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   auto bar_up_full = [&](int st) { return smem_u32(&bars[3 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
   auto bar_up_empty = [&](int st) { return smem_u32(&bars[4 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
   auto bar_up_done = [&](int st) { return smem_u32(&bars[5 * kGrpMaxStreams + 2 * kGrpMaxStages + st]); };
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6 * kGrpMaxStreams + 2 * kGrpMaxStages);
+  auto bar_turn = [&](int w) { return smem_u32(&bars[6 * kGrpMaxStreams + 2 * kGrpMaxStages + w]); };   // issue turn of MMA warp w
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7 * kGrpMaxStreams + 2 * kGrpMaxStages);
 
   const int valid = R - 2 * p.halo;
   __shared__ int tile_pre[kMaxMapItems + 1];
@@ -174,7 +176,9 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       mbar_init(bar_up_done(st), 1);
     }
     if (p.fuse_up) prefetch_tmap(&p.up_map);
-    for (int i = 0; i < kGrpMaxStages; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
+    for (int w = 0; w < kGrpMmaWarps; ++w) mbar_init(bar_turn(w), 1);
+    mbar_arrive(bar_turn(0));                                    // stream 0 issues first
+    for (int i = 0; i < kGrpMaxStages; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), kGrpMmaWarps); }   // w_empty: every MMA warp has read the stage
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), 512);
@@ -247,8 +251,15 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         }
       }
      }
-  } else if (warp == kWarpMma) {
-    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+  } else if (warp >= kWarpMma) {
+    // ===== MMA issuers, one warp per stream (warp-uniform loop, one elected lane issues) =====
+    // Whatever the issuing thread does between its tcgen05.mma instructions is NOT hidden behind the queued MMAs
+    // (tools/mma_bench5.cu: an already-complete try_wait + tcgen05.fence costs ~90 cycles, a commit ~50, a __syncwarp and
+    // the loop bookkeeping ~60; N = 64 MMAs then run at 62-85 cycles instead of 48), but the tensor pipe takes MMAs from a
+    // second warp meanwhile (tools/mma_bench6.cu: two issuing warps with that overhead: 48.0 cycles per MMA in aggregate).
+    // The streams are independent dependency chains, so each gets its own issuer; both read the shared weight ring (every
+    // stage is waited for and released by both: w_empty counts two arrivals).
+    const int my_st = warp - kWarpMma;
     // The first version walked the slices with a runtime count and per-MMA predicates: 16 issued instructions per MMA
     // and ~100 cycles per MMA on this single warp (ncu source view, profiles/r2_group_v1_*).  The slice count is a
     // compile-time constant per filter length now: one conv of one stream is straight-line code whose descriptors
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
     int slot = 0;
     uint32_t par = 0;
     bool ok = true;
+    uint32_t turn = 0;                                           // issue turns this warp has taken
 #ifdef SA_DIAG
     const bool timing = p.timing != nullptr;
 #else
@@ -285,35 +297,48 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
       constexpr int t_in = KIND == 1 ? 1 : 0;                                  // conv1 / up read A, conv2 reads T
       constexpr int d_idx = KIND == 0 ? 0 : 1;                                 // conv1 -> accumulator, conv2 / up -> residual
       const uint32_t rdy_parity = (ph0 + (uint32_t)(c >> 1)) & 1u;            // ph0: pairs completed before this chain
+      const int st = my_st;
+      if (!ok) return;
+      // 1. everything this conv depends on, outside the issue turn: activations of this stream, all weight stages
+      const long long tr0 = timing ? clock64() : 0;
+      if (KIND == 2) {
+        ok = mbar_wait(bar_up_full(st), n & 1u, p.error_flag);                 // input tile landed
+        if (timing) t_kind[2] += clock64() - tr0;
+      } else {
+        ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
+        if (timing) t_kind[KIND] += clock64() - tr0;
+      }
+      if (timing) t_ready += clock64() - tr0;
+      if (!ok) return;
       const int slot0 = slot;
-      const uint32_t par0 = par;
-#pragma unroll 1
-      for (int st = 0; st < kGrpStreams && ok; ++st) {
-        const long long tr0 = timing ? clock64() : 0;
-        if (KIND == 2) {
-          ok = mbar_wait(bar_up_full(st), n & 1u, p.error_flag);               // input tile landed
-          if (timing) t_kind[2] += clock64() - tr0;
-        } else {
-          ok = mbar_wait(bar_ready(st, t_in), rdy_parity, p.error_flag);
-          if (timing) t_kind[KIND] += clock64() - tr0;
-        }
-        if (timing) t_ready += clock64() - tr0;
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - lead);
-        // fuse_up: the column halves swap roles from chain to chain (see the epilogue): the transposed conv of chain n writes
-        // the half that was conv1's accumulator in chain n - 1 (drained long ago), never the residual still being read
-        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + (d_idx ^ (int)(p.fuse_up ? (n & 1u) : 0u))) * kGrpMS * 64);
-        slot = slot0; par = par0;
+      {
+        const long long tw0 = timing ? clock64() : 0;
 #pragma unroll
         for (int i = 0; i < NSTG; ++i) {
-          if (st == 0) {
-            const long long tw0 = timing ? clock64() : 0;
-            ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);
-            if (timing) t_w += clock64() - tw0;
-            tc_fence_after();
-          }
-          const uint32_t b_lo = b_lo0 + (uint32_t)slot * (kGrpStageBytes >> 4);
+          ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);
+          if (++slot == n_wst) { slot = 0; par ^= 1u; }
+        }
+        if (timing) t_w += clock64() - tw0;
+      }
+      if (!ok) return;
+      // 2. the issue turn: the two MMA warps alternate conv by conv (stream 0, stream 1, stream 0, ...), so that one stream's
+      // MMAs run under the other stream's epilogue as with a single issuer -- left to themselves the two issuers fall into
+      // lockstep (both streams in their MMA phase, then both in their epilogue phase with the tensor pipe idle: measured
+      // slower than one issuer) -- while the waits above and the commits below overlap the other warp's MMAs.
+      ok = mbar_wait(bar_turn(my_st), turn & 1u, p.error_flag);
+      ++turn;
+      if (!ok) return;
+      tc_fence_after();
+      const uint32_t a_lo0 = desc_lo(smem_u32(buf(st, t_in)) + kPadBytes - lead);
+      // fuse_up: the column halves swap roles from chain to chain (see the epilogue): the transposed conv of chain n writes
+      // the half that was conv1's accumulator in chain n - 1 (drained long ago), never the residual still being read
+      const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + (d_idx ^ (int)(p.fuse_up ? (n & 1u) : 0u))) * kGrpMS * 64);
+      // 3. NTOT x MS MMAs back to back
+      {
+        int sl = slot0;
+#pragma unroll
+        for (int i = 0; i < NSTG; ++i) {
+          const uint32_t b_lo = b_lo0 + (uint32_t)sl * (kGrpStageBytes >> 4);
 #pragma unroll
           for (int s = 0; s < kGrpMS; ++s) {
 #pragma unroll
@@ -327,16 +352,22 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
               }
             }
           }
-          if (st == kGrpStreams - 1 && leader) umma_commit(bar_w_empty(slot));     // both streams have read the stage
-          __syncwarp();
-          if (++slot == n_wst) { slot = 0; par ^= 1u; }
+          if (++sl == n_wst) sl = 0;
         }
-        if (leader) {
-          umma_commit(KIND == 2 ? bar_up_done(st) : bar_acc_full(st));
-          if (KIND == 0 && c == p.n_convs - 2 && p.fuse_up) umma_commit(bar_up_empty(st));   // buffer A read for the last time
-        }
-        __syncwarp();
       }
+      // 4. hand the turn over, then the completion tracking (commits follow this thread's MMAs whenever they are issued)
+      if (leader) {
+        mbar_arrive(bar_turn(my_st ^ 1));
+        int sl = slot0;
+#pragma unroll
+        for (int i = 0; i < NSTG; ++i) {
+          umma_commit(bar_w_empty(sl));                              // this stream has read the stage
+          if (++sl == n_wst) sl = 0;
+        }
+        umma_commit(KIND == 2 ? bar_up_done(st) : bar_acc_full(st));
+        if (KIND == 0 && c == p.n_convs - 2 && p.fuse_up) umma_commit(bar_up_empty(st));   // buffer A read for the last time
+      }
+      __syncwarp();
     };
     using K0 = std::integral_constant<int, 0>;
     using K1 = std::integral_constant<int, 1>;
@@ -360,7 +391,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
         else if (nsl == (G + 10) * CPP) chain(std::integral_constant<int, (G + 10) * CPP>{}, ph0, n);    // k = 11
         else { if (p.error_flag) atomicExch(p.error_flag, 1); ok = false; }                             // not instantiated (the host checks)
       }
-    if (timing && lane == 0) {
+    if (timing && lane == 0 && my_st == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 0), (unsigned long long)(clock64() - t_begin));
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_ready);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 2), (unsigned long long)t_w);

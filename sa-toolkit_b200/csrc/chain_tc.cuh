@@ -181,6 +181,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       bool ok = true;
       const bool timing = p.timing != nullptr;
       long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
+      long long t_issue = 0, n_issue = 0;      // SA_DIAG: cycles inside the MMA issue block of sub-tiles > 0 (no waits inside)
       for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
         for (int c = 0; c < p.n_convs && ok; ++c) {
           const uint32_t in_lo0 = desc_lo(smem_u32((c & 1) ? bufT : bufA)) + (uint32_t)(kChainPad - p.pad[c]) * row16;
@@ -226,8 +227,13 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
             // inputs of sub-tiles s-1..s+1 must be staged; s-1 and s were confirmed in earlier iterations
             // (an already-complete try_wait still costs ~90 cycles on this single issuing warp)
             const long long tr0 = timing ? clock64() : 0;
-            if (s == 0 && ok) ok = mbar_wait(bar_ready(c & 1, 0), rdy_parity, p.error_flag);
-            if (s + 1 < MS && ok) ok = mbar_wait(bar_ready(c & 1, s + 1), rdy_parity, p.error_flag);
+#ifdef SA_DIAG
+            const bool freerun = (p.flags & (1u << 30)) != 0;    // diagnostics: do not wait for the epilogue (results invalid)
+#else
+            constexpr bool freerun = false;
+#endif
+            if (s == 0 && ok && !freerun) ok = mbar_wait(bar_ready(c & 1, 0), rdy_parity, p.error_flag);
+            if (s + 1 < MS && ok && !freerun) ok = mbar_wait(bar_ready(c & 1, s + 1), rdy_parity, p.error_flag);
             if (timing) t_ready += clock64() - tr0;
             if (ok) {
               tc_fence_after();
@@ -236,6 +242,9 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
               int slot = slot0;
               uint32_t par = par0;
               uint32_t b_tap = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
+#ifdef SA_DIAG
+              const long long ti0 = (timing && s > 0) ? clock64() : 0;
+#endif
 #pragma unroll
               for (int tap = 0; tap < K; ++tap) {
                 if (s == 0 && (C == 64 || tap == 0)) {           // later sub-tiles reuse the landed weights
@@ -258,6 +267,9 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
                 }
               }
               slot_end = slot; par_end = par;
+#ifdef SA_DIAG
+              if (timing && s > 0) { t_issue += clock64() - ti0; ++n_issue; }
+#endif
               if (leader) umma_commit(bar_acc_full(c & 1, s));
               __syncwarp();
             }
@@ -271,6 +283,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
         atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 1), (unsigned long long)t_ready);
         atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 2), (unsigned long long)t_w);
         atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 3), (unsigned long long)(tot - t_ready - t_w));
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 10), (unsigned long long)t_issue);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing + 11), (unsigned long long)n_issue);
       }
     }
   } else {
@@ -289,6 +303,9 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     bool ok = true;
     const bool timing = p.timing != nullptr && warp == 0;
     long long t_p0 = 0, t_acc = 0, t_ld = 0, t_fence = 0, t_begin = timing ? clock64() : 0;
+#ifdef SA_DIAG
+    if (p.flags & (1u << 30)) ok = false;                        // diagnostics: free-running MMA warp, no epilogue at all
+#endif
     for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
       const long long tp0 = timing ? clock64() : 0;
       int b, mt;

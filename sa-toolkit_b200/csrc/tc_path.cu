@@ -744,7 +744,7 @@ struct Runner {
     const int min_tiles = min_tiles_env >= 0 ? min_tiles_env : 2 * pl.ns * a.n_sm;
     if (((L + pl.valid - 1) / pl.valid) * a.B < min_tiles) return false;
     const size_t fixed = 2 * (size_t)pl.ns * tc::grp_buf_bytes(pl.ms) + tc::kGrpOnesBytes +
-                         (6 * tc::kGrpMaxStreams + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
+                         (7 * tc::kGrpMaxStreams + 2 * tc::kGrpMaxStages) * 8 + 16 + 1024;
     int stages = std::min(tc::kGrpMaxStages, 2 * ch.g_stages);              // two convs deep: the next conv streams in behind
     while (stages > ch.g_stages && fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) --stages;
     if (stages < ch.g_stages + 1 || fixed + (size_t)stages * tc::kGrpStageBytes > (size_t)ctx.max_smem) return false;
@@ -858,6 +858,9 @@ struct Runner {
     p.map = tile_map(L);
     p.k16_per_stage = ch.k16_per_stage; p.stages_per_conv = ch.stages_per_conv; p.n_slots = pl.n_slots;
     p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+#ifdef SA_DIAG
+    if (getenv("SATOOLS_B200_DEBUG_FREERUN") && atoi(getenv("SATOOLS_B200_DEBUG_FREERUN"))) p.flags |= 1u << 30;
+#endif
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
     cudaError_t ce = cudaErrorInvalidValue;
