@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(chain_threads(MS, 4), 1) stage_chain3_kernel(c
   constexpr uint32_t kTmemCols = kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (barrier addresses,
+  // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int kWarpW = 4 * MS, kWarpMma = 4 * MS + 1;          // epilogue warps first, MMA issuer last (see chain_tc.cuh)
   // smem: buf[chain][A|T], weights (one conv per chain), bias, barriers
   auto buf = [&](int j, int t) { return smem + (uint32_t)(j * 2 + t) * kBufBytes; };

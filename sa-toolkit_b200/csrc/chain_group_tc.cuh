@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   constexpr uint32_t PB = 2u * C;                                // bytes per position
   constexpr uint32_t kPadBytes = kGrpPadRows * 128;
   constexpr int kGroupsPerPos = C / 16;                          // 16-column TMEM groups per position
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (barrier addresses,
+  // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int kWarpW = kGrpEpiWarps, kWarpMma = kGrpEpiWarps + 1;
   // smem: buf[stream][A|T], weight ring, ones tile (128 rows x 32 B, SWIZZLE_32B), barriers
   auto buf = [&](int st, int t) { return smem + (uint32_t)(st * 2 + t) * kGrpBufBytes; };

@@ -100,7 +100,9 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int K16 = C / 16;                                    // K=16 steps per tap
   constexpr uint32_t kTapBytes = (uint32_t)N * RB;               // one tap = one [N rows][C] weight block
   constexpr uint32_t stage_bytes = (C == 64) ? kTapBytes : (uint32_t)K * kTapBytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (barrier addresses,
+  // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int kWarpW = WPS * MS, kWarpMma = WPS * MS + 1;      // epilogue warps are 0 .. WPS*MS-1
   uint8_t* bufA = smem;
   uint8_t* bufT = smem + kBufBytes;

@@ -90,7 +90,9 @@ template <int N, int MSUB>
 __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (barrier addresses,
+  // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int phase = blockIdx.y / p.n_tiles, ntile = blockIdx.y % p.n_tiles;
   const uint32_t crank = cluster_ctarank();
   const bool is_leader = crank == 0;

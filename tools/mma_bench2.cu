@@ -89,6 +89,9 @@ int main() {
   run<128, 4>(it, 128, 0, 148, gsrc);
   run<128, 2>(it, 128, it * 2, 148, gsrc);
   run<64, 1>(it, 128, 0, 148, gsrc);
+  run<64, 2>(it, 128, 2736, 148, gsrc);        // 8 KB of weights per 12 MMAs, like the C = 64 chain kernel (k = 3 taps)
+  run<64, 2>(it, 128, 8192, 148, gsrc);        // 8 KB per 4 MMAs
+  run<64, 2>(it, 128, 32768, 148, gsrc);       // 8 KB per MMA
   run<64, 2>(it, 128, 0, 148, gsrc);
   run<64, 4>(it, 128, 0, 148, gsrc);
   run<64, 8>(it, 128, 0, 148, gsrc);
