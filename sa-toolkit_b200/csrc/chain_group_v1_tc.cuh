@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kGrpThreads, 1) group_chain_kernel(const __gri
   constexpr int kGroupsPerPos = C / 16;                          // 16-column TMEM groups per position
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (barrier addresses,
   // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;      // (the shuffle form of the other kernels makes ptxas spill more here: 684 vs 128 bytes of spill loads)
   constexpr int kWarpW = kGrpEpiWarps, kWarpMma = kGrpEpiWarps + 1;
   // smem: buf[stream][A|T], weight ring, ones tile (128 rows x 32 B, SWIZZLE_32B), barriers
   auto buf = [&](int st, int t) { return smem + (uint32_t)(st * 2 + t) * kGrpBufBytes; };

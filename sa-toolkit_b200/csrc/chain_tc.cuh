@@ -181,7 +181,11 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       int slot0 = 0;                                             // ring position of the running conv's first stage
       uint32_t par0 = 0;
       bool ok = true;
+#ifdef SA_DIAG
       const bool timing = p.timing != nullptr;
+#else
+      constexpr bool timing = false;   // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
       long long t_ready = 0, t_w = 0, t_begin = timing ? clock64() : 0;
       long long t_issue = 0, n_issue = 0;      // SA_DIAG: cycles inside the MMA issue block of sub-tiles > 0 (no waits inside)
       for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
@@ -303,7 +307,11 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
     for (int q = 0; q < kCPT; ++q) soff[q] = swz(row_off + (uint32_t)(ch0 + q) * 16u, RB);
     uint32_t it = 0;
     bool ok = true;
+#ifdef SA_DIAG
     const bool timing = p.timing != nullptr && warp == 0;
+#else
+    constexpr bool timing = false;   // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
     long long t_p0 = 0, t_acc = 0, t_ld = 0, t_fence = 0, t_begin = timing ? clock64() : 0;
 #ifdef SA_DIAG
     if (p.flags & (1u << 30)) ok = false;                        // diagnostics: free-running MMA warp, no epilogue at all

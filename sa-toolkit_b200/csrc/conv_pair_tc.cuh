@@ -213,7 +213,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
       int wslot = 0;
       uint32_t wpar = 0;
       bool ok = true;
+#ifdef SA_DIAG
       const bool timing = p.timing != nullptr;
+#else
+      constexpr bool timing = false;   // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
       long long t_a = 0, t_w = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
       for (int it = 0; it < n_rounds && ok; ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
@@ -274,7 +278,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
     // ===== epilogue (both CTAs): own TMEM lanes, a quarter of the N columns per warp (epi_tile, conv_tc.cuh) =====
     const int lg = warp & 3;
     const int col0 = (warp >> 2) * (N / 4);
+#ifdef SA_DIAG
     const bool timing = p.timing != nullptr && warp == 0;
+#else
+    constexpr bool timing = false;   // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
     long long t_full = 0, t_begin = timing ? clock64() : 0;
     for (int it = 0; it < n_rounds; ++it) {
       const int acc = it & 1, acc_use = it >> 1;

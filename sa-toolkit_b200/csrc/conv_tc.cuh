@@ -659,7 +659,11 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
       int it = 0, wslot = 0;
       uint32_t wpar = 0;
       bool ok = true, resident_ready = false;
+#ifdef SA_DIAG
       const bool timing = p.timing != nullptr;
+#else
+      constexpr bool timing = false;   // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
       long long t_a = 0, t_w = 0, t_acc = 0, t_begin = timing ? clock64() : 0;
       for (; it < my_rounds && ok; ++it) {
         const int buf = (p.n_abuf == 2) ? (it & 1) : 0, use = (p.n_abuf == 2) ? (it >> 1) : it;
@@ -729,7 +733,11 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
     constexpr int kColsPerWarp = (N >= 32) ? N / 2 : N;            // N = 16: only half 0 has columns
     const bool has_cols = (N >= 32) || half == 0;
     const int col0 = (N >= 32) ? half * kColsPerWarp : 0;
+#ifdef SA_DIAG
     const bool timing = p.timing != nullptr && warp == 0;
+#else
+    constexpr bool timing = false;   // in-kernel cycle counters: -DSA_DIAG builds only
+#endif
     long long t_full = 0, t_begin = timing ? clock64() : 0;
     for (int it = 0; it < my_rounds; ++it) {
       const int tile = tile_of(it);
