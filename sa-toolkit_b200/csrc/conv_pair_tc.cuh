@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv_pair_kernel(const __grid
   // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int phase = blockIdx.y / p.n_tiles, ntile = blockIdx.y % p.n_tiles;
-  const uint32_t crank = cluster_ctarank();
+  const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);   // warp-uniform for the compiler, like the warp index
   const bool is_leader = crank == 0;
 
   constexpr int NH = N / 2;                                       // B rows held by one CTA
