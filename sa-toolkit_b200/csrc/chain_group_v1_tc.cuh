@@ -1,9 +1,9 @@
 // Grouped (block-Toeplitz) fused ResBlock kernel, first epilogue mapping: one thread owns one whole 128-byte row of ONE
 // stream's tile (8 epilogue warps per stream), the fused transposed conv hands over through a res_free barrier, the running
-// multi-receptive-field sum uses the channel-blocked [C/8][L][8] layout.  Kept for C = 32: there a conv is 864-2400 cycles
-// of MMAs per stream, the epilogue latency is covered, and this mapping issues ~20 % fewer epilogue instructions than the
-// half-row mapping of chain_group_tc.cuh (measured on B200, stage 3: 4.4 vs 4.7-4.8 ms).  C = 16 (672-1440 cycles of MMAs per
-// conv and stream) is latency bound and uses the half-row mapping (stage 4: 3.5 -> 3.1 ms).
+// multi-receptive-field sum uses the channel-blocked [C/8][L][8] layout.  It issues ~20 % fewer epilogue instructions than
+// the half-row mapping of chain_group_tc.cuh and was the faster one for C = 32 (864-2400 cycles of MMAs per conv and stream
+// cover the epilogue latency) until the issue loops went uniform; now it only wins the k = 3 block (0.85 vs 0.93 ms) and
+// loses the stage (4.4-4.5 vs 4.25 ms), so it is an option (SATOOLS_B200_GROUP_V1 bit mask), not the default.
 // Data flow, shared-memory layout, weight packing and parameters are those of chain_group_tc.cuh.
 #pragma once
 #include "chain_group_tc.cuh"

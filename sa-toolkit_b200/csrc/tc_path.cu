@@ -812,10 +812,11 @@ struct Runner {
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
     cudaError_t ce = cudaErrorInvalidValue;
-    // Epilogue mapping per channel count (measured, see chain_group_v1_tc.cuh): bit 0: C = 16, bit 1: C = 32 on the first
-    // mapping (one thread per row and stream); default C = 32 only.  The two kernels lay the running sum out differently, but
-    // all ResBlocks of a stage share a channel count, so a stage never mixes them.
-    static const int v1_mask = getenv("SATOOLS_B200_GROUP_V1") ? atoi(getenv("SATOOLS_B200_GROUP_V1")) : 2;
+    // Epilogue mapping per channel count: bit 0: C = 16, bit 1: C = 32 on the first mapping (chain_group_v1_tc.cuh: one thread
+    // per row and stream).  Default: the half-row mapping for both -- measured on one box after the issue loops went
+    // uniform (stage 3: 4.25 vs 4.42-4.55 ms; v1 still wins the k = 3 block, 0.85 vs 0.93 ms, and loses k = 11, 2.25-2.33 vs
+    // 2.02 ms).  The two kernels lay the running sum out differently, so a stage never mixes them.
+    static const int v1_mask = getenv("SATOOLS_B200_GROUP_V1") ? atoi(getenv("SATOOLS_B200_GROUP_V1")) : 0;
     const bool v1 = (v1_mask & (ch.c == 16 ? 1 : 2)) != 0;
 #define SA_GROUP(CC, NN, MM)                                                                                          \
     if (ch.c == CC && pl.ns == NN)                                                                                    \
