@@ -44,6 +44,7 @@ __host__ __device__ constexpr int chain_threads(int ms, int wps) { return 64 + 3
 constexpr int kChainPad = 32;            // slack rows on both sides of the staged tile (>= max tap reach 25)
 constexpr int kChainMaxConvs = 8;
 constexpr int kChainMaxSlots = 16;
+constexpr int kChainTapsPerStage64 = 2;
 
 struct ChainParams {
   const float* x32;         // stage input h, fp32 blocked [B][C/8][L][8]
@@ -95,11 +96,15 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
 
-  constexpr int SPC = (C == 64) ? K : 1;                         // weight stages per conv
+  // Weight stages: C = 64 streams kChainTapsPerStage64 taps (16 KB) per stage -- every stage costs the issuing thread a
+  // try_wait on sub-tile 0 and a commit on the last sub-tile (~90 + ~50 cycles that are not hidden behind the queued MMAs,
+  // tools/mma_bench5.cu), so fewer, larger stages; C <= 32 holds a whole conv per stage.
+  constexpr int TPS = (C == 64) ? kChainTapsPerStage64 : K;      // taps per stage
+  constexpr int SPC = (K + TPS - 1) / TPS;                       // weight stages per conv
   const int NSLOTS = (C == 64) ? p.n_slots : 2;
   constexpr int K16 = C / 16;                                    // K=16 steps per tap
   constexpr uint32_t kTapBytes = (uint32_t)N * RB;               // one tap = one [N rows][C] weight block
-  constexpr uint32_t stage_bytes = (C == 64) ? kTapBytes : (uint32_t)K * kTapBytes;
+  constexpr uint32_t stage_bytes = (uint32_t)TPS * kTapBytes;    // slot pitch (the last stage of a conv may hold fewer taps)
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops (barrier addresses,
   // descriptors, counters) in uniform registers instead of converting them per use (R2UR), as CUTLASS' canonical_warp_idx_sync
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -151,15 +156,15 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       bool wrapped = false, ok = true;
       for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x)
         for (int c = 0; c < p.n_convs && ok; ++c) {
-          const uint8_t* src = static_cast<const uint8_t*>(p.w) + (size_t)c * SPC * stage_bytes;
+          const uint8_t* src = static_cast<const uint8_t*>(p.w) + (size_t)c * K * kTapBytes;
 #pragma unroll 1
           for (int i = 0; i < SPC; ++i) {
             if (wrapped) ok = mbar_wait_relaxed(bar_w_empty(slot), par, p.error_flag);
             if (!ok) break;
+            const uint32_t bytes = (uint32_t)min(TPS, K - i * TPS) * kTapBytes;
             if (leader) {
-              mbar_arrive_expect_tx(bar_w_full(slot), stage_bytes);
-              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, src + (size_t)i * stage_bytes, stage_bytes,
-                        bar_w_full(slot));
+              mbar_arrive_expect_tx(bar_w_full(slot), bytes);
+              bulk_load(smem_u32(w_smem) + (uint32_t)slot * stage_bytes, src + (size_t)i * stage_bytes, bytes, bar_w_full(slot));
             }
             __syncwarp();
             if (++slot == NSLOTS) { slot = 0; par ^= 1u; wrapped = true; }
@@ -253,23 +258,23 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
 #endif
 #pragma unroll
               for (int tap = 0; tap < K; ++tap) {
-                if (s == 0 && (C == 64 || tap == 0)) {           // later sub-tiles reuse the landed weights
+                const bool stage_begin = (tap % TPS) == 0, stage_end = ((tap + 1) % TPS) == 0 || tap == K - 1;
+                if (s == 0 && stage_begin) {                     // later sub-tiles reuse the landed weights
                   const long long tw0 = timing ? clock64() : 0;
-                  ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);
-                  tc_fence_after();
+                  ok = ok && mbar_wait(bar_w_full(slot), par, p.error_flag);   // TMA data: the wait is the acquire, no tcgen05 fence
                   if (timing) t_w += clock64() - tw0;
                 }
 #pragma unroll
                 for (int kk = 0; kk < K16; ++kk)
                   if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, (tap | kk) ? 1u : 0u);
                 a_tap += dil16;
-                if (s == MS - 1 && (C == 64 || tap == K - 1)) {  // last sub-tile: the slot may be refilled
+                if (s == MS - 1 && stage_end) {                  // last sub-tile: the slot may be refilled
                   if (leader) umma_commit(bar_w_empty(slot));
                 }
-                if (C == 64 || tap == K - 1) {                   // next weight stage
-                  if (++slot == NSLOTS) { slot = 0; par ^= 1u; b_tap = b_lo0; } else { b_tap += (stage_bytes >> 4); }
+                if (stage_end) {                                 // next weight stage
+                  if (++slot == NSLOTS) { slot = 0; par ^= 1u; b_tap = b_lo0; } else { b_tap = b_lo0 + (uint32_t)slot * (stage_bytes >> 4); }
                 } else {
-                  b_tap += tap16;                                // C <= 32: taps are consecutive inside the stage
+                  b_tap += tap16;                                // taps are consecutive inside a stage
                 }
               }
               slot_end = slot; par_end = par;

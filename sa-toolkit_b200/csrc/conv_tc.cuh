@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, (N < 64) ? 2 : 1) conv_tc_kernel(con
           }
           if (timing) t_w += clock64() - tw0;
           if (!ok) break;
-          tc_fence_after();
+          // (weights are TMA data: the wait above is the acquire; no tcgen05 fence needed here)
           uint32_t b_blk = b_lo0 + (uint32_t)slot * (stage_bytes >> 4);
           const int nb = min(blocks_per_stage, n_blocks_total - blk);
           for (int bi = 0; bi < nb; ++bi, ++blk) {

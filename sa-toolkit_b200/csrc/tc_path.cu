@@ -973,7 +973,10 @@ const char* tc_pack_chain(tc_chain& ch, int c, int k, int n_convs, const float* 
   for (int i = 0; i < n_convs; ++i) { ch.dil[i] = dil[i]; ch.pad[i] = pad[i]; ch.halo += pad[i]; }
   for (int i = 0; i < n_convs; ++i) if (pad[i] > 25 || (k - 1) * dil[i] - pad[i] > 25) return nullptr;   // tap reach > slack rows
   const int k16_per_tap = c / 16;
-  if (c == 64) { ch.k16_per_stage = k16_per_tap; ch.stages_per_conv = k; }     // one tap (8 KB) per stage
+  if (c == 64) {                                                              // kChainTapsPerStage64 taps (16 KB) per stage
+    ch.k16_per_stage = tc::kChainTapsPerStage64 * k16_per_tap;
+    ch.stages_per_conv = (k + tc::kChainTapsPerStage64 - 1) / tc::kChainTapsPerStage64;
+  }
   else { ch.k16_per_stage = k * k16_per_tap; ch.stages_per_conv = 1; }         // the whole conv per stage
   const int rb = 2 * c;                                          // one panel: row = all C channels
   const size_t tap_bytes = (size_t)c * rb, conv_bytes = (size_t)k * tap_bytes;
