@@ -74,7 +74,15 @@ struct ChainParams {
 // 8 KB) per stage through p.n_slots >= K slots (a ring deeper than one conv lets the first taps of the
 // next conv land before the current conv's last sub-tile is done); C <= 32 holds a whole conv per stage
 // in 2 slots.
-template <int C, int MS, int K, int WPS>
+// RT ("residual in tensor memory", round 2): conv2 accumulates on top of the residual stream, which lives in the TMEM buffer
+// conv2 uses (the epilogue adds the running sum of the conv2 biases when it reads it), so the epilogue threads hold no
+// residual registers and do no residual add, and the tile boundary is pipelined: the next tile's x is loaded and staged
+// (shared memory + the TMEM buffer that held conv1's accumulator: the two buffers swap roles from tile to tile) while the
+// last conv2 of the running tile executes, and the last epilogue hands its TMEM buffer back (res_free) as soon as the row is
+// in registers.  The MMA warp then walks from one tile into the next without waiting for global memory.  fp32 sums are
+// associated differently from the per-layer path (last-bit differences), so RT = false stays the bit-identical reference
+// form (SATOOLS_B200_GROUP=0) and the form of the C <= 32 instantiations.
+template <int C, int MS, int K, int WPS, bool RT = false>
 __global__ void __launch_bounds__(chain_threads(MS, WPS), (C <= 32 && MS <= 3) ? 2 : 1)
 resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -119,7 +127,8 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
   auto bar_acc_full = [&](int par, int s) { return smem_u32(&bars[16 + par * 8 + s]); };
   auto bar_w_full = [&](int i) { return smem_u32(&bars[32 + i]); };
   auto bar_w_empty = [&](int i) { return smem_u32(&bars[32 + kChainMaxSlots + i]); };
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32 + 2 * kChainMaxSlots);
+  auto bar_res_free = [&](int s) { return smem_u32(&bars[32 + 2 * kChainMaxSlots + s]); };   // RT: the last epilogue has read sub-tile s
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 40 + 2 * kChainMaxSlots);
 
   const int valid_rows = R - 2 * p.halo;
   __shared__ int tile_pre[kMaxMapItems + 1];
@@ -131,12 +140,24 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
       mbar_init(bar_ready(0, s), TM ? WPS * MS : WPS);           // the warps owning the sub-tile (TM: the whole tile)
       mbar_init(bar_ready(1, s), TM ? WPS * MS : WPS);
       mbar_init(bar_acc_full(0, s), 1); mbar_init(bar_acc_full(1, s), 1);
+      mbar_init(bar_res_free(s), WPS);
     }
     for (int i = 0; i < kChainMaxSlots; ++i) { mbar_init(bar_w_full(i), 1); mbar_init(bar_w_empty(i), 1); }
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
-  for (int i = threadIdx.x; i < p.n_convs * C; i += kThreads_) bias_s[i] = p.bias[i];
+  if constexpr (RT) {
+    // conv1: its own bias; conv2 of pair m: b2_0 + .. + b2_m (the TMEM residual accumulates the conv2 outputs without them)
+    for (int i = threadIdx.x; i < C; i += kThreads_) {
+      float run = 0.f;
+      for (int c = 0; c < p.n_convs; ++c) {
+        const float bv = p.bias[c * C + i];
+        if (c & 1) { run += bv; bias_s[c * C + i] = run; } else { bias_s[c * C + i] = bv; }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < p.n_convs * C; i += kThreads_) bias_s[i] = p.bias[i];
+  }
   // zero both staged tiles once: the PAD slack rows are never written afterwards
   for (uint32_t i = threadIdx.x; i < 2 * kBufBytes / 16; i += kThreads_)
     *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0, 0, 0, 0);
@@ -246,9 +267,12 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
             if (s == 0 && ok && !freerun) ok = mbar_wait(bar_ready(c & 1, 0), rdy_parity, p.error_flag);
             if (s + 1 < MS && ok && !freerun) ok = mbar_wait(bar_ready(c & 1, s + 1), rdy_parity, p.error_flag);
             if (timing) t_ready += clock64() - tr0;
+            if constexpr (RT) {                                  // the buffer this block overwrites held the previous tile's residual
+              if (c == 0 && it > 0 && ok) ok = mbar_wait(bar_res_free(s), (it - 1) & 1u, p.error_flag);
+            }
             if (ok) {
               tc_fence_after();
-              const uint32_t d_tmem = tmem_base + (uint32_t)(((c & 1) * MS + s) * N);
+              const uint32_t d_tmem = tmem_base + (uint32_t)((((c & 1) ^ (RT ? (int)(it & 1u) : 0)) * MS + s) * N);
               uint32_t a_tap = in_lo0 + (uint32_t)(s * 128) * row16;
               int slot = slot0;
               uint32_t par = par0;
@@ -266,7 +290,7 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
                 }
 #pragma unroll
                 for (int kk = 0; kk < K16; ++kk)
-                  if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, (tap | kk) ? 1u : 0u);
+                  if (leader) umma_f16(d_tmem, desc64(a_tap + 2u * kk, hi), desc64(b_tap + 2u * kk, hi), idesc, ((RT && (c & 1)) || (tap | kk)) ? 1u : 0u);
                 a_tap += dil16;
                 if (s == MS - 1 && stage_end) {                  // last sub-tile: the slot may be refilled
                   if (leader) umma_commit(bar_w_empty(slot));
@@ -321,6 +345,169 @@ resblock_chain_kernel(const __grid_constant__ ChainParams p) {
 #ifdef SA_DIAG
     if (p.flags & (1u << 30)) ok = false;                        // diagnostics: free-running MMA warp, no epilogue at all
 #endif
+    if constexpr (RT) {
+      static_assert(kCPT == 4, "RT: 32 accumulator columns per epilogue thread (C = 64, 8 warps per sub-tile)");
+      const uint32_t tcol = ((uint32_t)(lg * 32) << 16) + (uint32_t)(s * N + ch0 * 8);
+      auto t_buf = [&](uint32_t bufi) { return tmem_base + tcol + bufi * (uint32_t)(MS * N); };
+      const int n_pairs = p.n_convs / 2;
+      auto locate = [&](int tile, int& b, int& t) {
+        int mt;
+        tilemap_locate(tile_pre, p.map, p.tiles_per_item, tile, b, mt);
+        t = mt * valid_rows - p.halo + r;
+      };
+      // x of a tile: global -> registers ...
+      auto load_x = [&](int b, int t, float4 (&xa)[kCPT], float4 (&xb)[kCPT]) {
+#pragma unroll
+        for (int q = 0; q < kCPT; ++q) {
+          xa[q] = make_float4(0.f, 0.f, 0.f, 0.f); xb[q] = xa[q];
+          if (t >= 0 && t < p.L) ldg_f8(p.x32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8, xa[q], xb[q]);
+        }
+      };
+      // ... -> the residual buffer of tile number `itn` of this CTA (TMEM) and lrelu(x) -> bufA; then the inputs of pair 0 are ready
+      auto put_x = [&](uint32_t itn, const float4 (&xa)[kCPT], const float4 (&xb)[kCPT]) {
+        const uint32_t res = t_buf(1u ^ (itn & 1u));
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const float4 a0 = xa[2 * g], a1 = xb[2 * g], a2 = xa[2 * g + 1], a3 = xb[2 * g + 1];
+          const uint32_t rr[16] = {__float_as_uint(a0.x), __float_as_uint(a0.y), __float_as_uint(a0.z), __float_as_uint(a0.w),
+                                   __float_as_uint(a1.x), __float_as_uint(a1.y), __float_as_uint(a1.z), __float_as_uint(a1.w),
+                                   __float_as_uint(a2.x), __float_as_uint(a2.y), __float_as_uint(a2.z), __float_as_uint(a2.w),
+                                   __float_as_uint(a3.x), __float_as_uint(a3.y), __float_as_uint(a3.z), __float_as_uint(a3.w)};
+          __syncwarp();
+          tmem_st16(res + (uint32_t)(g * 16), rr);
+        }
+#pragma unroll
+        for (int q = 0; q < kCPT; ++q) {
+          const float v[8] = {xa[q].x, xa[q].y, xa[q].z, xa[q].w, xb[q].x, xb[q].y, xb[q].z, xb[q].w};
+          *reinterpret_cast<uint4*>(bufA + soff[q]) = pack8_lrelu(v, 0.1f, true, bf16);    // rows outside the utterance were loaded as zeros
+        }
+        tmem_st_wait();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready(0, s));
+      };
+      int b = 0, t = 0;
+      if ((int)blockIdx.x < n_live) {                            // prologue: the first tile's x
+        locate((int)blockIdx.x, b, t);
+        float4 xa[kCPT], xb[kCPT];
+        load_x(b, t, xa, xb);
+        put_x(0u, xa, xb);
+      }
+      for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
+        const bool inside = t >= 0 && t < p.L;
+        const bool keep = inside && r >= p.halo && r < R - p.halo;
+        const uint32_t acc_b = it & 1u, res_b = acc_b ^ 1u;        // TMEM buffers of this tile: conv1 accumulator, residual / conv2
+        const int tile_n = tile + (int)gridDim.x;
+        const bool has_next = tile_n < n_live;
+        int bn = 0, tn = 0;
+        if (has_next) {
+          locate(tile_n, bn, tn);
+          if (tn >= 0 && tn < p.L) {                             // the next tile's rows: into L2 now, into registers under the last conv2
+#pragma unroll
+            for (int q = 0; q < kCPT; ++q)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x32 + (((size_t)bn * cchunks + ch0 + q) * (size_t)p.L + tn) * 8));
+          }
+        }
+        if (keep && (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN))) {
+#pragma unroll
+          for (int q = 0; q < kCPT; ++q)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sum32 + (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8));
+        }
+#pragma unroll 1
+        for (int m = 0; m < n_pairs && ok; ++m) {
+          const uint32_t par = (it * (uint32_t)n_pairs + (uint32_t)m) & 1u;
+          const bool last = (m == n_pairs - 1);
+          // ---- conv1: accumulator + bias -> lrelu -> conv2's input ----
+          {
+            ok = mbar_wait_relaxed(bar_acc_full(0, s), par, p.error_flag);
+            if (!ok) break;
+            tc_fence_after();
+            uint32_t rr[32];
+            __syncwarp();
+            tmem_ld32(t_buf(acc_b), rr);
+            tmem_ld_wait();
+            const float* bias_c = bias_s + (2 * m) * C + ch0 * 8;
+#pragma unroll
+            for (int q = 0; q < kCPT; ++q) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_c + q * 8), b1 = *reinterpret_cast<const float4*>(bias_c + q * 8 + 4);
+              const float v[8] = {__uint_as_float(rr[q * 8 + 0]) + b0.x, __uint_as_float(rr[q * 8 + 1]) + b0.y,
+                                  __uint_as_float(rr[q * 8 + 2]) + b0.z, __uint_as_float(rr[q * 8 + 3]) + b0.w,
+                                  __uint_as_float(rr[q * 8 + 4]) + b1.x, __uint_as_float(rr[q * 8 + 5]) + b1.y,
+                                  __uint_as_float(rr[q * 8 + 6]) + b1.z, __uint_as_float(rr[q * 8 + 7]) + b1.w};
+              *reinterpret_cast<uint4*>(bufT + soff[q]) = pack8_lrelu(v, 0.1f, inside, bf16);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready(1, s));
+          }
+          // ---- under the last conv2: the next tile's x ----
+          if (last && has_next) {
+            float4 xa[kCPT], xb[kCPT];
+            load_x(bn, tn, xa, xb);
+            // bufA rows of this sub-tile are also read by the last conv1's MMAs of sub-tile s + 1 (those of s - 1 were issued,
+            // hence complete, before those of s)
+            if (s + 1 < MS) ok = mbar_wait_relaxed(bar_acc_full(0, s + 1), par, p.error_flag);
+            if (!ok) break;
+            put_x(it + 1u, xa, xb);
+          }
+          // ---- conv2: the accumulator is the residual stream; + the running conv2 bias ----
+          {
+            ok = mbar_wait_relaxed(bar_acc_full(1, s), par, p.error_flag);
+            if (!ok) break;
+            tc_fence_after();
+            uint32_t rr[32];
+            __syncwarp();
+            tmem_ld32(t_buf(res_b), rr);
+            tmem_ld_wait();
+            if (last) {                                          // the row is in registers: the buffer may be overwritten
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_res_free(s));
+            }
+            const float* bias_c = bias_s + (2 * m + 1) * C + ch0 * 8;
+#pragma unroll
+            for (int q = 0; q < kCPT; ++q) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_c + q * 8), b1 = *reinterpret_cast<const float4*>(bias_c + q * 8 + 4);
+              float v[8] = {__uint_as_float(rr[q * 8 + 0]) + b0.x, __uint_as_float(rr[q * 8 + 1]) + b0.y,
+                            __uint_as_float(rr[q * 8 + 2]) + b0.z, __uint_as_float(rr[q * 8 + 3]) + b0.w,
+                            __uint_as_float(rr[q * 8 + 4]) + b1.x, __uint_as_float(rr[q * 8 + 5]) + b1.y,
+                            __uint_as_float(rr[q * 8 + 6]) + b1.z, __uint_as_float(rr[q * 8 + 7]) + b1.w};
+              if (!last) {
+                *reinterpret_cast<uint4*>(bufA + soff[q]) = pack8_lrelu(v, 0.1f, inside, bf16);
+              } else if (keep) {
+                // final epilogue: multi-receptive-field combine + stores (v = x_final)
+                const size_t idx = (((size_t)b * cchunks + ch0 + q) * (size_t)p.L + t) * 8;
+                if (p.flags & (EPI_SUM_ADD | EPI_SUM_FIN)) {
+                  float4 s0, s1;
+                  ldg_f8(p.sum32 + idx, s0, s1);
+                  v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+                  v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+                }
+                if (p.flags & EPI_SUM_FIN) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = v[e] / p.n_blocks;
+                }
+                if (p.flags & (EPI_SUM_SET | EPI_SUM_ADD)) stg_f8(p.sum32 + idx, v);
+                if (p.flags & EPI_OUT32) stg_f8(p.out32 + idx, v);
+                if (p.flags & EPI_OUT16) {
+                  const size_t o16 = (((size_t)b * (size_t)p.L + t) * cchunks + ch0 + q) * 16;   // [B][1][L][C]
+                  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out16) + o16) = pack8_lrelu(v, p.slope_out, true, bf16);
+                }
+              }
+            }
+            if (!last) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_ready(0, s));
+            }
+          }
+        }
+        b = bn; t = tn;
+      }
+    } else
     for (int tile = blockIdx.x; tile < n_live && ok; tile += gridDim.x, ++it) {
       const long long tp0 = timing ? clock64() : 0;
       int b, mt;

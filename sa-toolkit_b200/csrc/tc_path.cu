@@ -370,7 +370,7 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   auto need = [&](int ms, int slots) {
     const size_t rows = (size_t)ms * 128 + 2 * tc::kChainPad;
     return 2 * rows * (size_t)C * 2 + slots * stage + (size_t)tc::kChainMaxConvs * C * 4 +
-           (32 + 2 * tc::kChainMaxSlots) * 8 + 16 + 1024;
+           (40 + 2 * tc::kChainMaxSlots) * 8 + 16 + 1024;
   };
   if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;          // instantiated tap counts
   // C = 64: 3 sub-tiles with 8 epilogue warps each (an epilogue then fits inside one sub-tile's MMA time) and as
@@ -386,7 +386,7 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   return true;
 }
 
-template <int C, int MS, int K, int WPS>
+template <int C, int MS, int K, int WPS, bool RT = false>
 cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaStream_t st) {
   static bool attr_set[16] = {false};
   static int occ_cache[16] = {0};
@@ -395,13 +395,13 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
   cudaGetDevice(&dev);
   dev &= 15;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
+    cudaError_t e = cudaFuncSetAttribute(tc::resblock_chain_kernel<C, MS, K, WPS, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
     int occ = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K, WPS>, tc::chain_threads(MS, WPS), smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::resblock_chain_kernel<C, MS, K, WPS, RT>, tc::chain_threads(MS, WPS), smem);
     if (e != cudaSuccess) return e;
     constexpr int need = 2 * MS * C;
     constexpr int cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -409,7 +409,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
     occ_smem[dev] = smem;
   }
   const int ctas = std::max(1, std::min(p.total_tiles, n_sm * occ_cache[dev]));
-  tc::resblock_chain_kernel<C, MS, K, WPS><<<ctas, tc::chain_threads(MS, WPS), smem, st>>>(p);
+  tc::resblock_chain_kernel<C, MS, K, WPS, RT><<<ctas, tc::chain_threads(MS, WPS), smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -865,14 +865,22 @@ struct Runner {
     p.slope_out = e.slope_out; p.n_blocks = e.n_blocks;
     mark(tag);
     cudaError_t ce = cudaErrorInvalidValue;
+    // C = 64: residual in tensor memory + pipelined tile boundary (chain_tc.cuh, RT); SATOOLS_B200_GROUP=0 / SATOOLS_B200_CHAIN_RT=0
+    // keep the form that is bit-identical to the per-layer path
+    static const int chain_rt = getenv("SATOOLS_B200_CHAIN_RT") ? atoi(getenv("SATOOLS_B200_CHAIN_RT")) : 1;
+    const bool rt = chain_rt && g_use_group && ch.c == 64;
 #define SA_CHAIN(CC, MM, KK, WW) \
     if (ch.c == CC && pl.ms == MM && ch.k == KK && pl.wps == WW) ce = launch_chain<CC, MM, KK, WW>(p, pl.smem, a.n_sm, a.stream);
-    SA_CHAIN(64, 3, 3, 8) SA_CHAIN(64, 3, 7, 8) SA_CHAIN(64, 3, 11, 8)
+#define SA_CHAIN_RT(CC, MM, KK, WW) \
+    if (ch.c == CC && pl.ms == MM && ch.k == KK && pl.wps == WW)          \
+      ce = rt ? launch_chain<CC, MM, KK, WW, true>(p, pl.smem, a.n_sm, a.stream) : launch_chain<CC, MM, KK, WW>(p, pl.smem, a.n_sm, a.stream);
+    SA_CHAIN_RT(64, 3, 3, 8) SA_CHAIN_RT(64, 3, 7, 8) SA_CHAIN_RT(64, 3, 11, 8)
     SA_CHAIN(32, 6, 3, 4) SA_CHAIN(32, 6, 7, 4) SA_CHAIN(32, 6, 11, 4)
     SA_CHAIN(16, 6, 3, 4) SA_CHAIN(16, 6, 7, 4) SA_CHAIN(16, 6, 11, 4)
     SA_CHAIN(32, 3, 3, 4) SA_CHAIN(32, 3, 7, 4) SA_CHAIN(32, 3, 11, 4)
     SA_CHAIN(16, 3, 3, 4) SA_CHAIN(16, 3, 7, 4) SA_CHAIN(16, 3, 11, 4)
 #undef SA_CHAIN
+#undef SA_CHAIN_RT
     if (ce != cudaSuccess) return msgf("resblock_chain launch: %s", cudaGetErrorString(ce));
     ++*launches;
     *done = true;
