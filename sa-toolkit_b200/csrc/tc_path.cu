@@ -1338,7 +1338,20 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
           return "grouped ResBlock launch failed";
         }
         // SATOOLS_B200_SPLIT: bit 0 = split the k = 11 blocks, bit 1 = also the k = 7 blocks
-        static const int split = getenv("SATOOLS_B200_SPLIT") ? atoi(getenv("SATOOLS_B200_SPLIT")) : 1;
+        // bit 2 = the k = 11 blocks as three launches (one pair each).  With the pipelined tile boundary of the RT kernel a short
+        // launch no longer pays for its boundaries, so less recomputed halo wins: k = 7 split 1.71 -> 1.62 ms (same-box A/B).
+        static const int split = getenv("SATOOLS_B200_SPLIT") ? atoi(getenv("SATOOLS_B200_SPLIT")) : 3;
+        if (all_fused && ch.n_convs == 6 && (split & 4) && ch.k == 11 && !tap_here && !last_stage && run.chain_usable(ch, L)) {
+          float* TMP32 = reinterpret_cast<float*>(AX16);        // AX16 + A16 are dead in a fully fused stage; so is R32 here
+          Epi mid;
+          mid.flags = tc::EPI_OUT32; mid.out32 = TMP32;
+          if ((err = run.chain(ch, X32, L, mid, tag, &done, 0, 2))) return err;
+          mid.out32 = R32;
+          if (done && (err = run.chain(ch, TMP32, L, mid, tag, &done, 2, 4))) return err;
+          if (done && (err = run.chain(ch, R32, L, fin, tag, &done, 4, 6))) return err;
+          if (done) continue;
+          return "split ResBlock launch failed";
+        }
         if (all_fused && ch.n_convs == 6 && (((split & 1) && ch.k == 11) || ((split & 2) && ch.k == 7)) && run.chain_usable(ch, L)) {
           // two launches (pairs 0-1 | pair 2): 30 instead of 60 halo rows per side, one extra fp32 round trip
           float* TMP32 = reinterpret_cast<float*>(AX16);        // AX16 + A16 are dead in a fully fused stage
