@@ -360,11 +360,11 @@ cudaError_t dispatch(int n, int msub, int pw, const tc::ConvParams& p, int grid_
 }
 
 // ---- fused ResBlock (chain) launch -------------------------------------------------------
-int g_chain_ms_narrow = 6;      // sub-tiles per CTA for C <= 32 (SATOOLS_B200_CHAIN_MS=3 -> two CTAs per SM)
+// tc_context::chain_ms_narrow: sub-tiles per CTA for C <= 32 (SATOOLS_B200_CHAIN_MS=3 -> two CTAs per SM)
 
 struct ChainPlan { int ms, wps, n_slots; size_t smem; };
 
-bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
+bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem, int ms_narrow) {
   const int C = ch.c;
   const size_t stage = (size_t)ch.k16_per_stage * C * 32;
   auto need = [&](int ms, int slots) {
@@ -375,7 +375,7 @@ bool chain_plan(ChainPlan& pl, const tc_chain& ch, int max_smem) {
   if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;          // instantiated tap counts
   // C = 64: 3 sub-tiles with 8 epilogue warps each (an epilogue then fits inside one sub-tile's MMA time) and as
   // many weight-tap slots as shared memory allows (>= K); C <= 32: 6 sub-tiles, 4 warps each, 2 whole-conv slots.
-  const int ms = (C == 64) ? 3 : g_chain_ms_narrow;
+  const int ms = (C == 64) ? 3 : ms_narrow;
   const int wps = (C == 64) ? 8 : 4;
   int slots = ch.stages_per_conv == 1 ? 2 : ch.stages_per_conv;
   if (need(ms, slots) > (size_t)max_smem) return false;
@@ -414,7 +414,7 @@ cudaError_t launch_chain(const tc::ChainParams& p, size_t smem, int n_sm, cudaSt
 }
 
 // ---- whole-stage fused launch (three ResBlocks in one kernel, C <= 32) -------------------------
-int g_use_chain3 = 1;           // SATOOLS_B200_CHAIN3=0 falls back to one fused kernel per ResBlock
+// tc_context::use_chain3: SATOOLS_B200_CHAIN3=0 falls back to one fused kernel per ResBlock
 
 template <int C, int MS>
 cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cudaStream_t st) {
@@ -433,7 +433,7 @@ cudaError_t launch_chain3(const tc::Chain3Params& p, size_t smem, int n_sm, cuda
 }
 
 // ---- grouped (block-Toeplitz) fused ResBlock for C <= 32 (chain_group_tc.cuh) -------------------
-int g_use_group = 1;            // SATOOLS_B200_GROUP=0: C <= 32 on the per-tap kernels (chain_tc / chain3_tc)
+// tc_context::use_group: SATOOLS_B200_GROUP=0: C <= 32 on the per-tap kernels (chain_tc / chain3_tc), C = 64 without RT
 
 template <int C, bool BF16, int NS, int MS>
 cudaError_t launch_group(const tc::GroupParams& p, size_t smem, int n_sm, cudaStream_t st) {
@@ -679,7 +679,7 @@ struct Runner {
   // The three ResBlocks of a stage in one kernel (chain3_tc.cuh); *done = false: run them one by one instead.
   const char* chain3(const tc_chain* ch, int nrb, const float* x32, int L, const Epi& e, int tag, bool* done) {
     *done = false;
-    if (!g_use_chain3 || nrb != 3 || !ch[0].d_w || !ch[1].d_w || !ch[2].d_w) return nullptr;
+    if (!ctx.use_chain3 || nrb != 3 || !ch[0].d_w || !ch[1].d_w || !ch[2].d_w) return nullptr;
     const int C = ch[0].c;
     if ((C != 16 && C != 32) || ch[0].k != 3 || ch[1].k != 7 || ch[2].k != 11) return nullptr;
     // C = 32: three per-ResBlock launches (6 sub-tiles each, the k = 11 block split in two) recompute 14 % halo rows
@@ -723,7 +723,7 @@ struct Runner {
   // Grouped kernel geometry for convs [c0, c1) of a block: halo (multiple of G), valid positions per tile, ring depth.
   struct GroupPlan { int halo, valid, n_wstages, ns, ms; size_t smem; };
   bool group_plan(GroupPlan& pl, const tc_chain& ch, int L, int c0, int c1) const {
-    if (!g_use_group || !ch.d_wg || (c0 & 1) || ((c1 - c0) & 1) || c1 <= c0) return false;
+    if (!ctx.use_group || !ch.d_wg || (c0 & 1) || ((c1 - c0) & 1) || c1 <= c0) return false;
     if (ch.k != 3 && ch.k != 7 && ch.k != 11) return false;                  // slice counts the MMA issue loop is instantiated for
     // Two streams of two sub-tiles: 1024 positions per tile for C = 16, 512 for C = 32.  (Four streams of one sub-tile for
     // C = 16 measured slower, 4.67 vs 4.13 ms for stage 4 -- twice the halo share, and the streams run in lockstep on one
@@ -740,7 +740,7 @@ struct Runner {
     // Little work (single short utterances, the latency path): every launch pays its fixed set-up (zeroing 140 KB of shared
     // memory, barriers, TMEM) and a stage is three launches here instead of one stage_chain3 launch; measured on a 5 s
     // utterance: 1.26 ms grouped vs 0.97 ms per-tap.  SATOOLS_B200_GROUP_MIN_TILES overrides the threshold (tests: 0).
-    static const int min_tiles_env = getenv("SATOOLS_B200_GROUP_MIN_TILES") ? atoi(getenv("SATOOLS_B200_GROUP_MIN_TILES")) : -1;
+    const int min_tiles_env = getenv("SATOOLS_B200_GROUP_MIN_TILES") ? atoi(getenv("SATOOLS_B200_GROUP_MIN_TILES")) : -1;
     const int min_tiles = min_tiles_env >= 0 ? min_tiles_env : 2 * pl.ns * a.n_sm;
     if (((L + pl.valid - 1) / pl.valid) * a.B < min_tiles) return false;
     const size_t fixed = 2 * (size_t)pl.ns * tc::grp_buf_bytes(pl.ms) + tc::kGrpOnesBytes +
@@ -816,7 +816,7 @@ struct Runner {
     // per row and stream).  Default: the half-row mapping for both -- measured on one box after the issue loops went
     // uniform (stage 3: 4.25 vs 4.42-4.55 ms; v1 still wins the k = 3 block, 0.85 vs 0.93 ms, and loses k = 11, 2.25-2.33 vs
     // 2.02 ms).  The two kernels lay the running sum out differently, so a stage never mixes them.
-    static const int v1_mask = getenv("SATOOLS_B200_GROUP_V1") ? atoi(getenv("SATOOLS_B200_GROUP_V1")) : 0;
+    const int v1_mask = getenv("SATOOLS_B200_GROUP_V1") ? atoi(getenv("SATOOLS_B200_GROUP_V1")) : 0;
     const bool v1 = (v1_mask & (ch.c == 16 ? 1 : 2)) != 0;
 #define SA_GROUP(CC, NN, MM)                                                                                          \
     if (ch.c == CC && pl.ns == NN)                                                                                    \
@@ -832,7 +832,7 @@ struct Runner {
 
   bool chain_usable(const tc_chain& ch, int L) const {
     ChainPlan pl;
-    if (!ch.d_w || !chain_plan(pl, ch, ctx.max_smem)) return false;
+    if (!ch.d_w || !chain_plan(pl, ch, ctx.max_smem, ctx.chain_ms_narrow)) return false;
     return L >= 2 * (pl.ms * 128 - 2 * ch.halo);                // short sequences: the per-layer path wastes less
   }
 
@@ -840,7 +840,7 @@ struct Runner {
   const char* chain(const tc_chain& ch, const float* x32, int L, const Epi& e, int tag, bool* done, int c0 = 0, int c1 = -1) {
     *done = false;
     ChainPlan pl;
-    if (!chain_usable(ch, L) || !chain_plan(pl, ch, ctx.max_smem)) return nullptr;
+    if (!chain_usable(ch, L) || !chain_plan(pl, ch, ctx.max_smem, ctx.chain_ms_narrow)) return nullptr;
     if (c1 < 0) c1 = ch.n_convs;
     int halo = 0;
     for (int c = c0; c < c1; ++c) halo += ch.pad[c];
@@ -867,8 +867,8 @@ struct Runner {
     cudaError_t ce = cudaErrorInvalidValue;
     // C = 64: residual in tensor memory + pipelined tile boundary (chain_tc.cuh, RT); SATOOLS_B200_GROUP=0 / SATOOLS_B200_CHAIN_RT=0
     // keep the form that is bit-identical to the per-layer path
-    static const int chain_rt = getenv("SATOOLS_B200_CHAIN_RT") ? atoi(getenv("SATOOLS_B200_CHAIN_RT")) : 1;
-    const bool rt = chain_rt && g_use_group && ch.c == 64;
+    const int chain_rt = getenv("SATOOLS_B200_CHAIN_RT") ? atoi(getenv("SATOOLS_B200_CHAIN_RT")) : 1;
+    const bool rt = chain_rt && ctx.use_group && ch.c == 64;
 #define SA_CHAIN(CC, MM, KK, WW) \
     if (ch.c == CC && pl.ms == MM && ch.k == KK && pl.wps == WW) ce = launch_chain<CC, MM, KK, WW>(p, pl.smem, a.n_sm, a.stream);
 #define SA_CHAIN_RT(CC, MM, KK, WW) \
@@ -1126,11 +1126,12 @@ const char* tc_init(tc_context& ctx, int device) {
     const uint32_t v = (uint32_t)atoi(env);
     TC_CUDA(cudaMemcpyToSymbol(tc::g_mbar_suspend_ns, &v, sizeof(v)));
   }
-  if (const char* env = getenv("SATOOLS_B200_CHAIN3")) g_use_chain3 = atoi(env);
-  if (const char* env = getenv("SATOOLS_B200_GROUP")) g_use_group = atoi(env);
+  ctx.use_chain3 = getenv("SATOOLS_B200_CHAIN3") ? atoi(getenv("SATOOLS_B200_CHAIN3")) : 1;
+  ctx.use_group = getenv("SATOOLS_B200_GROUP") ? atoi(getenv("SATOOLS_B200_GROUP")) : 1;
+  ctx.chain_ms_narrow = 6;
   if (const char* env = getenv("SATOOLS_B200_CHAIN_MS")) {
     const int v = atoi(env);
-    if (v == 3 || v == 6) g_chain_ms_narrow = v;
+    if (v == 3 || v == 6) ctx.chain_ms_narrow = v;
   }
   ctx.ready = true;
   return nullptr;
@@ -1260,7 +1261,8 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     // Grouped stages with a k = 4 / stride 2 upsampler run the transposed conv inside the grouped kernel (fuse_up): no
     // upsampler launch and no fp32 stage input in HBM.  The stage then reads Pcur while it writes its own 16-bit output, so
     // that goes to the other buffer.  SATOOLS_B200_GROUP_UP=0 keeps the separate upsampler launch.
-    static const int group_up = getenv("SATOOLS_B200_GROUP_UP") ? atoi(getenv("SATOOLS_B200_GROUP_UP")) : 1;
+    // (the variant switches are read per call, not once per process: a new handle / the tests can change them)
+    const int group_up = getenv("SATOOLS_B200_GROUP_UP") ? atoi(getenv("SATOOLS_B200_GROUP_UP")) : 1;
     bool fuse_up = false;
     if (stage_grouped && group_up && a.upg && a.upg[i].d_w) {
       Runner::GroupPlan gp;
@@ -1291,7 +1293,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
     // in L2, 2.5 GB instead of 7.3 GB of DRAM traffic per stage) -- bit 0: C = 16, bit 1: C = 32.  All chains then share the
     // widest halo (60 positions).  Measured: C = 16 (1024-position tiles) 4.00 vs 3.96 ms; C = 32 (512-position tiles: 23 %
     // halo for every chain) 4.94 vs 4.80 ms, so C = 32 keeps one launch per ResBlock.  SATOOLS_B200_GROUP_STAGE overrides.
-    static const int group_stage = getenv("SATOOLS_B200_GROUP_STAGE") ? atoi(getenv("SATOOLS_B200_GROUP_STAGE")) : 1;
+    const int group_stage = getenv("SATOOLS_B200_GROUP_STAGE") ? atoi(getenv("SATOOLS_B200_GROUP_STAGE")) : 1;
     if (stage_grouped && (group_stage & (up.cout == 16 ? 1 : 2)) && nrb > 1 && nrb <= tc::kGrpMaxChains) {
       Epi fin;
       fin.sum32 = S32; fin.n_blocks = (float)nrb;
@@ -1340,7 +1342,7 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
         // SATOOLS_B200_SPLIT: bit 0 = split the k = 11 blocks, bit 1 = also the k = 7 blocks
         // bit 2 = the k = 11 blocks as three launches (one pair each).  With the pipelined tile boundary of the RT kernel a short
         // launch no longer pays for its boundaries, so less recomputed halo wins: k = 7 split 1.71 -> 1.62 ms (same-box A/B).
-        static const int split = getenv("SATOOLS_B200_SPLIT") ? atoi(getenv("SATOOLS_B200_SPLIT")) : 3;
+        const int split = getenv("SATOOLS_B200_SPLIT") ? atoi(getenv("SATOOLS_B200_SPLIT")) : 3;
         if (all_fused && ch.n_convs == 6 && (split & 4) && ch.k == 11 && !tap_here && !last_stage && run.chain_usable(ch, L)) {
           float* TMP32 = reinterpret_cast<float*>(AX16);        // AX16 + A16 are dead in a fully fused stage; so is R32 here
           Epi mid;

@@ -57,6 +57,8 @@ struct tc_upgroup {
 };
 
 struct tc_context {
+  // kernel-family switches of THIS handle, read from the environment in tc_init (SATOOLS_B200_GROUP / _CHAIN3 / _CHAIN_MS)
+  int use_group = 1, use_chain3 = 1, chain_ms_narrow = 6;
   std::vector<tc_tmap_entry> tmaps;
   bool ready = false;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled

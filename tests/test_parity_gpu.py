@@ -297,10 +297,12 @@ def test_config5_corpus_sharding_covers_and_matches_single_item_runs():
 
 
 def test_fused_and_per_layer_paths_agree():
-    """The per-tap fused kernels (C = 64) perform the per-layer arithmetic in the same order: bit-identical.  The grouped
-    kernels (C <= 32, chain_group_tc.cuh) keep the residual stream in tensor memory and let conv2 accumulate onto it, so
-    their fp32 sums are associated differently (last-bit differences that occasionally flip a 16-bit rounding): the two
-    paths must agree far below the fp16 operand noise (73 dB vs the truth)."""
+    """The per-tap fused kernels with the residual in registers (SATOOLS_B200_GROUP=0) perform the per-layer arithmetic in
+    the same order: bit-identical.  The default kernels keep the residual stream in tensor memory and let conv2 accumulate
+    onto it (C = 64: chain_tc.cuh RT; C <= 32: chain_group_tc.cuh, bias inside the MMA), so their fp32 sums are associated
+    differently; with random-init weights the generator amplifies such last-bit differences to the level of the fp16
+    operand noise itself (either path is 73 dB from the fp64 truth, they are ~75 dB from each other), so the bar between two
+    paths is 65 dB while each path is held to the truth by the golden / oracle tests."""
     _need_gpu()
     x = conditioning.batch(12, [64, 50])
 
@@ -323,8 +325,45 @@ def test_fused_and_per_layer_paths_agree():
     y_default = fresh({})
     np.testing.assert_array_equal(y_pertap, y_layer)
     snr = helpers.snr_db(y_layer, y_default)
-    print(f"grouped kernels vs per-layer path: SNR {snr:.1f} dB, max-abs {helpers.max_abs(y_layer, y_default):.2e}")
-    assert snr >= 90.0
+    print(f"default kernels vs per-layer path: SNR {snr:.1f} dB, max-abs {helpers.max_abs(y_layer, y_default):.2e}")
+    assert snr >= 65.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [
+    {"SATOOLS_B200_GROUP_V1": "3"},        # first epilogue mapping of the grouped kernels (chain_group_v1_tc.cuh)
+    {"SATOOLS_B200_GROUP_STAGE": "3"},     # C = 32 as one whole-stage launch
+    {"SATOOLS_B200_GROUP_UP": "0"},        # separate upsampler launches for the grouped stages
+    {"SATOOLS_B200_CHAIN_RT": "0"},        # C = 64 with the residual in registers (the bit-identical form)
+    {"SATOOLS_B200_SPLIT": "7"},           # k = 11 blocks of C = 64 as three launches
+    {"SATOOLS_B200_SPLIT": "0"},           # no split launches
+])
+def test_kernel_variants_agree_with_the_per_layer_path(env):
+    """Every selectable kernel variant of the narrow stages computes the same network: against the per-layer path
+    (one conv per launch) they agree at the level of the fp16 operand noise (see test_fused_and_per_layer_paths_agree)."""
+    _need_gpu()
+    x = conditioning.batch(12, [64, 50])
+
+    def fresh(e):
+        e = dict(e, SATOOLS_B200_GROUP_MIN_TILES="0")             # small input: dispatch the grouped kernels anyway
+        old = {k: os.environ.get(k) for k in e}
+        os.environ.update(e)
+        try:
+            g = copy.deepcopy(helpers.seeded_generator(0)).to("cuda:0")
+            g.precision = "fp16"
+            return run(g, x)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = v
+
+    y_layer = fresh({"SATOOLS_B200_FUSED": "0"})
+    y = fresh(env)
+    snr = helpers.snr_db(y_layer, y)
+    print(f"{env}: SNR vs per-layer path {snr:.1f} dB, max-abs {helpers.max_abs(y_layer, y):.2e}")
+    assert np.isfinite(y).all() and snr >= 65.0
 
 
 def test_host_entry_two_stream_split_equals_device_entry():
