@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra configs, the eager-GPU leg and the corpus leg")
     ap.add_argument("--sustain-seconds", type=float, default=5.0)
-    ap.add_argument("--corpus-hours", type=float, default=100.0)
+    ap.add_argument("--corpus-hours", type=float, default=300.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

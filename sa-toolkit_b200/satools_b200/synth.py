@@ -18,6 +18,7 @@ x = [BN | F0 | speaker] (hifigan.py:83-97) or the compact form (VQFeatures: code
 """
 from __future__ import annotations
 
+import os
 import time
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
@@ -98,11 +99,15 @@ def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_s
                       out_dtype: torch.dtype = torch.int16, device: Optional[str] = None,
                       original_len: Optional[Dict[str, int]] = None,
                       sink: Optional[Callable[[str, np.ndarray], None]] = None,
-                      stats: Optional[dict] = None, staging_threads: int = 2) -> Dict[str, np.ndarray]:
+                      stats: Optional[dict] = None, staging_threads: Optional[int] = None) -> Dict[str, np.ndarray]:
     """gen: satools_b200.CoreHifiGan on a CUDA device (set_codebook() done when feats holds VQFeatures).
     feats: utterance id -> float32 [Cin, frames] or VQFeatures.  Returns utterance id -> waveform [samples] for the
     utterances of this rank (empty when `sink` consumes them).  out_dtype: torch.int16 (PCM16, default), float16, float32."""
     t_start = time.perf_counter()
+    if staging_threads is None:
+        # dense fp32 features are ~100 MB per batch: one copying thread moves ~5 GB/s, and with 8 ranks on one host the
+        # staging of a batch (21 ms) was longer than its GPU step (10.5 ms); the items of a batch are copied by up to 4 threads
+        staging_threads = max(2, min(4, (os.cpu_count() or 8) // max(1, world_size) - 1))
     ids = sorted(feats)
     lengths = [_frames(feats[u]) for u in ids]
     mine = scheduler.shard(lengths, world_size)[rank]
@@ -167,13 +172,24 @@ def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_s
             view = (idx, f0, spk)
         else:
             x = slabs.x[s][:B * cin * T].view(B, cin, T)
-            for b, (i, rlo, rhi, _, _) in enumerate(items):
-                src = torch.from_numpy(feats[ids[i]])
-                n = rhi - rlo
-                x[b, :, :n] = src[:, rlo:rhi]
-                if n < T:
-                    x[b, :N_BN_F0, n:] = 0.0
-                    x[b, N_BN_F0:, n:] = src[N_BN_F0:, rhi - 1:rhi]
+
+            def copy_items(b0: int, b1: int):
+                for b in range(b0, b1):
+                    i, rlo, rhi, _, _ = items[b]
+                    src = torch.from_numpy(feats[ids[i]])
+                    n = rhi - rlo
+                    x[b, :, :n] = src[:, rlo:rhi]
+                    if n < T:
+                        x[b, :N_BN_F0, n:] = 0.0
+                        x[b, N_BN_F0:, n:] = src[N_BN_F0:, rhi - 1:rhi]
+
+            n_par = min(staging_threads, B)
+            if n_par > 1:                                  # the items of one batch, copied by several threads
+                cuts = [B * j // n_par for j in range(n_par + 1)]
+                for fu in [copy_pool.submit(copy_items, cuts[j], cuts[j + 1]) for j in range(n_par)]:
+                    fu.result()
+            else:
+                copy_items(0, B)
             view = (x,)
         return view, time.perf_counter() - t0
 
@@ -214,7 +230,8 @@ def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_s
         st["collect_s"] += time.perf_counter() - t1
 
     pipe = HostPipeline(gen, depth=2, device=dev)
-    pool = ThreadPoolExecutor(max_workers=max(1, staging_threads))
+    pool = ThreadPoolExecutor(max_workers=2)                       # two batches staged ahead
+    copy_pool = ThreadPoolExecutor(max_workers=max(1, staging_threads))
     try:
         futures = {k: pool.submit(stage, k) for k in range(min(2, len(plan)))}
         pending: Optional[Tuple[int, int]] = None
@@ -239,6 +256,7 @@ def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_s
         pipe.drain()
     finally:
         pool.shutdown(wait=True)
+        copy_pool.shutdown(wait=True)
     st["h2d_bytes"], st["d2h_bytes"], st["gpu_launches"] = pipe.h2d_bytes, pipe.d2h_bytes, pipe.launches
     st["seconds"] = time.perf_counter() - t_start
     if stats is not None:
