@@ -183,7 +183,7 @@ def synthesize_corpus(gen, feats: Dict[str, Features], *, rank: int = 0, world_s
                         x[b, :N_BN_F0, n:] = 0.0
                         x[b, N_BN_F0:, n:] = src[N_BN_F0:, rhi - 1:rhi]
 
-            n_par = min(staging_threads, B)
+            n_par = min(staging_threads, B) if B * T * cin * 4 >= (32 << 20) else 1     # small batches: the hand-over costs more
             if n_par > 1:                                  # the items of one batch, copied by several threads
                 cuts = [B * j // n_par for j in range(n_par + 1)]
                 for fu in [copy_pool.submit(copy_items, cuts[j], cuts[j + 1]) for j in range(n_par)]:
