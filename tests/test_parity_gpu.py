@@ -366,6 +366,35 @@ def test_kernel_variants_agree_with_the_per_layer_path(env):
     assert np.isfinite(y).all() and snr >= 65.0
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("frames", [[51], [77, 33, 20], [129, 128, 127, 1, 64]])
+def test_grouped_and_rt_kernels_on_odd_shapes_against_the_oracle(frames, precision):
+    """The grouped (C <= 32) and RT (C = 64) kernels are dispatched only when a launch has enough tiles; with the threshold
+    lifted they run on small, odd and ragged shapes too (partial 32-row blocks of the private sum layout, tiles that end
+    inside an item, items shorter than one tile): padded and ragged runs against the fp64 oracle."""
+    _need_gpu()
+    old = os.environ.get("SATOOLS_B200_GROUP_MIN_TILES")
+    os.environ["SATOOLS_B200_GROUP_MIN_TILES"] = "0"
+    try:
+        gen = copy.deepcopy(helpers.seeded_generator(0)).to("cuda:0")
+        gen.precision = precision
+        x = conditioning.batch(21, frames)
+        ref = otc.generator_forward(otc.fold(helpers.seeded_generator(0).state_dict(), torch.float64),
+                                    torch.from_numpy(x).double()).numpy()
+        y = run(gen, x)
+        check(ref, y, precision, f"padded {frames}")
+        yr = run(gen, x, frames_per_item=frames)
+        for b, f in enumerate(frames):
+            n = 320 * f + 1
+            np.testing.assert_array_equal(yr[b, 0, :n], y[b, 0, :n])
+        gen.release()
+    finally:
+        if old is None:
+            del os.environ["SATOOLS_B200_GROUP_MIN_TILES"]
+        else:
+            os.environ["SATOOLS_B200_GROUP_MIN_TILES"] = old
+
+
 def test_host_entry_two_stream_split_equals_device_entry():
     """sa_hifigan_synthesize_host cuts batches of >= 8 items into two halves on two streams; the result is the
     same as one device-resident forward."""
