@@ -433,7 +433,9 @@ __device__ __forceinline__ void quad_transpose(uint4 (&a)[4], int j) {
 // ---------------------------------------------------------------------------------------
 template <int N, int MSUB, int COLS, typename WaitAcc>
 __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_s, uint32_t tmem_acc, int b, int m0, int phase,
-                                         int ntile, int lg, int lane, int col0, bool dummy, WaitAcc&& wait_acc) {
+                                         int ntile, int lg, int lane, int col0, bool dummy, WaitAcc&& wait_acc, int j_lo = 0,
+                                         int j_hi = 0x7fffffff) {
+  // j_lo / j_hi: only tile rows [j_lo, j_hi) are stored (resblock_pair_tc.cuh: the edge rows of a fused tile are not valid)
   constexpr int kGroups = COLS / 16;
   constexpr int U = MSUB * kGroups;
   constexpr bool kQuadStores = (kGroups % 2 == 0);
@@ -462,7 +464,8 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
   uint4 pk[kQuadStores ? 4 : 1];
   auto fetch_res = [&](int u, float4 (&q)[4]) {
     const int ms = u / kGroups, g = u % kGroups;
-    if (!has_res || dummy || t0 + ms * 128 >= m_rows) return;
+    const int j = ms * 128 + lg * 32 + lane;
+    if (!has_res || dummy || t0 + ms * 128 >= m_rows || j < j_lo || j >= j_hi) return;
     const float* a0 = p.res32 + base32 + ms * ms_step32 + (size_t)(2 * g) * plane;
     const float* a1 = a0 + plane;
     ldg_f8(a0, q[0], q[1]);
@@ -476,7 +479,8 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
   for (int u = 0; u < U; ++u) {
     const int ms = u / kGroups, g = u % kGroups;
     const int t = t0 + ms * 128;
-    const bool valid = t < m_rows;
+    const int jrow = ms * 128 + lg * 32 + lane;
+    const bool valid = t < m_rows && jrow >= j_lo && jrow < j_hi;
     uint32_t r[16];
     __syncwarp();                                            // tcgen05.ld is .sync.aligned
     tmem_ld16(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ms * N + col0 + g * 16), r);
@@ -530,7 +534,8 @@ __device__ __forceinline__ bool epi_tile(const ConvParams& p, const float* bias_
                        (size_t)(cg & 7) * 16;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (tq + k < m_rows) *reinterpret_cast<uint4*>(o + (size_t)k * out_stride * 128) = pk[k];
+            if (tq + k < m_rows && jrow - j4 + k >= j_lo && jrow - j4 + k < j_hi)
+              *reinterpret_cast<uint4*>(o + (size_t)k * out_stride * 128) = pk[k];
         }
       } else if (valid) {
         const int cg = chunk0 + g * 2;                       // even chunk; cg and cg + 1 share a panel row

@@ -13,6 +13,7 @@
 #include "tc_path.cuh"
 #include "conv_tc.cuh"
 #include "conv_pair_tc.cuh"
+#include "resblock_pair_tc.cuh"
 #include "chain_tc.cuh"
 #include "chain3_tc.cuh"
 #include "chain_group_tc.cuh"
@@ -541,6 +542,40 @@ cudaError_t dispatch_pair(int n, int msub, const tc::ConvParams& p, int grid_y, 
   return cudaErrorInvalidValue;
 }
 
+// ---- fused conv1 -> conv2 pair of a C = 128 ResBlock on CTA pairs (resblock_pair_tc.cuh) ----
+cudaError_t launch_pair_fused(const tc::PairFuseParams& q, size_t smem, int n_sm, cudaStream_t st) {
+  static bool attr_set[16] = {false};
+  static int max_clusters[16] = {0};
+  static size_t mc_smem[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc::resblock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kStaticSmemReserve);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(tc::kPfThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0 || mc_smem[dev] != smem) {
+    cfg.gridDim = dim3(2 * (unsigned)n_sm, 1, 1);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, tc::resblock_pair_kernel, &cfg) != cudaSuccess || nc < 1) nc = n_sm / 2 - 4;
+    max_clusters[dev] = nc;
+    mc_smem[dev] = smem;
+  }
+  const int pairs = std::max(1, std::min((q.c2.total_tiles + 1) / 2, max_clusters[dev]));
+  cfg.gridDim = dim3(2 * (unsigned)pairs, 1, 1);
+  return cudaLaunchKernelEx(&cfg, tc::resblock_pair_kernel, q);
+}
+
 struct Epi {
   uint32_t flags = 0;
   const float* res32 = nullptr;
@@ -671,6 +706,96 @@ struct Runner {
                             : dispatch(w.n, pl.msub, pw, p, w.n_phases * w.n_tiles, pl.smem, a.n_sm, a.stream);
     if (ce != cudaSuccess) return msgf("conv_tc launch: %s", cudaGetErrorString(ce));
     ++*launches;
+    return nullptr;
+  }
+
+  // conv1 -> lrelu -> conv2 (+ residual and the epilogue streams of conv2) of one dilation step of a C = 128 ResBlock in ONE
+  // launch (resblock_pair_tc.cuh; nn.py:169-174).  *done = false: the caller runs the two convs one after the other.
+  // SATOOLS_B200_PAIR_FUSE=0 switches it off (read per call, like the other variant switches); so does the per-layer mode
+  // (SATOOLS_B200_FUSED=0: a.chains == nullptr).
+  const char* pair_fused(const tc_layer& l1, const tc_layer& l2, const void* in16, int L, const Epi& e, int tag, bool* done) {
+    *done = false;
+    const int on = getenv("SATOOLS_B200_PAIR_FUSE") ? atoi(getenv("SATOOLS_B200_PAIR_FUSE")) : 1;
+    const tc_weights& w1 = *l1.w;
+    const tc_weights& w2 = *l2.w;
+    if (!on || !a.chains || !w1.pair || !w2.pair || w1.n != 128 || w2.n != 128 || w1.n_tiles != 1 || w2.n_tiles != 1) return nullptr;
+    if (w1.cin_pad != 128 || w2.cin_pad != 128 || l1.cout != 128 || l2.cout != 128 || l1.transposed || l2.transposed) return nullptr;
+    const int k = l1.k;
+    // k = 11: the two per-conv launches win (0.545 vs 0.58 ms per step at 64 x 15 s): 7.8 % of both convs is recomputed halo
+    // and conv1 alone already runs at the tensor peak.  SATOOLS_B200_PAIR_FUSE_KMAX moves the limit.
+    const int kmax = getenv("SATOOLS_B200_PAIR_FUSE_KMAX") ? atoi(getenv("SATOOLS_B200_PAIR_FUSE_KMAX")) : 7;
+    if (k > kmax) return nullptr;
+    if (l2.k != k || (k & 1) == 0 || k < 3 || (k - 1) / 2 > tc::kPfTPad || l2.dil != 1) return nullptr;
+    if (l1.pad != l1.dil * (k - 1) / 2 || l2.pad != (k - 1) / 2) return nullptr;
+    if (w1.n_taps[0] != k || w2.n_taps[0] != k || w1.tile_bytes != w2.tile_bytes) return nullptr;
+    const int V = tc::kPfRows - (k - 1);
+    if (L < 2 * V) return nullptr;                                 // short inputs: the per-layer launches
+    const int r1 = l1.dil * (k - 1) / 2;
+    const int rows = tc::kPfRows + 2 * r1;
+    const int nseg = (rows + 255) / 256;
+    const int box_rows = (int)align_up((size_t)(rows + nseg - 1) / nseg, 8);
+    if (box_rows > 256) return nullptr;
+    const int rows_alloc = nseg * box_rows;
+    const size_t a_bytes = (size_t)2 * (2 * rows_alloc * 128);    // two buffers of two panels
+    const size_t t_bytes = (size_t)2 * (2 * tc::kPfTRows * 128);   // two buffers of two panels
+    const size_t fixed = 2 * 128 * 4 + (12 + 2 * tc::kMaxStages) * 8 + 16 + 1024;
+    const size_t block_bytes = 64 * 128;                           // one [N/2][64] weight block
+    const int bps = 2;                                             // 16 KB stages; 2 k blocks per conv: whole stages
+    const size_t stage_bytes = bps * block_bytes;
+    if (a_bytes + t_bytes + fixed + 3 * stage_bytes > (size_t)ctx.max_smem) return nullptr;
+    const int stages = (int)std::min<size_t>(tc::kMaxStages, ((size_t)ctx.max_smem - fixed - a_bytes - t_bytes) / stage_bytes);
+    tc::PairFuseParams q;
+    memset(&q, 0, sizeof(q));
+    tc::ConvParams& p = q.c2;
+    const cuuint64_t rb = 128;
+    const cuuint64_t gdim[4] = {64, (cuuint64_t)L, 2, (cuuint64_t)a.B};
+    const cuuint64_t gstr[3] = {rb, (cuuint64_t)L * rb, (cuuint64_t)2 * L * rb};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    CUresult r = tmap(&p.tmap, a.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in16, gdim, gstr, box,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for the fused pair input (L=%d box_rows=%d)", (int)r, L, box_rows);
+      return g_msg;
+    }
+    const cuuint64_t wstr[1] = {128};
+    const cuuint32_t wbox[2] = {64, (cuuint32_t)(bps * 64)};
+    const cuuint64_t wdim1[2] = {64, (cuuint64_t)(w1.bytes / 128)};
+    const cuuint64_t wdim2[2] = {64, (cuuint64_t)(w2.bytes / 128)};
+    r = tmap(&q.wmap1, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w1.d_w, wdim1, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r == CUDA_SUCCESS) r = tmap(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w2.d_w, wdim2, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_msg, sizeof(g_msg), "cuTensorMapEncodeTiled failed (%d) for the fused pair weights", (int)r);
+      return g_msg;
+    }
+    q.bias1 = l1.d_bias;
+    q.k = k; q.dil1 = l1.dil; q.V = V;
+    p.w = w2.d_w;
+    p.bias = l2.d_bias;
+    p.res32 = e.res32; p.out32 = e.out32; p.sum32 = e.sum32; p.out16 = e.out16;
+    p.error_flag = ctx.d_error;
+    p.cin = 128; p.cout_total = 128;
+    p.m_rows = L; p.l_out = L; p.out_stride = 1;
+    p.n_phases = 1; p.n_tiles = 1;
+    p.rows_alloc = rows_alloc; p.box_rows = box_rows; p.nseg = nseg;
+    p.out_pw = 64;
+    p.k16_per_stage = 4 * bps;
+    p.n_wstages = stages;
+    p.m_tiles = (L + V - 1) / V;
+    p.total_tiles = p.m_tiles * a.B;
+    p.map = tile_map(L);
+    p.w_tile_bytes = (uint32_t)w2.tile_bytes;
+    p.flags = e.flags | (a.bf16 ? tc::EPI_BF16 : 0u);
+#ifdef SA_DIAG   // diagnostic builds only: drop epilogue streams to time what each costs (RESULTS ARE WRONG)
+    if (const char* dm = getenv("SATOOLS_B200_DEBUG_EPI_MASK")) p.flags &= ~(uint32_t)strtoul(dm, nullptr, 16);
+#endif
+    p.slope_out = e.slope_out;
+    p.n_blocks = e.n_blocks;
+    const size_t smem = a_bytes + t_bytes + stages * stage_bytes + fixed;
+    mark(tag);
+    cudaError_t ce = launch_pair_fused(q, smem, a.n_sm, a.stream);
+    if (ce != cudaSuccess) return msgf("resblock_pair launch: %s", cudaGetErrorString(ce));
+    ++*launches;
+    *done = true;
     return nullptr;
   }
 
@@ -1367,18 +1492,28 @@ const char* tc_forward(tc_context& ctx, const tc_forward_args& a, int64_t* launc
         if ((err = run.chain(ch, X32, L, fin, tag, &done))) return err;
         if (done) continue;
       }
+      // The fused pair kernel reads its 16-bit input with a halo while other CTAs store this step's 16-bit output, so the
+      // steps of a block alternate between A16 and T16 (the per-layer path needs T16 for conv1's output instead).
+      void* act_in = AX16;
       for (int m = 0; m < nd; ++m) {               // nn.py:169-174
-        Epi e1;
-        e1.flags = tc::EPI_OUT16; e1.out16 = T16; e1.slope_out = 0.1f;
-        if ((err = run.conv(a.layers[L_rb(i, j, 0, m)], m == 0 ? AX16 : A16, L, e1, tag))) return err;
         Epi e2 = (m < nd - 1) ? Epi() : fin;
         e2.flags |= tc::EPI_RES;
         e2.res32 = (m == 0) ? X32 : R32;
+        void* const act_out = (act_in == A16) ? T16 : A16;
         if (m < nd - 1) {
           e2.flags |= tc::EPI_OUT32 | tc::EPI_OUT16;
-          e2.out32 = R32; e2.out16 = A16; e2.slope_out = 0.1f;
+          e2.out32 = R32; e2.out16 = act_out; e2.slope_out = 0.1f;
         }
-        if ((err = run.conv(a.layers[L_rb(i, j, 1, m)], T16, L, e2, tag))) return err;
+        bool done = false;
+        if ((err = run.pair_fused(a.layers[L_rb(i, j, 0, m)], a.layers[L_rb(i, j, 1, m)], act_in, L, e2, tag, &done))) return err;
+        if (done) { act_in = act_out; continue; }
+        void* const tmp16 = (act_in == T16) ? A16 : T16;   // conv1's output; never the buffer this step reads
+        if (m < nd - 1) e2.out16 = (tmp16 == T16) ? A16 : T16;
+        Epi e1;
+        e1.flags = tc::EPI_OUT16; e1.out16 = tmp16; e1.slope_out = 0.1f;
+        if ((err = run.conv(a.layers[L_rb(i, j, 0, m)], act_in, L, e1, tag))) return err;
+        if ((err = run.conv(a.layers[L_rb(i, j, 1, m)], tmp16, L, e2, tag))) return err;
+        if (m < nd - 1) act_in = e2.out16;
       }
     }
     if ((err = unblock_tap(SA_TAP_STAGE0 + i, up.cout, L))) return err;

@@ -337,6 +337,7 @@ def test_fused_and_per_layer_paths_agree():
     {"SATOOLS_B200_CHAIN_RT": "0"},        # C = 64 with the residual in registers (the bit-identical form)
     {"SATOOLS_B200_SPLIT": "7"},           # k = 11 blocks of C = 64 as three launches
     {"SATOOLS_B200_SPLIT": "0"},           # no split launches
+    {"SATOOLS_B200_PAIR_FUSE": "0"},       # C = 128: conv1 and conv2 of a dilation step as two launches
 ])
 def test_kernel_variants_agree_with_the_per_layer_path(env):
     """Every selectable kernel variant of the narrow stages computes the same network: against the per-layer path
@@ -364,6 +365,40 @@ def test_kernel_variants_agree_with_the_per_layer_path(env):
     snr = helpers.snr_db(y_layer, y)
     print(f"{env}: SNR vs per-layer path {snr:.1f} dB, max-abs {helpers.max_abs(y_layer, y):.2e}")
     assert np.isfinite(y).all() and snr >= 65.0
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_fused_pair_kernel_of_the_c128_stage_is_bit_identical_to_two_launches(precision):
+    """resblock_pair_tc.cuh keeps lrelu(conv1) of a C = 128 dilation step in shared memory as conv2's operand: the same
+    MMAs in the same order and the same epilogue arithmetic as the two per-conv launches, so the output is bit-identical
+    (nn.py:169-174).  Items of 40 / 23 / 17 frames: stage 1 has 800 / 460 / 340 rows per item -- several 246..254-row tiles
+    per item, tiles that end inside an item, a ragged run."""
+    _need_gpu()
+    frames = [40, 23, 17]
+    x = conditioning.batch(31, frames)
+
+    def fresh(env, **kw):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            g = copy.deepcopy(helpers.seeded_generator(0)).to("cuda:0")
+            g.precision = precision
+            return run(g, x, **kw)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = v
+
+    y_two = fresh({"SATOOLS_B200_PAIR_FUSE": "0"})
+    y_one = fresh({"SATOOLS_B200_PAIR_FUSE_KMAX": "11"})          # every block of the stage fused (default: k <= 7)
+    np.testing.assert_array_equal(y_one, y_two)
+    np.testing.assert_array_equal(fresh({}), y_two)
+    yr = fresh({"SATOOLS_B200_PAIR_FUSE_KMAX": "11"}, frames_per_item=frames)
+    for b, f in enumerate(frames):
+        n = 320 * f + 1
+        np.testing.assert_array_equal(yr[b, 0, :n], y_one[b, 0, :n])
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
