@@ -1,0 +1,62 @@
+/* C ABI of the YAAPT front end on the GPU (row N2 of SURVEY.md section 8f, first step).
+ *
+ * What it replaces in the reference (/root/reference/satools/satools/hifigan/yaapt.py), for a whole batch at once:
+ *   _yaapt lines 873-880                zero padding by frame_length / 2, the squared ("nonlinear") signal
+ *   SignalObj.filtered_version 42-52    torchaudio lowpass_biquad(bp_low) -> highpass_biquad(bp_high), each clamped to [-1, 1]
+ *   nlfer 148-176                       Hann-windowed frames, |DFT| summed over the F0 band
+ *   PitchObj.set_energy 124-127         energy / mean(energy), voiced = energy > nlfer_thresh1
+ * The reference runs this per utterance on one CPU thread (yaapt.py:27, 947-952); the outputs are what its spectral and
+ * temporal trackers (spec_track, time_track) read: SignalObj.filtered of both signals, PitchObj.energy / vuv / mean_energy.
+ * The trackers themselves (spec_track, time_track, refine, dynamic) are not part of this library yet.
+ *
+ * Same conventions as sa_hifigan.h: plain pointers and sizes, 0 = success, negative = error with the text in
+ * sa_yaapt_last_error(); all tensor pointers are DEVICE pointers, `stream` is a cudaStream_t (NULL = default stream).
+ */
+#ifndef SA_YAAPT_H
+#define SA_YAAPT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* The options of `_yaapt` this part reads (yaapt.py:818-832), same names, same defaults. */
+typedef struct sa_yaapt_params {
+  double sr;            /* 16000 */
+  double frame_length;  /* 35 ms */
+  double frame_space;   /* 10 ms (bin/pipeline.py passes 20) */
+  double f0_min;        /* 60 Hz */
+  double f0_max;        /* 400 Hz */
+  double fft_length;    /* 8192 */
+  double bp_low;        /* 50 Hz   (handed to the LOW-pass, as the reference does) */
+  double bp_high;       /* 1500 Hz (handed to the HIGH-pass) */
+  double nlfer_thresh1; /* 0.75 */
+} sa_yaapt_params;
+
+const char* sa_yaapt_last_error(void);
+int sa_yaapt_default_params(sa_yaapt_params* p);
+
+/* Geometry for an utterance of n_samples (before padding): samples of the padded signal (n_samples + 2 pad) and NLFER frames
+ * (`len(samples)` of nlfer, yaapt.py:164-166).  Negative on bad arguments. */
+int64_t sa_yaapt_padded_length(const sa_yaapt_params* p, int64_t n_samples);
+int64_t sa_yaapt_num_frames(const sa_yaapt_params* p, int64_t n_samples);
+
+/* Scratch bytes of sa_yaapt_frontend for B utterances of at most n_max samples. */
+size_t sa_yaapt_frontend_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max);
+
+/* wav        [B, n_max] float32, item b valid in [0, lengths[b]) (lengths: HOST array, NULL = all n_max)
+ * filtered   [B, n_max + 2 pad] float32   SignalObj.filtered of the padded signal      (zero beyond the item's padded length)
+ * filtered_nl[B, n_max + 2 pad] float32   SignalObj.filtered of the squared signal
+ * energy     [B, F_max] float32           PitchObj.energy (normalised by the item's mean; 0 beyond the item's frames)
+ * vuv        [B, F_max] uint8             PitchObj.vuv
+ * mean_energy[B] float32                  PitchObj.mean_energy
+ * F_max = sa_yaapt_num_frames(p, n_max).  Any output pointer may be NULL (not written). */
+int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int64_t n_max, const int32_t* lengths,
+                      float* filtered, float* filtered_nl, float* energy, uint8_t* vuv, float* mean_energy, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+#!/usr/bin/env python3
+"""Mint tests/golden/yaapt_nlfer.npz by RUNNING THE REFERENCE's YAAPT front end (build container only).
+
+    SA_JIT_TWEAK=true PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden_yaapt.py
+
+Imports /root/reference/satools (read-only) and executes, on synthetic waveforms, exactly what `_yaapt` does before its
+spectral tracker (satools/satools/hifigan/yaapt.py:873-899): padding, SignalObj / squared SignalObj, `filtered_version`
+(torchaudio biquads), PitchObj, `nlfer`.  Recorded per case: the waveform, the two filtered signals, the normalised NLFER
+energy, the voiced flags and the mean energy.  The cases use the options the reference pipeline passes
+(`bin/pipeline.py`: frame_length 35, frame_space 20) and the defaults (frame_space 10).
+"""
+import os
+import sys
+from math import floor
+
+os.environ.setdefault("SA_JIT_TWEAK", "true")
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, "/root/reference/satools")
+sys.path.insert(0, os.path.join(ROOT, "sa-toolkit_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import satools  # noqa: E402,F401  (the reference)
+from satools.hifigan import yaapt as ref  # noqa: E402
+
+from satools_b200 import conditioning  # noqa: E402
+from oracle import yaapt_nlfer_numpy as onp  # noqa: E402
+
+CASES = [  # (seed, seconds, options)
+    (0, 1.5, dict(frame_length=35.0, frame_space=20.0)),
+    (1, 2.3, dict(frame_length=35.0, frame_space=20.0)),
+    (2, 0.9, dict()),
+    (3, 0.05, dict(frame_length=35.0, frame_space=20.0)),       # shorter than two frames
+]
+
+
+def run_reference(wav: np.ndarray, opts: dict):
+    p = onp.params(**opts)
+    x = torch.from_numpy(wav).reshape(1, -1)
+    to_pad = int(p["frame_length"] / 1000 * int(p["sr"])) // 2
+    x = torch.nn.functional.pad(x.squeeze(), (to_pad, to_pad))
+    signal = ref.SignalObj(x, p["sr"])
+    nonlinear = ref.SignalObj(signal.data ** 2, p["sr"])
+    signal.filtered_version(p)
+    nonlinear.filtered_version(p)
+    frame_size = floor(torch.tensor(p["frame_length"] * signal.fs / 1000))
+    frame_jump = floor(torch.tensor(p["frame_space"] * signal.fs / 1000))
+    pitch = ref.PitchObj(int(frame_size), int(frame_jump), int(p["fft_length"]))
+    ref.nlfer(signal, pitch, p)
+    return dict(filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
+                vuv=pitch.vuv.numpy(), mean_energy=np.float32(pitch.mean_energy.item()), nframes=np.int64(pitch.nframes))
+
+
+def main():
+    out = {}
+    for i, (seed, seconds, opts) in enumerate(CASES):
+        wav = conditioning.waveform(seed, seconds)
+        r = run_reference(wav, opts)
+        o = onp.nlfer(wav, onp.params(**opts))
+        rel = np.abs(o["energy"] - r["energy"]).max() / max(1e-12, np.abs(r["energy"]).max())
+        flips = int((o["vuv"] != r["vuv"]).sum())
+        print(f"case {i}: n={len(wav)} frames={int(r['nframes'])} voiced={int(r['vuv'].sum())} oracle-vs-reference energy rel-err {rel:.2e}, "
+              f"vuv flips {flips}, filtered max-abs {np.abs(r['filtered']).max():.3e} err {np.abs(o['filtered'] - r['filtered']).max():.2e}")
+        out[f"c{i}_seed"] = np.int64(seed)
+        out[f"c{i}_seconds"] = np.float64(seconds)
+        out[f"c{i}_opts"] = np.array([opts.get("frame_length", 35.0), opts.get("frame_space", 10.0)])
+        for k, v in r.items():
+            out[f"c{i}_{k}"] = v
+    out["n_cases"] = np.int64(len(CASES))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "yaapt_nlfer.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,120 @@
+"""CPU restatement of the FRONT END of the reference's YAAPT F0 extractor (row N2 of SURVEY.md section 8f).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, bench.py's cpu legs and __graft_entry__.smoke(); the product path
+(satools_b200.yaapt_frontend -> libsatools_hifigan.so) never imports it.
+
+What it restates (/root/reference/satools/satools/hifigan/yaapt.py):
+  * `_yaapt` lines 873-880: zero padding of the waveform by frame_length / 2 on both sides, the squared ("nonlinear") signal;
+  * `SignalObj.filtered_version` lines 42-52: torchaudio `lowpass_biquad(x, fs, bp_low)` then `highpass_biquad(., fs, bp_high)`
+    (Q = 0.707, each through `lfilter(clamp=True)`: FIR part b / a0, IIR recursion with a / a0, output clamped to [-1, 1]).
+    NB the reference passes bp_low = 50 Hz to the LOW-pass and bp_high = 1500 Hz to the HIGH-pass: what is left is the small
+    residue both filters leak.  A drop-in has to reproduce that, not fix it;
+  * `nlfer` lines 148-176: frames of frame_size samples every frame_jump samples, Hann window `hann_window(n + 2)[1:-1]`,
+    magnitude of the nfft-point DFT summed over bins [N_f0_min - 1, N_f0_max), N_f0_min = round(2 f0_min / fs * nfft),
+    N_f0_max = round(f0_max / fs * nfft);
+  * `PitchObj.set_energy` lines 124-127: energy / mean(energy), voiced = energy > nlfer_thresh1.
+
+Pinned by tests/golden/yaapt_nlfer.npz (outputs of the reference itself, oracle/make_golden_yaapt.py).  The filters are
+evaluated in float64 here: the reference runs them in float32, and its own rounding noise is what sets the tolerance of the
+comparison (see tests/test_yaapt_frontend.py).
+"""
+import math
+
+import numpy as np
+
+try:
+    from scipy.signal import lfilter as _scipy_lfilter
+except Exception:  # pragma: no cover
+    _scipy_lfilter = None
+
+DEFAULTS = dict(sr=16000.0, frame_length=35.0, frame_space=10.0, f0_min=60.0, f0_max=400.0, fft_length=8192.0, bp_low=50.0,
+                bp_high=1500.0, nlfer_thresh1=0.75)
+
+
+def params(**kw):
+    p = dict(DEFAULTS)
+    p.update(kw)
+    return p
+
+
+def biquad_coeffs(kind, fs, cutoff, q=0.707):
+    """torchaudio lowpass_biquad / highpass_biquad: (b0, b1, b2, a0, a1, a2), evaluated in float32 as torchaudio does for a
+    float32 waveform (`torch.as_tensor(cutoff, dtype=waveform.dtype)`)."""
+    f32 = np.float32
+    w0 = f32(2 * math.pi) * f32(cutoff) / f32(int(fs))
+    alpha = np.sin(w0, dtype=f32) / f32(2) / f32(q)
+    c = np.cos(w0, dtype=f32)
+    if kind == "low":
+        b0 = (f32(1) - c) / f32(2)
+        b1 = f32(1) - c
+    else:
+        b0 = (f32(1) + c) / f32(2)
+        b1 = f32(-1) - c
+    return tuple(float(v) for v in (b0, b1, b0, f32(1) + alpha, f32(-2) * c, f32(1) - alpha))
+
+
+def normalized_coeffs(kind, fs, cutoff):
+    """(b / a0, a / a0) as float32 arrays: what `_lfilter` hands to its FIR and IIR parts."""
+    b0, b1, b2, a0, a1, a2 = biquad_coeffs(kind, fs, cutoff)
+    f32 = np.float32
+    b = np.array([b0, b1, b2], dtype=f32) / f32(a0)
+    a = np.array([a0, a1, a2], dtype=f32) / f32(a0)
+    return b, a
+
+
+def lfilter_clamped(x, b, a, dtype=np.float64):
+    """y[n] = b0 x[n] + b1 x[n-1] + b2 x[n-2] - a1 y[n-1] - a2 y[n-2], zero initial state, clamped to [-1, 1]."""
+    x = np.asarray(x, dtype=dtype)
+    b = b.astype(dtype)
+    a = a.astype(dtype)
+    if _scipy_lfilter is not None and dtype == np.float64:       # same recursion, compiled
+        return np.clip(_scipy_lfilter(b, a, x), -1.0, 1.0)
+    xp = np.concatenate([np.zeros(2, dtype=dtype), x])
+    fir = b[0] * xp[2:] + b[1] * xp[1:-1] + b[2] * xp[:-2]
+    y = np.zeros(len(x) + 2, dtype=dtype)
+    a1, a2 = a[1], a[2]
+    for n in range(len(x)):
+        y[n + 2] = fir[n] - a2 * y[n] - a1 * y[n + 1]
+    return np.clip(y[2:], -1.0, 1.0)
+
+
+def filtered(x, p, dtype=np.float64):
+    bl, al = normalized_coeffs("low", p["sr"], p["bp_low"])
+    bh, ah = normalized_coeffs("high", p["sr"], p["bp_high"])
+    return lfilter_clamped(lfilter_clamped(x, bl, al, dtype), bh, ah, dtype)
+
+
+def geometry(n_samples, p):
+    """(pad, frame_size, frame_jump, n_frames, bin_lo, bin_hi) for a waveform of n_samples (before padding)."""
+    pad = int(p["frame_length"] / 1000 * int(p["sr"])) // 2
+    frame_size = int(math.floor(p["frame_length"] * p["sr"] / 1000))
+    frame_jump = int(math.floor(p["frame_space"] * p["sr"] / 1000))
+    size = n_samples + 2 * pad
+    half = frame_size // 2
+    n_frames = len(range(half, size - half, frame_jump))
+    nfft = int(p["fft_length"])
+    # torch.round: half to even, on float32 values
+    lo = int(np.round(np.float32(p["f0_min"] * 2 / float(p["sr"])) * np.float32(nfft)))
+    hi = int(np.round(np.float32(p["f0_max"] / float(p["sr"])) * np.float32(nfft)))
+    return pad, frame_size, frame_jump, n_frames, lo - 1, hi
+
+
+def nlfer(wav, p=None):
+    """wav: [n] float -> dict(energy [n_frames] normalised, vuv [n_frames] bool, mean_energy, frame_energy, filtered)."""
+    p = p or params()
+    wav = np.asarray(wav, dtype=np.float64).reshape(-1)
+    pad, frame_size, frame_jump, n_frames, lo, hi = geometry(len(wav), p)
+    x = np.concatenate([np.zeros(pad), wav, np.zeros(pad)])
+    filt = filtered(x, p)
+    n = np.arange(frame_size + 2, dtype=np.float64)
+    window = (0.5 - 0.5 * np.cos(2 * np.pi * n / (frame_size + 2)))[1:-1]        # periodic hann_window(frame_size + 2)[1:-1]
+    nfft = int(p["fft_length"])
+    k = np.arange(lo, hi, dtype=np.float64)
+    ang = -2j * np.pi * np.outer(np.arange(frame_size, dtype=np.float64), k) / nfft
+    basis = np.exp(ang)                                                           # [frame_size, bins]
+    frames = np.stack([filt[i * frame_jump:i * frame_jump + frame_size] for i in range(n_frames)]) * window
+    frame_energy = np.abs(frames @ basis).sum(1)
+    mean_energy = frame_energy.mean() if n_frames else 0.0
+    energy = frame_energy / mean_energy
+    return dict(energy=energy, vuv=energy > p["nlfer_thresh1"], mean_energy=mean_energy, frame_energy=frame_energy, filtered=filt,
+                filtered_nl=filtered(x * x, p), nframes=n_frames)

@@ -1,0 +1,291 @@
+// YAAPT front end on the GPU (include/sa_yaapt.h): padding, squared signal, the two torchaudio biquads and the NLFER
+// frame energies / voiced flags of a whole batch -- what `_yaapt` (satools/satools/hifigan/yaapt.py:873-899) does per
+// utterance on one CPU thread before its trackers run.
+//
+// Kernels (all HBM / latency bound; nothing here is GEMM shaped):
+//   biquad_chunk_kernel   one thread per 1024-sample chunk of one signal.  An IIR recursion is sequential, but its impulse
+//                         response decays (pole radius 0.986 for the 50 Hz low-pass, 0.66 for the 1500 Hz high-pass), so a
+//                         chunk can start from a zero state W samples early: after W = ln(1e-18) / ln(r) samples (3000 /
+//                         100) what is left of the unknown true state is below double rounding.  Chunks that start at
+//                         sample 0 have the exact zero state of torchaudio's lfilter.  Recursion in double (the reference's
+//                         float32 recursion carries ~5e-5 relative noise on this signal; double is the value it approximates),
+//                         one DFMA on the critical path per sample, output clamped to [-1, 1] and stored as float32 like
+//                         the reference's tensors.
+//   nlfer_frame_kernel    one block per frame: the Hann-windowed frame in shared memory, one thread per DFT bin of the F0
+//                         band (bins 60..204 of 8192 for the defaults): direct DFT with an exact twiddle every 16 samples
+//                         (sincospi of the reduced integer phase) and a complex rotation in between, |X| summed over the band.
+//   nlfer_normalize_kernel one block per utterance: mean over its frames, energy / mean, voiced = energy > threshold.
+#include "../../include/sa_yaapt.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+thread_local char g_err[256] = "";
+int fail(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return -1;
+}
+
+struct Biquad { double b0, b1, b2, a1, a2; int warm; };
+
+// torchaudio lowpass_biquad / highpass_biquad for a float32 waveform: every step in float32 (filtering.py), then
+// lfilter's b / a0 and a / a0, also float32.
+Biquad design(bool lowpass, double fs, double cutoff) {
+  const float w0 = (float)(2.0 * M_PI) * (float)cutoff / (float)(int)fs;
+  const float alpha = sinf(w0) / 2.0f / 0.707f;
+  const float c = cosf(w0);
+  const float b0 = lowpass ? (1.0f - c) / 2.0f : (1.0f + c) / 2.0f;
+  const float b1 = lowpass ? 1.0f - c : -1.0f - c;
+  const float a0 = 1.0f + alpha, a1 = -2.0f * c, a2 = 1.0f - alpha;
+  Biquad q;
+  q.b0 = (double)(b0 / a0); q.b1 = (double)(b1 / a0); q.b2 = q.b0;
+  q.a1 = (double)(a1 / a0); q.a2 = (double)(a2 / a0);
+  // warm-up: the state decays like r^n, r = sqrt(a2) for complex poles (else the larger real pole)
+  const double disc = q.a1 * q.a1 - 4.0 * q.a2;
+  double r = disc < 0 ? sqrt(q.a2) : fmax(fabs((-q.a1 + sqrt(disc)) / 2), fabs((-q.a1 - sqrt(disc)) / 2));
+  r = fmin(fmax(r, 0.05), 0.99995);
+  q.warm = (int)ceil(log(1e-18) / log(r));
+  q.warm = (q.warm + 3) / 4 * 4;
+  return q;
+}
+
+struct Geometry { int pad, frame_size, frame_jump, nfft, bin_lo, bin_hi; };
+
+bool geometry(const sa_yaapt_params* p, Geometry& g) {
+  if (!p || p->sr < 1000 || p->frame_length <= 0 || p->frame_space <= 0 || p->fft_length < 16) return false;
+  g.pad = (int)(p->frame_length / 1000 * (int)p->sr) / 2;
+  g.frame_size = (int)floor(p->frame_length * p->sr / 1000);
+  g.frame_jump = (int)floor(p->frame_space * p->sr / 1000);
+  g.nfft = (int)p->fft_length;
+  // torch.round (half to even) of float32 products, yaapt.py:153-154
+  const float lo = (float)(p->f0_min * 2 / p->sr) * (float)g.nfft, hi = (float)(p->f0_max / p->sr) * (float)g.nfft;
+  g.bin_lo = (int)nearbyintf(lo) - 1;
+  g.bin_hi = (int)nearbyintf(hi);
+  return g.frame_size > 15 && g.frame_size < 2048 && g.frame_jump >= 1 && g.bin_lo >= 0 && g.bin_hi > g.bin_lo &&
+         g.bin_hi <= g.nfft / 2 + 1 && g.frame_size <= g.nfft;
+}
+
+int64_t frames_of(const Geometry& g, int64_t n_samples) {
+  const int64_t size = n_samples + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;                       // len(range(half, size - half, jump))
+  return span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump;
+}
+
+constexpr int kChunk = 1024;
+
+// src_mode 0: input = padded (and for odd signals squared) waveform; 1: input = `in` [2B, stride]
+__global__ void biquad_chunk_kernel(const float* __restrict__ wav, const float* __restrict__ in, float* __restrict__ out_a,
+                                    float* __restrict__ out_b, const int* __restrict__ lengths, int64_t n_max, int64_t stride,
+                                    int pad, int n_chunks, Biquad q, int src_mode, int B) {
+  const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sig = blockIdx.y;                                     // 2 b + (0: signal, 1: squared signal)
+  if (chunk >= n_chunks) return;
+  const int b = sig >> 1, squared = sig & 1;
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * pad;                             // samples of this item's padded signal
+  float* out = (squared ? out_b : out_a);
+  const int64_t o0 = (int64_t)chunk * kChunk, o1 = min(o0 + kChunk, stride);
+  if (out) out += (src_mode == 0 ? (int64_t)sig : (int64_t)b) * stride;
+  if (o0 >= size) {                                               // beyond the item: zeros
+    if (out) for (int64_t i = o0; i < o1; ++i) out[i] = 0.f;
+    return;
+  }
+  const float* w = wav ? wav + (int64_t)b * n_max : nullptr;
+  const float* src = in ? in + (int64_t)sig * stride : nullptr;
+  auto x_at = [&](int64_t i) -> double {
+    if (src_mode == 0) {
+      const int64_t j = i - pad;
+      if (j < 0 || j >= len) return 0.0;
+      const float v = w[j];
+      return squared ? (double)(v * v) : (double)v;              // signal.data ** 2 is a float32 product (yaapt.py:877)
+    }
+    return (double)src[i];
+  };
+  const int64_t start = max((int64_t)0, o0 - q.warm);
+  double x1 = start > 0 ? x_at(start - 1) : 0.0, x2 = start > 1 ? x_at(start - 2) : 0.0, y1 = 0.0, y2 = 0.0;
+  const int64_t end = min(o1, size);
+  for (int64_t i = start; i < end; ++i) {
+    const double x0 = x_at(i);
+    const double t = fma(q.b2, x2, fma(q.b1, x1, q.b0 * x0)) - q.a2 * y2;   // off the critical path
+    const double y = fma(-q.a1, y1, t);
+    x2 = x1; x1 = x0; y2 = y1; y1 = y;
+    if (i >= o0 && out) out[i] = (float)fmin(1.0, fmax(-1.0, y));
+  }
+  if (out) for (int64_t i = end; i < o1; ++i) out[i] = 0.f;
+}
+
+// The second biquad reads the first one's CLAMPED float32 output; both outputs of pass 2 go to separate user buffers, so
+// the destination row is the item index there (out_a / out_b each [B, stride]) and the signal index in pass 1 ([2B, stride]).
+
+__global__ void nlfer_frame_kernel(const float* __restrict__ filtered, float* __restrict__ frame_energy,
+                                   const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max, Geometry g) {
+  extern __shared__ float frame[];                                // [frame_size] windowed samples, then [warps] partial sums
+  const int f = blockIdx.x, b = blockIdx.y;
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int64_t n_frames = span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump;
+  if (f >= n_frames) {
+    if (threadIdx.x == 0) frame_energy[(int64_t)b * f_max + f] = 0.f;
+    return;
+  }
+  const float* x = filtered + (int64_t)b * stride + (int64_t)f * g.frame_jump;
+  for (int n = threadIdx.x; n < g.frame_size; n += blockDim.x) {
+    // torch.hann_window(frame_size + 2)[1:-1] (periodic): 0.5 - 0.5 cos(2 pi (n + 1) / (frame_size + 2))
+    const float wgt = (float)(0.5 - 0.5 * cospi(2.0 * (double)(n + 1) / (double)(g.frame_size + 2)));
+    frame[n] = x[n] * wgt;
+  }
+  __syncthreads();
+  float mag = 0.f;
+  const int k = g.bin_lo + (int)threadIdx.x;
+  if (k < g.bin_hi) {
+    double sd, cd;
+    sincospi(-2.0 * (double)k / (double)g.nfft, &sd, &cd);        // one-sample rotation e^{-2 pi i k / nfft}
+    const float rc = (float)cd, rs = (float)sd;
+    float re = 0.f, im = 0.f;
+    for (int n0 = 0; n0 < g.frame_size; n0 += 16) {
+      const int idx = (int)(((int64_t)k * n0) % g.nfft);          // exact phase of sample n0
+      float ws, wc;
+      sincospif(-2.0f * (float)idx / (float)g.nfft, &ws, &wc);
+      const int n1 = min(n0 + 16, g.frame_size);
+      for (int n = n0; n < n1; ++n) {
+        const float v = frame[n];
+        re = fmaf(v, wc, re);
+        im = fmaf(v, ws, im);
+        const float t = wc * rc - ws * rs;
+        ws = wc * rs + ws * rc;
+        wc = t;
+      }
+    }
+    mag = sqrtf(re * re + im * im);
+  }
+  // block sum (fixed order: lanes by shuffle, warps in order)
+  for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(0xffffffffu, mag, d);
+  __syncthreads();
+  float* part = frame;
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = mag;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += part[w];
+    frame_energy[(int64_t)b * f_max + f] = s;
+  }
+}
+
+__global__ void nlfer_normalize_kernel(const float* __restrict__ frame_energy, float* __restrict__ energy, uint8_t* __restrict__ vuv,
+                                       float* __restrict__ mean_energy, const int* __restrict__ lengths, int64_t n_max, int f_max,
+                                       Geometry g, float threshold) {
+  __shared__ double part[32];
+  const int b = blockIdx.x;
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int n_frames = (int)(span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump);
+  const float* e = frame_energy + (int64_t)b * f_max;
+  double s = 0.0;
+  for (int f = threadIdx.x; f < n_frames; f += blockDim.x) s += (double)e[f];
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x + 31) / 32 ? part[threadIdx.x] : 0.0;
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (threadIdx.x == 0) part[0] = s;
+  }
+  __syncthreads();
+  const float mean = n_frames > 0 ? (float)(part[0] / (double)n_frames) : 0.f;     // torch.mean of float32 energies
+  if (threadIdx.x == 0 && mean_energy) mean_energy[b] = mean;
+  for (int f = threadIdx.x; f < f_max; f += blockDim.x) {
+    const float v = f < n_frames ? e[f] / mean : 0.f;
+    if (energy) energy[(int64_t)b * f_max + f] = v;
+    if (vuv) vuv[(int64_t)b * f_max + f] = (f < n_frames && v > threshold) ? 1 : 0;
+  }
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+const char* sa_yaapt_last_error(void) { return g_err; }
+
+int sa_yaapt_default_params(sa_yaapt_params* p) {
+  if (!p) return fail("sa_yaapt_default_params: NULL params");
+  p->sr = 16000.0; p->frame_length = 35.0; p->frame_space = 10.0; p->f0_min = 60.0; p->f0_max = 400.0;
+  p->fft_length = 8192.0; p->bp_low = 50.0; p->bp_high = 1500.0; p->nlfer_thresh1 = 0.75;
+  return 0;
+}
+
+int64_t sa_yaapt_padded_length(const sa_yaapt_params* p, int64_t n_samples) {
+  Geometry g;
+  if (!geometry(p, g) || n_samples < 0) { fail("sa_yaapt_padded_length: bad parameters"); return -1; }
+  return n_samples + 2 * g.pad;
+}
+
+int64_t sa_yaapt_num_frames(const sa_yaapt_params* p, int64_t n_samples) {
+  Geometry g;
+  if (!geometry(p, g) || n_samples < 0) { fail("sa_yaapt_num_frames: bad parameters"); return -1; }
+  return frames_of(g, n_samples);
+}
+
+size_t sa_yaapt_frontend_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max) {
+  Geometry g;
+  if (!geometry(p, g) || B <= 0 || n_max <= 0) return 0;
+  const size_t stride = (size_t)(n_max + 2 * g.pad);
+  // [lengths B][pass-1 output 2B x stride][pass-2 outputs 2 x B x stride (when the caller keeps none)][frame energies]
+  return align256((size_t)B * 4) + 2 * align256((size_t)2 * B * stride * 4) + align256((size_t)B * (size_t)frames_of(g, n_max) * 4) + 256;
+}
+
+int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int64_t n_max, const int32_t* lengths,
+                      float* filtered, float* filtered_nl, float* energy, uint8_t* vuv, float* mean_energy, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  Geometry g;
+  if (!geometry(p, g)) return fail("sa_yaapt_frontend: bad parameters (frame_length must give 16..2047 samples, band inside the FFT)");
+  if (!wav || B <= 0 || n_max <= 0) return fail("sa_yaapt_frontend: NULL waveform or empty batch");
+  if (B > 32767) return fail("sa_yaapt_frontend: at most 32767 utterances per call");
+  if (!workspace || workspace_bytes < sa_yaapt_frontend_workspace_bytes(p, B, n_max)) return fail("sa_yaapt_frontend: workspace too small");
+  if (lengths)
+    for (int b = 0; b < B; ++b)
+      if (lengths[b] < 0 || lengths[b] > n_max) return fail("sa_yaapt_frontend: lengths[b] outside [0, n_max]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t stride = n_max + 2 * g.pad;
+  const int f_max = (int)frames_of(g, n_max);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  int* d_len = reinterpret_cast<int*>(base);
+  base += align256((size_t)B * 4);
+  float* tmp1 = reinterpret_cast<float*>(base);                   // [2B, stride]
+  base += align256((size_t)2 * B * stride * 4);
+  float* own = reinterpret_cast<float*>(base);                    // [2, B, stride] when the caller keeps no filtered output
+  base += align256((size_t)2 * B * stride * 4);
+  float* d_fe = reinterpret_cast<float*>(base);                   // [B, f_max]
+  if (lengths) {
+    cudaError_t e = cudaMemcpyAsync(d_len, lengths, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  }
+  const int* dl = lengths ? d_len : nullptr;
+  const Biquad lp = design(true, p->sr, p->bp_low), hp = design(false, p->sr, p->bp_high);
+  const int n_chunks = (int)((stride + kChunk - 1) / kChunk);
+  const dim3 grid((unsigned)((n_chunks + 63) / 64), (unsigned)(2 * B));
+  biquad_chunk_kernel<<<grid, 64, 0, st>>>(wav, nullptr, tmp1, tmp1, dl, n_max, stride, g.pad, n_chunks, lp, 0, B);
+  float* fa = filtered ? filtered : own;
+  float* fb = filtered_nl ? filtered_nl : own + (size_t)B * stride;
+  biquad_chunk_kernel<<<grid, 64, 0, st>>>(nullptr, tmp1, fa, fb, dl, n_max, stride, g.pad, n_chunks, hp, 1, B);
+  if (f_max > 0 && (energy || vuv || mean_energy)) {
+    const int bins = g.bin_hi - g.bin_lo;
+    const int threads = (bins + 31) / 32 * 32;
+    if (threads > 1024) return fail("sa_yaapt_frontend: more than 1024 bins in the F0 band");
+    const size_t smem = (size_t)(g.frame_size > 32 ? g.frame_size : 32) * sizeof(float);
+    nlfer_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(fa, d_fe, dl, n_max, stride, f_max, g);
+    nlfer_normalize_kernel<<<B, 256, 0, st>>>(d_fe, energy, vuv, mean_energy, dl, n_max, f_max, g, (float)p->nlfer_thresh1);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

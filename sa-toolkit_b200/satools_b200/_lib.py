@@ -35,6 +35,23 @@ class Cfg(C.Structure):
     ]
 
 
+class YaaptParams(C.Structure):
+    """sa_yaapt_params (include/sa_yaapt.h): the `_yaapt` options the front end reads, same names and defaults."""
+    _fields_ = [(n, C.c_double) for n in ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low",
+                                          "bp_high", "nlfer_thresh1")]
+
+
+# every symbol include/sa_yaapt.h declares
+YAAPT_SYMBOLS = {
+    "sa_yaapt_last_error": (C.c_char_p, []),
+    "sa_yaapt_default_params": (C.c_int, [C.POINTER(YaaptParams)]),
+    "sa_yaapt_padded_length": (C.c_int64, [C.POINTER(YaaptParams), C.c_int64]),
+    "sa_yaapt_num_frames": (C.c_int64, [C.POINTER(YaaptParams), C.c_int64]),
+    "sa_yaapt_frontend_workspace_bytes": (C.c_size_t, [C.POINTER(YaaptParams), C.c_int32, C.c_int64]),
+    "sa_yaapt_frontend": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
 # name -> (restype, argtypes): every symbol include/sa_hifigan.h declares.
 SYMBOLS = {
     "sa_hifigan_abi_version": (C.c_int, []),
@@ -92,7 +109,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: the CUDA extension has not been built "
             "(run `python __graft_entry__.py build`). There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SYMBOLS.items():
+    for name, (res, args) in list(SYMBOLS.items()) + list(YAAPT_SYMBOLS.items()):
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

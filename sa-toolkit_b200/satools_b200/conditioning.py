@@ -87,3 +87,30 @@ def batch(seed: int, frames: Sequence[int], n_spk: int = N_SPEAKERS, pad_to: Opt
             raise ValueError("only quant_16_awgn_2 is generated")
         out[:, N_BN] = quant_awgn_f0(out[:, N_BN], np.random.default_rng(seed + 7919))
     return out
+
+
+def waveform(seed: int, seconds: float, sr: int = 16000) -> np.ndarray:
+    """Speech-like synthetic waveform, float32 [n] in [-1, 1]: voiced segments (a harmonic series on a slowly moving F0 of
+    80-300 Hz under a formant-like envelope), unvoiced noise bursts and silences -- what the YAAPT front end
+    (`satools/hifigan/yaapt.py`) has to tell apart.  numpy PCG64: the same samples on any host."""
+    rng = np.random.default_rng(seed)
+    n = int(round(seconds * sr))
+    y = np.zeros(n, dtype=np.float64)
+    t = 0
+    while t < n:
+        seg = int(rng.integers(int(0.08 * sr), int(0.45 * sr)))
+        seg = min(seg, n - t)
+        kind = rng.random()
+        if kind < 0.55:                                     # voiced
+            f0 = rng.uniform(80.0, 300.0) * (1.0 + 0.15 * np.sin(2 * np.pi * rng.uniform(1.0, 4.0) * np.arange(seg) / sr + rng.uniform(0, 6.28)))
+            phase = 2 * np.pi * np.cumsum(f0) / sr
+            s = np.zeros(seg)
+            for h in range(1, 13):
+                s += np.sin(h * phase + rng.uniform(0, 6.28)) / (h ** rng.uniform(0.8, 1.6))
+            env = np.hanning(seg + 2)[1:-1] ** 0.5
+            y[t:t + seg] = rng.uniform(0.1, 0.5) * env * s / 3.0
+        elif kind < 0.8:                                    # unvoiced burst
+            y[t:t + seg] = rng.uniform(0.01, 0.08) * rng.standard_normal(seg) * np.hanning(seg + 2)[1:-1]
+        t += seg                                            # else: silence
+    y += 1e-4 * rng.standard_normal(n)
+    return np.clip(y, -1.0, 1.0).astype(np.float32)

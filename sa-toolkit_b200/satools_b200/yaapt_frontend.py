@@ -1,0 +1,88 @@
+"""Front end of the reference's YAAPT F0 extractor on the GPU, for a whole batch at once (first step).
+
+Mirrors what `_yaapt` (/root/reference/satools/satools/hifigan/yaapt.py:873-899) computes before its trackers run, with the
+reference's names: `SignalObj.filtered` of the signal and of the squared signal (`filtered_version`, lines 42-52), and
+`PitchObj.energy / vuv / mean_energy / nframes` as `nlfer` (lines 148-176) and `set_energy` (124-127) leave them.  Options are
+the `_yaapt` keyword options (`frame_length`, `frame_space`, `f0_min`, `f0_max`, `fft_length`, `bp_low`, `bp_high`,
+`nlfer_thresh1`; `bin/pipeline.py` passes frame_length 35 / frame_space 20).
+
+The compute runs in libsatools_hifigan.so (csrc/yaapt_frontend.cu through the C ABI of include/sa_yaapt.h); there is no CPU
+path here.  The spectral / temporal trackers and the dynamic programming of YAAPT are not on the GPU yet.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+OPTION_NAMES = ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low", "bp_high", "nlfer_thresh1")
+
+
+def params(**kwargs) -> "_lib.YaaptParams":
+    lib = _lib.load()
+    p = _lib.YaaptParams()
+    if lib.sa_yaapt_default_params(p) != 0:
+        raise _lib.SaHifiganError(lib.sa_yaapt_last_error().decode())
+    for k, v in kwargs.items():
+        if k not in OPTION_NAMES:
+            raise KeyError(f"unknown YAAPT front-end option {k!r} (the trackers' options are not used here)")
+        setattr(p, k, float(v))
+    return p
+
+
+def num_frames(n_samples: int, **kwargs) -> int:
+    """`pitch.nframes` for an utterance of n_samples (yaapt.py:164-166, 131)."""
+    return int(_lib.load().sa_yaapt_num_frames(params(**kwargs), int(n_samples)))
+
+
+@dataclass
+class FrontEnd:
+    filtered: torch.Tensor        # [B, n_max + 2 pad] float32: SignalObj.filtered (zero beyond an item's padded length)
+    filtered_nl: torch.Tensor     # [B, n_max + 2 pad] float32: the squared signal's
+    energy: torch.Tensor          # [B, F_max] float32: PitchObj.energy (0 beyond an item's frames)
+    vuv: torch.Tensor             # [B, F_max] bool: PitchObj.vuv
+    mean_energy: torch.Tensor     # [B] float32: PitchObj.mean_energy
+    nframes: list                 # per item: PitchObj.nframes
+    padded_lengths: list          # per item: SignalObj.size
+
+
+def nlfer(wav: torch.Tensor, lengths: Optional[Sequence[int]] = None, **kwargs) -> FrontEnd:
+    """wav: [B, n] (or [n]) float32 on a CUDA device, item b valid in [0, lengths[b])."""
+    if wav.dim() == 1:
+        wav = wav.unsqueeze(0)
+    if not wav.is_cuda:
+        raise ValueError("yaapt_frontend.nlfer needs a CUDA tensor: this path has no CPU implementation")
+    lib = _lib.load()
+    p = params(**kwargs)
+    wav = wav.contiguous().float()
+    B, n = wav.shape
+    n_pad = int(lib.sa_yaapt_padded_length(p, n))
+    f_max = int(lib.sa_yaapt_num_frames(p, n))
+    if n_pad < 0 or f_max < 0:
+        raise _lib.SaHifiganError(lib.sa_yaapt_last_error().decode())
+    dev = wav.device
+    with torch.cuda.device(dev):
+        out = FrontEnd(torch.empty(B, n_pad, device=dev), torch.empty(B, n_pad, device=dev), torch.empty(B, f_max, device=dev),
+                       torch.empty(B, f_max, dtype=torch.uint8, device=dev), torch.empty(B, device=dev), [], [])
+        ws = torch.empty(int(lib.sa_yaapt_frontend_workspace_bytes(p, B, n)), dtype=torch.uint8, device=dev)
+        lens = None
+        if lengths is not None:
+            if len(lengths) != B:
+                raise ValueError("lengths must have one entry per item")
+            lens = (C.c_int32 * B)(*[int(v) for v in lengths])
+        rc = lib.sa_yaapt_frontend(p, wav.data_ptr(), B, n, lens, out.filtered.data_ptr(), out.filtered_nl.data_ptr(),
+                                   out.energy.data_ptr(), out.vuv.data_ptr(), out.mean_energy.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise _lib.SaHifiganError(f"sa_yaapt_frontend: {lib.sa_yaapt_last_error().decode()}")
+        torch.cuda.current_stream(dev).synchronize()          # `ws` and `lens` are released when this returns
+    out.vuv = out.vuv.bool()
+    for b in range(B):
+        nb = n if lengths is None else int(lengths[b])
+        out.nframes.append(int(lib.sa_yaapt_num_frames(p, nb)))
+        out.padded_lengths.append(int(lib.sa_yaapt_padded_length(p, nb)))
+    return out

@@ -1,0 +1,168 @@
+"""YAAPT front end (first step): band-pass biquads, NLFER energy, voiced flags.
+
+CPU tests: the numpy oracle against the outputs of the reference itself (tests/golden/yaapt_nlfer.npz, minted by
+oracle/make_golden_yaapt.py from satools/hifigan/yaapt.py), the C ABI symbol table, the frame geometry.
+GPU tests: the CUDA path (csrc/yaapt_frontend.cu through include/sa_yaapt.h) against the same fixtures, against the oracle at
+batch sizes the fixtures do not cover, and through size-independent properties.
+
+Tolerances.  The reference evaluates the two biquads in float32; the low-pass at 50 Hz has its poles at radius 0.986 and the
+high-pass at 1500 Hz then removes all but ~1e-3 of its output, so the reference's own rounding noise on `filtered` is ~5e-5
+of its peak (measured: float64 restatement vs reference, make_golden_yaapt.py).  Both the oracle and the CUDA path run the
+recursion in double; they are held to the reference within 5e-4 of the peak for `filtered`, 1e-4 for the normalised NLFER
+energy (measured 4e-6), identical voiced flags except for frames whose energy is within 1e-3 of the threshold.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import yaapt_nlfer_numpy as onp
+from satools_b200 import _lib, conditioning
+
+GOLDEN = os.path.join(helpers.ROOT, "tests", "golden", "yaapt_nlfer.npz")
+HEADER = os.path.join(helpers.ROOT, "include", "sa_yaapt.h")
+
+
+def cases():
+    z = np.load(GOLDEN)
+    for i in range(int(z["n_cases"])):
+        fl, fs = [float(v) for v in z[f"c{i}_opts"]]
+        wav = conditioning.waveform(int(z[f"c{i}_seed"]), float(z[f"c{i}_seconds"]))
+        yield i, wav, dict(frame_length=fl, frame_space=fs), {k: z[f"c{i}_{k}"] for k in ("filtered", "filtered_nl", "energy", "vuv",
+                                                                                          "mean_energy", "nframes")}
+
+
+def compare(got, ref, what, thr=0.75):
+    """got / ref: dicts with filtered, filtered_nl, energy, vuv, mean_energy for ONE utterance."""
+    n, f = len(ref["filtered"]), len(ref["energy"])
+    for k in ("filtered", "filtered_nl"):
+        peak = np.abs(ref[k]).max()
+        err = np.abs(np.asarray(got[k][:n], dtype=np.float64) - ref[k]).max()
+        assert err <= 5e-4 * peak, f"{what}: {k} differs by {err:.3e} (peak {peak:.3e})"
+    e_ref = np.asarray(ref["energy"], dtype=np.float64)
+    e_got = np.asarray(got["energy"][:f], dtype=np.float64)
+    assert np.abs(e_got - e_ref).max() <= 1e-4 * max(1.0, e_ref.max()), f"{what}: energy differs by {np.abs(e_got - e_ref).max():.3e}"
+    decided = np.abs(e_ref - thr) > 1e-3
+    assert np.array_equal(np.asarray(got["vuv"][:f]).astype(bool)[decided], np.asarray(ref["vuv"]).astype(bool)[decided]), f"{what}: vuv"
+    assert abs(float(got["mean_energy"]) - float(ref["mean_energy"])) <= 1e-3 * float(ref["mean_energy"]), f"{what}: mean energy"
+
+
+def test_oracle_matches_the_reference_outputs():
+    n = 0
+    for i, wav, opts, ref in cases():
+        o = onp.nlfer(wav, onp.params(**opts))
+        assert o["nframes"] == int(ref["nframes"])
+        compare(o, ref, f"oracle case {i}")
+        n += 1
+    assert n >= 4
+
+
+def test_oracle_loop_and_compiled_recursions_agree():
+    """The documented sample loop of the oracle and the compiled recursion it normally uses are the same filter."""
+    wav = conditioning.waveform(5, 0.2).astype(np.float64)
+    b, a = onp.normalized_coeffs("low", 16000.0, 50.0)
+    saved = onp._scipy_lfilter
+    try:
+        onp._scipy_lfilter = None
+        slow = onp.lfilter_clamped(wav, b, a)
+    finally:
+        onp._scipy_lfilter = saved
+    assert np.abs(slow - onp.lfilter_clamped(wav, b, a)).max() < 1e-15
+
+
+def test_library_exports_every_symbol_of_the_yaapt_header():
+    lib = _lib.load()
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(sa_yaapt_[a-z_0-9]+)\s*\(", src)))
+    assert len(declared) >= 6
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sa_yaapt.h but not exported"
+    assert sorted(_lib.YAAPT_SYMBOLS) == declared
+
+
+def test_frame_geometry_matches_the_reference():
+    """No GPU needed: pitch.nframes / signal.size as the reference computes them (yaapt.py:164-166, 875-876)."""
+    from satools_b200 import yaapt_frontend as yf
+    lib = _lib.load()
+    for i, wav, opts, ref in cases():
+        assert yf.num_frames(len(wav), **opts) == int(ref["nframes"])
+        assert lib.sa_yaapt_padded_length(yf.params(**opts), len(wav)) == len(ref["filtered"])
+    assert lib.sa_yaapt_num_frames(None, 10) < 0 and b"bad" in lib.sa_yaapt_last_error()
+    with pytest.raises(KeyError):
+        yf.params(nccf_thresh1=0.25)                  # a tracker option: not read by the front end
+    p = yf.params()
+    assert (p.sr, p.frame_length, p.frame_space, p.fft_length, p.bp_low, p.bp_high) == (16000.0, 35.0, 10.0, 8192.0, 50.0, 1500.0)
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _item(out, b):
+    return dict(filtered=out.filtered[b].cpu().numpy(), filtered_nl=out.filtered_nl[b].cpu().numpy(), energy=out.energy[b].cpu().numpy(),
+                vuv=out.vuv[b].cpu().numpy(), mean_energy=float(out.mean_energy[b]))
+
+
+@pytest.mark.gpu
+def test_cuda_front_end_matches_the_reference_outputs():
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    for i, wav, opts, ref in cases():
+        out = yf.nlfer(torch.from_numpy(wav).to("cuda:0"), **opts)
+        assert out.nframes == [int(ref["nframes"])] and out.padded_lengths == [len(ref["filtered"])]
+        compare(_item(out, 0), ref, f"cuda case {i}")
+
+
+@pytest.mark.gpu
+def test_cuda_front_end_ragged_batch_against_the_oracle_and_alone():
+    """A padded batch with true lengths (chunks that end inside an item, items shorter than one chunk, one of 20 s: 300+
+    chunks with a warm-up start) against the float64 oracle; every item also bit-identical to its solo run."""
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    opts = dict(frame_length=35.0, frame_space=20.0)
+    secs = [20.0, 3.1, 0.064, 7.77, 0.5, 12.3]
+    wavs = [conditioning.waveform(100 + i, s) for i, s in enumerate(secs)]
+    n = max(len(w) for w in wavs)
+    x = np.zeros((len(wavs), n), dtype=np.float32)
+    rng = np.random.default_rng(0)
+    for b, w in enumerate(wavs):
+        x[b, :len(w)] = w
+        x[b, len(w):] = rng.standard_normal(n - len(w)) * 0.1      # garbage beyond the true length must not matter
+    out = yf.nlfer(torch.from_numpy(x).to("cuda:0"), lengths=[len(w) for w in wavs], **opts)
+    for b, w in enumerate(wavs):
+        o = onp.nlfer(w, onp.params(**opts))
+        assert out.nframes[b] == o["nframes"]
+        compare(_item(out, b), {k: o[k] for k in ("filtered", "filtered_nl", "energy", "vuv", "mean_energy")}, f"batch item {b}")
+        f, npad = out.nframes[b], out.padded_lengths[b]
+        assert float(out.energy[b, f:].abs().sum()) == 0.0 and float(out.filtered[b, npad:].abs().sum()) == 0.0
+        solo = yf.nlfer(torch.from_numpy(w).to("cuda:0"), **opts)
+        assert torch.equal(solo.energy[0], out.energy[b, :f]) and torch.equal(solo.vuv[0], out.vuv[b, :f])
+        assert torch.equal(solo.filtered[0], out.filtered[b, :npad]) and torch.equal(solo.filtered_nl[0], out.filtered_nl[b, :npad])
+
+
+@pytest.mark.gpu
+def test_cuda_front_end_properties_at_full_size():
+    """BASELINE configs[1] size (64 utterances of 10-15 s).  Scaling the input by a power of two scales `filtered` by the same
+    factor exactly (every rounding commutes with it, and nothing reaches the clamp), `filtered_nl` by its square, and leaves
+    the normalised energy and the voiced flags bit-identical; items 0 / 31 / 63 against the oracle."""
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    opts = dict(frame_length=35.0, frame_space=20.0)
+    rng = np.random.default_rng(3)
+    lens = [int(v) for v in rng.integers(160000, 240001, size=64)]
+    x = np.zeros((64, 240000), dtype=np.float32)
+    for b, n in enumerate(lens):
+        x[b, :n] = conditioning.waveform(200 + b, n / 16000.0)[:n]
+    xd = torch.from_numpy(x).to("cuda:0")
+    a = yf.nlfer(xd, lengths=lens, **opts)
+    h = yf.nlfer(xd * 0.5, lengths=lens, **opts)
+    assert torch.equal(h.filtered, a.filtered * 0.5) and torch.equal(h.filtered_nl, a.filtered_nl * 0.25)
+    assert torch.equal(h.energy, a.energy) and torch.equal(h.vuv, a.vuv)
+    assert 0.2 < float(a.vuv.float().mean()) < 0.9
+    for b in (0, 31, 63):
+        o = onp.nlfer(x[b, :lens[b]], onp.params(**opts))
+        compare(_item(a, b), {k: o[k] for k in ("filtered", "filtered_nl", "energy", "vuv", "mean_energy")}, f"full-size item {b}")
