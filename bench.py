@@ -469,6 +469,50 @@ def main():
                                          "chunks": "6 windows of 512 + 2 x 20 halo frames in one batch, host features in, PCM16 out",
                                          "unit": "ms per 60 s utterance (median)"}
         del x60d
+        # N2 (first step): the YAAPT front end (band-pass biquads + NLFER energy + voiced flags, yaapt.py:42-52,148-176) of the
+        # same 64 utterances, waveforms of frames * 320 samples, options of bin/pipeline.py (frame_length 35, frame_space 20)
+        from satools_b200 import yaapt_frontend as yf
+        yopts = dict(frame_length=35.0, frame_space=20.0)
+        lens = [f * 320 for f in frames]
+        wav_h = torch.zeros(len(frames), max(lens)).pin_memory()
+        for b, n_s in enumerate(lens):
+            wav_h[b, :n_s] = torch.from_numpy(conditioning.waveform(500 + b, n_s / 16000.0)[:n_s])
+        wav_d = wav_h.to(dev)
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0.record()
+            for _ in range(n):
+                fn()
+            t1.record()
+            torch.cuda.synchronize()
+            return t0.elapsed_time(t1) / n
+
+        def from_host():
+            r = yf.nlfer(wav_h.to(dev, non_blocking=True), lengths=lens, **yopts)
+            return r.energy.cpu(), r.vuv.cpu()
+        ms_dev = timed(lambda: yf.nlfer(wav_d, lengths=lens, **yopts), args.steps)
+        ms_host = timed(from_host, args.steps)
+        from oracle import yaapt_nlfer_numpy as onp
+        t0 = time.perf_counter()
+        n_cpu = 0
+        while time.perf_counter() - t0 < 4.0 and n_cpu < 2 * len(lens):
+            onp.nlfer(wav_h[n_cpu % len(lens), :lens[n_cpu % len(lens)]].numpy(), onp.params(**yopts))
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        cpu_sec = sum(lens[i % len(lens)] for i in range(n_cpu)) / 16000.0
+        extras["yaapt_frontend_b64"] = {
+            "value": audio_s / (ms_dev / 1e3), "unit": "audio-s/s", "ms_per_step": ms_dev,
+            "host_buffers_value": audio_s / (ms_host / 1e3), "host_buffers_ms_per_step": ms_host,
+            "h2d_bytes_per_step": int(wav_h.numel() * 4), "d2h_bytes_per_step": int(len(lens) * yf.num_frames(max(lens), **yopts) * 5),
+            "what": "SignalObj.filtered of the signal and the squared signal + PitchObj.energy / vuv / mean_energy for the batch "
+                    "(the part of _yaapt before spec_track); the trackers are not on the GPU yet",
+            "cpu_port": {"value": cpu_sec / dt, "unit": "audio-s/s", "cores": 1, "kind": "port",
+                         "sample": f"{n_cpu} utterances through oracle/yaapt_nlfer_numpy.py (float64, scipy recursion) in {dt:.1f} s"}}
+        del wav_d
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------
     if single and not args.no_cpu_baseline:

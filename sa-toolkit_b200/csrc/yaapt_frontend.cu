@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -75,12 +76,11 @@ int64_t frames_of(const Geometry& g, int64_t n_samples) {
   return span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump;
 }
 
-constexpr int kChunk = 1024;
 
 // src_mode 0: input = padded (and for odd signals squared) waveform; 1: input = `in` [2B, stride]
 __global__ void biquad_chunk_kernel(const float* __restrict__ wav, const float* __restrict__ in, float* __restrict__ out_a,
                                     float* __restrict__ out_b, const int* __restrict__ lengths, int64_t n_max, int64_t stride,
-                                    int pad, int n_chunks, Biquad q, int src_mode, int B) {
+                                    int pad, int n_chunks, int chunk_len, Biquad q, int src_mode, int B) {
   const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
   const int sig = blockIdx.y;                                     // 2 b + (0: signal, 1: squared signal)
   if (chunk >= n_chunks) return;
@@ -88,7 +88,7 @@ __global__ void biquad_chunk_kernel(const float* __restrict__ wav, const float* 
   const int64_t len = lengths ? lengths[b] : n_max;
   const int64_t size = len + 2 * pad;                             // samples of this item's padded signal
   float* out = (squared ? out_b : out_a);
-  const int64_t o0 = (int64_t)chunk * kChunk, o1 = min(o0 + kChunk, stride);
+  const int64_t o0 = (int64_t)chunk * chunk_len, o1 = min(o0 + chunk_len, stride);
   if (out) out += (src_mode == 0 ? (int64_t)sig : (int64_t)b) * stride;
   if (o0 >= size) {                                               // beyond the item: zeros
     if (out) for (int64_t i = o0; i < o1; ++i) out[i] = 0.f;
@@ -108,12 +108,19 @@ __global__ void biquad_chunk_kernel(const float* __restrict__ wav, const float* 
   const int64_t start = max((int64_t)0, o0 - q.warm);
   double x1 = start > 0 ? x_at(start - 1) : 0.0, x2 = start > 1 ? x_at(start - 2) : 0.0, y1 = 0.0, y2 = 0.0;
   const int64_t end = min(o1, size);
-  for (int64_t i = start; i < end; ++i) {
-    const double x0 = x_at(i);
-    const double t = fma(q.b2, x2, fma(q.b1, x1, q.b0 * x0)) - q.a2 * y2;   // off the critical path
-    const double y = fma(-q.a1, y1, t);
-    x2 = x1; x1 = x0; y2 = y1; y1 = y;
-    if (i >= o0 && out) out[i] = (float)fmin(1.0, fmax(-1.0, y));
+  for (int64_t i0 = start; i0 < end; i0 += 8) {                   // inputs of eight steps first: their loads overlap
+    double xs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xs[j] = i0 + j < end ? x_at(i0 + j) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t i = i0 + j;
+      const double x0 = xs[j];
+      const double t = fma(q.b2, x2, fma(q.b1, x1, q.b0 * x0)) - q.a2 * y2;   // off the critical path
+      const double y = fma(-q.a1, y1, t);
+      x2 = x1; x1 = x0; y2 = y1; y1 = y;
+      if (i >= o0 && i < end && out) out[i] = (float)fmin(1.0, fmax(-1.0, y));
+    }
   }
   if (out) for (int64_t i = end; i < o1; ++i) out[i] = 0.f;
 }
@@ -269,12 +276,24 @@ int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int
   }
   const int* dl = lengths ? d_len : nullptr;
   const Biquad lp = design(true, p->sr, p->bp_low), hp = design(false, p->sr, p->bp_high);
-  const int n_chunks = (int)((stride + kChunk - 1) / kChunk);
-  const dim3 grid((unsigned)((n_chunks + 63) / 64), (unsigned)(2 * B));
-  biquad_chunk_kernel<<<grid, 64, 0, st>>>(wav, nullptr, tmp1, tmp1, dl, n_max, stride, g.pad, n_chunks, lp, 0, B);
+  // Chunk length: every thread also runs `warm` samples of warm-up, and the recursion is a latency chain.  Measured at
+  // 64 x 10-15 s (whole front end): 128 -> 5.5 ms, 256 -> 3.8, 512 -> 3.2, 1024 -> 2.9, 2048 -> 3.0.  SATOOLS_B200_YAAPT_CHUNK overrides.
+  auto chunk_for = [](const Biquad&) {
+    if (const char* e = getenv("SATOOLS_B200_YAAPT_CHUNK")) { const int v = atoi(e); if (v >= 16 && v <= 65536) return v; }
+    return 1024;
+  };
   float* fa = filtered ? filtered : own;
   float* fb = filtered_nl ? filtered_nl : own + (size_t)B * stride;
-  biquad_chunk_kernel<<<grid, 64, 0, st>>>(nullptr, tmp1, fa, fb, dl, n_max, stride, g.pad, n_chunks, hp, 1, B);
+  {
+    const int cl = chunk_for(lp), n_chunks = (int)((stride + cl - 1) / cl);
+    const dim3 grid((unsigned)((n_chunks + 127) / 128), (unsigned)(2 * B));
+    biquad_chunk_kernel<<<grid, 128, 0, st>>>(wav, nullptr, tmp1, tmp1, dl, n_max, stride, g.pad, n_chunks, cl, lp, 0, B);
+  }
+  {
+    const int cl = chunk_for(hp), n_chunks = (int)((stride + cl - 1) / cl);
+    const dim3 grid((unsigned)((n_chunks + 127) / 128), (unsigned)(2 * B));
+    biquad_chunk_kernel<<<grid, 128, 0, st>>>(nullptr, tmp1, fa, fb, dl, n_max, stride, g.pad, n_chunks, cl, hp, 1, B);
+  }
   if (f_max > 0 && (energy || vuv || mean_energy)) {
     const int bins = g.bin_hi - g.bin_lo;
     const int threads = (bins + 31) / 32 * 32;
