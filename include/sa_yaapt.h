@@ -6,8 +6,9 @@
  *   nlfer 148-176                       Hann-windowed frames, |DFT| summed over the F0 band
  *   PitchObj.set_energy 124-127         energy / mean(energy), voiced = energy > nlfer_thresh1
  * The reference runs this per utterance on one CPU thread (yaapt.py:27, 947-952); the outputs are what its spectral and
- * temporal trackers (spec_track, time_track) read: SignalObj.filtered of both signals, PitchObj.energy / vuv / mean_energy.
- * The trackers themselves (spec_track, time_track, refine, dynamic) are not part of this library yet.
+ * temporal trackers (spec_track, time_track) read: SignalObj.filtered of both signals, PitchObj.energy / vuv / mean_energy --
+ * plus the per-frame spectral part of spec_track (its SHC vectors, sa_yaapt_shc).  Peak picking, the NCCF tracker, refine
+ * and the dynamic programming (peaks, time_track, refine, dynamic) are not part of this library yet.
  *
  * Same conventions as sa_hifigan.h: plain pointers and sizes, 0 = success, negative = error with the text in
  * sa_yaapt_last_error(); all tensor pointers are DEVICE pointers, `stream` is a cudaStream_t (NULL = default stream).
@@ -32,6 +33,9 @@ typedef struct sa_yaapt_params {
   double bp_low;        /* 50 Hz   (handed to the LOW-pass, as the reference does) */
   double bp_high;       /* 1500 Hz (handed to the HIGH-pass) */
   double nlfer_thresh1; /* 0.75 */
+  double shc_numharms;  /* 3    harmonics in the SHC product besides the fundamental (spec_track) */
+  double shc_window;    /* 40 Hz  SHC window length */
+  double shc_pwidth;    /* 50 Hz  peak-picking width: max_SHC = floor((f0_max + 2 shc_pwidth) / (sr / fft_length)) */
 } sa_yaapt_params;
 
 const char* sa_yaapt_last_error(void);
@@ -55,6 +59,17 @@ size_t sa_yaapt_frontend_workspace_bytes(const sa_yaapt_params* p, int32_t B, in
 int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int64_t n_max, const int32_t* lengths,
                       float* filtered, float* filtered_nl, float* energy, uint8_t* vuv, float* mean_energy, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* spec_track lines 184-231 (up to the call of `peaks`): the spectral harmonics correlation of every VOICED frame of the
+ * squared signal -- 2 frame_size samples x Kaiser(beta 0.5) window, mean removed, |DFT_nfft|,
+ * SHC[k] = sum_c prod_{h = 1 .. numharms + 1} |X|[h k + c - half_window],  k in [min_SHC, max_SHC] stored at index k - 1.
+ * sa_yaapt_shc_length = max_SHC = the length of the vector `peaks` receives (256 for the defaults).
+ * filtered_nl [B, n_max + 2 pad] and vuv [B, F_max] are sa_yaapt_frontend's outputs; shc [B, F_max, max_SHC] float32 (rows
+ * of unvoiced frames and frames beyond an item's count are zero). */
+int64_t sa_yaapt_shc_length(const sa_yaapt_params* p);
+size_t sa_yaapt_shc_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max);
+int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, int64_t n_max, const int32_t* lengths,
+                 const uint8_t* vuv, float* shc, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

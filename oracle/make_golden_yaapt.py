@@ -50,7 +50,30 @@ def run_reference(wav: np.ndarray, opts: dict):
     frame_jump = floor(torch.tensor(p["frame_space"] * signal.fs / 1000))
     pitch = ref.PitchObj(int(frame_size), int(frame_jump), int(p["fft_length"]))
     ref.nlfer(signal, pitch, p)
-    return dict(filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
+    # spec_track's SHC vectors: run the reference's own spec_track and record what it hands to `peaks` per voiced frame
+    full = dict(p)
+    full.update(dict(nlfer_thresh2=0.1, shc_maxpeaks=4.0, shc_thresh1=5.0, shc_thresh2=1.25, f0_double=150.0, f0_half=150.0,
+                     dp5_k1=11.0, nccf_thresh1=0.3, nccf_thresh2=0.9, nccf_maxcands=3.0, nccf_pwidth=5.0, merit_boost=0.2,
+                     merit_pivot=0.99, merit_extra=0.4, median_value=7.0, dp_w1=0.15, dp_w2=0.5, dp_w3=0.1, dp_w4=0.9,
+                     spec_pitch_min_std=0.05, tda_frame_length=35.0))               # the defaults of _yaapt (yaapt.py:818-866)
+    captured = []
+    original = ref.peaks
+
+    def spy(shc, delta, maxpeaks, parameters):
+        captured.append(shc.clone().numpy())
+        return original(shc, delta, maxpeaks, parameters)
+    ref.peaks = spy
+    try:
+        ref.spec_track(nonlinear, pitch, full)
+    except IndexError:
+        # fewer than four frames: the reference's spec_track raises at `spec_pitch[1] = spec_pitch[3]` (yaapt.py:311), AFTER
+        # the per-frame loop -- the SHC vectors it computed up to there are recorded all the same
+        pass
+    finally:
+        ref.peaks = original
+    shc = np.zeros((int(pitch.nframes), len(captured[0]) if captured else 0), dtype=np.float32)
+    shc[np.nonzero(pitch.vuv.numpy())[0]] = np.stack(captured) if captured else 0
+    return dict(shc=shc, filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
                 vuv=pitch.vuv.numpy(), mean_energy=np.float32(pitch.mean_energy.item()), nframes=np.int64(pitch.nframes))
 
 
@@ -62,6 +85,8 @@ def main():
         o = onp.nlfer(wav, onp.params(**opts))
         rel = np.abs(o["energy"] - r["energy"]).max() / max(1e-12, np.abs(r["energy"]).max())
         flips = int((o["vuv"] != r["vuv"]).sum())
+        so = onp.shc(r["filtered_nl"], r["vuv"], onp.params(**opts))
+        print(f"        SHC peak {r['shc'].max():.3e}, oracle-vs-reference max err / peak {np.abs(so - r['shc']).max() / r['shc'].max():.2e}")
         print(f"case {i}: n={len(wav)} frames={int(r['nframes'])} voiced={int(r['vuv'].sum())} oracle-vs-reference energy rel-err {rel:.2e}, "
               f"vuv flips {flips}, filtered max-abs {np.abs(r['filtered']).max():.3e} err {np.abs(o['filtered'] - r['filtered']).max():.2e}")
         out[f"c{i}_seed"] = np.int64(seed)

@@ -12,7 +12,10 @@ What it restates (/root/reference/satools/satools/hifigan/yaapt.py):
   * `nlfer` lines 148-176: frames of frame_size samples every frame_jump samples, Hann window `hann_window(n + 2)[1:-1]`,
     magnitude of the nfft-point DFT summed over bins [N_f0_min - 1, N_f0_max), N_f0_min = round(2 f0_min / fs * nfft),
     N_f0_max = round(f0_max / fs * nfft);
-  * `PitchObj.set_energy` lines 124-127: energy / mean(energy), voiced = energy > nlfer_thresh1.
+  * `PitchObj.set_energy` lines 124-127: energy / mean(energy), voiced = energy > nlfer_thresh1;
+  * `spec_track` lines 184-231 up to the call of `peaks`: for every voiced frame the spectral harmonics correlation SHC of the
+    squared signal: 2 frame_size samples x Kaiser(beta 0.5, periodic) window, mean removed, |rfft_nfft|, then
+    SHC[k] = sum_c prod_{h=1..numharms+1} |X|[h k + c - half_window] over a window of `window_length` bins, k in [min_SHC, max_SHC].
 
 Pinned by tests/golden/yaapt_nlfer.npz (outputs of the reference itself, oracle/make_golden_yaapt.py).  The filters are
 evaluated in float64 here: the reference runs them in float32, and its own rounding noise is what sets the tolerance of the
@@ -28,7 +31,7 @@ except Exception:  # pragma: no cover
     _scipy_lfilter = None
 
 DEFAULTS = dict(sr=16000.0, frame_length=35.0, frame_space=10.0, f0_min=60.0, f0_max=400.0, fft_length=8192.0, bp_low=50.0,
-                bp_high=1500.0, nlfer_thresh1=0.75)
+                bp_high=1500.0, nlfer_thresh1=0.75, shc_numharms=3.0, shc_window=40.0, shc_pwidth=50.0)
 
 
 def params(**kw):
@@ -118,3 +121,43 @@ def nlfer(wav, p=None):
     energy = frame_energy / mean_energy
     return dict(energy=energy, vuv=energy > p["nlfer_thresh1"], mean_energy=mean_energy, frame_energy=frame_energy, filtered=filt,
                 filtered_nl=filtered(x * x, p), nframes=n_frames)
+
+
+def shc_geometry(p):
+    """(nframe_size, window_length, half_window_length, min_SHC, max_SHC, n_harm) of spec_track (yaapt.py:189-201)."""
+    frame_size = int(math.floor(p["frame_length"] * p["sr"] / 1000))
+    delta = p["sr"] / int(p["fft_length"])
+    window_length = int(math.floor(p["shc_window"] / delta))
+    half = int(math.floor(float(window_length) / 2))
+    if not (window_length % 2):
+        window_length += 1
+    max_shc = int(math.floor((p["f0_max"] + p["shc_pwidth"] * 2) / delta))
+    min_shc = int(math.ceil(p["f0_min"] / delta))
+    return 2 * frame_size, window_length, half, min_shc, max_shc, int(p["shc_numharms"]) + 1
+
+
+def shc(filtered_nl, vuv, p=None):
+    """filtered_nl: SignalObj.filtered of the squared signal [size]; vuv [n_frames] -> [n_frames, max_SHC] (zero rows for
+    unvoiced frames; entries outside [min_SHC - 1, max_SHC) are zero, as in the reference's SHC buffer)."""
+    p = p or params()
+    nframe, wl, half, min_shc, max_shc, n_harm = shc_geometry(p)
+    frame_jump = int(math.floor(p["frame_space"] * p["sr"] / 1000))
+    nfft = int(p["fft_length"])
+    x = np.asarray(filtered_nl, dtype=np.float64)
+    n_frames = len(vuv)
+    need = nframe + (n_frames - 1) * frame_jump
+    if need > len(x):
+        x = np.concatenate([x, np.zeros(need - len(x))])
+    window = np.kaiser(nframe + 1, 0.5)[:-1]                     # torch.kaiser_window(nframe, periodic=True, beta=0.5)
+    out = np.zeros((n_frames, max_shc))
+    rows = max_shc - min_shc + 1
+    for f in np.nonzero(np.asarray(vuv))[0]:
+        sl = x[f * frame_jump:f * frame_jump + nframe] * window
+        sl = sl - sl.mean()
+        mag = np.concatenate([np.zeros(half), np.abs(np.fft.rfft(sl, nfft))])
+        acc = np.ones((rows, wl))
+        for h in range(1, n_harm + 1):
+            idx = min_shc * h + np.arange(rows)[:, None] * h + np.arange(wl)[None, :]
+            acc = acc * mag[idx]
+        out[f, min_shc - 1:max_shc] = acc.sum(1)
+    return out

@@ -215,6 +215,116 @@ __global__ void nlfer_normalize_kernel(const float* __restrict__ frame_energy, f
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// ---- spec_track's SHC (yaapt.py:184-231) ----------------------------------------------------------------------
+struct ShcGeometry { int nframe, wl, half, min_shc, max_shc, n_harm, bin_lo, n_bins; };
+
+bool shc_geometry(const sa_yaapt_params* p, const Geometry& g, ShcGeometry& s) {
+  if (p->shc_numharms < 0 || p->shc_numharms > 7 || p->shc_window <= 0 || p->shc_pwidth < 0) return false;
+  const double delta = p->sr / g.nfft;
+  s.nframe = 2 * g.frame_size;
+  s.wl = (int)floor(p->shc_window / delta);
+  s.half = (int)floor((double)s.wl / 2);
+  if (s.wl % 2 == 0) s.wl += 1;
+  s.max_shc = (int)floor((p->f0_max + p->shc_pwidth * 2) / delta);
+  s.min_shc = (int)ceil(p->f0_min / delta);
+  s.n_harm = (int)p->shc_numharms + 1;
+  s.bin_lo = s.min_shc - s.half < 0 ? 0 : s.min_shc - s.half;
+  const int bin_hi = s.max_shc * s.n_harm + s.wl - 1 - s.half;          // last bin any product reads
+  s.n_bins = bin_hi - s.bin_lo + 1;
+  return s.min_shc >= 1 && s.max_shc >= s.min_shc && bin_hi <= g.nfft / 2 && s.nframe <= g.nfft && s.wl <= 64;
+}
+
+// torch.kaiser_window(n, periodic=True, beta): I0(beta sqrt(1 - (2 i / n - 1)^2)) / I0(beta)
+__global__ void kaiser_kernel(float* w, int n, double beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto i0 = [](double x) {
+    double t = 1.0, sum = 1.0;
+    for (int k = 1; k < 40; ++k) { t *= (x / 2) / k; sum += t * t; if (t * t < 1e-20 * sum) break; }
+    return sum;
+  };
+  const double r = 2.0 * i / n - 1.0;
+  w[i] = (float)(i0(beta * sqrt(fmax(0.0, 1.0 - r * r))) / i0(beta));
+}
+
+// One block per (frame, item).  smem: [nframe] windowed, mean-free samples | [n_bins] magnitudes | [32] partial sums.
+__global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const uint8_t* __restrict__ vuv, const float* __restrict__ window,
+                                 float* __restrict__ shc, const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max,
+                                 Geometry g, ShcGeometry s) {
+  extern __shared__ float sm[];
+  float* frame = sm;
+  float* mag = sm + s.nframe;
+  float* part = mag + s.n_bins;
+  const int f = blockIdx.x, b = blockIdx.y;
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int64_t n_frames = span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump;
+  float* out = shc + ((int64_t)b * f_max + f) * s.max_shc;
+  if (f >= n_frames || !vuv[(int64_t)b * f_max + f]) {
+    for (int k = threadIdx.x; k < s.max_shc; k += blockDim.x) out[k] = 0.f;
+    return;
+  }
+  // data[f jump : f jump + nframe] * window, zero beyond the signal (the reference pads `data` with zeros, yaapt.py:208-212)
+  const float* x = filtered_nl + (int64_t)b * stride;
+  const int64_t i0 = (int64_t)f * g.frame_jump;
+  float psum = 0.f;
+  for (int n = threadIdx.x; n < s.nframe; n += blockDim.x) {
+    const int64_t i = i0 + n;
+    const float v = (i < size && i < stride) ? x[i] * window[n] : 0.f;
+    frame[n] = v;
+    psum += v;
+  }
+  for (int d = 16; d > 0; d >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = psum;
+  __syncthreads();
+  float total = 0.f;
+  for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) total += part[w];
+  const float mean = total / (float)s.nframe;
+  __syncthreads();
+  for (int n = threadIdx.x; n < s.nframe; n += blockDim.x) frame[n] -= mean;
+  __syncthreads();
+  for (int kb = threadIdx.x; kb < s.n_bins; kb += blockDim.x) {
+    const int k = s.bin_lo + kb;
+    double sd, cd;
+    sincospi(-2.0 * (double)k / (double)g.nfft, &sd, &cd);
+    const float rc = (float)cd, rs = (float)sd;
+    float re = 0.f, im = 0.f;
+    for (int n0 = 0; n0 < s.nframe; n0 += 16) {
+      const int idx = (int)(((int64_t)k * n0) % g.nfft);
+      float ws, wc;
+      sincospif(-2.0f * (float)idx / (float)g.nfft, &ws, &wc);
+      const int n1 = min(n0 + 16, s.nframe);
+      for (int n = n0; n < n1; ++n) {
+        const float v = frame[n];
+        re = fmaf(v, wc, re);
+        im = fmaf(v, ws, im);
+        const float t = wc * rc - ws * rs;
+        ws = wc * rs + ws * rc;
+        wc = t;
+      }
+    }
+    mag[kb] = sqrtf(re * re + im * im);
+  }
+  __syncthreads();
+  const int rows = s.max_shc - s.min_shc + 1;
+  for (int k = threadIdx.x; k < s.max_shc; k += blockDim.x) {
+    const int r = k - (s.min_shc - 1);
+    float acc = 0.f;
+    if (r >= 0 && r < rows) {
+      for (int c = 0; c < s.wl; ++c) {
+        float prod = 1.f;
+        for (int h = 1; h <= s.n_harm; ++h) {
+          const int bin = (s.min_shc + r) * h + c - s.half;                // magnitude[half + bin] of the reference
+          prod *= (bin >= s.bin_lo) ? mag[bin - s.bin_lo] : 0.f;
+        }
+        acc += prod;
+      }
+    }
+    out[k] = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -225,6 +335,7 @@ int sa_yaapt_default_params(sa_yaapt_params* p) {
   if (!p) return fail("sa_yaapt_default_params: NULL params");
   p->sr = 16000.0; p->frame_length = 35.0; p->frame_space = 10.0; p->f0_min = 60.0; p->f0_max = 400.0;
   p->fft_length = 8192.0; p->bp_low = 50.0; p->bp_high = 1500.0; p->nlfer_thresh1 = 0.75;
+  p->shc_numharms = 3.0; p->shc_window = 40.0; p->shc_pwidth = 50.0;
   return 0;
 }
 
@@ -302,6 +413,53 @@ int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int
     nlfer_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(fa, d_fe, dl, n_max, stride, f_max, g);
     nlfer_normalize_kernel<<<B, 256, 0, st>>>(d_fe, energy, vuv, mean_energy, dl, n_max, f_max, g, (float)p->nlfer_thresh1);
   }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  return 0;
+}
+
+int64_t sa_yaapt_shc_length(const sa_yaapt_params* p) {
+  Geometry g;
+  ShcGeometry sg;
+  if (!geometry(p, g) || !shc_geometry(p, g, sg)) { fail("sa_yaapt_shc_length: bad parameters"); return -1; }
+  return sg.max_shc;
+}
+
+size_t sa_yaapt_shc_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max) {
+  Geometry g;
+  ShcGeometry sg;
+  if (!geometry(p, g) || !shc_geometry(p, g, sg) || B <= 0 || n_max <= 0) return 0;
+  return align256((size_t)B * 4) + align256((size_t)sg.nframe * 4) + 256;
+}
+
+int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, int64_t n_max, const int32_t* lengths,
+                 const uint8_t* vuv, float* shc, void* workspace, size_t workspace_bytes, void* stream) {
+  Geometry g;
+  ShcGeometry sg;
+  if (!geometry(p, g) || !shc_geometry(p, g, sg)) return fail("sa_yaapt_shc: bad parameters (the SHC products must stay inside the FFT)");
+  if (!filtered_nl || !vuv || !shc || B <= 0 || n_max <= 0 || B > 32767) return fail("sa_yaapt_shc: NULL argument or bad batch size");
+  if (!workspace || workspace_bytes < sa_yaapt_shc_workspace_bytes(p, B, n_max)) return fail("sa_yaapt_shc: workspace too small");
+  if (lengths)
+    for (int b = 0; b < B; ++b)
+      if (lengths[b] < 0 || lengths[b] > n_max) return fail("sa_yaapt_shc: lengths[b] outside [0, n_max]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t stride = n_max + 2 * g.pad;
+  const int f_max = (int)frames_of(g, n_max);
+  if (f_max == 0) return 0;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  int* d_len = reinterpret_cast<int*>(base);
+  base += align256((size_t)B * 4);
+  float* d_win = reinterpret_cast<float*>(base);
+  if (lengths) {
+    cudaError_t e = cudaMemcpyAsync(d_len, lengths, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  }
+  kaiser_kernel<<<(sg.nframe + 255) / 256, 256, 0, st>>>(d_win, sg.nframe, 0.5);
+  const int threads = sg.n_bins >= 1024 ? 1024 : (sg.n_bins + 31) / 32 * 32;
+  const size_t smem = (size_t)(sg.nframe + sg.n_bins + 32) * sizeof(float);
+  if (smem > 48 * 1024) return fail("sa_yaapt_shc: frame + spectrum do not fit in 48 KB of shared memory");
+  shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(filtered_nl, vuv, d_win, shc, lengths ? d_len : nullptr, n_max,
+                                                                            stride, f_max, g, sg);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   return 0;

@@ -19,7 +19,8 @@ import torch
 
 from . import _lib
 
-OPTION_NAMES = ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low", "bp_high", "nlfer_thresh1")
+OPTION_NAMES = ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low", "bp_high", "nlfer_thresh1",
+                "shc_numharms", "shc_window", "shc_pwidth")
 
 
 def params(**kwargs) -> "_lib.YaaptParams":
@@ -85,4 +86,33 @@ def nlfer(wav: torch.Tensor, lengths: Optional[Sequence[int]] = None, **kwargs) 
         nb = n if lengths is None else int(lengths[b])
         out.nframes.append(int(lib.sa_yaapt_num_frames(p, nb)))
         out.padded_lengths.append(int(lib.sa_yaapt_padded_length(p, nb)))
+    return out
+
+
+def spec_shc(front: FrontEnd, lengths: Optional[Sequence[int]] = None, **kwargs) -> torch.Tensor:
+    """The SHC vectors `spec_track` (yaapt.py:184-231) hands to `peaks`, for every voiced frame of the batch:
+    [B, F_max, max_SHC] float32 (zero rows for unvoiced frames).  `front` is the result of `nlfer` with the same
+    lengths and options."""
+    lib = _lib.load()
+    p = params(**kwargs)
+    x = front.filtered_nl
+    B, n_pad = x.shape
+    n = n_pad - (int(lib.sa_yaapt_padded_length(p, 0)))
+    f_max = front.vuv.shape[1]
+    k = int(lib.sa_yaapt_shc_length(p))
+    if k < 0 or int(lib.sa_yaapt_num_frames(p, n)) != f_max:
+        raise _lib.SaHifiganError(f"spec_shc: options do not match the front end ({lib.sa_yaapt_last_error().decode()})")
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty(B, f_max, k, device=dev)
+        vuv = front.vuv.to(torch.uint8).contiguous()
+        ws = torch.empty(int(lib.sa_yaapt_shc_workspace_bytes(p, B, n)), dtype=torch.uint8, device=dev)
+        lens = None
+        if lengths is not None:
+            lens = (C.c_int32 * B)(*[int(v) for v in lengths])
+        rc = lib.sa_yaapt_shc(p, x.data_ptr(), B, n, lens, vuv.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                              torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise _lib.SaHifiganError(f"sa_yaapt_shc: {lib.sa_yaapt_last_error().decode()}")
+        torch.cuda.current_stream(dev).synchronize()
     return out

@@ -32,7 +32,7 @@ def cases():
         fl, fs = [float(v) for v in z[f"c{i}_opts"]]
         wav = conditioning.waveform(int(z[f"c{i}_seed"]), float(z[f"c{i}_seconds"]))
         yield i, wav, dict(frame_length=fl, frame_space=fs), {k: z[f"c{i}_{k}"] for k in ("filtered", "filtered_nl", "energy", "vuv",
-                                                                                          "mean_energy", "nframes")}
+                                                                                          "mean_energy", "nframes", "shc")}
 
 
 def compare(got, ref, what, thr=0.75):
@@ -60,6 +60,28 @@ def test_oracle_matches_the_reference_outputs():
     assert n >= 4
 
 
+def compare_shc(got, ref, vuv, what, tol=2e-3):
+    """SHC is a sum of products of four magnitudes: four times the relative noise of the filtered signal.  Per voiced frame
+    within `tol` of that frame's peak (the float64 oracle is 5e-7 from the reference on the reference's own filtered signal)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, f"{what}: {got.shape} vs {ref.shape}"
+    for f in range(ref.shape[0]):
+        if not vuv[f]:
+            assert not got[f].any(), f"{what}: unvoiced frame {f} must be zero"
+            continue
+        peak = ref[f].max()
+        assert peak > 0 and np.abs(got[f] - ref[f]).max() <= tol * peak, f"{what}: frame {f} differs by {np.abs(got[f] - ref[f]).max() / peak:.2e} of its peak"
+
+
+def test_oracle_shc_matches_the_vectors_the_reference_hands_to_peaks():
+    for i, wav, opts, ref in cases():
+        p = onp.params(**opts)
+        compare_shc(onp.shc(ref["filtered_nl"], ref["vuv"], p), ref["shc"], ref["vuv"], f"oracle SHC case {i} (reference's filtered)", 1e-5)
+        o = onp.nlfer(wav, p)
+        compare_shc(onp.shc(o["filtered_nl"], ref["vuv"], p), ref["shc"], ref["vuv"], f"oracle SHC case {i} (own filtered)")
+
+
 def test_oracle_loop_and_compiled_recursions_agree():
     """The documented sample loop of the oracle and the compiled recursion it normally uses are the same filter."""
     wav = conditioning.waveform(5, 0.2).astype(np.float64)
@@ -77,7 +99,7 @@ def test_library_exports_every_symbol_of_the_yaapt_header():
     lib = _lib.load()
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     declared = sorted(set(re.findall(r"\b(sa_yaapt_[a-z_0-9]+)\s*\(", src)))
-    assert len(declared) >= 6
+    assert len(declared) >= 9
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/sa_yaapt.h but not exported"
     assert sorted(_lib.YAAPT_SYMBOLS) == declared
@@ -115,6 +137,13 @@ def test_cuda_front_end_matches_the_reference_outputs():
         out = yf.nlfer(torch.from_numpy(wav).to("cuda:0"), **opts)
         assert out.nframes == [int(ref["nframes"])] and out.padded_lengths == [len(ref["filtered"])]
         compare(_item(out, 0), ref, f"cuda case {i}")
+        shc = yf.spec_shc(out, **opts)
+        assert tuple(shc.shape) == (1,) + ref["shc"].shape
+        if np.array_equal(out.vuv[0].cpu().numpy(), ref["vuv"]):
+            compare_shc(shc[0].cpu().numpy(), ref["shc"], ref["vuv"], f"cuda SHC case {i}")
+        else:                                               # a frame at the threshold flipped: compare the common voiced frames
+            both = out.vuv[0].cpu().numpy() & ref["vuv"].astype(bool)
+            compare_shc(shc[0].cpu().numpy() * both[:, None], ref["shc"] * both[:, None], both, f"cuda SHC case {i}")
 
 
 @pytest.mark.gpu
@@ -133,13 +162,18 @@ def test_cuda_front_end_ragged_batch_against_the_oracle_and_alone():
         x[b, :len(w)] = w
         x[b, len(w):] = rng.standard_normal(n - len(w)) * 0.1      # garbage beyond the true length must not matter
     out = yf.nlfer(torch.from_numpy(x).to("cuda:0"), lengths=[len(w) for w in wavs], **opts)
+    shc = yf.spec_shc(out, lengths=[len(w) for w in wavs], **opts)
     for b, w in enumerate(wavs):
         o = onp.nlfer(w, onp.params(**opts))
         assert out.nframes[b] == o["nframes"]
         compare(_item(out, b), {k: o[k] for k in ("filtered", "filtered_nl", "energy", "vuv", "mean_energy")}, f"batch item {b}")
         f, npad = out.nframes[b], out.padded_lengths[b]
         assert float(out.energy[b, f:].abs().sum()) == 0.0 and float(out.filtered[b, npad:].abs().sum()) == 0.0
+        vb = out.vuv[b, :f].cpu().numpy()
+        compare_shc(shc[b, :f].cpu().numpy(), onp.shc(o["filtered_nl"], vb, onp.params(**opts)), vb, f"batch item {b} SHC")
+        assert float(shc[b, f:].abs().sum()) == 0.0
         solo = yf.nlfer(torch.from_numpy(w).to("cuda:0"), **opts)
+        assert torch.equal(yf.spec_shc(solo, **opts)[0], shc[b, :f])
         assert torch.equal(solo.energy[0], out.energy[b, :f]) and torch.equal(solo.vuv[0], out.vuv[b, :f])
         assert torch.equal(solo.filtered[0], out.filtered[b, :npad]) and torch.equal(solo.filtered_nl[0], out.filtered_nl[b, :npad])
 
@@ -162,7 +196,12 @@ def test_cuda_front_end_properties_at_full_size():
     h = yf.nlfer(xd * 0.5, lengths=lens, **opts)
     assert torch.equal(h.filtered, a.filtered * 0.5) and torch.equal(h.filtered_nl, a.filtered_nl * 0.25)
     assert torch.equal(h.energy, a.energy) and torch.equal(h.vuv, a.vuv)
+    sa, sh = yf.spec_shc(a, lengths=lens, **opts), yf.spec_shc(h, lengths=lens, **opts)
+    assert torch.equal(sh, sa * (0.25 ** 4))                 # four magnitudes of the squared signal per product
     assert 0.2 < float(a.vuv.float().mean()) < 0.9
     for b in (0, 31, 63):
         o = onp.nlfer(x[b, :lens[b]], onp.params(**opts))
         compare(_item(a, b), {k: o[k] for k in ("filtered", "filtered_nl", "energy", "vuv", "mean_energy")}, f"full-size item {b}")
+        f = a.nframes[b]
+        vb = a.vuv[b, :f].cpu().numpy()
+        compare_shc(sa[b, :f].cpu().numpy(), onp.shc(o["filtered_nl"], vb, onp.params(**opts)), vb, f"full-size item {b} SHC")
