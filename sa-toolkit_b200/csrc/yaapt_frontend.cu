@@ -12,7 +12,7 @@
 //                         one DFMA on the critical path per sample, output clamped to [-1, 1] and stored as float32 like
 //                         the reference's tensors.
 //   nlfer_frame_kernel    one block per frame: the Hann-windowed frame in shared memory, one thread per DFT bin of the F0
-//                         band (bins 60..204 of 8192 for the defaults): direct DFT with an exact twiddle every 16 samples
+//                         band (bins 60..204 of 8192 for the defaults): direct DFT with an exact twiddle every 64 samples
 //                         (sincospi of the reduced integer phase) and a complex rotation in between, |X| summed over the band.
 //   nlfer_normalize_kernel one block per utterance: mean over its frames, energy / mean, voiced = energy > threshold.
 #include "../../include/sa_yaapt.h"
@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 
 namespace {
@@ -55,6 +56,11 @@ Biquad design(bool lowpass, double fs, double cutoff) {
 }
 
 struct Geometry { int pad, frame_size, frame_jump, nfft, bin_lo, bin_hi; };
+
+// Direct DFTs below: the twiddle of a bin advances by a complex rotation per sample and is recomputed exactly (sincospi of the
+// integer phase reduced mod nfft) every kResync samples: 64 rotations accumulate ~4e-6 of relative error, and the exact
+// twiddle costs ~45 instructions (every 16 samples it was a quarter of the issue slots of these issue-bound kernels).
+constexpr int kResync = 64;
 
 bool geometry(const sa_yaapt_params* p, Geometry& g) {
   if (!p || p->sr < 1000 || p->frame_length <= 0 || p->frame_space <= 0 || p->fft_length < 16) return false;
@@ -154,11 +160,11 @@ __global__ void nlfer_frame_kernel(const float* __restrict__ filtered, float* __
     sincospi(-2.0 * (double)k / (double)g.nfft, &sd, &cd);        // one-sample rotation e^{-2 pi i k / nfft}
     const float rc = (float)cd, rs = (float)sd;
     float re = 0.f, im = 0.f;
-    for (int n0 = 0; n0 < g.frame_size; n0 += 16) {
+    for (int n0 = 0; n0 < g.frame_size; n0 += kResync) {
       const int idx = (int)(((int64_t)k * n0) % g.nfft);          // exact phase of sample n0
       float ws, wc;
       sincospif(-2.0f * (float)idx / (float)g.nfft, &ws, &wc);
-      const int n1 = min(n0 + 16, g.frame_size);
+      const int n1 = min(n0 + kResync, g.frame_size);
       for (int n = n0; n < n1; ++n) {
         const float v = frame[n];
         re = fmaf(v, wc, re);
@@ -284,27 +290,38 @@ __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const ui
   __syncthreads();
   for (int n = threadIdx.x; n < s.nframe; n += blockDim.x) frame[n] -= mean;
   __syncthreads();
-  for (int kb = threadIdx.x; kb < s.n_bins; kb += blockDim.x) {
-    const int k = s.bin_lo + kb;
+  // two bins per thread (kb and kb + half_bins) share every sample load
+  const int half_bins = (s.n_bins + 1) / 2;
+  for (int kb = threadIdx.x; kb < half_bins; kb += blockDim.x) {
+    const int ka = s.bin_lo + kb, kc = min(ka + half_bins, s.bin_lo + s.n_bins - 1);
     double sd, cd;
-    sincospi(-2.0 * (double)k / (double)g.nfft, &sd, &cd);
-    const float rc = (float)cd, rs = (float)sd;
-    float re = 0.f, im = 0.f;
-    for (int n0 = 0; n0 < s.nframe; n0 += 16) {
-      const int idx = (int)(((int64_t)k * n0) % g.nfft);
-      float ws, wc;
-      sincospif(-2.0f * (float)idx / (float)g.nfft, &ws, &wc);
-      const int n1 = min(n0 + 16, s.nframe);
+    sincospi(-2.0 * (double)ka / (double)g.nfft, &sd, &cd);
+    const float rca = (float)cd, rsa = (float)sd;
+    sincospi(-2.0 * (double)kc / (double)g.nfft, &sd, &cd);
+    const float rcc = (float)cd, rsc = (float)sd;
+    float rea = 0.f, ima = 0.f, rec = 0.f, imc = 0.f;
+    for (int n0 = 0; n0 < s.nframe; n0 += kResync) {
+      float wsa, wca, wsc, wcc;
+      sincospif(-2.0f * (float)(int)(((int64_t)ka * n0) % g.nfft) / (float)g.nfft, &wsa, &wca);
+      sincospif(-2.0f * (float)(int)(((int64_t)kc * n0) % g.nfft) / (float)g.nfft, &wsc, &wcc);
+      const int n1 = min(n0 + kResync, s.nframe);
+#pragma unroll 8
       for (int n = n0; n < n1; ++n) {
         const float v = frame[n];
-        re = fmaf(v, wc, re);
-        im = fmaf(v, ws, im);
-        const float t = wc * rc - ws * rs;
-        ws = wc * rs + ws * rc;
-        wc = t;
+        rea = fmaf(v, wca, rea);
+        ima = fmaf(v, wsa, ima);
+        rec = fmaf(v, wcc, rec);
+        imc = fmaf(v, wsc, imc);
+        const float ta = wca * rca - wsa * rsa;
+        wsa = wca * rsa + wsa * rca;
+        wca = ta;
+        const float tc = wcc * rcc - wsc * rsc;
+        wsc = wcc * rsc + wsc * rcc;
+        wcc = tc;
       }
     }
-    mag[kb] = sqrtf(re * re + im * im);
+    mag[kb] = sqrtf(rea * rea + ima * ima);
+    if (kb + half_bins < s.n_bins) mag[kb + half_bins] = sqrtf(rec * rec + imc * imc);
   }
   __syncthreads();
   const int rows = s.max_shc - s.min_shc + 1;
@@ -455,7 +472,8 @@ int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, 
     if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   }
   kaiser_kernel<<<(sg.nframe + 255) / 256, 256, 0, st>>>(d_win, sg.nframe, 0.5);
-  const int threads = sg.n_bins >= 1024 ? 1024 : (sg.n_bins + 31) / 32 * 32;
+  const int half_bins = (sg.n_bins + 1) / 2;
+  const int threads = half_bins >= 1024 ? 1024 : (std::max(half_bins, sg.max_shc > 256 ? 256 : sg.max_shc) + 31) / 32 * 32;
   const size_t smem = (size_t)(sg.nframe + sg.n_bins + 32) * sizeof(float);
   if (smem > 48 * 1024) return fail("sa_yaapt_shc: frame + spectrum do not fit in 48 KB of shared memory");
   shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(filtered_nl, vuv, d_win, shc, lengths ? d_len : nullptr, n_max,

@@ -25,4 +25,14 @@ for _ in range(5):
     r = yf.nlfer(x, lengths=lens, frame_length=35.0, frame_space=20.0)
 e1.record()
 torch.cuda.synchronize()
+opts = dict(frame_length=35.0, frame_space=20.0)
+for _ in range(2):
+    shc = yf.spec_shc(r, lengths=lens, **opts)
+s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s0.record()
+for _ in range(5):
+    shc = yf.spec_shc(r, lengths=lens, **opts)
+s1.record()
+torch.cuda.synchronize()
+print(f"SHC: {s0.elapsed_time(s1) / 5:.3f} ms per batch ({int(r.vuv.sum())} voiced frames of {sum(r.nframes)})")
 print(f"B={B}: {e0.elapsed_time(e1) / 5:.3f} ms per batch, {sum(lens) / 16000.0 / (e0.elapsed_time(e1) / 5e3):.0f} audio-s/s, voiced {float(r.vuv.float().mean()):.2f}")
