@@ -19,3 +19,14 @@ y1 = gen(x, frames_per_item=frames)[0]
 gen.check()
 ok = all(torch.equal(y0[b, 0, :320 * f + 1], y1[b, 0, :320 * f + 1]) for b, f in enumerate(frames))
 print("kept samples identical:", ok, "launches:", gen.last_launch_count)
+
+# YAAPT front end + SHC on a small ragged batch
+import numpy as np
+from satools_b200 import yaapt_frontend as yf
+lens = [9000, 4000, 700]
+w = np.zeros((3, 9000), dtype=np.float32)
+for b, n in enumerate(lens):
+    w[b, :n] = conditioning.waveform(40 + b, n / 16000.0)[:n]
+fr = yf.nlfer(torch.from_numpy(w).to("cuda:0"), lengths=lens, frame_length=35.0, frame_space=20.0)
+shc = yf.spec_shc(fr, lengths=lens, frame_length=35.0, frame_space=20.0)
+print("yaapt front end:", fr.nframes, int(fr.vuv.sum()), "voiced; SHC", tuple(shc.shape), bool(torch.isfinite(shc).all()))
