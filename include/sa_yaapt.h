@@ -7,8 +7,8 @@
  *   PitchObj.set_energy 124-127         energy / mean(energy), voiced = energy > nlfer_thresh1
  * The reference runs this per utterance on one CPU thread (yaapt.py:27, 947-952); the outputs are what its spectral and
  * temporal trackers (spec_track, time_track) read: SignalObj.filtered of both signals, PitchObj.energy / vuv / mean_energy --
- * plus the per-frame spectral part of spec_track (its SHC vectors, sa_yaapt_shc).  Peak picking, the NCCF tracker, refine
- * and the dynamic programming (peaks, time_track, refine, dynamic) are not part of this library yet.
+ * plus the per-frame part of spec_track (SHC vectors and the candidates `peaks` picks from them, sa_yaapt_shc).  The
+ * dynamic programming of spec_track, the NCCF tracker, refine and dynamic are not part of this library yet.
  *
  * Same conventions as sa_hifigan.h: plain pointers and sizes, 0 = success, negative = error with the text in
  * sa_yaapt_last_error(); all tensor pointers are DEVICE pointers, `stream` is a cudaStream_t (NULL = default stream).
@@ -36,6 +36,12 @@ typedef struct sa_yaapt_params {
   double shc_numharms;  /* 3    harmonics in the SHC product besides the fundamental (spec_track) */
   double shc_window;    /* 40 Hz  SHC window length */
   double shc_pwidth;    /* 50 Hz  peak-picking width: max_SHC = floor((f0_max + 2 shc_pwidth) / (sr / fft_length)) */
+  double shc_maxpeaks;  /* 4    candidates per frame (peaks) */
+  double shc_thresh1;   /* 5.0  */
+  double shc_thresh2;   /* 1.25 */
+  double f0_double;     /* 150 Hz */
+  double f0_half;       /* 150 Hz */
+  double merit_extra;   /* 0.4  */
 } sa_yaapt_params;
 
 const char* sa_yaapt_last_error(void);
@@ -65,11 +71,15 @@ int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int
  * SHC[k] = sum_c prod_{h = 1 .. numharms + 1} |X|[h k + c - half_window],  k in [min_SHC, max_SHC] stored at index k - 1.
  * sa_yaapt_shc_length = max_SHC = the length of the vector `peaks` receives (256 for the defaults).
  * filtered_nl [B, n_max + 2 pad] and vuv [B, F_max] are sa_yaapt_frontend's outputs; shc [B, F_max, max_SHC] float32 (rows
- * of unvoiced frames and frames beyond an item's count are zero). */
+ * of unvoiced frames and frames beyond an item's count are zero).
+ * cand_pitch / cand_merit [B, maxpeaks, F_max] float32: what `peaks` (yaapt.py:383-497) returns for each of those vectors,
+ * laid out like spec_track's cand_pitch / cand_merit (0 / 1 for unvoiced frames, lines 204-205).  shc, cand_pitch and
+ * cand_merit may each be NULL (not written); cand_pitch and cand_merit go together. */
 int64_t sa_yaapt_shc_length(const sa_yaapt_params* p);
 size_t sa_yaapt_shc_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max);
 int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, int64_t n_max, const int32_t* lengths,
-                 const uint8_t* vuv, float* shc, void* workspace, size_t workspace_bytes, void* stream);
+                 const uint8_t* vuv, float* shc, float* cand_pitch, float* cand_merit, void* workspace, size_t workspace_bytes,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,9 +59,13 @@ def run_reference(wav: np.ndarray, opts: dict):
     captured = []
     original = ref.peaks
 
+    returned = []
+
     def spy(shc, delta, maxpeaks, parameters):
         captured.append(shc.clone().numpy())
-        return original(shc, delta, maxpeaks, parameters)
+        out = original(shc, delta, maxpeaks, parameters)
+        returned.append((out[0].clone().numpy(), out[1].clone().numpy()))
+        return out
     ref.peaks = spy
     try:
         ref.spec_track(nonlinear, pitch, full)
@@ -73,7 +77,12 @@ def run_reference(wav: np.ndarray, opts: dict):
         ref.peaks = original
     shc = np.zeros((int(pitch.nframes), len(captured[0]) if captured else 0), dtype=np.float32)
     shc[np.nonzero(pitch.vuv.numpy())[0]] = np.stack(captured) if captured else 0
-    return dict(shc=shc, filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
+    voiced = np.nonzero(pitch.vuv.numpy())[0]
+    cand_pitch = np.zeros((4, int(pitch.nframes)), dtype=np.float32)
+    cand_merit = np.ones((4, int(pitch.nframes)), dtype=np.float32)
+    for f, (cp, cm) in zip(voiced, returned):
+        cand_pitch[:, f], cand_merit[:, f] = cp, cm
+    return dict(cand_pitch=cand_pitch, cand_merit=cand_merit, shc=shc, filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
                 vuv=pitch.vuv.numpy(), mean_energy=np.float32(pitch.mean_energy.item()), nframes=np.int64(pitch.nframes))
 
 
@@ -86,6 +95,10 @@ def main():
         rel = np.abs(o["energy"] - r["energy"]).max() / max(1e-12, np.abs(r["energy"]).max())
         flips = int((o["vuv"] != r["vuv"]).sum())
         so = onp.shc(r["filtered_nl"], r["vuv"], onp.params(**opts))
+        cp, cm = onp.spec_candidates(so, r["vuv"], onp.params(**opts))
+        same = (cp == r["cand_pitch"]).all(0)
+        print(f"        peaks on the oracle's SHC: candidate pitches identical in {int(same.sum())} of {len(same)} frames, "
+              f"merit max err {np.abs(cm - r['cand_merit'])[:, same].max():.2e}")
         print(f"        SHC peak {r['shc'].max():.3e}, oracle-vs-reference max err / peak {np.abs(so - r['shc']).max() / r['shc'].max():.2e}")
         print(f"case {i}: n={len(wav)} frames={int(r['nframes'])} voiced={int(r['vuv'].sum())} oracle-vs-reference energy rel-err {rel:.2e}, "
               f"vuv flips {flips}, filtered max-abs {np.abs(r['filtered']).max():.3e} err {np.abs(o['filtered'] - r['filtered']).max():.2e}")

@@ -15,7 +15,8 @@ What it restates (/root/reference/satools/satools/hifigan/yaapt.py):
   * `PitchObj.set_energy` lines 124-127: energy / mean(energy), voiced = energy > nlfer_thresh1;
   * `spec_track` lines 184-231 up to the call of `peaks`: for every voiced frame the spectral harmonics correlation SHC of the
     squared signal: 2 frame_size samples x Kaiser(beta 0.5, periodic) window, mean removed, |rfft_nfft|, then
-    SHC[k] = sum_c prod_{h=1..numharms+1} |X|[h k + c - half_window] over a window of `window_length` bins, k in [min_SHC, max_SHC].
+    SHC[k] = sum_c prod_{h=1..numharms+1} |X|[h k + c - half_window] over a window of `window_length` bins, k in [min_SHC, max_SHC];
+  * `peaks` lines 383-497: the (up to shc_maxpeaks) pitch candidates and merits of one SHC vector.
 
 Pinned by tests/golden/yaapt_nlfer.npz (outputs of the reference itself, oracle/make_golden_yaapt.py).  The filters are
 evaluated in float64 here: the reference runs them in float32, and its own rounding noise is what sets the tolerance of the
@@ -31,7 +32,8 @@ except Exception:  # pragma: no cover
     _scipy_lfilter = None
 
 DEFAULTS = dict(sr=16000.0, frame_length=35.0, frame_space=10.0, f0_min=60.0, f0_max=400.0, fft_length=8192.0, bp_low=50.0,
-                bp_high=1500.0, nlfer_thresh1=0.75, shc_numharms=3.0, shc_window=40.0, shc_pwidth=50.0)
+                bp_high=1500.0, nlfer_thresh1=0.75, shc_numharms=3.0, shc_window=40.0, shc_pwidth=50.0, shc_maxpeaks=4.0,
+                shc_thresh1=5.0, shc_thresh2=1.25, f0_double=150.0, f0_half=150.0, merit_extra=0.4)
 
 
 def params(**kw):
@@ -161,3 +163,71 @@ def shc(filtered_nl, vuv, p=None):
             acc = acc * mag[idx]
         out[f, min_shc - 1:max_shc] = acc.sum(1)
     return out
+
+
+def peaks(data, p=None):
+    """`peaks(data, delta, maxpeaks, parameters)` of the reference (yaapt.py:383-497) on one SHC vector: (pitch [maxpeaks],
+    merit [maxpeaks]) float32.  float32 arithmetic where the reference has float32 tensors."""
+    p = p or params()
+    f32 = np.float32
+    data = np.asarray(data, dtype=f32)
+    delta = p["sr"] / int(p["fft_length"])
+    maxpeaks = int(p["shc_maxpeaks"])
+    t1, t2 = p["shc_thresh1"], p["shc_thresh2"]
+    width = int(math.floor(p["shc_pwidth"] / delta))
+    if not (float(width) % 2):
+        width += 1
+    center = int(math.ceil(width / 2))
+    min_lag = int(math.floor(p["f0_min"] / delta - center))
+    max_lag = int(math.floor(p["f0_max"] / delta + center))
+    min_lag = max(min_lag, 1)
+    max_lag = min(max_lag, len(data) - width)
+    unvoiced = (np.zeros(maxpeaks, dtype=f32), np.ones(maxpeaks, dtype=f32))
+    max_data = data[min_lag:max_lag + 1].max()
+    if max_data > 1e-14:
+        data = data / max_data
+    avg = data[min_lag:max_lag + 1].mean(dtype=f32)
+    if avg > 1 / t1:
+        return unvoiced
+    lo, hi = min_lag + center + 1, max_lag - center + 1
+    mid = data[lo:hi]
+    is_peak = (mid > data[lo - 1:hi - 1]) & (mid > data[lo + 1:hi + 1]) & (mid > t2 * avg)
+    pitch, merit = [], []
+    for n in (np.nonzero(is_peak)[0] + lo):
+        if int(np.argmax(data[n - center:n + center + 1])) == center:
+            pitch.append(f32(float(n) * delta))
+            merit.append(data[n])
+    numpeaks = len(pitch)
+    pitch = np.array(pitch + [0.0] * max(0, maxpeaks - numpeaks), dtype=f32)
+    merit = np.array(merit + [0.0] * max(0, maxpeaks - numpeaks), dtype=f32)
+    if merit.max() / avg < t1:
+        return unvoiced
+    idx = np.argsort(-merit, kind="stable")
+    merit, pitch = merit[idx], pitch[idx]
+    numpeaks = min(numpeaks, maxpeaks)
+    pitch = np.concatenate([pitch[:numpeaks], np.zeros(maxpeaks - numpeaks, dtype=f32)])
+    merit = np.concatenate([merit[:numpeaks], np.zeros(maxpeaks - numpeaks, dtype=f32)])
+    if numpeaks == 0:
+        return unvoiced
+    if pitch[0] > p["f0_double"]:
+        numpeaks = min(numpeaks + 1, maxpeaks)
+        pitch[numpeaks - 1] = pitch[0] / f32(2.0)
+        merit[numpeaks - 1] = p["merit_extra"]
+    if pitch[0] < p["f0_half"]:
+        numpeaks = min(numpeaks + 1, maxpeaks)
+        pitch[numpeaks - 1] = pitch[0] * f32(2.0)
+        merit[numpeaks - 1] = p["merit_extra"]
+    if numpeaks < maxpeaks:
+        pitch[numpeaks:] = pitch[0]
+        merit[numpeaks:] = merit[0]
+    return pitch, merit
+
+
+def spec_candidates(shc_rows, vuv, p=None):
+    """cand_pitch / cand_merit [maxpeaks, n_frames] as spec_track fills them (yaapt.py:204-205, 231): zeros / ones for unvoiced frames."""
+    p = p or params()
+    m = int(p["shc_maxpeaks"])
+    cp, cm = np.zeros((m, len(vuv)), dtype=np.float32), np.ones((m, len(vuv)), dtype=np.float32)
+    for f in np.nonzero(np.asarray(vuv))[0]:
+        cp[:, f], cm[:, f] = peaks(shc_rows[f], p)
+    return cp, cm

@@ -223,6 +223,10 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // ---- spec_track's SHC (yaapt.py:184-231) ----------------------------------------------------------------------
 struct ShcGeometry { int nframe, wl, half, min_shc, max_shc, n_harm, bin_lo, n_bins; };
+// `peaks` (yaapt.py:383-497)
+struct PeakParams { int maxpeaks, center, min_lag, max_lag; float t1, t2, inv_t1, f0_double, f0_half, merit_extra; double delta; };
+constexpr int kMaxPeakList = 96;
+constexpr int kMaxPeaksOut = 8;
 
 bool shc_geometry(const sa_yaapt_params* p, const Geometry& g, ShcGeometry& s) {
   if (p->shc_numharms < 0 || p->shc_numharms > 7 || p->shc_window <= 0 || p->shc_pwidth < 0) return false;
@@ -255,8 +259,9 @@ __global__ void kaiser_kernel(float* w, int n, double beta) {
 
 // One block per (frame, item).  smem: [nframe] windowed, mean-free samples | [n_bins] magnitudes | [32] partial sums.
 __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const uint8_t* __restrict__ vuv, const float* __restrict__ window,
-                                 float* __restrict__ shc, const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max,
-                                 Geometry g, ShcGeometry s) {
+                                 float* __restrict__ shc, float* __restrict__ cand_pitch, float* __restrict__ cand_merit,
+                                 const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max, Geometry g, ShcGeometry s,
+                                 PeakParams pk) {
   extern __shared__ float sm[];
   float* frame = sm;
   float* mag = sm + s.nframe;
@@ -266,9 +271,13 @@ __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const ui
   const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
   const int64_t span = size - half - half;
   const int64_t n_frames = span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump;
-  float* out = shc + ((int64_t)b * f_max + f) * s.max_shc;
+  float* out = shc ? shc + ((int64_t)b * f_max + f) * s.max_shc : nullptr;
   if (f >= n_frames || !vuv[(int64_t)b * f_max + f]) {
-    for (int k = threadIdx.x; k < s.max_shc; k += blockDim.x) out[k] = 0.f;
+    if (out) for (int k = threadIdx.x; k < s.max_shc; k += blockDim.x) out[k] = 0.f;
+    if (cand_pitch && (int)threadIdx.x < pk.maxpeaks) {                    // spec_track's initial values (yaapt.py:204-205)
+      cand_pitch[((int64_t)b * pk.maxpeaks + threadIdx.x) * f_max + f] = 0.f;
+      cand_merit[((int64_t)b * pk.maxpeaks + threadIdx.x) * f_max + f] = 1.f;
+    }
     return;
   }
   // data[f jump : f jump + nframe] * window, zero beyond the signal (the reference pads `data` with zeros, yaapt.py:208-212)
@@ -338,8 +347,89 @@ __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const ui
         acc += prod;
       }
     }
-    out[k] = acc;
+    if (out) out[k] = acc;
+    frame[k] = acc;                                                        // the samples are no longer needed: `data` of peaks
   }
+  if (!cand_pitch) return;
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  // ---- peaks(SHC) by warp 0 (yaapt.py:383-497); float32 arithmetic where the reference has float32 tensors ----
+  const int lane = threadIdx.x;
+  float* data = frame;
+  float* lst_p = frame + s.max_shc;                                        // candidates in increasing n
+  float* lst_m = lst_p + kMaxPeakList;
+  float vmax = -INFINITY;
+  for (int n = pk.min_lag + lane; n <= pk.max_lag; n += 32) vmax = fmaxf(vmax, data[n]);
+  for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+  if (vmax > 1e-14f)
+    for (int n = lane; n < s.max_shc; n += 32) data[n] = data[n] / vmax;
+  __syncwarp();
+  float sum = 0.f;
+  for (int n = pk.min_lag + lane; n <= pk.max_lag; n += 32) sum += data[n];
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float avg = sum / (float)(pk.max_lag - pk.min_lag + 1);
+  float* op = cand_pitch + (int64_t)b * pk.maxpeaks * f_max + f;
+  float* om = cand_merit + (int64_t)b * pk.maxpeaks * f_max + f;
+  auto unvoiced = [&]() {
+    if (lane < pk.maxpeaks) { op[(int64_t)lane * f_max] = 0.f; om[(int64_t)lane * f_max] = 1.f; }
+  };
+  if (avg > pk.inv_t1) { unvoiced(); return; }
+  // Step 1: strict local maxima above thresh2 * avg that are the first maximum of their +-center window, in increasing n
+  const int lo = pk.min_lag + pk.center + 1, hi = pk.max_lag - pk.center + 1;
+  const float floor_v = pk.t2 * avg;
+  int count = 0;
+  for (int n0 = lo; n0 < hi; n0 += 32) {
+    const int n = n0 + lane;
+    bool is = false;
+    if (n < hi) {
+      const float v = data[n];
+      is = v > data[n - 1] && v > data[n + 1] && v > floor_v;
+      if (is) {
+        for (int j = n - pk.center; j < n; ++j) is = is && v > data[j];          // argmax returns the FIRST maximum
+        for (int j = n + 1; j <= n + pk.center; ++j) is = is && v >= data[j];
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (is) {
+      const int at = count + __popc(m & ((1u << lane) - 1u));
+      if (at < kMaxPeakList) { lst_p[at] = (float)((double)n * pk.delta); lst_m[at] = data[n]; }
+    }
+    count += __popc(m);
+  }
+  count = min(count, kMaxPeakList);
+  __syncwarp();
+  if (lane != 0) return;
+  // Step 2: the reference's merit vector has at least maxpeaks entries (zeros when fewer peaks were found)
+  float best = count < pk.maxpeaks ? 0.f : -INFINITY;
+  for (int i = 0; i < count; ++i) best = fmaxf(best, lst_m[i]);
+  auto unvoiced0 = [&]() {
+    for (int i = 0; i < pk.maxpeaks; ++i) { op[(int64_t)i * f_max] = 0.f; om[(int64_t)i * f_max] = 1.f; }
+  };
+  if (best / avg < pk.t1) { unvoiced0(); return; }
+  // Step 3: the maxpeaks largest merits, descending (ties keep their order)
+  float pit[kMaxPeaksOut], mer[kMaxPeaksOut];
+  int numpeaks = min(count, pk.maxpeaks);
+  for (int i = 0; i < pk.maxpeaks; ++i) {
+    pit[i] = 0.f; mer[i] = 0.f;
+    if (i >= numpeaks) continue;
+    int arg = -1;
+    for (int j = 0; j < count; ++j)
+      if (lst_m[j] >= 0.f && (arg < 0 || lst_m[j] > lst_m[arg])) arg = j;
+    pit[i] = lst_p[arg]; mer[i] = lst_m[arg];
+    lst_m[arg] = -1.f;                                                    // taken (merits are >= 0)
+  }
+  // Step 4
+  if (numpeaks == 0) { unvoiced0(); return; }
+  if (pit[0] > pk.f0_double) {
+    numpeaks = min(numpeaks + 1, pk.maxpeaks);
+    pit[numpeaks - 1] = pit[0] / 2.0f; mer[numpeaks - 1] = pk.merit_extra;
+  }
+  if (pit[0] < pk.f0_half) {
+    numpeaks = min(numpeaks + 1, pk.maxpeaks);
+    pit[numpeaks - 1] = pit[0] * 2.0f; mer[numpeaks - 1] = pk.merit_extra;
+  }
+  for (int i = numpeaks; i < pk.maxpeaks; ++i) { pit[i] = pit[0]; mer[i] = mer[0]; }
+  for (int i = 0; i < pk.maxpeaks; ++i) { op[(int64_t)i * f_max] = pit[i]; om[(int64_t)i * f_max] = mer[i]; }
 }
 
 }  // namespace
@@ -353,6 +443,7 @@ int sa_yaapt_default_params(sa_yaapt_params* p) {
   p->sr = 16000.0; p->frame_length = 35.0; p->frame_space = 10.0; p->f0_min = 60.0; p->f0_max = 400.0;
   p->fft_length = 8192.0; p->bp_low = 50.0; p->bp_high = 1500.0; p->nlfer_thresh1 = 0.75;
   p->shc_numharms = 3.0; p->shc_window = 40.0; p->shc_pwidth = 50.0;
+  p->shc_maxpeaks = 4.0; p->shc_thresh1 = 5.0; p->shc_thresh2 = 1.25; p->f0_double = 150.0; p->f0_half = 150.0; p->merit_extra = 0.4;
   return 0;
 }
 
@@ -450,11 +541,32 @@ size_t sa_yaapt_shc_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t
 }
 
 int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, int64_t n_max, const int32_t* lengths,
-                 const uint8_t* vuv, float* shc, void* workspace, size_t workspace_bytes, void* stream) {
+                 const uint8_t* vuv, float* shc, float* cand_pitch, float* cand_merit, void* workspace, size_t workspace_bytes,
+                 void* stream) {
   Geometry g;
   ShcGeometry sg;
   if (!geometry(p, g) || !shc_geometry(p, g, sg)) return fail("sa_yaapt_shc: bad parameters (the SHC products must stay inside the FFT)");
-  if (!filtered_nl || !vuv || !shc || B <= 0 || n_max <= 0 || B > 32767) return fail("sa_yaapt_shc: NULL argument or bad batch size");
+  if (!filtered_nl || !vuv || B <= 0 || n_max <= 0 || B > 32767) return fail("sa_yaapt_shc: NULL argument or bad batch size");
+  if ((cand_pitch == nullptr) != (cand_merit == nullptr)) return fail("sa_yaapt_shc: cand_pitch and cand_merit go together");
+  if (!shc && !cand_pitch) return fail("sa_yaapt_shc: no output requested");
+  PeakParams pk;
+  {                                                                       // peaks, yaapt.py:388-410
+    const double delta = p->sr / g.nfft;
+    int width = (int)floor(p->shc_pwidth / delta);
+    if (width % 2 == 0) width += 1;
+    pk.center = (int)ceil(width / 2.0);
+    pk.min_lag = (int)floor(p->f0_min / delta - pk.center);
+    pk.max_lag = (int)floor(p->f0_max / delta + pk.center);
+    if (pk.min_lag < 1) pk.min_lag = 1;
+    if (pk.max_lag > sg.max_shc - width) pk.max_lag = sg.max_shc - width;
+    pk.maxpeaks = (int)p->shc_maxpeaks;
+    pk.t1 = (float)p->shc_thresh1; pk.t2 = (float)p->shc_thresh2; pk.inv_t1 = (float)(1.0 / p->shc_thresh1);
+    pk.f0_double = (float)p->f0_double; pk.f0_half = (float)p->f0_half; pk.merit_extra = (float)p->merit_extra;
+    pk.delta = delta;
+    if (cand_pitch && (pk.maxpeaks < 1 || pk.maxpeaks > kMaxPeaksOut || pk.max_lag - pk.center <= pk.min_lag + pk.center + 1 ||
+                       pk.max_lag + 1 >= sg.max_shc || sg.max_shc + 2 * kMaxPeakList > sg.nframe))
+      return fail("sa_yaapt_shc: peak-picking parameters out of range");
+  }
   if (!workspace || workspace_bytes < sa_yaapt_shc_workspace_bytes(p, B, n_max)) return fail("sa_yaapt_shc: workspace too small");
   if (lengths)
     for (int b = 0; b < B; ++b)
@@ -476,8 +588,8 @@ int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, 
   const int threads = half_bins >= 1024 ? 1024 : (std::max(half_bins, sg.max_shc > 256 ? 256 : sg.max_shc) + 31) / 32 * 32;
   const size_t smem = (size_t)(sg.nframe + sg.n_bins + 32) * sizeof(float);
   if (smem > 48 * 1024) return fail("sa_yaapt_shc: frame + spectrum do not fit in 48 KB of shared memory");
-  shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(filtered_nl, vuv, d_win, shc, lengths ? d_len : nullptr, n_max,
-                                                                            stride, f_max, g, sg);
+  shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(filtered_nl, vuv, d_win, shc, cand_pitch, cand_merit,
+                                                                            lengths ? d_len : nullptr, n_max, stride, f_max, g, sg, pk);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   return 0;

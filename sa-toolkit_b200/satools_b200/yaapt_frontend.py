@@ -20,7 +20,8 @@ import torch
 from . import _lib
 
 OPTION_NAMES = ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low", "bp_high", "nlfer_thresh1",
-                "shc_numharms", "shc_window", "shc_pwidth")
+                "shc_numharms", "shc_window", "shc_pwidth", "shc_maxpeaks", "shc_thresh1", "shc_thresh2", "f0_double", "f0_half",
+                "merit_extra")
 
 
 def params(**kwargs) -> "_lib.YaaptParams":
@@ -89,10 +90,11 @@ def nlfer(wav: torch.Tensor, lengths: Optional[Sequence[int]] = None, **kwargs) 
     return out
 
 
-def spec_shc(front: FrontEnd, lengths: Optional[Sequence[int]] = None, **kwargs) -> torch.Tensor:
+def spec_shc(front: FrontEnd, lengths: Optional[Sequence[int]] = None, candidates: bool = False, **kwargs):
     """The SHC vectors `spec_track` (yaapt.py:184-231) hands to `peaks`, for every voiced frame of the batch:
     [B, F_max, max_SHC] float32 (zero rows for unvoiced frames).  `front` is the result of `nlfer` with the same
-    lengths and options."""
+    lengths and options.  candidates=True: returns (shc, cand_pitch, cand_merit), the last two [B, maxpeaks, F_max] as
+    `spec_track` fills them from `peaks` (yaapt.py:204-205, 231, 383-497)."""
     lib = _lib.load()
     p = params(**kwargs)
     x = front.filtered_nl
@@ -105,14 +107,18 @@ def spec_shc(front: FrontEnd, lengths: Optional[Sequence[int]] = None, **kwargs)
     dev = x.device
     with torch.cuda.device(dev):
         out = torch.empty(B, f_max, k, device=dev)
+        m = int(p.shc_maxpeaks)
+        cp = torch.empty(B, m, f_max, device=dev) if candidates else None
+        cm = torch.empty(B, m, f_max, device=dev) if candidates else None
         vuv = front.vuv.to(torch.uint8).contiguous()
         ws = torch.empty(int(lib.sa_yaapt_shc_workspace_bytes(p, B, n)), dtype=torch.uint8, device=dev)
         lens = None
         if lengths is not None:
             lens = (C.c_int32 * B)(*[int(v) for v in lengths])
-        rc = lib.sa_yaapt_shc(p, x.data_ptr(), B, n, lens, vuv.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+        rc = lib.sa_yaapt_shc(p, x.data_ptr(), B, n, lens, vuv.data_ptr(), out.data_ptr(), cp.data_ptr() if candidates else None,
+                              cm.data_ptr() if candidates else None, ws.data_ptr(), ws.numel(),
                               torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise _lib.SaHifiganError(f"sa_yaapt_shc: {lib.sa_yaapt_last_error().decode()}")
         torch.cuda.current_stream(dev).synchronize()
-    return out
+    return (out, cp, cm) if candidates else out

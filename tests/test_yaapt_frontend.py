@@ -32,7 +32,7 @@ def cases():
         fl, fs = [float(v) for v in z[f"c{i}_opts"]]
         wav = conditioning.waveform(int(z[f"c{i}_seed"]), float(z[f"c{i}_seconds"]))
         yield i, wav, dict(frame_length=fl, frame_space=fs), {k: z[f"c{i}_{k}"] for k in ("filtered", "filtered_nl", "energy", "vuv",
-                                                                                          "mean_energy", "nframes", "shc")}
+                                                                                          "mean_energy", "nframes", "shc", "cand_pitch", "cand_merit")}
 
 
 def compare(got, ref, what, thr=0.75):
@@ -80,6 +80,26 @@ def test_oracle_shc_matches_the_vectors_the_reference_hands_to_peaks():
         compare_shc(onp.shc(ref["filtered_nl"], ref["vuv"], p), ref["shc"], ref["vuv"], f"oracle SHC case {i} (reference's filtered)", 1e-5)
         o = onp.nlfer(wav, p)
         compare_shc(onp.shc(o["filtered_nl"], ref["vuv"], p), ref["shc"], ref["vuv"], f"oracle SHC case {i} (own filtered)")
+
+
+def test_oracle_peaks_matches_what_the_reference_returns():
+    """`peaks` restated (oracle) on the reference's own SHC vectors: the same candidates, merits to float32 rounding."""
+    total = 0
+    for i, wav, opts, ref in cases():
+        cp, cm = onp.spec_candidates(ref["shc"], ref["vuv"], onp.params(**opts))
+        np.testing.assert_array_equal(cp, ref["cand_pitch"])
+        np.testing.assert_allclose(cm, ref["cand_merit"], rtol=0, atol=2e-7)
+        total += int(ref["vuv"].sum())
+    assert total >= 150
+
+
+def check_candidates(cp, cm, shc_rows, vuv, opts, what):
+    """The GPU's candidates against `peaks` (oracle) run on the GPU's OWN SHC rows: same input, so the same decisions --
+    identical pitches, merits to rounding (the mean over the lag range is summed in another order)."""
+    ocp, ocm = onp.spec_candidates(shc_rows, vuv, onp.params(**opts))
+    same = (cp == ocp).all(0)
+    assert same.mean() >= 0.99, f"{what}: candidate pitches differ in {int((~same).sum())} of {len(same)} frames"
+    assert np.abs(cm - ocm)[:, same].max() <= 1e-5, f"{what}: merits differ by {np.abs(cm - ocm)[:, same].max():.2e}"
 
 
 def test_oracle_loop_and_compiled_recursions_agree():
@@ -137,8 +157,13 @@ def test_cuda_front_end_matches_the_reference_outputs():
         out = yf.nlfer(torch.from_numpy(wav).to("cuda:0"), **opts)
         assert out.nframes == [int(ref["nframes"])] and out.padded_lengths == [len(ref["filtered"])]
         compare(_item(out, 0), ref, f"cuda case {i}")
-        shc = yf.spec_shc(out, **opts)
-        assert tuple(shc.shape) == (1,) + ref["shc"].shape
+        shc, cp, cm = yf.spec_shc(out, candidates=True, **opts)
+        assert tuple(shc.shape) == (1,) + ref["shc"].shape and tuple(cp.shape) == (1,) + ref["cand_pitch"].shape
+        check_candidates(cp[0].cpu().numpy(), cm[0].cpu().numpy(), shc[0].cpu().numpy(), out.vuv[0].cpu().numpy(), opts, f"cuda peaks case {i}")
+        if np.array_equal(out.vuv[0].cpu().numpy(), ref["vuv"]):        # against the reference's own candidates: SHC noise may move a
+            same = (cp[0].cpu().numpy() == ref["cand_pitch"]).all(0)     # borderline peak, so a fraction, and merits where they agree
+            assert same.mean() >= 0.95, f"case {i}: {int((~same).sum())} of {len(same)} frames differ from the reference's candidates"
+            assert np.abs(cm[0].cpu().numpy() - ref["cand_merit"])[:, same].max() <= 5e-3
         if np.array_equal(out.vuv[0].cpu().numpy(), ref["vuv"]):
             compare_shc(shc[0].cpu().numpy(), ref["shc"], ref["vuv"], f"cuda SHC case {i}")
         else:                                               # a frame at the threshold flipped: compare the common voiced frames
@@ -162,7 +187,7 @@ def test_cuda_front_end_ragged_batch_against_the_oracle_and_alone():
         x[b, :len(w)] = w
         x[b, len(w):] = rng.standard_normal(n - len(w)) * 0.1      # garbage beyond the true length must not matter
     out = yf.nlfer(torch.from_numpy(x).to("cuda:0"), lengths=[len(w) for w in wavs], **opts)
-    shc = yf.spec_shc(out, lengths=[len(w) for w in wavs], **opts)
+    shc, cp, cm = yf.spec_shc(out, lengths=[len(w) for w in wavs], candidates=True, **opts)
     for b, w in enumerate(wavs):
         o = onp.nlfer(w, onp.params(**opts))
         assert out.nframes[b] == o["nframes"]
@@ -172,8 +197,11 @@ def test_cuda_front_end_ragged_batch_against_the_oracle_and_alone():
         vb = out.vuv[b, :f].cpu().numpy()
         compare_shc(shc[b, :f].cpu().numpy(), onp.shc(o["filtered_nl"], vb, onp.params(**opts)), vb, f"batch item {b} SHC")
         assert float(shc[b, f:].abs().sum()) == 0.0
+        check_candidates(cp[b, :, :f].cpu().numpy(), cm[b, :, :f].cpu().numpy(), shc[b, :f].cpu().numpy(), vb, opts, f"batch item {b} peaks")
+        assert float(cp[b, :, f:].abs().sum()) == 0.0 and bool((cm[b, :, f:] == 1).all())
         solo = yf.nlfer(torch.from_numpy(w).to("cuda:0"), **opts)
-        assert torch.equal(yf.spec_shc(solo, **opts)[0], shc[b, :f])
+        s_shc, s_cp, s_cm = yf.spec_shc(solo, candidates=True, **opts)
+        assert torch.equal(s_shc[0], shc[b, :f]) and torch.equal(s_cp[0], cp[b, :, :f]) and torch.equal(s_cm[0], cm[b, :, :f])
         assert torch.equal(solo.energy[0], out.energy[b, :f]) and torch.equal(solo.vuv[0], out.vuv[b, :f])
         assert torch.equal(solo.filtered[0], out.filtered[b, :npad]) and torch.equal(solo.filtered_nl[0], out.filtered_nl[b, :npad])
 
@@ -196,8 +224,11 @@ def test_cuda_front_end_properties_at_full_size():
     h = yf.nlfer(xd * 0.5, lengths=lens, **opts)
     assert torch.equal(h.filtered, a.filtered * 0.5) and torch.equal(h.filtered_nl, a.filtered_nl * 0.25)
     assert torch.equal(h.energy, a.energy) and torch.equal(h.vuv, a.vuv)
-    sa, sh = yf.spec_shc(a, lengths=lens, **opts), yf.spec_shc(h, lengths=lens, **opts)
+    (sa, cpa, cma), sh = yf.spec_shc(a, lengths=lens, candidates=True, **opts), yf.spec_shc(h, lengths=lens, **opts)
     assert torch.equal(sh, sa * (0.25 ** 4))                 # four magnitudes of the squared signal per product
+    voiced = a.vuv.unsqueeze(1).expand_as(cpa)
+    assert bool(((cpa[voiced] == 0) | ((cpa[voiced] >= 30.0) & (cpa[voiced] <= 860.0))).all())     # n * delta, halved or doubled
+    assert bool((cma[voiced] >= 0).all()) and bool((cma[voiced] <= 1.0).all())
     assert 0.2 < float(a.vuv.float().mean()) < 0.9
     for b in (0, 31, 63):
         o = onp.nlfer(x[b, :lens[b]], onp.params(**opts))

@@ -28,5 +28,5 @@ w = np.zeros((3, 9000), dtype=np.float32)
 for b, n in enumerate(lens):
     w[b, :n] = conditioning.waveform(40 + b, n / 16000.0)[:n]
 fr = yf.nlfer(torch.from_numpy(w).to("cuda:0"), lengths=lens, frame_length=35.0, frame_space=20.0)
-shc = yf.spec_shc(fr, lengths=lens, frame_length=35.0, frame_space=20.0)
+shc, cp, cm = yf.spec_shc(fr, lengths=lens, candidates=True, frame_length=35.0, frame_space=20.0)
 print("yaapt front end:", fr.nframes, int(fr.vuv.sum()), "voiced; SHC", tuple(shc.shape), bool(torch.isfinite(shc).all()))

@@ -27,11 +27,11 @@ e1.record()
 torch.cuda.synchronize()
 opts = dict(frame_length=35.0, frame_space=20.0)
 for _ in range(2):
-    shc = yf.spec_shc(r, lengths=lens, **opts)
+    shc, cp, cm = yf.spec_shc(r, lengths=lens, candidates=True, **opts)
 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s0.record()
 for _ in range(5):
-    shc = yf.spec_shc(r, lengths=lens, **opts)
+    shc, cp, cm = yf.spec_shc(r, lengths=lens, candidates=True, **opts)
 s1.record()
 torch.cuda.synchronize()
 print(f"SHC: {s0.elapsed_time(s1) / 5:.3f} ms per batch ({int(r.vuv.sum())} voiced frames of {sum(r.nframes)})")
