@@ -497,28 +497,33 @@ def main():
         ms_dev = timed(lambda: yf.nlfer(wav_d, lengths=lens, **yopts), args.steps)
         front = yf.nlfer(wav_d, lengths=lens, **yopts)
         ms_shc = timed(lambda: yf.spec_shc(front, lengths=lens, candidates=True, **yopts), args.steps)
+        ms_track = timed(lambda: yf.spec_track(front, lengths=lens, **yopts), args.steps)
         ms_host = timed(from_host, args.steps)
         from oracle import yaapt_nlfer_numpy as onp
         t0 = time.perf_counter()
         n_cpu = 0
         while time.perf_counter() - t0 < 6.0 and n_cpu < len(lens):
             o_cpu = onp.nlfer(wav_h[n_cpu, :lens[n_cpu]].numpy(), onp.params(**yopts))
-            onp.spec_candidates(onp.shc(o_cpu["filtered_nl"], o_cpu["vuv"], onp.params(**yopts)), o_cpu["vuv"], onp.params(**yopts))
+            onp.spec_track_finish(*onp.spec_candidates(onp.shc(o_cpu["filtered_nl"], o_cpu["vuv"], onp.params(**yopts)), o_cpu["vuv"],
+                                                       onp.params(**yopts)), onp.params(**yopts))
             n_cpu += 1
         dt = time.perf_counter() - t0
         cpu_sec = sum(lens[i] for i in range(n_cpu)) / 16000.0
         extras["yaapt_frontend_b64"] = {
             "value": audio_s / (ms_dev / 1e3), "unit": "audio-s/s", "ms_per_step": ms_dev,
             "host_buffers_value": audio_s / (ms_host / 1e3), "host_buffers_ms_per_step": ms_host,
-            "spec_shc_ms_per_step": ms_shc, "with_spec_shc_value": audio_s / ((ms_dev + ms_shc) / 1e3),
+            "spec_shc_ms_per_step": ms_shc, "spec_track_ms_per_step": ms_track,
+            "with_spec_track_value": audio_s / ((ms_dev + ms_track) / 1e3),
             "voiced_frames": int(front.vuv.sum()), "frames": int(sum(front.nframes)),
             "h2d_bytes_per_step": int(wav_h.numel() * 4), "d2h_bytes_per_step": int(len(lens) * yf.num_frames(max(lens), **yopts) * 5),
             "what": "SignalObj.filtered of the signal and the squared signal + PitchObj.energy / vuv / mean_energy for the batch "
                     "(the part of _yaapt before spec_track); spec_shc = the SHC vector of every voiced frame and the candidates peaks() picks from it "
-                    "(spec_track's per-frame loop); its DP, the NCCF tracker, refine and dynamic are not on the GPU yet",
+                    "(spec_track's per-frame loop); spec_track = that + its per-utterance DP / smoothing / re-sampling = "
+                    "spec_pitch, pitch_std as the reference's spec_track returns them; the NCCF tracker, refine and dynamic "
+                    "are not on the GPU yet",
             "cpu_port": {"value": cpu_sec / dt, "unit": "audio-s/s", "cores": 1, "kind": "port",
-                         "sample": f"{n_cpu} utterances through oracle/yaapt_nlfer_numpy.py (nlfer + shc + peaks; float64, scipy recursion, "
-                                   f"numpy rfft) in {dt:.1f} s; compare with with_spec_shc_value"}}
+                         "sample": f"{n_cpu} utterances through oracle/yaapt_nlfer_numpy.py (nlfer + spec_track; float64, scipy recursion, "
+                                   f"numpy rfft) in {dt:.1f} s; compare with with_spec_track_value"}}
         del wav_d
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------

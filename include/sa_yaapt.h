@@ -7,8 +7,8 @@
  *   PitchObj.set_energy 124-127         energy / mean(energy), voiced = energy > nlfer_thresh1
  * The reference runs this per utterance on one CPU thread (yaapt.py:27, 947-952); the outputs are what its spectral and
  * temporal trackers (spec_track, time_track) read: SignalObj.filtered of both signals, PitchObj.energy / vuv / mean_energy --
- * plus the per-frame part of spec_track (SHC vectors and the candidates `peaks` picks from them, sa_yaapt_shc).  The
- * dynamic programming of spec_track, the NCCF tracker, refine and dynamic are not part of this library yet.
+ * plus spec_track itself: its per-frame part (SHC vectors and the candidates `peaks` picks from them, sa_yaapt_shc) and its
+ * per-utterance part (sa_yaapt_spec_track).  The NCCF tracker (time_track), refine and dynamic are not part of this library yet.
  *
  * Same conventions as sa_hifigan.h: plain pointers and sizes, 0 = success, negative = error with the text in
  * sa_yaapt_last_error(); all tensor pointers are DEVICE pointers, `stream` is a cudaStream_t (NULL = default stream).
@@ -42,6 +42,9 @@ typedef struct sa_yaapt_params {
   double f0_double;     /* 150 Hz */
   double f0_half;       /* 150 Hz */
   double merit_extra;   /* 0.4  */
+  double median_value;  /* 7    order of the median filters (spec_track uses median_value - 2) */
+  double dp5_k1;        /* 11   weight of the transition costs in dynamic5 */
+  double spec_pitch_min_std; /* 0.05 */
 } sa_yaapt_params;
 
 const char* sa_yaapt_last_error(void);
@@ -80,6 +83,17 @@ size_t sa_yaapt_shc_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t
 int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, int64_t n_max, const int32_t* lengths,
                  const uint8_t* vuv, float* shc, float* cand_pitch, float* cand_merit, void* workspace, size_t workspace_bytes,
                  void* stream);
+
+/* The rest of spec_track (yaapt.py:233-316), per utterance: voiced candidates, lowest-merit smoothing (medfilt), dynamic5 / path1
+ * over the candidates, median filter, pitch_avg / pitch_std, end-point fixes, the linear re-sampling of the non-zero values and
+ * the copy of elements 2, 3 into 0, 1.  cand_pitch / cand_merit [B, maxpeaks, F_max] are sa_yaapt_shc's outputs.
+ * spec_pitch [B, F_max] float32 (zero beyond an item's frames), pitch_std [B] float32: what spec_track returns.
+ * Items with fewer than four frames get NaN in pitch_std and zeros in spec_pitch: the reference raises IndexError there
+ * (yaapt.py:311); the Python mirror raises the same. */
+size_t sa_yaapt_spec_track_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max);
+int sa_yaapt_spec_track(const sa_yaapt_params* p, const float* cand_pitch, const float* cand_merit, int32_t B, int64_t n_max,
+                        const int32_t* lengths, float* spec_pitch, float* pitch_std, void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,8 +67,9 @@ def run_reference(wav: np.ndarray, opts: dict):
         returned.append((out[0].clone().numpy(), out[1].clone().numpy()))
         return out
     ref.peaks = spy
+    spec_pitch, pitch_std = None, None
     try:
-        ref.spec_track(nonlinear, pitch, full)
+        spec_pitch, pitch_std = ref.spec_track(nonlinear, pitch, full)
     except IndexError:
         # fewer than four frames: the reference's spec_track raises at `spec_pitch[1] = spec_pitch[3]` (yaapt.py:311), AFTER
         # the per-frame loop -- the SHC vectors it computed up to there are recorded all the same
@@ -82,7 +83,9 @@ def run_reference(wav: np.ndarray, opts: dict):
     cand_merit = np.ones((4, int(pitch.nframes)), dtype=np.float32)
     for f, (cp, cm) in zip(voiced, returned):
         cand_pitch[:, f], cand_merit[:, f] = cp, cm
-    return dict(cand_pitch=cand_pitch, cand_merit=cand_merit, shc=shc, filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
+    spec_pitch = np.zeros(0, dtype=np.float32) if spec_pitch is None else spec_pitch.numpy().astype(np.float32)
+    pitch_std = np.float32(np.nan) if pitch_std is None else np.float32(float(pitch_std))
+    return dict(spec_pitch=spec_pitch, pitch_std=pitch_std, cand_pitch=cand_pitch, cand_merit=cand_merit, shc=shc, filtered=signal.filtered.numpy(), filtered_nl=nonlinear.filtered.numpy(), energy=pitch.energy.numpy(),
                 vuv=pitch.vuv.numpy(), mean_energy=np.float32(pitch.mean_energy.item()), nframes=np.int64(pitch.nframes))
 
 
@@ -99,6 +102,10 @@ def main():
         same = (cp == r["cand_pitch"]).all(0)
         print(f"        peaks on the oracle's SHC: candidate pitches identical in {int(same.sum())} of {len(same)} frames, "
               f"merit max err {np.abs(cm - r['cand_merit'])[:, same].max():.2e}")
+        if len(r["spec_pitch"]):
+            sp, sd = onp.spec_track_finish(r["cand_pitch"], r["cand_merit"], onp.params(**opts))
+            print(f"        spec_track finish on the reference's candidates: spec_pitch max err {np.abs(sp - r['spec_pitch']).max():.2e} Hz, "
+                  f"pitch_std {float(sd):.6f} vs {float(r['pitch_std']):.6f}")
         print(f"        SHC peak {r['shc'].max():.3e}, oracle-vs-reference max err / peak {np.abs(so - r['shc']).max() / r['shc'].max():.2e}")
         print(f"case {i}: n={len(wav)} frames={int(r['nframes'])} voiced={int(r['vuv'].sum())} oracle-vs-reference energy rel-err {rel:.2e}, "
               f"vuv flips {flips}, filtered max-abs {np.abs(r['filtered']).max():.3e} err {np.abs(o['filtered'] - r['filtered']).max():.2e}")

@@ -231,3 +231,98 @@ def spec_candidates(shc_rows, vuv, p=None):
     for f in np.nonzero(np.asarray(vuv))[0]:
         cp[:, f], cm[:, f] = peaks(shc_rows[f], p)
     return cp, cm
+
+
+# ---- the rest of spec_track (yaapt.py:233-316): from the per-frame candidates to the spectral pitch track -------------------
+def _medfilt(x, k):
+    """`medfilt` (yaapt.py:54-70): zero padding, median of k (odd) samples."""
+    pad = k // 2
+    xp = np.concatenate([np.zeros(pad, dtype=x.dtype), x, np.zeros(pad, dtype=x.dtype)])
+    return np.array([np.sort(xp[i:i + k])[(k - 1) // 2] for i in range(len(x))], dtype=x.dtype)
+
+
+def _path1(local, trans):
+    """`path1` (yaapt.py:530-569): lowest-cost path; ties go to the LAST minimum (the flip / argmin idiom)."""
+    n_lin, n_col = local.shape
+    pred = np.zeros((n_lin, n_col), dtype=np.int64)
+    p_small = np.zeros(n_col, dtype=np.int64)
+    pcost = local[:, 0].copy()
+    for i in range(1, n_col):
+        aux = pcost[None, :] + trans[:, :, i]                       # aux[a, b] = PCOST[b] + trans[a, b, i]
+        k = n_lin - np.argmin(aux[:, ::-1], axis=1) - 1
+        pred[:, i] = k
+        ccost = pcost[k] + trans[k, np.arange(n_lin), i] + local[:, i]
+        pcost = ccost.astype(np.float32)
+        p_small[i] = n_lin - np.argmin(ccost[::-1]) - 1
+    path = np.ones(n_col, dtype=np.int64)
+    path[-1] = p_small[-1]
+    for i in range(n_col - 2, -1, -1):
+        path[i] = pred[path[i + 1], i + 1]
+    return path
+
+
+def _dynamic5(pitch, merit, k1, f0_min):
+    f32 = np.float32
+    n_cand, n_frames = pitch.shape
+    local = (f32(1) - merit).astype(f32)
+    trans = np.zeros((n_cand, n_cand, n_frames), dtype=f32)
+    d = np.abs(pitch[None, :, 1:] - pitch[:, None, :-1]) / f32(f0_min)      # trans[a, b, t] = |pitch[b, t] - pitch[a, t - 1]| / f0_min
+    trans[:, :, 1:] = f32(0.05) * d + d * d
+    trans = (f32(k1) * trans).astype(f32)
+    path = _path1(local, trans)
+    return pitch[path, np.arange(n_frames)]
+
+
+def _interp_linear(x, size):
+    """torch.nn.functional.interpolate(mode='linear', align_corners=False) of a 1-D float32 signal."""
+    f32 = np.float32
+    n = len(x)
+    scale = f32(n) / f32(size)
+    out = np.empty(size, dtype=f32)
+    for i in range(size):
+        src = max(f32(0), scale * (f32(i) + f32(0.5)) - f32(0.5))
+        i0 = min(int(src), n - 1)
+        i1 = min(i0 + 1, n - 1)
+        lam = f32(src - f32(i0))
+        out[i] = (f32(1) - lam) * x[i0] + lam * x[i1]
+    return out
+
+
+def spec_track_finish(cand_pitch, cand_merit, p=None, median_value=7.0, dp5_k1=11.0, spec_pitch_min_std=0.05):
+    """(spec_pitch [n_frames], pitch_std) from spec_track's candidate matrices, float32 like the reference's tensors."""
+    p = p or params()
+    f32 = np.float32
+    cand_pitch = np.array(cand_pitch, dtype=f32)
+    cand_merit = np.array(cand_merit, dtype=f32)
+    spec_pitch = cand_pitch[0].copy()
+    mask = cand_pitch[0] > 0
+    vcp, vcm = cand_pitch[:, mask].copy(), cand_merit[:, mask].copy()
+    num = vcp.shape[1]
+    k = max(1, int(median_value) - 2)
+    if num > 2:
+        avg_v = vcp[0].mean(dtype=f32)
+        std_v = vcp[0].std(ddof=1, dtype=f32)
+        delta1 = np.abs(vcp - f32(0.8) * avg_v) * (f32(3) - vcm)
+        index = delta1.argmin(0)
+        cols = np.arange(num)
+        vcp[index, cols] = _medfilt(vcp[index, cols], k)
+        weight = f32(dp5_k1) * std_v / avg_v
+        voiced = _medfilt(_dynamic5(vcp, vcm, weight, p["f0_min"]), k)
+    elif num > 0:
+        voiced = np.full(num, 150.0, dtype=f32)
+    else:
+        voiced = np.array([150.0], dtype=f32)
+    pitch_avg = voiced.mean(dtype=f32)
+    std = voiced.std(ddof=1, dtype=f32) if len(voiced) > 1 else f32(np.nan)
+    pitch_std = np.maximum(std, pitch_avg * f32(spec_pitch_min_std))
+    if num > 0:
+        spec_pitch[mask] = voiced
+    if spec_pitch[0] < pitch_avg / 2:
+        spec_pitch[0] = pitch_avg
+    if spec_pitch[-1] < pitch_avg / 2:
+        spec_pitch[-1] = pitch_avg
+    nz = spec_pitch[spec_pitch != 0]
+    out = _interp_linear(nz, len(spec_pitch))
+    out[0] = out[2]
+    out[1] = out[3]
+    return out, f32(pitch_std)

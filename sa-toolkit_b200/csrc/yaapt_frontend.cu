@@ -432,6 +432,150 @@ __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const ui
   for (int i = 0; i < pk.maxpeaks; ++i) { op[(int64_t)i * f_max] = pit[i]; om[(int64_t)i * f_max] = mer[i]; }
 }
 
+// ---- the rest of spec_track (yaapt.py:233-316): one warp per utterance, lane 0 walks the frames ----------------------
+// The work is a few hundred frames x 16 candidate pairs of sequential control logic per utterance; utterances run in parallel.
+struct TrackParams { int maxpeaks, median_k; float f0_min, dp5_k1, min_std; };
+
+__device__ float median_of(float* v, int k) {                  // k <= 9, sorts in place
+  for (int i = 1; i < k; ++i) {
+    const float x = v[i];
+    int j = i - 1;
+    while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+    v[j + 1] = x;
+  }
+  return v[(k - 1) / 2];
+}
+// medfilt (yaapt.py:54-70): zero padding on both sides
+__device__ void medfilt_dev(const float* x, float* y, int n, int k) {
+  const int pad = k / 2;
+  for (int i = 0; i < n; ++i) {
+    float w[9];
+    for (int j = 0; j < k; ++j) { const int t = i - pad + j; w[j] = (t >= 0 && t < n) ? x[t] : 0.f; }
+    y[i] = median_of(w, k);
+  }
+}
+
+__global__ void spec_track_finish_kernel(const float* __restrict__ cand_pitch, const float* __restrict__ cand_merit,
+                                         float* __restrict__ spec_pitch, float* __restrict__ pitch_std, float* __restrict__ work,
+                                         const int* __restrict__ lengths, int64_t n_max, int f_max, Geometry g, TrackParams tp) {
+  const int b = blockIdx.x;
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int F = (int)(span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump);
+  float* out = spec_pitch + (int64_t)b * f_max;
+  for (int f = threadIdx.x; f < f_max; f += blockDim.x) out[f] = 0.f;
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  if (F < 4) { pitch_std[b] = nanf(""); return; }
+  const int M = tp.maxpeaks;
+  const float* cp = cand_pitch + (int64_t)b * M * f_max;
+  const float* cm = cand_merit + (int64_t)b * M * f_max;
+  // per-item scratch: [M][F] vcp | [M][F] vcm | [F] a | [F] c | [F] voiced | [F] spec | [F] idx | [F] sel | [M][F] pred
+  float* base = work + (int64_t)b * (size_t)(2 * M + 6 + M) * f_max;
+  float* vcp = base;
+  float* vcm = vcp + (size_t)M * f_max;
+  float* ta = vcm + (size_t)M * f_max;
+  float* tc = ta + f_max;
+  float* voiced = tc + f_max;
+  float* spec = voiced + f_max;
+  int* idx = reinterpret_cast<int*>(spec + f_max);
+  int* sel = idx + f_max;
+  int* pred = sel + f_max;
+  int num = 0;
+  for (int f = 0; f < F; ++f) {
+    spec[f] = cp[f];
+    if (cp[f] > 0.f) {
+      idx[num] = f;
+      for (int m = 0; m < M; ++m) { vcp[(size_t)m * f_max + num] = cp[(size_t)m * f_max + f]; vcm[(size_t)m * f_max + num] = cm[(size_t)m * f_max + f]; }
+      ++num;
+    }
+  }
+  int n_voiced_out = num;
+  if (num > 2) {
+    float s = 0.f;
+    for (int i = 0; i < num; ++i) s += vcp[i];
+    const float avg = s / (float)num;
+    float q = 0.f;
+    for (int i = 0; i < num; ++i) { const float d = vcp[i] - avg; q += d * d; }
+    const float sd = sqrtf(q / (float)(num - 1));
+    // the candidate closest (merit weighted) to 0.8 avg of every frame, median smoothed (yaapt.py:243-255)
+    for (int i = 0; i < num; ++i) {
+      int arg = 0;
+      float best = INFINITY;
+      for (int m = 0; m < M; ++m) {
+        const float d1 = fabsf(vcp[(size_t)m * f_max + i] - 0.8f * avg) * (3.f - vcm[(size_t)m * f_max + i]);
+        if (d1 < best) { best = d1; arg = m; }
+      }
+      sel[i] = arg;
+      ta[i] = vcp[(size_t)arg * f_max + i];
+    }
+    medfilt_dev(ta, tc, num, tp.median_k);
+    for (int i = 0; i < num; ++i) vcp[(size_t)sel[i] * f_max + i] = tc[i];
+    // dynamic5 / path1 (yaapt.py:506-569)
+    const float k1 = tp.dp5_k1 * sd / avg;
+    float pcost[kMaxPeaksOut], ccost[kMaxPeaksOut];
+    for (int m = 0; m < M; ++m) pcost[m] = 1.f - vcm[(size_t)m * f_max];
+    int last = 0;
+    for (int t = 1; t < num; ++t) {
+      auto trans = [&](int a, int c) {                                   // trans[a, c, t] = k1 (0.05 d + d^2), d = |p[c, t] - p[a, t-1]| / f0_min
+        const float d = fabsf(vcp[(size_t)c * f_max + t] - vcp[(size_t)a * f_max + t - 1]) / tp.f0_min;
+        return k1 * (0.05f * d + d * d);
+      };
+      for (int a = 0; a < M; ++a) {
+        int kk = 0;
+        float best = INFINITY;
+        for (int c = 0; c < M; ++c) {                                    // the LAST minimum (flip / argmin idiom)
+          const float v = pcost[c] + trans(a, c);
+          if (v <= best) { best = v; kk = c; }
+        }
+        pred[(size_t)a * f_max + t] = kk;
+        ccost[a] = pcost[kk] + trans(kk, a) + (1.f - vcm[(size_t)a * f_max + t]);
+      }
+      float bestc = INFINITY;
+      for (int a = 0; a < M; ++a) {
+        pcost[a] = ccost[a];
+        if (ccost[a] <= bestc) { bestc = ccost[a]; last = a; }
+      }
+    }
+    int pth = last;                                                      // P[-1] = p_small[-1]
+    for (int t = num - 1; t >= 0; --t) {
+      ta[t] = vcp[(size_t)pth * f_max + t];
+      if (t > 0) pth = pred[(size_t)pth * f_max + t];
+    }
+    medfilt_dev(ta, voiced, num, tp.median_k);
+  } else {
+    n_voiced_out = num > 0 ? num : 1;
+    for (int i = 0; i < n_voiced_out; ++i) voiced[i] = 150.f;
+  }
+  float s = 0.f;
+  for (int i = 0; i < n_voiced_out; ++i) s += voiced[i];
+  const float pavg = s / (float)n_voiced_out;
+  float sd = nanf("");
+  if (n_voiced_out > 1) {
+    float q = 0.f;
+    for (int i = 0; i < n_voiced_out; ++i) { const float d = voiced[i] - pavg; q += d * d; }
+    sd = sqrtf(q / (float)(n_voiced_out - 1));
+  }
+  const float floor_sd = pavg * tp.min_std;
+  pitch_std[b] = (sd != sd) ? sd : fmaxf(sd, floor_sd);                  // torch.maximum propagates NaN
+  for (int i = 0; i < num; ++i) spec[idx[i]] = voiced[i];
+  if (spec[0] < pavg / 2.f) spec[0] = pavg;
+  if (spec[F - 1] < pavg / 2.f) spec[F - 1] = pavg;
+  int nz = 0;
+  for (int f = 0; f < F; ++f) if (spec[f] != 0.f) ta[nz++] = spec[f];
+  // F.interpolate(mode='linear', align_corners=False) of the nz non-zero values to F samples
+  const float scale = (float)nz / (float)F;
+  for (int f = 0; f < F; ++f) {
+    const float src = fmaxf(0.f, scale * ((float)f + 0.5f) - 0.5f);
+    const int i0 = min((int)src, nz - 1), i1 = min(i0 + 1, nz - 1);
+    const float lam = src - (float)i0;
+    out[f] = (1.f - lam) * ta[i0] + lam * ta[i1];
+  }
+  out[0] = out[2];
+  out[1] = out[3];
+}
+
 }  // namespace
 
 extern "C" {
@@ -444,6 +588,7 @@ int sa_yaapt_default_params(sa_yaapt_params* p) {
   p->fft_length = 8192.0; p->bp_low = 50.0; p->bp_high = 1500.0; p->nlfer_thresh1 = 0.75;
   p->shc_numharms = 3.0; p->shc_window = 40.0; p->shc_pwidth = 50.0;
   p->shc_maxpeaks = 4.0; p->shc_thresh1 = 5.0; p->shc_thresh2 = 1.25; p->f0_double = 150.0; p->f0_half = 150.0; p->merit_extra = 0.4;
+  p->median_value = 7.0; p->dp5_k1 = 11.0; p->spec_pitch_min_std = 0.05;
   return 0;
 }
 
@@ -590,6 +735,45 @@ int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, 
   if (smem > 48 * 1024) return fail("sa_yaapt_shc: frame + spectrum do not fit in 48 KB of shared memory");
   shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(filtered_nl, vuv, d_win, shc, cand_pitch, cand_merit,
                                                                             lengths ? d_len : nullptr, n_max, stride, f_max, g, sg, pk);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  return 0;
+}
+
+size_t sa_yaapt_spec_track_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max) {
+  Geometry g;
+  if (!geometry(p, g) || B <= 0 || n_max <= 0 || p->shc_maxpeaks < 1 || p->shc_maxpeaks > kMaxPeaksOut) return 0;
+  const size_t f_max = (size_t)frames_of(g, n_max), M = (size_t)p->shc_maxpeaks;
+  return align256((size_t)B * 4) + align256((size_t)B * (3 * M + 6) * f_max * 4) + 256;
+}
+
+int sa_yaapt_spec_track(const sa_yaapt_params* p, const float* cand_pitch, const float* cand_merit, int32_t B, int64_t n_max,
+                        const int32_t* lengths, float* spec_pitch, float* pitch_std, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  Geometry g;
+  if (!geometry(p, g)) return fail("sa_yaapt_spec_track: bad parameters");
+  if (!cand_pitch || !cand_merit || !spec_pitch || !pitch_std || B <= 0 || n_max <= 0) return fail("sa_yaapt_spec_track: NULL argument or empty batch");
+  const int k = (int)p->median_value - 2 < 1 ? 1 : (int)p->median_value - 2;
+  if (p->shc_maxpeaks < 1 || p->shc_maxpeaks > kMaxPeaksOut || k > 9 || k % 2 == 0) return fail("sa_yaapt_spec_track: maxpeaks must be 1..8, median_value - 2 odd and <= 9");
+  if (!workspace || workspace_bytes < sa_yaapt_spec_track_workspace_bytes(p, B, n_max)) return fail("sa_yaapt_spec_track: workspace too small");
+  if (lengths)
+    for (int b = 0; b < B; ++b)
+      if (lengths[b] < 0 || lengths[b] > n_max) return fail("sa_yaapt_spec_track: lengths[b] outside [0, n_max]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int f_max = (int)frames_of(g, n_max);
+  if (f_max == 0) return 0;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  int* d_len = reinterpret_cast<int*>(base);
+  base += align256((size_t)B * 4);
+  if (lengths) {
+    cudaError_t e = cudaMemcpyAsync(d_len, lengths, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  }
+  TrackParams tp;
+  tp.maxpeaks = (int)p->shc_maxpeaks; tp.median_k = k; tp.f0_min = (float)p->f0_min; tp.dp5_k1 = (float)p->dp5_k1;
+  tp.min_std = (float)p->spec_pitch_min_std;
+  spec_track_finish_kernel<<<B, 32, 0, st>>>(cand_pitch, cand_merit, spec_pitch, pitch_std, reinterpret_cast<float*>(base),
+                                             lengths ? d_len : nullptr, n_max, f_max, g, tp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   return 0;

@@ -39,7 +39,8 @@ class YaaptParams(C.Structure):
     """sa_yaapt_params (include/sa_yaapt.h): the `_yaapt` options the front end reads, same names and defaults."""
     _fields_ = [(n, C.c_double) for n in ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low",
                                           "bp_high", "nlfer_thresh1", "shc_numharms", "shc_window", "shc_pwidth",
-                                          "shc_maxpeaks", "shc_thresh1", "shc_thresh2", "f0_double", "f0_half", "merit_extra")]
+                                          "shc_maxpeaks", "shc_thresh1", "shc_thresh2", "f0_double", "f0_half", "merit_extra",
+                                          "median_value", "dp5_k1", "spec_pitch_min_std")]
 
 
 # every symbol include/sa_yaapt.h declares
@@ -53,6 +54,9 @@ YAAPT_SYMBOLS = {
     "sa_yaapt_shc_workspace_bytes": (C.c_size_t, [C.POINTER(YaaptParams), C.c_int32, C.c_int64]),
     "sa_yaapt_shc": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_yaapt_spec_track_workspace_bytes": (C.c_size_t, [C.POINTER(YaaptParams), C.c_int32, C.c_int64]),
+    "sa_yaapt_spec_track": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sa_yaapt_frontend": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

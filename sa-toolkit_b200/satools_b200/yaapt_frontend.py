@@ -21,7 +21,7 @@ from . import _lib
 
 OPTION_NAMES = ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low", "bp_high", "nlfer_thresh1",
                 "shc_numharms", "shc_window", "shc_pwidth", "shc_maxpeaks", "shc_thresh1", "shc_thresh2", "f0_double", "f0_half",
-                "merit_extra")
+                "merit_extra", "median_value", "dp5_k1", "spec_pitch_min_std")
 
 
 def params(**kwargs) -> "_lib.YaaptParams":
@@ -122,3 +122,43 @@ def spec_shc(front: FrontEnd, lengths: Optional[Sequence[int]] = None, candidate
             raise _lib.SaHifiganError(f"sa_yaapt_shc: {lib.sa_yaapt_last_error().decode()}")
         torch.cuda.current_stream(dev).synchronize()
     return (out, cp, cm) if candidates else out
+
+
+def spec_track_from_candidates(cand_pitch: torch.Tensor, cand_merit: torch.Tensor, n_samples: int,
+                               lengths: Optional[Sequence[int]] = None, **kwargs):
+    """The per-utterance part of `spec_track` (yaapt.py:233-316) on candidate matrices [B, maxpeaks, F_max] (CUDA tensors):
+    (spec_pitch [B, F_max], pitch_std [B]).  n_samples: samples per row of the waveform batch the candidates came from."""
+    lib = _lib.load()
+    p = params(**kwargs)
+    cp, cm = cand_pitch.contiguous().float(), cand_merit.contiguous().float()
+    B, m, f_max = cp.shape
+    if m != int(p.shc_maxpeaks) or f_max != int(lib.sa_yaapt_num_frames(p, int(n_samples))):
+        raise ValueError("candidate matrices do not match shc_maxpeaks / the frame count of n_samples")
+    nfr = [int(lib.sa_yaapt_num_frames(p, int(v))) for v in (lengths if lengths is not None else [n_samples] * B)]
+    if min(nfr) < 4:
+        raise IndexError("spec_track: an utterance has fewer than four frames (the reference fails the same way, yaapt.py:311)")
+    dev = cp.device
+    with torch.cuda.device(dev):
+        spec = torch.empty(B, f_max, device=dev)
+        std = torch.empty(B, device=dev)
+        ws = torch.empty(int(lib.sa_yaapt_spec_track_workspace_bytes(p, B, int(n_samples))), dtype=torch.uint8, device=dev)
+        lens = (C.c_int32 * B)(*[int(v) for v in lengths]) if lengths is not None else None
+        rc = lib.sa_yaapt_spec_track(p, cp.data_ptr(), cm.data_ptr(), B, int(n_samples), lens, spec.data_ptr(), std.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise _lib.SaHifiganError(f"sa_yaapt_spec_track: {lib.sa_yaapt_last_error().decode()}")
+        torch.cuda.current_stream(dev).synchronize()
+    return spec, std
+
+
+def spec_track(front: FrontEnd, lengths: Optional[Sequence[int]] = None, **kwargs):
+    """`spec_track(nonlinear_sign, pitch, parameters)` of the reference (yaapt.py:184-316) for the whole batch:
+    (spec_pitch [B, F_max] float32, pitch_std [B] float32).  Like the reference it raises IndexError for an utterance of
+    fewer than four frames (yaapt.py:311)."""
+    lib = _lib.load()
+    p = params(**kwargs)
+    if min(front.nframes) < 4:
+        raise IndexError("spec_track: an utterance has fewer than four frames (the reference fails the same way, yaapt.py:311)")
+    _, cp, cm = spec_shc(front, lengths=lengths, candidates=True, **kwargs)
+    n = front.filtered_nl.shape[1] - int(lib.sa_yaapt_padded_length(p, 0))
+    return spec_track_from_candidates(cp, cm, n, lengths=lengths, **kwargs)

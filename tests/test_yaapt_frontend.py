@@ -32,7 +32,8 @@ def cases():
         fl, fs = [float(v) for v in z[f"c{i}_opts"]]
         wav = conditioning.waveform(int(z[f"c{i}_seed"]), float(z[f"c{i}_seconds"]))
         yield i, wav, dict(frame_length=fl, frame_space=fs), {k: z[f"c{i}_{k}"] for k in ("filtered", "filtered_nl", "energy", "vuv",
-                                                                                          "mean_energy", "nframes", "shc", "cand_pitch", "cand_merit")}
+                                                                                          "mean_energy", "nframes", "shc", "cand_pitch", "cand_merit",
+                                                                                          "spec_pitch", "pitch_std")}
 
 
 def compare(got, ref, what, thr=0.75):
@@ -91,6 +92,19 @@ def test_oracle_peaks_matches_what_the_reference_returns():
         np.testing.assert_allclose(cm, ref["cand_merit"], rtol=0, atol=2e-7)
         total += int(ref["vuv"].sum())
     assert total >= 150
+
+
+def test_oracle_spec_track_finish_matches_the_reference():
+    """The per-utterance part of spec_track restated (median smoothing, dynamic5 / path1, re-sampling) on the reference's own
+    candidates against what the reference's spec_track returned."""
+    n = 0
+    for i, wav, opts, ref in cases():
+        if not len(ref["spec_pitch"]):
+            continue                                            # fewer than four frames: the reference raises (yaapt.py:311)
+        sp, sd = onp.spec_track_finish(ref["cand_pitch"], ref["cand_merit"], onp.params(**opts))
+        assert np.abs(sp - ref["spec_pitch"]).max() <= 1e-3 and abs(float(sd) - float(ref["pitch_std"])) <= 1e-4 * float(ref["pitch_std"])
+        n += 1
+    assert n >= 3
 
 
 def check_candidates(cp, cm, shc_rows, vuv, opts, what):
@@ -236,3 +250,54 @@ def test_cuda_front_end_properties_at_full_size():
         f = a.nframes[b]
         vb = a.vuv[b, :f].cpu().numpy()
         compare_shc(sa[b, :f].cpu().numpy(), onp.shc(o["filtered_nl"], vb, onp.params(**opts)), vb, f"full-size item {b} SHC")
+
+
+@pytest.mark.gpu
+def test_cuda_spec_track_against_the_reference():
+    """sa_yaapt_spec_track on the reference's own candidate matrices reproduces the reference's spec_pitch / pitch_std (same
+    decisions, float32 rounding); the whole GPU chain (waveform -> spec_pitch) stays close to it: its candidates differ from
+    the reference's in a few borderline frames, which the dynamic programming and the median filters mostly absorb."""
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    for i, wav, opts, ref in cases():
+        front = yf.nlfer(torch.from_numpy(wav).to("cuda:0"), **opts)
+        if not len(ref["spec_pitch"]):
+            with pytest.raises(IndexError):
+                yf.spec_track(front, **opts)
+            continue
+        cp = torch.from_numpy(ref["cand_pitch"][None]).to("cuda:0")
+        cm = torch.from_numpy(ref["cand_merit"][None]).to("cuda:0")
+        sp, sd = yf.spec_track_from_candidates(cp, cm, len(wav), **opts)
+        assert np.abs(sp[0].cpu().numpy() - ref["spec_pitch"]).max() <= 1e-3, f"case {i}"
+        assert abs(float(sd[0]) - float(ref["pitch_std"])) <= 1e-4 * float(ref["pitch_std"])
+        sp2, sd2 = yf.spec_track(front, **opts)
+        dev = np.abs(sp2[0].cpu().numpy() - ref["spec_pitch"])
+        print(f"case {i}: whole chain vs reference spec_pitch: median |d| {np.median(dev):.3f} Hz, 90 % {np.quantile(dev, 0.9):.3f} Hz, "
+              f"max {dev.max():.2f} Hz; pitch_std {float(sd2[0]):.3f} vs {float(ref['pitch_std']):.3f}")
+        assert np.median(dev) <= 0.5 and np.quantile(dev, 0.9) <= 5.0
+        assert abs(float(sd2[0]) - float(ref["pitch_std"])) <= 0.1 * float(ref["pitch_std"])
+
+
+@pytest.mark.gpu
+def test_cuda_spec_track_batch_against_the_oracle():
+    """Ragged batch: every item's spec_pitch / pitch_std against the oracle's restatement run on the GPU's own candidates
+    (same input -> same decisions), zero beyond the item's frames."""
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    opts = dict(frame_length=35.0, frame_space=20.0)
+    secs = [6.0, 2.2, 9.4, 0.7]
+    wavs = [conditioning.waveform(300 + i, s) for i, s in enumerate(secs)]
+    n = max(len(w) for w in wavs)
+    x = np.zeros((len(wavs), n), dtype=np.float32)
+    for b, w in enumerate(wavs):
+        x[b, :len(w)] = w
+    lens = [len(w) for w in wavs]
+    front = yf.nlfer(torch.from_numpy(x).to("cuda:0"), lengths=lens, **opts)
+    _, cp, cm = yf.spec_shc(front, lengths=lens, candidates=True, **opts)
+    sp, sd = yf.spec_track(front, lengths=lens, **opts)
+    for b in range(len(wavs)):
+        f = front.nframes[b]
+        osp, osd = onp.spec_track_finish(cp[b, :, :f].cpu().numpy(), cm[b, :, :f].cpu().numpy(), onp.params(**opts))
+        assert np.abs(sp[b, :f].cpu().numpy() - osp).max() <= 1e-3, f"item {b}"
+        assert abs(float(sd[b]) - float(osd)) <= 1e-4 * float(osd)
+        assert float(sp[b, f:].abs().sum()) == 0.0

@@ -29,4 +29,5 @@ for b, n in enumerate(lens):
     w[b, :n] = conditioning.waveform(40 + b, n / 16000.0)[:n]
 fr = yf.nlfer(torch.from_numpy(w).to("cuda:0"), lengths=lens, frame_length=35.0, frame_space=20.0)
 shc, cp, cm = yf.spec_shc(fr, lengths=lens, candidates=True, frame_length=35.0, frame_space=20.0)
+sp, sd = yf.spec_track(fr, lengths=lens, frame_length=35.0, frame_space=20.0) if min(fr.nframes) >= 4 else (None, None)
 print("yaapt front end:", fr.nframes, int(fr.vuv.sum()), "voiced; SHC", tuple(shc.shape), bool(torch.isfinite(shc).all()))

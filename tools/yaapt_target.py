@@ -34,5 +34,12 @@ for _ in range(5):
     shc, cp, cm = yf.spec_shc(r, lengths=lens, candidates=True, **opts)
 s1.record()
 torch.cuda.synchronize()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(5):
+    sp, sd = yf.spec_track(r, lengths=lens, **opts)
+t1.record()
+torch.cuda.synchronize()
+print(f"spec_track (SHC + peaks + DP): {t0.elapsed_time(t1) / 5:.3f} ms per batch")
 print(f"SHC: {s0.elapsed_time(s1) / 5:.3f} ms per batch ({int(r.vuv.sum())} voiced frames of {sum(r.nframes)})")
 print(f"B={B}: {e0.elapsed_time(e1) / 5:.3f} ms per batch, {sum(lens) / 16000.0 / (e0.elapsed_time(e1) / 5e3):.0f} audio-s/s, voiced {float(r.vuv.float().mean()):.2f}")
