@@ -8,7 +8,8 @@
  * The reference runs this per utterance on one CPU thread (yaapt.py:27, 947-952); the outputs are what its spectral and
  * temporal trackers (spec_track, time_track) read: SignalObj.filtered of both signals, PitchObj.energy / vuv / mean_energy --
  * plus spec_track itself: its per-frame part (SHC vectors and the candidates `peaks` picks from them, sa_yaapt_shc) and its
- * per-utterance part (sa_yaapt_spec_track).  The NCCF tracker (time_track), refine and dynamic are not part of this library yet.
+ * per-utterance part (sa_yaapt_spec_track), and the temporal tracker with the final stages (time_track, refine, dynamic:
+ * sa_yaapt_track).  Together: everything `yaapt()` computes.
  *
  * Same conventions as sa_hifigan.h: plain pointers and sizes, 0 = success, negative = error with the text in
  * sa_yaapt_last_error(); all tensor pointers are DEVICE pointers, `stream` is a cudaStream_t (NULL = default stream).
@@ -45,6 +46,15 @@ typedef struct sa_yaapt_params {
   double median_value;  /* 7    order of the median filters (spec_track uses median_value - 2) */
   double dp5_k1;        /* 11   weight of the transition costs in dynamic5 */
   double spec_pitch_min_std; /* 0.05 */
+  double tda_frame_length;   /* 35 ms (bin/pipeline.py passes 25): frame length of the time-domain analysis */
+  double nccf_thresh1;       /* 0.3  (bin/pipeline.py passes 0.25) */
+  double nccf_thresh2;       /* 0.9  */
+  double nccf_maxcands;      /* 3    */
+  double nccf_pwidth;        /* 5    */
+  double merit_boost;        /* 0.2  */
+  double nlfer_thresh2;      /* 0.1  */
+  double merit_pivot;        /* 0.99 */
+  double dp_w1, dp_w2, dp_w3, dp_w4;  /* 0.15, 0.5, 0.1, 0.9 */
 } sa_yaapt_params;
 
 const char* sa_yaapt_last_error(void);
@@ -94,6 +104,18 @@ size_t sa_yaapt_spec_track_workspace_bytes(const sa_yaapt_params* p, int32_t B, 
 int sa_yaapt_spec_track(const sa_yaapt_params* p, const float* cand_pitch, const float* cand_merit, int32_t B, int64_t n_max,
                         const int32_t* lengths, float* spec_pitch, float* pitch_std, void* workspace, size_t workspace_bytes,
                         void* stream);
+
+/* The temporal tracker and the final stages: time_track (yaapt.py:681-731, with crs_corr 577-602 and cmp_rate 609-673) on
+ * the filtered signal and on the filtered squared signal, the zero padding of _yaapt (lines 921-931), refine (732-787) and
+ * dynamic (321-372).  Inputs are the outputs of sa_yaapt_frontend (filtered, filtered_nl, energy, vuv) and of
+ * sa_yaapt_spec_track (spec_pitch, pitch_std).  final_pitch [B, F_max] float32: `pitch.samp_values`, what yaapt() returns per
+ * utterance (0 = unvoiced; zero beyond an item's frames).  Reference quirks reproduced on purpose: crs_corr removes the frame
+ * mean in place from a view of the signal buffer, so later overlapping frames see shifted samples; cmp_rate looks at the first
+ * local maximum of the NCCF only. */
+size_t sa_yaapt_track_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max);
+int sa_yaapt_track(const sa_yaapt_params* p, const float* filtered, const float* filtered_nl, const float* energy, const uint8_t* vuv,
+                   const float* spec_pitch, const float* pitch_std, int32_t B, int64_t n_max, const int32_t* lengths,
+                   float* final_pitch, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

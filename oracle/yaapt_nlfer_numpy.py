@@ -326,3 +326,136 @@ def spec_track_finish(cand_pitch, cand_merit, p=None, median_value=7.0, dp5_k1=1
     out[0] = out[2]
     out[1] = out[3]
     return out, f32(pitch_std)
+
+
+# ---- time_track / crs_corr / cmp_rate (yaapt.py:577-731) ------------------------------------------------------------
+TRACK_DEFAULTS = dict(tda_frame_length=35.0, nccf_thresh1=0.3, nccf_thresh2=0.9, nccf_maxcands=3.0, nccf_pwidth=5.0, merit_boost=0.2,
+                      nlfer_thresh2=0.1, merit_pivot=0.99, median_value=7.0, dp_w1=0.15, dp_w2=0.5, dp_w3=0.1, dp_w4=0.9)
+
+
+def track_params(**kw):
+    p = params(**{k: v for k, v in kw.items() if k in DEFAULTS})
+    p.update(TRACK_DEFAULTS)
+    p.update({k: v for k, v in kw.items() if k in TRACK_DEFAULTS})
+    return p
+
+
+def time_track(filtered_sig, spec_pitch, pitch_std, p):
+    """`time_track` with `crs_corr` and `cmp_rate` inlined.  Quirks kept: `crs_corr` removes the frame mean IN PLACE from a
+    view of the signal buffer, so later (overlapping) frames see samples already shifted (yaapt.py:588, 709-711); `cmp_rate`
+    looks at the FIRST local maximum only (`nonzero()[0]`, yaapt.py:636) and so returns at most one candidate per frame."""
+    f32 = np.float32
+    fs = p["sr"]
+    jump = int(math.floor(p["frame_space"] * fs / 1000))
+    tda_len = int(p["tda_frame_length"] * fs / 1000)
+    data = np.array(filtered_sig, dtype=f32)
+    n_frames = int((len(data) - (tda_len - jump)) / jump)
+    spec_pitch = np.asarray(spec_pitch, dtype=f32)
+    if n_frames < len(spec_pitch):
+        spec_pitch = spec_pitch[:n_frames]
+    elif n_frames > len(spec_pitch):
+        n_frames = len(spec_pitch)
+    maxcands = int(p["nccf_maxcands"])
+    pitch_std = f32(pitch_std)
+    freq_thresh = f32(5.0) * pitch_std
+    lo = np.maximum(spec_pitch - f32(2.0) * pitch_std, f32(p["f0_min"]))
+    hi = np.minimum(spec_pitch + f32(2.0) * pitch_std, f32(p["f0_max"]))
+    center = int(math.floor(p["nccf_pwidth"] / 2.0))
+    t1, t2 = p["nccf_thresh1"], p["nccf_thresh2"]
+    time_pitch = np.zeros((maxcands, n_frames), dtype=f32)
+    time_merit = np.zeros((maxcands, n_frames), dtype=f32)
+    for f in range(n_frames):
+        qa, qb = f32(fs) / hi[f], f32(fs) / lo[f]
+        if np.isnan(qa) or np.isnan(qb):
+            continue
+        lag_min = int(math.floor(qa)) - center
+        lag_max = int(math.floor(qb)) + center
+        x = data[f * jump:f * jump + tda_len]                       # a VIEW: the mean removal below stays in `data`
+        n = tda_len - lag_max
+        assert n > 0
+        x -= x.mean(dtype=f32)
+        xj = x[:n]
+        pw = f32(np.dot(xj, xj))
+        phi = np.zeros(tda_len, dtype=f32)
+        for lag in range(lag_min, lag_max):
+            xr = x[lag:lag + n]
+            phi[lag] = f32(np.dot(xr, xj)) / np.sqrt(f32(np.dot(xr, xr)) * pw)
+        seg = phi[lag_min + center:lag_max - center + 1]
+        pk = (seg > phi[lag_min + center - 1:lag_max - center]) & (seg > phi[lag_min + center + 1:lag_max - center + 2]) & (seg > t1)
+        nz = np.nonzero(pk)[0]
+        if len(nz):
+            n0 = int(nz[0]) + lag_min + center
+            if phi.max() > t2 or int(np.argmax(phi[n0 - center:n0 + center + 1])) == center:
+                time_pitch[0, f] = f32(fs / float(n0 + 1))
+                time_merit[0, f] = phi[n0]
+        if time_merit[:, f].max() > 1.0:
+            time_merit[:, f] = time_merit[:, f] / time_merit[:, f].max()
+    diff = np.abs(time_pitch - spec_pitch[None, :])
+    match = (f32(1) - diff / freq_thresh) * (diff < freq_thresh)
+    time_merit = (f32(1 + p["merit_boost"]) * time_merit) * match
+    return time_pitch, time_merit.astype(f32)
+
+
+# ---- refine / dynamic (yaapt.py:732-787, 321-372) and the assembly in _yaapt (lines 921-944) ---------------------------
+def refine(tp1, tm1, tp2, tm2, spec_pitch, energy, vuv, p):
+    f32 = np.float32
+    n = len(spec_pitch)
+
+    def padded(a):                                                  # _yaapt lines 921-931
+        a = np.asarray(a, dtype=f32)
+        return a if a.shape[1] >= n else np.concatenate([a, np.zeros((a.shape[0], n - a.shape[1]), dtype=f32)], 1)
+    time_pitch = np.concatenate([padded(tp1), padded(tp2)], 0)
+    time_merit = np.concatenate([padded(tm1), padded(tm2)], 0)
+    c = time_pitch.shape[0]
+    idx = np.argsort(-time_merit, axis=0, kind="stable")
+    cols = np.arange(n)
+    time_merit = time_merit[idx, cols]
+    time_pitch = time_pitch[idx, cols]
+    energy = np.asarray(energy, dtype=f32)
+    best = _medfilt(time_pitch[0].copy(), int(p["median_value"])) * np.asarray(vuv, dtype=f32)
+    t2 = f32(p["nlfer_thresh2"])
+    idx1 = energy <= t2
+    idx2 = (energy > t2) & (time_pitch[0] > 0)
+    idx3 = (energy > t2) & (time_pitch[0] <= 0)
+    merit_mat = np.zeros((c, n), dtype=bool)
+    merit_mat[1:c - 1] = (time_pitch[1:c - 1] == 0) & idx2
+    time_pitch[:, idx1] = 0
+    time_merit[:, idx1] = f32(p["merit_pivot"])
+    time_pitch[c - 1, idx2] = 0
+    time_merit[c - 1, idx2] = f32(1) - time_merit[0, idx2]
+    time_merit[merit_mat] = 0
+    time_pitch[0, idx3] = np.asarray(spec_pitch, dtype=f32)[idx3]
+    time_merit[0, idx3] = np.minimum(f32(1), energy[idx3] / f32(2))
+    time_pitch[1:, idx3] = 0
+    time_merit[1:, idx3] = f32(1) - time_merit[0, idx3]
+    time_pitch[c - 2] = best
+    nzf = best > 0
+    time_merit[c - 2, nzf] = time_merit[0, nzf]
+    time_merit[c - 2, ~nzf] = f32(1) - np.minimum(f32(1), energy[~nzf] / f32(2))
+    time_pitch[c - 3] = spec_pitch
+    time_merit[c - 3] = energy / f32(5)
+    return time_pitch, time_merit
+
+
+def dynamic(ref_pitch, ref_merit, energy, p):
+    f32 = np.float32
+    c, n = ref_pitch.shape
+    best = ref_pitch[c - 2]
+    mean_pitch = best[best > 0].mean(dtype=f32)
+    local = (f32(1) - ref_merit).astype(f32)
+    energy = np.asarray(energy, dtype=f32)
+    trans = np.ones((c, c, n), dtype=f32)
+    cur = ref_pitch[None, :, 1:]                                    # [a, b, t] = pitch[b, t]
+    prev = ref_pitch[:, None, :-1]                                  # [a, b, t] = pitch[a, t - 1]
+    cur, prev = np.broadcast_to(cur, (c, c, n - 1)), np.broadcast_to(prev, (c, c, n - 1))
+    benefit = np.minimum(f32(1), np.abs(energy[:-1] - energy[1:]))
+    t = trans[:, :, 1:]
+    both = (cur > 0) & (prev > 0)
+    one = ((cur == 0) & (prev > 0)) | ((cur > 0) & (prev == 0))
+    none = (cur == 0) & (prev == 0)
+    t[both] = (f32(p["dp_w1"]) * (np.abs(cur - prev) / mean_pitch))[both]
+    t[one] = np.broadcast_to(f32(p["dp_w2"]) * (f32(1) - benefit), (c, c, n - 1))[one]
+    t[none] = f32(p["dp_w3"])
+    trans = (trans / f32(p["dp_w4"])).astype(f32)
+    path = _path1(local, trans)
+    return ref_pitch[path, np.arange(n)]

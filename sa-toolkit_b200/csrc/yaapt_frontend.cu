@@ -576,6 +576,221 @@ __global__ void spec_track_finish_kernel(const float* __restrict__ cand_pitch, c
   out[1] = out[3];
 }
 
+// ---- time_track / refine / dynamic (yaapt.py:577-787, 321-372) -------------------------------------------------------
+struct TdaParams { int tda_len, maxcands, center; float fs, f0_min, f0_max, t1, t2, boost; };
+
+__device__ __forceinline__ int tda_frames(int64_t size, const TdaParams& q, int jump, int n_frames) {
+  const int t = (int)((size - (q.tda_len - jump)) / jump);          // int((len(data) - noverlap) / frame_jump)
+  return max(0, min(t, n_frames));
+}
+
+// crs_corr's `data -= mean(data)` acts on a view of the signal buffer: frame f + 1 sees what frame f left behind.  One block
+// per (utterance, signal) walks the frames in order on a private copy of the signal.
+__global__ void tda_mean_kernel(const float* __restrict__ fa, const float* __restrict__ fb, float* __restrict__ copy,
+                                const float* __restrict__ pitch_std, const int* __restrict__ lengths, int64_t n_max, int64_t stride,
+                                Geometry g, TdaParams q) {
+  __shared__ float part[8];
+  const int b = blockIdx.x, sig = blockIdx.y;
+  const float* src = (sig ? fb : fa) + (int64_t)b * stride;
+  float* x = copy + ((int64_t)sig * gridDim.x + b) * stride;
+  for (int64_t i = threadIdx.x; i < stride; i += blockDim.x) x[i] = src[i];
+  __syncthreads();
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int n_frames = (int)(span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump);
+  const float sd = pitch_std[b];
+  if (sd != sd) return;                                              // NaN range: time_track skips every frame (yaapt.py:714)
+  const int F = tda_frames(size, q, g.frame_jump, n_frames);
+  for (int f = 0; f < F; ++f) {
+    float* fr = x + (int64_t)f * g.frame_jump;
+    float s = 0.f;
+    for (int n = threadIdx.x; n < q.tda_len; n += blockDim.x) s += fr[n];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)blockDim.x / 32; ++w) tot += part[w];
+    const float mean = tot / (float)q.tda_len;
+    for (int n = threadIdx.x; n < q.tda_len; n += blockDim.x) fr[n] -= mean;
+    __syncthreads();
+  }
+}
+
+// One block per (frame, utterance, signal): NCCF over the lag range the spectral track allows, then cmp_rate and the merit
+// weighting at the end of time_track.  tracks [2][B][maxcands][2 (pitch, merit)][F_max].
+__global__ void nccf_frame_kernel(const float* __restrict__ copy, const float* __restrict__ spec_pitch, const float* __restrict__ pitch_std,
+                                  float* __restrict__ tracks, const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max,
+                                  Geometry g, TdaParams q, int B) {
+  extern __shared__ float sm[];
+  float* x = sm;                          // [tda_len]
+  float* phi = sm + q.tda_len;            // [tda_len]
+  __shared__ float red[32];
+  const int f = blockIdx.x, b = blockIdx.y, sig = blockIdx.z;
+  float* tp = tracks + (((int64_t)sig * B + b) * q.maxcands) * 2 * f_max;
+  auto put = [&](int row, float pitch, float merit) { tp[((int64_t)row * 2) * f_max + f] = pitch; tp[((int64_t)row * 2 + 1) * f_max + f] = merit; };
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int n_frames = (int)(span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump);
+  const int F = tda_frames(size, q, g.frame_jump, n_frames);
+  const float sd = pitch_std[b];
+  const float sp = f < n_frames ? spec_pitch[(int64_t)b * f_max + f] : 0.f;
+  const float lo = fmaxf(sp - 2.0f * sd, q.f0_min), hi = fminf(sp + 2.0f * sd, q.f0_max);
+  const float qa = q.fs / hi, qb = q.fs / lo;
+  if (f >= F || sd != sd || qa != qa || qb != qb) {                  // beyond the tracker's frames (zero padding of _yaapt) or skipped
+    if ((int)threadIdx.x < q.maxcands) put(threadIdx.x, 0.f, 0.f);
+    return;
+  }
+  const int lag_min = (int)floorf(qa) - q.center, lag_max = (int)floorf(qb) + q.center;
+  const int N = q.tda_len - lag_max;                                 // > 0: checked on the host for the widest range
+  const float* src = copy + ((int64_t)sig * B + b) * stride + (int64_t)f * g.frame_jump;
+  for (int n = threadIdx.x; n < q.tda_len; n += blockDim.x) { x[n] = src[n]; phi[n] = 0.f; }
+  __syncthreads();
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) s += x[n] * x[n];
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float pw = 0.f;
+  for (int w = 0; w < (int)blockDim.x / 32; ++w) pw += red[w];
+  for (int lag = lag_min + (int)threadIdx.x; lag < lag_max; lag += blockDim.x) {
+    if (lag < 0) continue;
+    float nu = 0.f, de = 0.f;
+    for (int j = 0; j < N; ++j) { const float v = x[lag + j]; nu = fmaf(v, x[j], nu); de = fmaf(v, v, de); }
+    phi[lag] = nu / sqrtf(de * pw);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  // cmp_rate: the first strict local maximum above thresh1 in [lag_min + center, lag_max - center]
+  float pitch = 0.f, merit = 0.f;
+  int n0 = -1;
+  for (int n = lag_min + q.center; n <= lag_max - q.center; ++n)
+    if (phi[n] > phi[n - 1] && phi[n] > phi[n + 1] && phi[n] > q.t1) { n0 = n; break; }
+  if (n0 >= 0) {
+    float amax = 0.f;                                                  // phi is zero outside [lag_min, lag_max)
+    for (int n = max(lag_min, 0); n < lag_max; ++n) amax = fmaxf(amax, phi[n]);
+    bool take = amax > q.t2;
+    if (!take) {                                                       // first maximum of its +-center window
+      take = true;
+      for (int j = n0 - q.center; j < n0; ++j) take = take && phi[n0] > phi[j];
+      for (int j = n0 + 1; j <= n0 + q.center; ++j) take = take && phi[n0] >= phi[j];
+    }
+    if (take) { pitch = (float)((double)q.fs / (double)(n0 + 1)); merit = phi[n0]; }
+  }
+  if (merit > 1.0f) merit = merit / merit;
+  const float thr = 5.0f * sd;
+  for (int r = 0; r < q.maxcands; ++r) {
+    const float pr = r == 0 ? pitch : 0.f, mr = r == 0 ? merit : 0.f;
+    const float diff = fabsf(pr - sp);
+    const float match = (1.0f - diff / thr) * (diff < thr ? 1.f : 0.f);
+    put(r, pr, (q.boost * mr) * match);
+  }
+}
+
+struct RefineParams { int maxcands, median_k; float thresh2, pivot, w1, w2, w3, w4; };
+
+// refine + dynamic: one warp per utterance, lane 0 walks the frames.  C = 2 maxcands candidate rows.
+__global__ void refine_dynamic_kernel(const float* __restrict__ tracks, const float* __restrict__ energy, const uint8_t* __restrict__ vuv,
+                                      const float* __restrict__ spec_pitch, float* __restrict__ final_pitch, float* __restrict__ work,
+                                      const int* __restrict__ lengths, int64_t n_max, int f_max, Geometry g, RefineParams rp, int B) {
+  const int b = blockIdx.x;
+  float* out = final_pitch + (int64_t)b * f_max;
+  for (int f = threadIdx.x; f < f_max; f += blockDim.x) out[f] = 0.f;
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  const int64_t len = lengths ? lengths[b] : n_max;
+  const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
+  const int64_t span = size - half - half;
+  const int F = (int)(span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump);
+  if (F < 4) return;
+  const int mc = rp.maxcands, C = 2 * mc;
+  // scratch per item: P [C][F] | M [C][F] | best [F] | row0 [F] | pred (int) [C][F]
+  float* P = work + (int64_t)b * (size_t)(3 * C + 2) * f_max;
+  float* M = P + (size_t)C * f_max;
+  float* best = M + (size_t)C * f_max;
+  float* row0 = best + f_max;
+  int* pred = reinterpret_cast<int*>(row0 + f_max);
+  const float* e = energy + (int64_t)b * f_max;
+  const float* sp = spec_pitch + (int64_t)b * f_max;
+  const uint8_t* vv = vuv + (int64_t)b * f_max;
+  for (int t = 0; t < F; ++t) {                                        // candidates of both trackers, merits descending (stable)
+    float pp[2 * kMaxPeaksOut], mm[2 * kMaxPeaksOut];
+    for (int sgn = 0; sgn < 2; ++sgn)
+      for (int r = 0; r < mc; ++r) {
+        const float* tp = tracks + (((int64_t)sgn * B + b) * mc + r) * 2 * f_max;
+        pp[sgn * mc + r] = tp[t]; mm[sgn * mc + r] = tp[f_max + t];
+      }
+    for (int i = 1; i < C; ++i) {
+      const float pv = pp[i], mv = mm[i];
+      int j = i - 1;
+      while (j >= 0 && mm[j] < mv) { pp[j + 1] = pp[j]; mm[j + 1] = mm[j]; --j; }
+      pp[j + 1] = pv; mm[j + 1] = mv;
+    }
+    for (int r = 0; r < C; ++r) { P[(size_t)r * f_max + t] = pp[r]; M[(size_t)r * f_max + t] = mm[r]; }
+    row0[t] = pp[0];
+  }
+  medfilt_dev(row0, best, F, rp.median_k);
+  for (int t = 0; t < F; ++t) {
+    best[t] = best[t] * (vv[t] ? 1.f : 0.f);
+    const float en = e[t], p0 = row0[t];
+    const bool i1 = en <= rp.thresh2, i2 = en > rp.thresh2 && p0 > 0.f, i3 = en > rp.thresh2 && p0 <= 0.f;
+    bool zero_mid[2 * kMaxPeaksOut];
+    for (int r = 1; r < C - 1; ++r) zero_mid[r] = i2 && P[(size_t)r * f_max + t] == 0.f;
+    if (i1) for (int r = 0; r < C; ++r) { P[(size_t)r * f_max + t] = 0.f; M[(size_t)r * f_max + t] = rp.pivot; }
+    if (i2) { P[(size_t)(C - 1) * f_max + t] = 0.f; M[(size_t)(C - 1) * f_max + t] = 1.0f - M[t]; }
+    for (int r = 1; r < C - 1; ++r) if (zero_mid[r]) M[(size_t)r * f_max + t] = 0.f;
+    if (i3) {
+      P[t] = sp[t];
+      M[t] = fminf(1.0f, en / 2.0f);
+      for (int r = 1; r < C; ++r) { P[(size_t)r * f_max + t] = 0.f; M[(size_t)r * f_max + t] = 1.0f - M[t]; }
+    }
+    P[(size_t)(C - 2) * f_max + t] = best[t];
+    M[(size_t)(C - 2) * f_max + t] = best[t] > 0.f ? M[t] : 1.0f - fminf(1.0f, en / 2.0f);
+    P[(size_t)(C - 3) * f_max + t] = sp[t];
+    M[(size_t)(C - 3) * f_max + t] = en / 5.0f;
+  }
+  // dynamic (yaapt.py:321-372)
+  float s = 0.f;
+  int cnt = 0;
+  for (int t = 0; t < F; ++t) if (best[t] > 0.f) { s += best[t]; ++cnt; }
+  const float mean_pitch = s / (float)cnt;
+  float pcost[2 * kMaxPeaksOut], ccost[2 * kMaxPeaksOut];
+  for (int a = 0; a < C; ++a) pcost[a] = 1.0f - M[(size_t)a * f_max];
+  int last = 0;
+  for (int t = 1; t < F; ++t) {
+    const float benefit = fminf(1.0f, fabsf(e[t - 1] - e[t]));
+    auto trans = [&](int a, int c) {                                   // [a, c, t]: current = P[c, t], previous = P[a, t - 1]
+      const float cur = P[(size_t)c * f_max + t], prv = P[(size_t)a * f_max + t - 1];
+      float v = 1.0f;
+      if (cur > 0.f && prv > 0.f) v = rp.w1 * (fabsf(cur - prv) / mean_pitch);
+      else if ((cur == 0.f && prv > 0.f) || (cur > 0.f && prv == 0.f)) v = rp.w2 * (1.0f - benefit);
+      else if (cur == 0.f && prv == 0.f) v = rp.w3;
+      return v / rp.w4;
+    };
+    for (int a = 0; a < C; ++a) {
+      int kk = 0;
+      float bst = INFINITY;
+      for (int c = 0; c < C; ++c) {
+        const float v = pcost[c] + trans(a, c);
+        if (v <= bst) { bst = v; kk = c; }
+      }
+      pred[(size_t)a * f_max + t] = kk;
+      ccost[a] = pcost[kk] + trans(kk, a) + (1.0f - M[(size_t)a * f_max + t]);
+    }
+    float bc = INFINITY;
+    for (int a = 0; a < C; ++a) {
+      pcost[a] = ccost[a];
+      if (ccost[a] <= bc) { bc = ccost[a]; last = a; }
+    }
+  }
+  int pth = last;
+  for (int t = F - 1; t >= 0; --t) {
+    out[t] = P[(size_t)pth * f_max + t];
+    if (t > 0) pth = pred[(size_t)pth * f_max + t];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -589,6 +804,8 @@ int sa_yaapt_default_params(sa_yaapt_params* p) {
   p->shc_numharms = 3.0; p->shc_window = 40.0; p->shc_pwidth = 50.0;
   p->shc_maxpeaks = 4.0; p->shc_thresh1 = 5.0; p->shc_thresh2 = 1.25; p->f0_double = 150.0; p->f0_half = 150.0; p->merit_extra = 0.4;
   p->median_value = 7.0; p->dp5_k1 = 11.0; p->spec_pitch_min_std = 0.05;
+  p->tda_frame_length = 35.0; p->nccf_thresh1 = 0.3; p->nccf_thresh2 = 0.9; p->nccf_maxcands = 3.0; p->nccf_pwidth = 5.0;
+  p->merit_boost = 0.2; p->nlfer_thresh2 = 0.1; p->merit_pivot = 0.99; p->dp_w1 = 0.15; p->dp_w2 = 0.5; p->dp_w3 = 0.1; p->dp_w4 = 0.9;
   return 0;
 }
 
@@ -774,6 +991,67 @@ int sa_yaapt_spec_track(const sa_yaapt_params* p, const float* cand_pitch, const
   tp.min_std = (float)p->spec_pitch_min_std;
   spec_track_finish_kernel<<<B, 32, 0, st>>>(cand_pitch, cand_merit, spec_pitch, pitch_std, reinterpret_cast<float*>(base),
                                              lengths ? d_len : nullptr, n_max, f_max, g, tp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  return 0;
+}
+
+size_t sa_yaapt_track_workspace_bytes(const sa_yaapt_params* p, int32_t B, int64_t n_max) {
+  Geometry g;
+  if (!geometry(p, g) || B <= 0 || n_max <= 0 || p->nccf_maxcands < 1 || p->nccf_maxcands > kMaxPeaksOut) return 0;
+  const size_t f_max = (size_t)frames_of(g, n_max), mc = (size_t)p->nccf_maxcands, stride = (size_t)(n_max + 2 * g.pad);
+  return align256((size_t)B * 4) + align256((size_t)2 * B * stride * 4) + align256((size_t)2 * B * mc * 2 * f_max * 4) +
+         align256((size_t)B * (3 * 2 * mc + 2) * f_max * 4) + 256;
+}
+
+int sa_yaapt_track(const sa_yaapt_params* p, const float* filtered, const float* filtered_nl, const float* energy, const uint8_t* vuv,
+                   const float* spec_pitch, const float* pitch_std, int32_t B, int64_t n_max, const int32_t* lengths,
+                   float* final_pitch, void* workspace, size_t workspace_bytes, void* stream) {
+  Geometry g;
+  if (!geometry(p, g)) return fail("sa_yaapt_track: bad parameters");
+  if (!filtered || !filtered_nl || !energy || !vuv || !spec_pitch || !pitch_std || !final_pitch || B <= 0 || n_max <= 0 || B > 32767)
+    return fail("sa_yaapt_track: NULL argument or bad batch size");
+  TdaParams q;
+  q.tda_len = (int)(p->tda_frame_length * p->sr / 1000);
+  q.maxcands = (int)p->nccf_maxcands;
+  q.center = (int)floor(p->nccf_pwidth / 2.0);
+  q.fs = (float)p->sr; q.f0_min = (float)p->f0_min; q.f0_max = (float)p->f0_max;
+  q.t1 = (float)p->nccf_thresh1; q.t2 = (float)p->nccf_thresh2; q.boost = (float)(1.0 + p->merit_boost);
+  const int k = (int)p->median_value;
+  if (q.maxcands < 1 || q.maxcands > kMaxPeaksOut || k < 1 || k > 9 || k % 2 == 0 || q.tda_len < 16 || q.tda_len > 4096)
+    return fail("sa_yaapt_track: nccf_maxcands must be 1..8, median_value odd and <= 9, tda_frame_length 16..4096 samples");
+  // crs_corr asserts N = frame - lag_max > 0 (yaapt.py:583-587); the widest lag range is floor(fs / f0_min) + center
+  if ((int)floor(p->sr / p->f0_min) + q.center + 2 >= q.tda_len || (int)floor(p->sr / p->f0_max) - q.center - 1 < 1)
+    return fail("sa_yaapt_track: negative index in the cross correlation: increase tda_frame_length (as the reference asks)");
+  if (!workspace || workspace_bytes < sa_yaapt_track_workspace_bytes(p, B, n_max)) return fail("sa_yaapt_track: workspace too small");
+  if (lengths)
+    for (int b = 0; b < B; ++b)
+      if (lengths[b] < 0 || lengths[b] > n_max) return fail("sa_yaapt_track: lengths[b] outside [0, n_max]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t stride = n_max + 2 * g.pad;
+  const int f_max = (int)frames_of(g, n_max);
+  if (f_max == 0) return 0;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  int* d_len = reinterpret_cast<int*>(base);
+  base += align256((size_t)B * 4);
+  float* copy = reinterpret_cast<float*>(base);
+  base += align256((size_t)2 * B * stride * 4);
+  float* tracks = reinterpret_cast<float*>(base);
+  base += align256((size_t)2 * B * q.maxcands * 2 * f_max * 4);
+  float* work = reinterpret_cast<float*>(base);
+  if (lengths) {
+    cudaError_t e = cudaMemcpyAsync(d_len, lengths, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  }
+  const int* dl = lengths ? d_len : nullptr;
+  tda_mean_kernel<<<dim3((unsigned)B, 2), 128, 0, st>>>(filtered, filtered_nl, copy, pitch_std, dl, n_max, stride, g, q);
+  const int lag_threads = 128;
+  nccf_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B, 2), lag_threads, (size_t)2 * q.tda_len * sizeof(float), st>>>(
+      copy, spec_pitch, pitch_std, tracks, dl, n_max, stride, f_max, g, q, B);
+  RefineParams rp;
+  rp.maxcands = q.maxcands; rp.median_k = k; rp.thresh2 = (float)p->nlfer_thresh2; rp.pivot = (float)p->merit_pivot;
+  rp.w1 = (float)p->dp_w1; rp.w2 = (float)p->dp_w2; rp.w3 = (float)p->dp_w3; rp.w4 = (float)p->dp_w4;
+  refine_dynamic_kernel<<<B, 32, 0, st>>>(tracks, energy, vuv, spec_pitch, final_pitch, work, dl, n_max, f_max, g, rp, B);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   return 0;

@@ -40,7 +40,9 @@ class YaaptParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low",
                                           "bp_high", "nlfer_thresh1", "shc_numharms", "shc_window", "shc_pwidth",
                                           "shc_maxpeaks", "shc_thresh1", "shc_thresh2", "f0_double", "f0_half", "merit_extra",
-                                          "median_value", "dp5_k1", "spec_pitch_min_std")]
+                                          "median_value", "dp5_k1", "spec_pitch_min_std", "tda_frame_length", "nccf_thresh1",
+                                          "nccf_thresh2", "nccf_maxcands", "nccf_pwidth", "merit_boost", "nlfer_thresh2", "merit_pivot",
+                                          "dp_w1", "dp_w2", "dp_w3", "dp_w4")]
 
 
 # every symbol include/sa_yaapt.h declares
@@ -57,6 +59,9 @@ YAAPT_SYMBOLS = {
     "sa_yaapt_spec_track_workspace_bytes": (C.c_size_t, [C.POINTER(YaaptParams), C.c_int32, C.c_int64]),
     "sa_yaapt_spec_track": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_yaapt_track_workspace_bytes": (C.c_size_t, [C.POINTER(YaaptParams), C.c_int32, C.c_int64]),
+    "sa_yaapt_track": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_int64, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sa_yaapt_frontend": (C.c_int, [C.POINTER(YaaptParams), C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

@@ -21,7 +21,8 @@ from . import _lib
 
 OPTION_NAMES = ("sr", "frame_length", "frame_space", "f0_min", "f0_max", "fft_length", "bp_low", "bp_high", "nlfer_thresh1",
                 "shc_numharms", "shc_window", "shc_pwidth", "shc_maxpeaks", "shc_thresh1", "shc_thresh2", "f0_double", "f0_half",
-                "merit_extra", "median_value", "dp5_k1", "spec_pitch_min_std")
+                "merit_extra", "median_value", "dp5_k1", "spec_pitch_min_std", "tda_frame_length", "nccf_thresh1", "nccf_thresh2",
+                "nccf_maxcands", "nccf_pwidth", "merit_boost", "nlfer_thresh2", "merit_pivot", "dp_w1", "dp_w2", "dp_w3", "dp_w4")
 
 
 def params(**kwargs) -> "_lib.YaaptParams":
@@ -31,7 +32,7 @@ def params(**kwargs) -> "_lib.YaaptParams":
         raise _lib.SaHifiganError(lib.sa_yaapt_last_error().decode())
     for k, v in kwargs.items():
         if k not in OPTION_NAMES:
-            raise KeyError(f"unknown YAAPT front-end option {k!r} (the trackers' options are not used here)")
+            raise KeyError(f"unknown YAAPT option {k!r}")
         setattr(p, k, float(v))
     return p
 
@@ -162,3 +163,31 @@ def spec_track(front: FrontEnd, lengths: Optional[Sequence[int]] = None, **kwarg
     _, cp, cm = spec_shc(front, lengths=lengths, candidates=True, **kwargs)
     n = front.filtered_nl.shape[1] - int(lib.sa_yaapt_padded_length(p, 0))
     return spec_track_from_candidates(cp, cm, n, lengths=lengths, **kwargs)
+
+
+def yaapt(wav: torch.Tensor, lengths: Optional[Sequence[int]] = None, **kwargs) -> torch.Tensor:
+    """`yaapt(_in, kwargs)` of the reference (yaapt.py:947-952) for a batch on the GPU: the final pitch track per frame,
+    [B, F_max] float32 (0 = unvoiced; zero beyond an item's frames), i.e. `pitch.samp_values` of every utterance.
+    `frame_lengtht` is accepted for `tda_frame_length` as in `_yaapt` (lines 803-810)."""
+    if "frame_lengtht" in kwargs:
+        v = kwargs.pop("frame_lengtht")
+        kwargs.setdefault("tda_frame_length", v)
+    lib = _lib.load()
+    p = params(**kwargs)
+    front = nlfer(wav, lengths=lengths, **kwargs)
+    spec, std = spec_track(front, lengths=lengths, **kwargs)
+    B, f_max = spec.shape
+    n = front.filtered.shape[1] - int(lib.sa_yaapt_padded_length(p, 0))
+    dev = spec.device
+    with torch.cuda.device(dev):
+        final = torch.empty(B, f_max, device=dev)
+        vuv = front.vuv.to(torch.uint8).contiguous()
+        ws = torch.empty(int(lib.sa_yaapt_track_workspace_bytes(p, B, n)), dtype=torch.uint8, device=dev)
+        lens = (C.c_int32 * B)(*[int(v) for v in lengths]) if lengths is not None else None
+        rc = lib.sa_yaapt_track(p, front.filtered.data_ptr(), front.filtered_nl.data_ptr(), front.energy.data_ptr(), vuv.data_ptr(),
+                                spec.data_ptr(), std.data_ptr(), B, n, lens, final.data_ptr(), ws.data_ptr(), ws.numel(),
+                                torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise _lib.SaHifiganError(f"sa_yaapt_track: {lib.sa_yaapt_last_error().decode()}")
+        torch.cuda.current_stream(dev).synchronize()
+    return final

@@ -26,6 +26,12 @@ GOLDEN = os.path.join(helpers.ROOT, "tests", "golden", "yaapt_nlfer.npz")
 HEADER = os.path.join(helpers.ROOT, "include", "sa_yaapt.h")
 
 
+def track_opts(i):
+    """tda_frame_length / nccf_thresh1 of golden case i (bin/pipeline.py passes 25 ms / 0.25; the defaults are 35 ms / 0.3)."""
+    t = np.load(GOLDEN)[f"c{i}_track_opts"]
+    return dict(tda_frame_length=float(t[0]), nccf_thresh1=float(t[1]))
+
+
 def cases():
     z = np.load(GOLDEN)
     for i in range(int(z["n_cases"])):
@@ -33,7 +39,9 @@ def cases():
         wav = conditioning.waveform(int(z[f"c{i}_seed"]), float(z[f"c{i}_seconds"]))
         yield i, wav, dict(frame_length=fl, frame_space=fs), {k: z[f"c{i}_{k}"] for k in ("filtered", "filtered_nl", "energy", "vuv",
                                                                                           "mean_energy", "nframes", "shc", "cand_pitch", "cand_merit",
-                                                                                          "spec_pitch", "pitch_std")}
+                                                                                          "spec_pitch", "pitch_std", "time_pitch1", "time_merit1",
+                                                                                          "time_pitch2", "time_merit2", "final_pitch")
+                                                              if f"c{i}_{k}" in z}
 
 
 def compare(got, ref, what, thr=0.75):
@@ -107,6 +115,26 @@ def test_oracle_spec_track_finish_matches_the_reference():
     assert n >= 3
 
 
+def test_oracle_trackers_match_the_reference():
+    """time_track (NCCF + cmp_rate, with the in-place mean removal of crs_corr), refine and dynamic restated: on the
+    reference's own intermediate results the oracle returns the reference's tracks (pitches identical but for a borderline
+    frame, merits to float32 rounding) and EXACTLY the final pitch yaapt() returns."""
+    n = 0
+    for i, wav, opts, ref in cases():
+        if "final_pitch" not in ref:
+            continue
+        tp = onp.track_params(**opts, **track_opts(i))
+        for tag, sig in (("1", ref["filtered"]), ("2", ref["filtered_nl"])):
+            op, om = onp.time_track(sig, ref["spec_pitch"], ref["pitch_std"], tp)
+            same = (op == ref["time_pitch" + tag]).all(0)
+            assert same.mean() >= 0.98 and np.abs(om - ref["time_merit" + tag])[:, same].max() <= 1e-5
+        rp, rm = onp.refine(ref["time_pitch1"], ref["time_merit1"], ref["time_pitch2"], ref["time_merit2"], ref["spec_pitch"],
+                            ref["energy"], ref["vuv"], tp)
+        np.testing.assert_array_equal(onp.dynamic(rp, rm, ref["energy"], tp), ref["final_pitch"])
+        n += 1
+    assert n >= 3
+
+
 def check_candidates(cp, cm, shc_rows, vuv, opts, what):
     """The GPU's candidates against `peaks` (oracle) run on the GPU's OWN SHC rows: same input, so the same decisions --
     identical pitches, merits to rounding (the mean over the lag range is summed in another order)."""
@@ -148,7 +176,7 @@ def test_frame_geometry_matches_the_reference():
         assert lib.sa_yaapt_padded_length(yf.params(**opts), len(wav)) == len(ref["filtered"])
     assert lib.sa_yaapt_num_frames(None, 10) < 0 and b"bad" in lib.sa_yaapt_last_error()
     with pytest.raises(KeyError):
-        yf.params(nccf_thresh1=0.25)                  # a tracker option: not read by the front end
+        yf.params(frame_len=35.0)                     # not an option of _yaapt
     p = yf.params()
     assert (p.sr, p.frame_length, p.frame_space, p.fft_length, p.bp_low, p.bp_high) == (16000.0, 35.0, 10.0, 8192.0, 50.0, 1500.0)
 
@@ -301,3 +329,59 @@ def test_cuda_spec_track_batch_against_the_oracle():
         assert np.abs(sp[b, :f].cpu().numpy() - osp).max() <= 1e-3, f"item {b}"
         assert abs(float(sd[b]) - float(osd)) <= 1e-4 * float(osd)
         assert float(sp[b, f:].abs().sum()) == 0.0
+
+
+@pytest.mark.gpu
+def test_cuda_yaapt_final_pitch_against_the_reference():
+    """The whole extractor on the GPU, waveform -> final pitch per frame, against what the reference's yaapt() returned for
+    the same waveform and options: voiced / unvoiced decisions and pitch values."""
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    seen = 0
+    for i, wav, opts, ref in cases():
+        if "final_pitch" not in ref:
+            continue
+        got = yf.yaapt(torch.from_numpy(wav).to("cuda:0"), **opts, **track_opts(i))[0].cpu().numpy()
+        want = ref["final_pitch"]
+        assert got.shape == want.shape
+        vuv_same = ((got > 0) == (want > 0)).mean()
+        close = (np.abs(got - want) <= 1e-2).mean()
+        print(f"case {i}: voiced/unvoiced decisions equal in {100 * vuv_same:.1f} % of {len(want)} frames, pitch within 0.01 Hz in "
+              f"{100 * close:.1f} %, max |d| {np.abs(got - want).max():.2f} Hz")
+        assert vuv_same >= 0.97 and close >= 0.95
+        seen += 1
+    assert seen >= 3
+
+
+@pytest.mark.gpu
+def test_cuda_yaapt_batch_equals_solo_and_oracle_chain():
+    """A ragged batch through yaapt(): every item bit-identical to its solo run, and equal to the oracle's trackers run on the
+    GPU's own front-end / spec_track results (same inputs -> the same decisions in all but borderline frames)."""
+    _need_gpu()
+    from satools_b200 import yaapt_frontend as yf
+    opts = dict(frame_length=35.0, frame_space=20.0, nccf_thresh1=0.25, tda_frame_length=25.0)
+    fopts = dict(frame_length=35.0, frame_space=20.0)
+    secs = [4.0, 1.3, 6.5]
+    wavs = [conditioning.waveform(400 + i, s) for i, s in enumerate(secs)]
+    n = max(len(w) for w in wavs)
+    x = np.zeros((len(wavs), n), dtype=np.float32)
+    for b, w in enumerate(wavs):
+        x[b, :len(w)] = w
+    lens = [len(w) for w in wavs]
+    xd = torch.from_numpy(x).to("cuda:0")
+    final = yf.yaapt(xd, lengths=lens, **opts)
+    front = yf.nlfer(xd, lengths=lens, **fopts)
+    spec, std = yf.spec_track(front, lengths=lens, **fopts)
+    tp = onp.track_params(**opts)
+    for b, w in enumerate(wavs):
+        f, npad = front.nframes[b], front.padded_lengths[b]
+        solo = yf.yaapt(torch.from_numpy(w).to("cuda:0"), **opts)
+        assert torch.equal(solo[0], final[b, :f]) and float(final[b, f:].abs().sum()) == 0.0
+        sp, sd = spec[b, :f].cpu().numpy(), float(std[b])
+        t1 = onp.time_track(front.filtered[b, :npad].cpu().numpy(), sp, sd, tp)
+        t2 = onp.time_track(front.filtered_nl[b, :npad].cpu().numpy(), sp, sd, tp)
+        rp, rm = onp.refine(t1[0], t1[1], t2[0], t2[1], sp, front.energy[b, :f].cpu().numpy(), front.vuv[b, :f].cpu().numpy(), tp)
+        want = onp.dynamic(rp, rm, front.energy[b, :f].cpu().numpy(), tp)
+        got = final[b, :f].cpu().numpy()
+        close = (np.abs(got - want) <= 1e-2).mean()
+        assert close >= 0.97, f"item {b}: {100 * close:.1f} % of the frames agree with the oracle chain"
