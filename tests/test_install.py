@@ -127,3 +127,25 @@ def test_conditioning_assembly_of_the_reference_net_reaches_the_drop_in_unchange
     assert torch.equal(seen["ref"], seen["b200"])
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "net_forward.npz"))
     np.testing.assert_array_equal(seen["b200"].numpy(), z["plain/x"])
+
+
+def test_install_can_rebind_the_f0_extractor_too(ref_env):
+    """`Net.get_f0` calls `hifigan.yaapt.yaapt(wav, opts)` through the module attribute (hifigan.py:121): install(yaapt_too=True)
+    rebinds it to the batched GPU extractor, uninstall() restores the TorchScript original.  Without a GPU the rebound
+    function fails loudly instead of falling back to a CPU path."""
+    import satools.hifigan.yaapt as ref_yaapt
+    import satools_b200
+    import importlib
+    inst = importlib.import_module("satools_b200.install")      # the module (satools_b200.install is the function)
+    original = ref_yaapt.yaapt
+    satools_b200.install(yaapt_too=True)
+    try:
+        assert ref_yaapt.yaapt is inst.yaapt
+        net = _build_net("f0")
+        wav = torch.zeros(1, 8000)
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError, match="CUDA"):
+                net.get_f0(wav)
+    finally:
+        satools_b200.uninstall()
+    assert ref_yaapt.yaapt is original

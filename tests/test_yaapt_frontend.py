@@ -385,3 +385,19 @@ def test_cuda_yaapt_batch_equals_solo_and_oracle_chain():
         got = final[b, :f].cpu().numpy()
         close = (np.abs(got - want) <= 1e-2).mean()
         assert close >= 0.97, f"item {b}: {100 * close:.1f} % of the frames agree with the oracle chain"
+
+
+@pytest.mark.gpu
+def test_drop_in_yaapt_call_signature():
+    """satools_b200.install.yaapt(_in, kwargs) -- the reference's call (`hifigan.yaapt.yaapt(wav, self.f0_yaapt_opts)`): CPU
+    tensor in, option dict with the reference's names (unknown names ignored), [B, n_frames] on the input's device out."""
+    _need_gpu()
+    import importlib
+    from satools_b200 import yaapt_frontend as yf
+    inst = importlib.import_module("satools_b200.install")      # the module (satools_b200.install is the function)
+    wav = torch.from_numpy(np.stack([conditioning.waveform(7, 1.0), conditioning.waveform(8, 1.0)]))
+    opts = {"frame_length": 35.0, "frame_space": 20.0, "nccf_thresh1": 0.25, "tda_frame_length": 25.0, "not_an_option": 1.0}
+    f0 = inst.yaapt(wav, opts)
+    assert f0.device == wav.device and tuple(f0.shape) == (2, yf.num_frames(16000, frame_length=35.0, frame_space=20.0))
+    ref = yf.yaapt(wav.to("cuda:0"), frame_length=35.0, frame_space=20.0, nccf_thresh1=0.25, tda_frame_length=25.0)
+    assert torch.equal(f0, ref.cpu()) and bool((f0 >= 0).all()) and float(f0.max()) > 60.0

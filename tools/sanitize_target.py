@@ -31,3 +31,5 @@ fr = yf.nlfer(torch.from_numpy(w).to("cuda:0"), lengths=lens, frame_length=35.0,
 shc, cp, cm = yf.spec_shc(fr, lengths=lens, candidates=True, frame_length=35.0, frame_space=20.0)
 sp, sd = yf.spec_track(fr, lengths=lens, frame_length=35.0, frame_space=20.0) if min(fr.nframes) >= 4 else (None, None)
 print("yaapt front end:", fr.nframes, int(fr.vuv.sum()), "voiced; SHC", tuple(shc.shape), bool(torch.isfinite(shc).all()))
+f0 = yf.yaapt(torch.from_numpy(w[:2]).to("cuda:0"), lengths=lens[:2], frame_length=35.0, frame_space=20.0, nccf_thresh1=0.25, tda_frame_length=25.0)
+print("yaapt final pitch:", tuple(f0.shape), float(f0.max()))

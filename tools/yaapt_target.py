@@ -40,6 +40,17 @@ for _ in range(5):
     sp, sd = yf.spec_track(r, lengths=lens, **opts)
 t1.record()
 torch.cuda.synchronize()
+fo = dict(opts, nccf_thresh1=0.25, tda_frame_length=25.0)
+for _ in range(2):
+    f0 = yf.yaapt(x, lengths=lens, **fo)
+y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+y0.record()
+for _ in range(5):
+    f0 = yf.yaapt(x, lengths=lens, **fo)
+y1.record()
+torch.cuda.synchronize()
+print(f"yaapt (whole extractor): {y0.elapsed_time(y1) / 5:.3f} ms per batch = {sum(lens) / 16000.0 / (y0.elapsed_time(y1) / 5e3):.0f} audio-s/s, "
+      f"{float((f0 > 0).float().mean()):.2f} of the frames voiced")
 print(f"spec_track (SHC + peaks + DP): {t0.elapsed_time(t1) / 5:.3f} ms per batch")
 print(f"SHC: {s0.elapsed_time(s1) / 5:.3f} ms per batch ({int(r.vuv.sum())} voiced frames of {sum(r.nframes)})")
 print(f"B={B}: {e0.elapsed_time(e1) / 5:.3f} ms per batch, {sum(lens) / 16000.0 / (e0.elapsed_time(e1) / 5e3):.0f} audio-s/s, voiced {float(r.vuv.float().mean()):.2f}")
