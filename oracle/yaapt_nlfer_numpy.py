@@ -377,9 +377,10 @@ def time_track(filtered_sig, spec_pitch, pitch_std, p):
         xj = x[:n]
         pw = f32(np.dot(xj, xj))
         phi = np.zeros(tda_len, dtype=f32)
-        for lag in range(lag_min, lag_max):
-            xr = x[lag:lag + n]
-            phi[lag] = f32(np.dot(xr, xj)) / np.sqrt(f32(np.dot(xr, xr)) * pw)
+        with np.errstate(divide="ignore", invalid="ignore"):       # silent frames: 0 / 0 as in the reference (eps1 = 0, yaapt.py:579)
+            for lag in range(lag_min, lag_max):
+                xr = x[lag:lag + n]
+                phi[lag] = f32(np.dot(xr, xj)) / np.sqrt(f32(np.dot(xr, xr)) * pw)
         seg = phi[lag_min + center:lag_max - center + 1]
         pk = (seg > phi[lag_min + center - 1:lag_max - center]) & (seg > phi[lag_min + center + 1:lag_max - center + 2]) & (seg > t1)
         nz = np.nonzero(pk)[0]

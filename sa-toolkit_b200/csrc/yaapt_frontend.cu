@@ -432,8 +432,7 @@ __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const ui
   for (int i = 0; i < pk.maxpeaks; ++i) { op[(int64_t)i * f_max] = pit[i]; om[(int64_t)i * f_max] = mer[i]; }
 }
 
-// ---- the rest of spec_track (yaapt.py:233-316): one warp per utterance, lane 0 walks the frames ----------------------
-// The work is a few hundred frames x 16 candidate pairs of sequential control logic per utterance; utterances run in parallel.
+// ---- the rest of spec_track (yaapt.py:233-316): one warp per utterance; utterances run in parallel --------------------
 struct TrackParams { int maxpeaks, median_k; float f0_min, dp5_k1, min_std; };
 
 __device__ float median_of(float* v, int k) {                  // k <= 9, sorts in place
@@ -445,34 +444,25 @@ __device__ float median_of(float* v, int k) {                  // k <= 9, sorts 
   }
   return v[(k - 1) / 2];
 }
-// medfilt (yaapt.py:54-70): zero padding on both sides
-__device__ void medfilt_dev(const float* x, float* y, int n, int k) {
-  const int pad = k / 2;
-  for (int i = 0; i < n; ++i) {
-    float w[9];
-    for (int j = 0; j < k; ++j) { const int t = i - pad + j; w[j] = (t >= 0 && t < n) ? x[t] : 0.f; }
-    y[i] = median_of(w, k);
-  }
-}
-
 __global__ void spec_track_finish_kernel(const float* __restrict__ cand_pitch, const float* __restrict__ cand_merit,
                                          float* __restrict__ spec_pitch, float* __restrict__ pitch_std, float* __restrict__ work,
                                          const int* __restrict__ lengths, int64_t n_max, int f_max, Geometry g, TrackParams tp) {
-  const int b = blockIdx.x;
+  // One warp per utterance.  Per-frame steps run with the frames spread over the lanes (ordered compactions by ballot + prefix
+  // count); the dynamic programming is a chain over the voiced frames: lane a owns candidate row a, transition costs by shuffle.
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const unsigned below = (1u << lane) - 1u;
   const int64_t len = lengths ? lengths[b] : n_max;
   const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
   const int64_t span = size - half - half;
   const int F = (int)(span <= 0 ? 0 : (span + g.frame_jump - 1) / g.frame_jump);
   float* out = spec_pitch + (int64_t)b * f_max;
-  for (int f = threadIdx.x; f < f_max; f += blockDim.x) out[f] = 0.f;
-  __syncwarp();
-  if (threadIdx.x != 0) return;
-  if (F < 4) { pitch_std[b] = nanf(""); return; }
+  for (int f = lane; f < f_max; f += 32) out[f] = 0.f;
+  if (F < 4) { if (lane == 0) pitch_std[b] = nanf(""); return; }
   const int M = tp.maxpeaks;
   const float* cp = cand_pitch + (int64_t)b * M * f_max;
   const float* cm = cand_merit + (int64_t)b * M * f_max;
   // per-item scratch: [M][F] vcp | [M][F] vcm | [F] a | [F] c | [F] voiced | [F] spec | [F] idx | [F] sel | [M][F] pred
-  float* base = work + (int64_t)b * (size_t)(2 * M + 6 + M) * f_max;
+  float* base = work + (int64_t)b * (size_t)(3 * M + 6) * f_max;
   float* vcp = base;
   float* vcm = vcp + (size_t)M * f_max;
   float* ta = vcm + (size_t)M * f_max;
@@ -483,97 +473,135 @@ __global__ void spec_track_finish_kernel(const float* __restrict__ cand_pitch, c
   int* sel = idx + f_max;
   int* pred = sel + f_max;
   int num = 0;
-  for (int f = 0; f < F; ++f) {
-    spec[f] = cp[f];
-    if (cp[f] > 0.f) {
-      idx[num] = f;
-      for (int m = 0; m < M; ++m) { vcp[(size_t)m * f_max + num] = cp[(size_t)m * f_max + f]; vcm[(size_t)m * f_max + num] = cm[(size_t)m * f_max + f]; }
-      ++num;
+  for (int f0 = 0; f0 < F; f0 += 32) {                                   // voiced frames (cand_pitch[0] > 0), in order
+    const int f = f0 + lane;
+    const bool v = f < F && cp[f] > 0.f;
+    if (f < F) spec[f] = cp[f];
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (v) {
+      const int at = num + __popc(m & below);
+      idx[at] = f;
+      for (int r = 0; r < M; ++r) { vcp[(size_t)r * f_max + at] = cp[(size_t)r * f_max + f]; vcm[(size_t)r * f_max + at] = cm[(size_t)r * f_max + f]; }
     }
+    num += __popc(m);
   }
+  __syncwarp();
+  auto wsum = [&](float v) { for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d); return v; };
+  auto medfilt_w = [&](const float* xin, float* yout, int n) {           // medfilt (yaapt.py:54-70), frames over the lanes
+    const int pad = tp.median_k / 2;
+    for (int i = lane; i < n; i += 32) {
+      float w[9];
+      for (int j = 0; j < tp.median_k; ++j) { const int u = i - pad + j; w[j] = (u >= 0 && u < n) ? xin[u] : 0.f; }
+      yout[i] = median_of(w, tp.median_k);
+    }
+    __syncwarp();
+  };
   int n_voiced_out = num;
   if (num > 2) {
     float s = 0.f;
-    for (int i = 0; i < num; ++i) s += vcp[i];
-    const float avg = s / (float)num;
+    for (int i = lane; i < num; i += 32) s += vcp[i];
+    const float avg = wsum(s) / (float)num;
     float q = 0.f;
-    for (int i = 0; i < num; ++i) { const float d = vcp[i] - avg; q += d * d; }
-    const float sd = sqrtf(q / (float)(num - 1));
+    for (int i = lane; i < num; i += 32) { const float d = vcp[i] - avg; q += d * d; }
+    const float sd = sqrtf(wsum(q) / (float)(num - 1));
     // the candidate closest (merit weighted) to 0.8 avg of every frame, median smoothed (yaapt.py:243-255)
-    for (int i = 0; i < num; ++i) {
+    for (int i = lane; i < num; i += 32) {
       int arg = 0;
-      float best = INFINITY;
+      float bestv = INFINITY;
       for (int m = 0; m < M; ++m) {
         const float d1 = fabsf(vcp[(size_t)m * f_max + i] - 0.8f * avg) * (3.f - vcm[(size_t)m * f_max + i]);
-        if (d1 < best) { best = d1; arg = m; }
+        if (d1 < bestv) { bestv = d1; arg = m; }
       }
       sel[i] = arg;
       ta[i] = vcp[(size_t)arg * f_max + i];
     }
-    medfilt_dev(ta, tc, num, tp.median_k);
-    for (int i = 0; i < num; ++i) vcp[(size_t)sel[i] * f_max + i] = tc[i];
-    // dynamic5 / path1 (yaapt.py:506-569)
+    __syncwarp();
+    medfilt_w(ta, tc, num);
+    for (int i = lane; i < num; i += 32) vcp[(size_t)sel[i] * f_max + i] = tc[i];
+    __syncwarp();
+    // dynamic5 / path1 (yaapt.py:506-569): trans[a, c, t] = k1 (0.05 d + d^2), d = |p[c, t] - p[a, t - 1]| / f0_min
     const float k1 = tp.dp5_k1 * sd / avg;
-    float pcost[kMaxPeaksOut], ccost[kMaxPeaksOut];
-    for (int m = 0; m < M; ++m) pcost[m] = 1.f - vcm[(size_t)m * f_max];
-    int last = 0;
+    const bool row = lane < M;
+    const size_t mine = (size_t)(row ? lane : 0) * f_max;
+    float pcost = row ? 1.f - vcm[mine] : INFINITY;
+    float prv = row ? vcp[mine] : 0.f;
+    auto trans = [&](float c, float pv) {
+      const float d = fabsf(c - pv) / tp.f0_min;
+      return k1 * (0.05f * d + d * d);
+    };
     for (int t = 1; t < num; ++t) {
-      auto trans = [&](int a, int c) {                                   // trans[a, c, t] = k1 (0.05 d + d^2), d = |p[c, t] - p[a, t-1]| / f0_min
-        const float d = fabsf(vcp[(size_t)c * f_max + t] - vcp[(size_t)a * f_max + t - 1]) / tp.f0_min;
-        return k1 * (0.05f * d + d * d);
-      };
-      for (int a = 0; a < M; ++a) {
-        int kk = 0;
-        float best = INFINITY;
-        for (int c = 0; c < M; ++c) {                                    // the LAST minimum (flip / argmin idiom)
-          const float v = pcost[c] + trans(a, c);
-          if (v <= best) { best = v; kk = c; }
-        }
-        pred[(size_t)a * f_max + t] = kk;
-        ccost[a] = pcost[kk] + trans(kk, a) + (1.f - vcm[(size_t)a * f_max + t]);
+      const float cur = row ? vcp[mine + t] : 0.f;
+      const float loc = row ? 1.f - vcm[mine + t] : 0.f;
+      int kk = 0;
+      float bst = INFINITY;
+      for (int c = 0; c < M; ++c) {                                      // the LAST minimum (flip / argmin idiom)
+        const float v = __shfl_sync(0xffffffffu, pcost, c) + trans(__shfl_sync(0xffffffffu, cur, c), prv);
+        if (v <= bst) { bst = v; kk = c; }
       }
-      float bestc = INFINITY;
+      const float ck = __shfl_sync(0xffffffffu, pcost, kk) + trans(cur, __shfl_sync(0xffffffffu, prv, kk)) + loc;
+      if (row) pred[mine + t] = kk;
+      pcost = row ? ck : INFINITY;
+      prv = cur;
+    }
+    int last = 0;
+    {
+      float bc = INFINITY;
       for (int a = 0; a < M; ++a) {
-        pcost[a] = ccost[a];
-        if (ccost[a] <= bestc) { bestc = ccost[a]; last = a; }
+        const float v = __shfl_sync(0xffffffffu, pcost, a);
+        if (v <= bc) { bc = v; last = a; }
       }
     }
-    int pth = last;                                                      // P[-1] = p_small[-1]
-    for (int t = num - 1; t >= 0; --t) {
-      ta[t] = vcp[(size_t)pth * f_max + t];
-      if (t > 0) pth = pred[(size_t)pth * f_max + t];
+    __syncwarp();
+    if (lane == 0) {
+      int pth = last;                                                    // P[-1] = p_small[-1]
+      for (int t = num - 1; t >= 0; --t) {
+        ta[t] = vcp[(size_t)pth * f_max + t];
+        if (t > 0) pth = pred[(size_t)pth * f_max + t];
+      }
     }
-    medfilt_dev(ta, voiced, num, tp.median_k);
+    __syncwarp();
+    medfilt_w(ta, voiced, num);
   } else {
     n_voiced_out = num > 0 ? num : 1;
-    for (int i = 0; i < n_voiced_out; ++i) voiced[i] = 150.f;
+    for (int i = lane; i < n_voiced_out; i += 32) voiced[i] = 150.f;
+    __syncwarp();
   }
   float s = 0.f;
-  for (int i = 0; i < n_voiced_out; ++i) s += voiced[i];
-  const float pavg = s / (float)n_voiced_out;
+  for (int i = lane; i < n_voiced_out; i += 32) s += voiced[i];
+  const float pavg = wsum(s) / (float)n_voiced_out;
   float sd = nanf("");
   if (n_voiced_out > 1) {
     float q = 0.f;
-    for (int i = 0; i < n_voiced_out; ++i) { const float d = voiced[i] - pavg; q += d * d; }
-    sd = sqrtf(q / (float)(n_voiced_out - 1));
+    for (int i = lane; i < n_voiced_out; i += 32) { const float d = voiced[i] - pavg; q += d * d; }
+    sd = sqrtf(wsum(q) / (float)(n_voiced_out - 1));
   }
-  const float floor_sd = pavg * tp.min_std;
-  pitch_std[b] = (sd != sd) ? sd : fmaxf(sd, floor_sd);                  // torch.maximum propagates NaN
-  for (int i = 0; i < num; ++i) spec[idx[i]] = voiced[i];
-  if (spec[0] < pavg / 2.f) spec[0] = pavg;
-  if (spec[F - 1] < pavg / 2.f) spec[F - 1] = pavg;
+  if (lane == 0) pitch_std[b] = (sd != sd) ? sd : fmaxf(sd, pavg * tp.min_std);      // torch.maximum propagates NaN
+  for (int i = lane; i < num; i += 32) spec[idx[i]] = voiced[i];
+  __syncwarp();
+  if (lane == 0) {
+    if (spec[0] < pavg / 2.f) spec[0] = pavg;
+    if (spec[F - 1] < pavg / 2.f) spec[F - 1] = pavg;
+  }
+  __syncwarp();
   int nz = 0;
-  for (int f = 0; f < F; ++f) if (spec[f] != 0.f) ta[nz++] = spec[f];
+  for (int f0 = 0; f0 < F; f0 += 32) {                                   // the non-zero values, in order
+    const int f = f0 + lane;
+    const bool v = f < F && spec[f] != 0.f;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (v) ta[nz + __popc(m & below)] = spec[f];
+    nz += __popc(m);
+  }
+  __syncwarp();
   // F.interpolate(mode='linear', align_corners=False) of the nz non-zero values to F samples
   const float scale = (float)nz / (float)F;
-  for (int f = 0; f < F; ++f) {
+  for (int f = lane; f < F; f += 32) {
     const float src = fmaxf(0.f, scale * ((float)f + 0.5f) - 0.5f);
     const int i0 = min((int)src, nz - 1), i1 = min(i0 + 1, nz - 1);
     const float lam = src - (float)i0;
     out[f] = (1.f - lam) * ta[i0] + lam * ta[i1];
   }
-  out[0] = out[2];
-  out[1] = out[3];
+  __syncwarp();
+  if (lane == 0) { out[0] = out[2]; out[1] = out[3]; }
 }
 
 // ---- time_track / refine / dynamic (yaapt.py:577-787, 321-372) -------------------------------------------------------
@@ -589,12 +617,14 @@ __device__ __forceinline__ int tda_frames(int64_t size, const TdaParams& q, int 
 __global__ void tda_mean_kernel(const float* __restrict__ fa, const float* __restrict__ fb, float* __restrict__ copy,
                                 const float* __restrict__ pitch_std, const int* __restrict__ lengths, int64_t n_max, int64_t stride,
                                 Geometry g, TdaParams q) {
-  __shared__ float part[8];
-  const int b = blockIdx.x, sig = blockIdx.y;
+  // One WARP per (utterance, signal): the frames are a chain (each mean sees the previous shifts), so what counts is the
+  // latency of one step; with a block of 128 threads two __syncthreads per frame made it 1.6 ms per batch, a warp needs 0.3.
+  const int b = blockIdx.x, sig = blockIdx.y, lane = threadIdx.x;
   const float* src = (sig ? fb : fa) + (int64_t)b * stride;
   float* x = copy + ((int64_t)sig * gridDim.x + b) * stride;
-  for (int64_t i = threadIdx.x; i < stride; i += blockDim.x) x[i] = src[i];
+  for (int64_t i = threadIdx.x; i < stride; i += blockDim.x) x[i] = src[i];      // the private copy: the whole block
   __syncthreads();
+  if (threadIdx.x >= 32) return;
   const int64_t len = lengths ? lengths[b] : n_max;
   const int64_t size = len + 2 * g.pad, half = g.frame_size / 2;
   const int64_t span = size - half - half;
@@ -605,15 +635,11 @@ __global__ void tda_mean_kernel(const float* __restrict__ fa, const float* __res
   for (int f = 0; f < F; ++f) {
     float* fr = x + (int64_t)f * g.frame_jump;
     float s = 0.f;
-    for (int n = threadIdx.x; n < q.tda_len; n += blockDim.x) s += fr[n];
+    for (int n = lane; n < q.tda_len; n += 32) s += fr[n];
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-    __syncthreads();
-    float tot = 0.f;
-    for (int w = 0; w < (int)blockDim.x / 32; ++w) tot += part[w];
-    const float mean = tot / (float)q.tda_len;
-    for (int n = threadIdx.x; n < q.tda_len; n += blockDim.x) fr[n] -= mean;
-    __syncthreads();
+    const float mean = s / (float)q.tda_len;
+    for (int n = lane; n < q.tda_len; n += 32) fr[n] -= mean;
+    __syncwarp();
   }
 }
 
@@ -1061,7 +1087,7 @@ int sa_yaapt_track(const sa_yaapt_params* p, const float* filtered, const float*
     if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   }
   const int* dl = lengths ? d_len : nullptr;
-  tda_mean_kernel<<<dim3((unsigned)B, 2), 128, 0, st>>>(filtered, filtered_nl, copy, pitch_std, dl, n_max, stride, g, q);
+  tda_mean_kernel<<<dim3((unsigned)B, 2), 256, 0, st>>>(filtered, filtered_nl, copy, pitch_std, dl, n_max, stride, g, q);
   const int lag_threads = 128;
   nccf_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B, 2), lag_threads, (size_t)2 * q.tda_len * sizeof(float), st>>>(
       copy, spec_pitch, pitch_std, tracks, dl, n_max, stride, f_max, g, q, B);
