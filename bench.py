@@ -538,6 +538,24 @@ def main():
             "cpu_port": {"value": cpu_sec / dt, "unit": "audio-s/s", "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} utterances through oracle/yaapt_nlfer_numpy.py (the whole extractor; float64 filters, scipy recursion, "
                                    f"numpy rfft) in {dt:.1f} s; compare with yaapt_value; the reference's own TorchScript yaapt runs at ~20 audio-s/s per core (BASELINE.md)"}}
+        # N3 (last step): nearest-codeword assignment of the batch's 64 x 750 bottleneck rows (chain/nn.py:402-477)
+        rng_v = np.random.default_rng(9)
+        cb_v = conditioning.codebook()
+        bn_d = torch.from_numpy((cb_v[rng_v.integers(0, cb_v.shape[0], size=(len(frames), max(frames)))]
+                                 + 0.5 * rng_v.standard_normal((len(frames), max(frames), cb_v.shape[1]))).astype(np.float32)).to(dev)
+        gen.set_codebook(torch.from_numpy(cb_v))
+        ms_vq = timed(lambda: gen.vq_assign(bn_d), max(args.steps, 20))
+        vq_bytes = bn_d.numel() * 4 + bn_d.numel() // cb_v.shape[1]
+        vq_rows = int(bn_d.numel() // cb_v.shape[1])
+        vq_flop = 2.0 * vq_rows * cb_v.shape[1] * cb_v.shape[0]
+        extras["vq_assign_b64"] = {"ms_per_step": ms_vq, "rows": vq_rows, "algorithmic_bytes": int(vq_bytes),
+                                   "achieved_gbs": vq_bytes / (ms_vq * 1e-3) / 1e9, "hbm_peak_gbs": load_peaks()["hbm_gbs"],
+                                   "hbm_frac": vq_bytes / (ms_vq * 1e-3) / 1e9 / load_peaks()["hbm_gbs"],
+                                   "achieved_fp32_tflops": vq_flop / (ms_vq * 1e-3) / 1e12,
+                                   "what": "sa_hifigan_vq_assign: fp32 [64 x 750, 256] rows in, uint8 code index out (48 codes), "
+                                           "through CoreHifiGan.vq_assign; 24.6 kFLOP per 1 KB row in exact fp32 puts the step on the "
+                                           "fp32 FMA pipe (ncu: profiles/r2_vq_assign_summary.txt), not on HBM"}
+        del bn_d
         del wav_d
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------

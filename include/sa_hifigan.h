@@ -191,6 +191,17 @@ int sa_hifigan_forward_vq(sa_hifigan* h, const uint8_t* vq_idx, const float* f0,
                           int32_t B, int32_t T, const int32_t* frames_per_item, void* y, int32_t y_dtype,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Nearest-codeword assignment (the last step of the ASR-BN extractor): what VectorQuantizerEMA.forward
+ * does in eval mode (satools/satools/chain/nn.py:402-477) at the end of extract_bn
+ * (egs/asr/librispeech/local/chain/tuning/tdnnf_wav2vec2_vq.py:96-112,312), against the codebook of sa_hifigan_set_codebook.
+ *   bn        fp32 [n_rows, dim]  the pre-quantisation bottleneck rows (the [N, T, C] tensor flattened as inputs.view(-1, C))
+ *   vq_idx    uint8 [n_rows]      encoding_indices (first minimum of |x|^2 + |e|^2 - 2 x.e, chain/nn.py:423-436)
+ *   quantized fp32 [n_rows, dim]  or NULL: the returned tensor, inputs + (codeword - inputs) in fp32 (chain/nn.py:448-456)
+ * all on the device.  vq_idx [B, T] is exactly what sa_hifigan_forward_vq consumes, so the dense [B, dim, T] feature tensor
+ * never has to exist.  dim <= 512. */
+int sa_hifigan_vq_assign(sa_hifigan* h, const float* bn, int64_t n_rows, uint8_t* vq_idx,
+                         float* quantized, void* stream);
+
 /* Stream-ordered host entries with TRIMMED output (the reference copies the whole padded batch back and
  * trims on the host, bin/pipeline.py:148-156): frames_per_item is required; after the forward only the kept samples of
  * every item, 320 * frames_per_item[b] + 1, are copied to y_host, packed one item after the other (item b starts at

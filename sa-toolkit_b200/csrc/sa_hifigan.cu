@@ -662,6 +662,223 @@ int sa_hifigan_forward_vq(sa_hifigan* h, const uint8_t* vq_idx, const float* f0,
                       stream, vq_idx, spk_ids);
 }
 
+// ---- N3, last step of extract_bn: nearest-codeword assignment (VectorQuantizerEMA.forward in eval mode) -------------
+// chain/nn.py:423-436 computes |x|^2 + |e|^2 - 2 x.e for every row against every code and takes the first argmin; :448-456
+// returns inputs + (codeword - inputs).  HBM bound: one read of the row (4 dim bytes), one index byte (+ 4 dim bytes when
+// the quantised rows are wanted).  One warp per row, dims over the lanes; the codebook and |e|^2 sit in shared memory.
+constexpr int kVqMaxDimRegs = 16;                                         // dim <= 32 * 16
+__global__ void __launch_bounds__(256) vq_assign_kernel(const float* __restrict__ bn, const float* __restrict__ codebook,
+                                                        int64_t n_rows, int n_codes, int dim, int in_smem,
+                                                        uint8_t* __restrict__ vq_idx, float* __restrict__ quantized) {
+  extern __shared__ float vq_smem[];
+  float* ee = vq_smem;                                                    // [n_codes]
+  const float* cb = codebook;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  if (in_smem) {
+    float* s = vq_smem + n_codes;
+    for (int i = threadIdx.x; i < n_codes * dim; i += blockDim.x) s[i] = codebook[i];
+    cb = s;
+    __syncthreads();
+  }
+  for (int c = warp; c < n_codes; c += n_warps) {
+    float a = 0.f;
+    for (int d = lane; d < dim; d += 32) a = fmaf(cb[(size_t)c * dim + d], cb[(size_t)c * dim + d], a);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) ee[c] = a;
+  }
+  __syncthreads();
+  for (int64_t r = (int64_t)blockIdx.x * n_warps + warp; r < n_rows; r += (int64_t)gridDim.x * n_warps) {
+    const float* x = bn + r * dim;
+    float xr[kVqMaxDimRegs];
+    float xx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVqMaxDimRegs; ++j) {
+      const int d = lane + 32 * j;
+      xr[j] = d < dim ? __ldg(x + d) : 0.f;
+      xx = fmaf(xr[j], xr[j], xx);
+    }
+    for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    int best = 0;
+    float best_d = INFINITY;
+    for (int c = 0; c < n_codes; ++c) {
+      const float* e = cb + (size_t)c * dim;
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < kVqMaxDimRegs; ++j) {
+        const int d = lane + 32 * j;
+        if (d < dim) dot = fmaf(xr[j], e[d], dot);
+      }
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float dist = __fsub_rn(__fadd_rn(xx, ee[c]), __fmul_rn(2.f, dot));
+      if (dist < best_d || c == 0) { best_d = dist; best = c; }          // first minimum, as torch.argmin
+    }
+    if (lane == 0) vq_idx[r] = (uint8_t)best;
+    if (quantized) {
+      const float* e = cb + (size_t)best * dim;
+#pragma unroll
+      for (int j = 0; j < kVqMaxDimRegs; ++j) {
+        const int d = lane + 32 * j;
+        if (d < dim) quantized[r * dim + d] = __fadd_rn(xr[j], __fsub_rn(e[d], xr[j]));
+      }
+    }
+  }
+}
+
+// The same assignment as a register-tiled fp32 product (dim % 4 == 0): 0.6 kFLOP per input byte makes the step bound by the
+// fp32 FMA pipe, not by HBM, so the warp-per-row form above (a shuffle tree per code) is kept for odd dims only.  A CTA takes
+// 128 rows; per 32-wide slice of the dimension the rows and 48 codewords are staged k-major in shared memory; a thread owns
+// 4 rows x 6 codes (one 16-byte row read + three broadcast 8-byte code reads per 24 FMAs); warp w owns codes 6w .. 6w + 5.
+constexpr int kVqRows = 128, kVqCodes = 48, kVqK = 32, kVqXStride = kVqRows + 4;
+__global__ void __launch_bounds__(256, 3) vq_assign_tiled_kernel(const float* __restrict__ bn, const float* __restrict__ codebook,
+                                                              int64_t n_rows, int n_codes, int dim,
+                                                              uint8_t* __restrict__ vq_idx, float* __restrict__ quantized) {
+  __shared__ __align__(16) float xs[kVqK][kVqXStride];
+  __shared__ __align__(16) float es[kVqK][kVqCodes];
+  __shared__ float xxs[kVqRows];
+  __shared__ float ees[kVqCodes];
+  __shared__ float best_d[8][kVqRows];
+  __shared__ int best_i[8][kVqRows];
+  __shared__ int win[kVqRows];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = lane * 4, c0 = warp * 6;
+  const int n_tiles = (int)((n_rows + kVqRows - 1) / kVqRows);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = (int64_t)tile * kVqRows;
+    float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    int bi[4] = {0, 0, 0, 0};
+    for (int g0 = 0; g0 < n_codes; g0 += kVqCodes) {
+      float acc[4][6];
+      float xx[4] = {0.f, 0.f, 0.f, 0.f}, eq[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+      for (int k0 = 0; k0 < dim; k0 += kVqK) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                      // rows: 128 x 32 floats, 8 lanes per row
+          const int e = tid + 256 * i, r = e >> 3, kq = (e & 7) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + r < n_rows && k0 + kq < dim) v = __ldg(reinterpret_cast<const float4*>(bn + (row0 + r) * dim + k0 + kq));
+          xs[kq][r] = v.x; xs[kq + 1][r] = v.y; xs[kq + 2][r] = v.z; xs[kq + 3][r] = v.w;
+        }
+        for (int e = tid; e < kVqCodes * 8; e += 256) {                    // codes: 48 x 32 floats
+          const int c = e >> 3, kq = (e & 7) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g0 + c < n_codes && k0 + kq < dim) v = __ldg(reinterpret_cast<const float4*>(codebook + (size_t)(g0 + c) * dim + k0 + kq));
+          es[kq][c] = v.x; es[kq + 1][c] = v.y; es[kq + 2][c] = v.z; es[kq + 3][c] = v.w;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < kVqK; ++k) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[k][r0]);
+          const float2 e01 = *reinterpret_cast<const float2*>(&es[k][c0]);
+          const float2 e23 = *reinterpret_cast<const float2*>(&es[k][c0 + 2]);
+          const float2 e45 = *reinterpret_cast<const float2*>(&es[k][c0 + 4]);
+          const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+          const float e[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(x[i], e[j], acc[i][j]);
+          }
+          if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xx[i] = fmaf(x[i], x[i], xx[i]);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) eq[j] = fmaf(e[j], e[j], eq[j]);
+          }
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xxs[r0 + i] = xx[i];
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ees[c0 + j] = eq[j];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {                                      // ascending codes, strict <: the first minimum
+          const int c = g0 + c0 + j;
+          const float dist = __fsub_rn(__fadd_rn(xxs[r0 + i], ees[c0 + j]), __fmul_rn(2.f, acc[i][j]));
+          if (c < n_codes && (dist < bd[i] || (c == 0))) { bd[i] = dist; bi[i] = c; }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best_d[warp][r0 + i] = bd[i]; best_i[warp][r0 + i] = bi[i]; }
+    __syncthreads();
+    if (tid < kVqRows) {
+      // warp w holds codes {g0 + 6w .. g0 + 6w + 5 for every group g0}: the first minimum is the lowest index among the
+      // smallest distances
+      float d = best_d[0][tid];
+      int c = best_i[0][tid];
+      for (int w = 1; w < 8; ++w) {
+        const float dw = best_d[w][tid];
+        const int cw = best_i[w][tid];
+        if (dw < d || (dw == d && cw < c)) { d = dw; c = cw; }
+      }
+      win[tid] = c;
+      if (row0 + tid < n_rows) vq_idx[row0 + tid] = (uint8_t)c;
+    }
+    if (quantized) {                                                       // inputs + (codeword - inputs), chain/nn.py:456
+      __syncthreads();
+      const int q4 = dim >> 2;
+      for (int e = tid; e < kVqRows * q4; e += 256) {
+        const int r = e / q4, k = (e - r * q4) * 4;
+        if (row0 + r >= n_rows) break;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(bn + (row0 + r) * dim + k));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(codebook + (size_t)win[r] * dim + k));
+        float4 o;
+        o.x = __fadd_rn(x.x, __fsub_rn(c.x, x.x)); o.y = __fadd_rn(x.y, __fsub_rn(c.y, x.y));
+        o.z = __fadd_rn(x.z, __fsub_rn(c.z, x.z)); o.w = __fadd_rn(x.w, __fsub_rn(c.w, x.w));
+        *reinterpret_cast<float4*>(quantized + (row0 + r) * dim + k) = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int sa_hifigan_vq_assign(sa_hifigan* h, const float* bn, int64_t n_rows, uint8_t* vq_idx, float* quantized, void* stream) {
+  if (!h) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (!h->d_codebook) return fail(SA_ERR_NOT_FINALIZED, "call sa_hifigan_set_codebook first");
+  if (n_rows == 0) return SA_OK;
+  if (!bn || !vq_idx) return fail(SA_ERR_INVALID_ARG, "NULL argument");
+  if (n_rows < 0) return fail(SA_ERR_INVALID_ARG, "n_rows %lld < 0", (long long)n_rows);
+  if (n_rows == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(h->device));
+  if (h->code_dim % 4 == 0 && (reinterpret_cast<uintptr_t>(bn) & 15) == 0 && (!quantized || (reinterpret_cast<uintptr_t>(quantized) & 15) == 0)) {
+    int n_sm = 0;
+    SA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    const int64_t tiles = (n_rows + kVqRows - 1) / kVqRows;
+    vq_assign_tiled_kernel<<<(int)std::min<int64_t>(tiles, (int64_t)n_sm * 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bn, h->d_codebook, n_rows, h->n_codes, h->code_dim, vq_idx, quantized);
+    SA_CUDA(cudaGetLastError());
+    return SA_OK;
+  }
+  if (h->code_dim > 32 * kVqMaxDimRegs) return fail(SA_ERR_UNSUPPORTED, "codebook dimension %d > %d", h->code_dim, 32 * kVqMaxDimRegs);
+  const size_t full = ((size_t)h->n_codes * h->code_dim + h->n_codes) * sizeof(float);
+  const int in_smem = full <= 200 * 1024;
+  const size_t smem = in_smem ? full : (size_t)h->n_codes * sizeof(float);
+  if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  SA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  const int64_t blocks_needed = (n_rows + 7) / 8;
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 50 * 1024 ? 2 : 4);
+  const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)sms * per_sm);
+  vq_assign_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(bn, h->d_codebook, n_rows, h->n_codes, h->code_dim,
+                                                                          in_smem, vq_idx, quantized);
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
 // Shared tail of the stream-ordered host entries with TRIMMED output: after the forward, only the kept
 // samples of every item, 320 * frames_per_item[b] + 1, go back to the host, packed one item after the other
 // (pipeline.py:156 trims to the original length on the host after copying the whole padded batch).

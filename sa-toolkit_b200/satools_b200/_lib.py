@@ -93,6 +93,7 @@ SYMBOLS = {
     "sa_hifigan_set_codebook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "sa_hifigan_forward_vq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sa_hifigan_vq_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sa_hifigan_synthesize_host_trimmed_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sa_hifigan_synthesize_host_vq_trimmed_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -247,6 +247,27 @@ class CoreHifiGan(nn.Module):
             self.last_launch_count = int(lib.sa_hifigan_last_launch_count(self._handle))
         return (y, torch.empty((1)))
 
+    @torch.no_grad()
+    def vq_assign(self, bn: torch.Tensor, return_quantized: bool = False):
+        """bn fp32 [..., n_bn] on a CUDA device (the bottleneck rows VectorQuantizerEMA.forward receives, chain/nn.py:402):
+        returns encoding_indices uint8 [...] -- the vq_idx of forward_vq -- and, on request, the module's `quantized`
+        output (inputs + (codeword - inputs), chain/nn.py:448-456)."""
+        if not bn.is_cuda:
+            raise RuntimeError("satools_b200.CoreHifiGan runs on CUDA (sm_100a) only; there is no CPU fallback.")
+        lib = _lib.load()
+        x = bn.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(x.device):
+            self._ensure_handle(x.device)                 # the codebook only: no weight signature walk on this path
+            self._ensure_codebook()
+            if x.shape[-1] != self._codebook.shape[1]:
+                raise ValueError(f"rows of {x.shape[-1]} values against a codebook of dimension {self._codebook.shape[1]}")
+            idx = torch.empty(x.shape[:-1], dtype=torch.uint8, device=x.device)
+            q = torch.empty_like(x) if return_quantized else None
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.sa_hifigan_vq_assign(self._handle, x.data_ptr(), idx.numel(), idx.data_ptr(),
+                                                q.data_ptr() if q is not None else None, stream))
+        return (idx, q) if return_quantized else idx
+
     # ---- latency path: one CUDA graph launch instead of ~50 kernel launches ---------------------
     def graphed(self, B: int, T: int, device=None, out_dtype: torch.dtype = torch.float32) -> "GraphedForward":
         """Capture forward() for one fixed input shape [B, imput_dim, T] into a CUDA graph (single utterances,
@@ -362,7 +383,8 @@ class CoreHifiGan(nn.Module):
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _ensure_ready(self, device: torch.device) -> None:
+    def _ensure_handle(self, device: torch.device) -> None:
+        """The native handle on `device` (no weight upload: enough for the entries that only use the codebook)."""
         lib = _lib.load()
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if self._handle is not None and (self._handle_pid != os.getpid() or self._handle_device != idx):
@@ -376,6 +398,10 @@ class CoreHifiGan(nn.Module):
             self._handle, self._handle_pid, self._handle_device = out.value, os.getpid(), idx
             self._weights_sig = None
             self._codebook_handle = None
+
+    def _ensure_ready(self, device: torch.device) -> None:
+        lib = _lib.load()
+        self._ensure_handle(device)
         if self.precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}")
         sig = self._signature()

@@ -129,3 +129,15 @@ def test_reference_conditioning_layout():
     # quant+awgn changes only the F0 channel
     assert not np.array_equal(z["plain/x"][:, 256], z["quant_16_awgn_2/x"][:, 256])
     np.testing.assert_array_equal(z["plain/x"][:, :256], z["quant_16_awgn_2/x"][:, :256])
+
+
+# ---- N3 last step: VectorQuantizerEMA assignment (oracle/vq_numpy.py against outputs of the reference's own module) ----
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_vq_assign_oracle_matches_reference(case):
+    from oracle import vq_numpy as ovq
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vq_assign.npz"))
+    x, cb = g[f"c{case}_inputs"], g[f"c{case}_codebook"]
+    idx, q = ovq.assign(x, cb)
+    np.testing.assert_array_equal(idx, g[f"c{case}_indices"])
+    np.testing.assert_array_equal(q, g[f"c{case}_quantized"])
+    assert ovq.margin(x, cb).min() > 1e-5            # no fixture row sits on an fp32 tie

@@ -741,3 +741,65 @@ def test_corpus_driver_dense_and_compact_inputs_agree_and_stream_to_a_sink():
         # SURVEY Appendix B), everything before is independent of the batching
         keep = 320 * (frames[i] - 20)
         np.testing.assert_array_equal(seen[u][:keep], a[u][:keep], err_msg=u)
+
+
+# ---- N3 last step: nearest-codeword assignment (sa_hifigan_vq_assign) ---------------------------------------------------
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_vq_assign_matches_the_reference_module(case):
+    """encoding_indices and `quantized` of the reference's VectorQuantizerEMA in eval mode (fixtures minted by
+    oracle/make_golden_vq.py): indices identical, quantized rows bit for bit."""
+    _need_gpu()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vq_assign.npz"))
+    x, cb = g[f"c{case}_inputs"], g[f"c{case}_codebook"]
+    gen = dev_gen(2, "fp16")
+    gen.set_codebook(torch.from_numpy(cb))
+    idx, q = gen.vq_assign(torch.from_numpy(x).cuda(), return_quantized=True)
+    assert idx.dtype == torch.uint8 and tuple(idx.shape) == x.shape[:-1]
+    np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), g[f"c{case}_indices"])
+    np.testing.assert_array_equal(q.cpu().numpy(), g[f"c{case}_quantized"])
+    only = gen.vq_assign(torch.from_numpy(x).cuda())
+    assert torch.equal(only, idx)
+
+
+def test_vq_assign_full_size_against_the_oracle_and_into_the_generator():
+    """configs[1] size (64 x 750 rows of 256): indices equal to the fp64 oracle wherever the two best codes are further
+    apart than fp32 resolution; exact codewords map to themselves (idempotence); the indices drive forward_vq."""
+    _need_gpu()
+    from oracle import vq_numpy as ovq
+    rng = np.random.default_rng(5)
+    cb = rng.standard_normal((48, 256)).astype(np.float32)
+    B, T = 64, 750
+    pick = rng.integers(0, 48, size=(B, T))
+    x = (cb[pick] + 0.8 * rng.standard_normal((B, T, 256))).astype(np.float32)
+    x[:, ::7] = rng.standard_normal((B, (T + 6) // 7, 256)).astype(np.float32)
+    gen = dev_gen(2, "fp16")
+    gen.set_codebook(torch.from_numpy(cb))
+    idx, q = gen.vq_assign(torch.from_numpy(x).cuda(), return_quantized=True)
+    idx_h = idx.cpu().numpy().astype(np.int64)
+    want, want_q = ovq.assign(x, cb)
+    safe = ovq.margin(x, cb).reshape(B, T) > 1e-5
+    assert safe.mean() > 0.999
+    np.testing.assert_array_equal(idx_h[safe], want[safe])
+    np.testing.assert_array_equal(q.cpu().numpy()[safe], want_q[safe])
+    again = gen.vq_assign(torch.from_numpy(cb[idx_h]).cuda())
+    assert torch.equal(again, idx)
+    # empty input
+    assert gen.vq_assign(torch.empty((0, 256), device="cuda")).numel() == 0
+    # other codebook shapes: more codes than one 48-wide group, a dimension that is not a multiple of 4 (warp-per-row kernel),
+    # a ragged last tile
+    for n_codes, dim, rows in [(100, 64, 1000), (20, 250, 333), (255, 32, 129), (1, 8, 5)]:
+        cb2 = rng.standard_normal((n_codes, dim)).astype(np.float32)
+        x2 = (cb2[rng.integers(0, n_codes, size=rows)] + 0.6 * rng.standard_normal((rows, dim))).astype(np.float32)
+        gen.set_codebook(torch.from_numpy(cb2))
+        i2, q2 = gen.vq_assign(torch.from_numpy(x2).cuda(), return_quantized=True)
+        w2, wq2 = ovq.assign(x2, cb2)
+        ok = ovq.margin(x2, cb2) > 1e-5 if n_codes > 1 else np.ones(rows, dtype=bool)
+        np.testing.assert_array_equal(i2.cpu().numpy().astype(np.int64)[ok], w2[ok])
+        np.testing.assert_array_equal(q2.cpu().numpy()[ok], wq2[ok])
+    gen.set_codebook(torch.from_numpy(cb))
+    # the index tensor is forward_vq's input: same waveform as the dense tensor assembled from the quantised rows
+    f0 = rng.uniform(0.0, 1.0, size=(2, 40)).astype(np.float32)
+    spk = np.array([3, 100], dtype=np.int32)
+    y_v = gen.forward_vq(idx[:2, :40], torch.from_numpy(f0).cuda(), torch.from_numpy(spk).cuda())[0].cpu().numpy()
+    dense = np.stack([conditioning.assemble(idx_h[b, :40], f0[b], int(spk[b]), cb=cb) for b in range(2)])
+    np.testing.assert_array_equal(y_v, run(gen, dense))
