@@ -724,103 +724,113 @@ __global__ void __launch_bounds__(256) vq_assign_kernel(const float* __restrict_
   }
 }
 
-// The same assignment as a register-tiled fp32 product (dim % 4 == 0): 0.6 kFLOP per input byte makes the step bound by the
-// fp32 FMA pipe, not by HBM, so the warp-per-row form above (a shuffle tree per code) is kept for odd dims only.  A CTA takes
-// 128 rows; per 32-wide slice of the dimension the rows and 48 codewords are staged k-major in shared memory; a thread owns
-// 4 rows x 6 codes (one 16-byte row read + three broadcast 8-byte code reads per 24 FMAs); warp w owns codes 6w .. 6w + 5.
-constexpr int kVqRows = 128, kVqCodes = 48, kVqK = 32, kVqXStride = kVqRows + 4;
-__global__ void __launch_bounds__(256, 3) vq_assign_tiled_kernel(const float* __restrict__ bn, const float* __restrict__ codebook,
-                                                              int64_t n_rows, int n_codes, int dim,
-                                                              uint8_t* __restrict__ vq_idx, float* __restrict__ quantized) {
-  __shared__ __align__(16) float xs[kVqK][kVqXStride];
-  __shared__ __align__(16) float es[kVqK][kVqCodes];
-  __shared__ float xxs[kVqRows];
-  __shared__ float ees[kVqCodes];
-  __shared__ float best_d[8][kVqRows];
-  __shared__ int best_i[8][kVqRows];
+// The same assignment as a register-tiled fp32 product (dim % 4 == 0): 24.6 kFLOP per 1 KB row in exact fp32 makes the step
+// bound by the fp32 FMA pipe, not by HBM, so the warp-per-row form above (a shuffle tree per code) is kept for odd dims only.
+// A CTA of 4 warps takes 128 rows; 16-wide slices of the dimension of the rows and of 48 codewords flow through a three-stage
+// cp.async ring in shared memory (row-major, 20-float pitch: the 16-byte reads of a quarter warp fall on distinct banks).  A
+// thread owns rows lane + 32 i (i < 4) x 12 codes: four 16-byte row reads + twelve broadcast 16-byte code reads per 192
+// FMAs; warp w owns codes 12w .. 12w + 11 of each 48-wide group.  |e|^2 once per CTA, |x|^2 beside the products.
+constexpr int kVqRows = 128, kVqCodes = 48, kVqK = 16, kVqPitch = 20, kVqStages = 3, kVqThreads = 128;
+__device__ __forceinline__ void vq_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__global__ void __launch_bounds__(kVqThreads, 3) vq_assign_tiled_kernel(const float* __restrict__ bn, const float* __restrict__ codebook,
+                                                                        int64_t n_rows, int n_codes, int dim,
+                                                                        uint8_t* __restrict__ vq_idx, float* __restrict__ quantized) {
+  __shared__ __align__(16) float xs[kVqStages][kVqRows][kVqPitch];
+  __shared__ __align__(16) float es[kVqStages][kVqCodes][kVqPitch];
+  __shared__ float ees[256];
+  __shared__ float best_d[4][kVqRows];
+  __shared__ int best_i[4][kVqRows];
   __shared__ int win[kVqRows];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = lane * 4, c0 = warp * 6;
+  const int c0 = warp * 12;
+  for (int c = warp; c < n_codes; c += 4) {                                // |e|^2 of every code
+    float a = 0.f;
+    for (int d = lane; d < dim; d += 32) { const float v = __ldg(codebook + (size_t)c * dim + d); a = fmaf(v, v, a); }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) ees[c] = a;
+  }
   const int n_tiles = (int)((n_rows + kVqRows - 1) / kVqRows);
+  const int n_chunks = (dim + kVqK - 1) / kVqK;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kVqRows;
     float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     int bi[4] = {0, 0, 0, 0};
     for (int g0 = 0; g0 < n_codes; g0 += kVqCodes) {
-      float acc[4][6];
-      float xx[4] = {0.f, 0.f, 0.f, 0.f}, eq[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      auto load = [&](int chunk) {                                         // one slice of the rows and of the codes; always commits
+        if (chunk < n_chunks) {
+          const int st = chunk % kVqStages, k0 = chunk * kVqK;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = tid + kVqThreads * i, r = e >> 2, kq = (e & 3) * 4;
+            const bool ok = row0 + r < n_rows && k0 + kq < dim;
+            vq_cp_async16(&xs[st][r][kq], ok ? bn + (row0 + r) * dim + k0 + kq : bn, ok ? 16 : 0);
+          }
+          for (int e = tid; e < kVqCodes * 4; e += kVqThreads) {
+            const int c = e >> 2, kq = (e & 3) * 4;
+            const bool ok = g0 + c < n_codes && k0 + kq < dim;
+            vq_cp_async16(&es[st][c][kq], ok ? codebook + (size_t)(g0 + c) * dim + k0 + kq : codebook, ok ? 16 : 0);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      float acc[4][12];
+      float xx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
-      for (int k0 = 0; k0 < dim; k0 += kVqK) {
-        __syncthreads();
+        for (int j = 0; j < 12; ++j) acc[i][j] = 0.f;
+      __syncthreads();                                                     // the ring is free (previous group / tile done)
+      load(0);
+      load(1);
+      for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();                                                   // slice `chunk` landed; slice chunk - 1 consumed by all
+        load(chunk + 2);
+        const int st = chunk % kVqStages;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                                      // rows: 128 x 32 floats, 8 lanes per row
-          const int e = tid + 256 * i, r = e >> 3, kq = (e & 7) * 4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + r < n_rows && k0 + kq < dim) v = __ldg(reinterpret_cast<const float4*>(bn + (row0 + r) * dim + k0 + kq));
-          xs[kq][r] = v.x; xs[kq + 1][r] = v.y; xs[kq + 2][r] = v.z; xs[kq + 3][r] = v.w;
-        }
-        for (int e = tid; e < kVqCodes * 8; e += 256) {                    // codes: 48 x 32 floats
-          const int c = e >> 3, kq = (e & 7) * 4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g0 + c < n_codes && k0 + kq < dim) v = __ldg(reinterpret_cast<const float4*>(codebook + (size_t)(g0 + c) * dim + k0 + kq));
-          es[kq][c] = v.x; es[kq + 1][c] = v.y; es[kq + 2][c] = v.z; es[kq + 3][c] = v.w;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < kVqK; ++k) {
-          const float4 xv = *reinterpret_cast<const float4*>(&xs[k][r0]);
-          const float2 e01 = *reinterpret_cast<const float2*>(&es[k][c0]);
-          const float2 e23 = *reinterpret_cast<const float2*>(&es[k][c0 + 2]);
-          const float2 e45 = *reinterpret_cast<const float2*>(&es[k][c0 + 4]);
-          const float x[4] = {xv.x, xv.y, xv.z, xv.w};
-          const float e[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+        for (int kk = 0; kk < kVqK; kk += 4) {
+          float4 xv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(x[i], e[j], acc[i][j]);
+            xv[i] = *reinterpret_cast<const float4*>(&xs[st][lane + 32 * i][kk]);
+            xx[i] = fmaf(xv[i].x, xv[i].x, xx[i]); xx[i] = fmaf(xv[i].y, xv[i].y, xx[i]);
+            xx[i] = fmaf(xv[i].z, xv[i].z, xx[i]); xx[i] = fmaf(xv[i].w, xv[i].w, xx[i]);
           }
-          if (warp == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xx[i] = fmaf(x[i], x[i], xx[i]);
-          }
-          if (lane == 0) {
+          for (int j = 0; j < 12; ++j) {
+            const float4 ev = *reinterpret_cast<const float4*>(&es[st][c0 + j][kk]);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) eq[j] = fmaf(e[j], e[j], eq[j]);
+            for (int i = 0; i < 4; ++i) {
+              acc[i][j] = fmaf(xv[i].x, ev.x, acc[i][j]); acc[i][j] = fmaf(xv[i].y, ev.y, acc[i][j]);
+              acc[i][j] = fmaf(xv[i].z, ev.z, acc[i][j]); acc[i][j] = fmaf(xv[i].w, ev.w, acc[i][j]);
+            }
           }
         }
       }
-      __syncthreads();
-      if (warp == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xxs[r0 + i] = xx[i];
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) ees[c0 + j] = eq[j];
-      }
-      __syncthreads();
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {                                      // ascending codes, strict <: the first minimum
+        for (int j = 0; j < 12; ++j) {                                     // ascending codes, strict <: the first minimum
           const int c = g0 + c0 + j;
-          const float dist = __fsub_rn(__fadd_rn(xxs[r0 + i], ees[c0 + j]), __fmul_rn(2.f, acc[i][j]));
-          if (c < n_codes && (dist < bd[i] || (c == 0))) { bd[i] = dist; bi[i] = c; }
+          if (c < n_codes) {
+            const float dist = __fsub_rn(__fadd_rn(xx[i], ees[c]), __fmul_rn(2.f, acc[i][j]));
+            if (dist < bd[i] || c == 0) { bd[i] = dist; bi[i] = c; }
+          }
         }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { best_d[warp][r0 + i] = bd[i]; best_i[warp][r0 + i] = bi[i]; }
+    for (int i = 0; i < 4; ++i) { best_d[warp][lane + 32 * i] = bd[i]; best_i[warp][lane + 32 * i] = bi[i]; }
     __syncthreads();
-    if (tid < kVqRows) {
-      // warp w holds codes {g0 + 6w .. g0 + 6w + 5 for every group g0}: the first minimum is the lowest index among the
-      // smallest distances
+    {
+      // the first minimum over the four warps' code subsets: the lowest index among the smallest distances
       float d = best_d[0][tid];
       int c = best_i[0][tid];
-      for (int w = 1; w < 8; ++w) {
+      for (int w = 1; w < 4; ++w) {
         const float dw = best_d[w][tid];
         const int cw = best_i[w][tid];
         if (dw < d || (dw == d && cw < c)) { d = dw; c = cw; }
@@ -831,7 +841,7 @@ __global__ void __launch_bounds__(256, 3) vq_assign_tiled_kernel(const float* __
     if (quantized) {                                                       // inputs + (codeword - inputs), chain/nn.py:456
       __syncthreads();
       const int q4 = dim >> 2;
-      for (int e = tid; e < kVqRows * q4; e += 256) {
+      for (int e = tid; e < kVqRows * q4; e += kVqThreads) {
         const int r = e / q4, k = (e - r * q4) * 4;
         if (row0 + r >= n_rows) break;
         const float4 x = __ldg(reinterpret_cast<const float4*>(bn + (row0 + r) * dim + k));
@@ -858,7 +868,7 @@ int sa_hifigan_vq_assign(sa_hifigan* h, const float* bn, int64_t n_rows, uint8_t
     int n_sm = 0;
     SA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
     const int64_t tiles = (n_rows + kVqRows - 1) / kVqRows;
-    vq_assign_tiled_kernel<<<(int)std::min<int64_t>(tiles, (int64_t)n_sm * 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    vq_assign_tiled_kernel<<<(int)std::min<int64_t>(tiles, (int64_t)n_sm * 3), kVqThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         bn, h->d_codebook, n_rows, h->n_codes, h->code_dim, vq_idx, quantized);
     SA_CUDA(cudaGetLastError());
     return SA_OK;
