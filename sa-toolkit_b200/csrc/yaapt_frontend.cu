@@ -261,10 +261,16 @@ __global__ void kaiser_kernel(float* w, int n, double beta) {
 __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const uint8_t* __restrict__ vuv, const float* __restrict__ window,
                                  float* __restrict__ shc, float* __restrict__ cand_pitch, float* __restrict__ cand_merit,
                                  const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max, Geometry g, ShcGeometry s,
-                                 PeakParams pk) {
-  extern __shared__ float sm[];
+                                 PeakParams pk, int split_p) {
+  // split_p = nfft / 64 when the two-level DFT below is used (0: the direct loop).  Its layout: [nfp] samples, zero padded to
+  // a multiple of 64 | [64][P] inner sums | [P] e^{-2 pi i m / P} | [64] e^{-2 pi i m / nfft} | magnitudes | partial sums.
+  extern __shared__ __align__(16) float sm[];
   float* frame = sm;
-  float* mag = sm + s.nframe;
+  const int nfp = split_p ? (s.nframe + 63) & ~63 : s.nframe;
+  float2* S = reinterpret_cast<float2*>(sm + nfp);
+  float2* WP = S + 64 * split_p;
+  float2* WF = WP + split_p;
+  float* mag = split_p ? reinterpret_cast<float*>(WF + 64) : sm + s.nframe;
   float* part = mag + s.n_bins;
   const int f = blockIdx.x, b = blockIdx.y;
   const int64_t len = lengths ? lengths[b] : n_max;
@@ -298,9 +304,68 @@ __global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const ui
   const float mean = total / (float)s.nframe;
   __syncthreads();
   for (int n = threadIdx.x; n < s.nframe; n += blockDim.x) frame[n] -= mean;
+  if (split_p) {
+    // Two-level DFT: n = 64 a + b gives X[k] = sum_b w^{k b} S[b][k mod P], S[b][r] = sum_a x[64 a + b] e^{-2 pi i r a / P}
+    // with P = nfft / 64 -- the inner sums depend on k only through k mod P, so they are formed once for P residues
+    // (~0.14 M real x complex products) and every bin costs 64 complex products instead of nframe (~1.1 M in all for
+    // 1014 bins x 1120 samples).  Inner twiddles come exact from a table; the outer ones rotate 16 steps from an exact
+    // product of two table entries.
+    const int P = split_p;
+    for (int n = s.nframe + threadIdx.x; n < nfp; n += blockDim.x) frame[n] = 0.f;
+    for (int m = threadIdx.x; m < P + 64; m += blockDim.x) {
+      double sd, cd;
+      if (m < P) { sincospi(-2.0 * (double)m / (double)P, &sd, &cd); WP[m] = make_float2((float)cd, (float)sd); }
+      else { sincospi(-2.0 * (double)(m - P) / (double)g.nfft, &sd, &cd); WF[m - P] = make_float2((float)cd, (float)sd); }
+    }
+    __syncthreads();
+    const int A = nfp / 64;
+    for (int task = threadIdx.x; task < 4 * P; task += blockDim.x) {     // (residue r, 16 of the 64 offsets b); r over the lanes
+      const int r = task % P, bg = task / P;
+      float ar[16], ai[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { ar[j] = 0.f; ai[j] = 0.f; }
+      for (int a = 0; a < A; ++a) {
+        const float2 tw = WP[(r * a) % P];
+        const float4* xp = reinterpret_cast<const float4*>(frame + 64 * a + 16 * bg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = xp[q];
+          ar[4 * q + 0] = fmaf(v.x, tw.x, ar[4 * q + 0]); ai[4 * q + 0] = fmaf(v.x, tw.y, ai[4 * q + 0]);
+          ar[4 * q + 1] = fmaf(v.y, tw.x, ar[4 * q + 1]); ai[4 * q + 1] = fmaf(v.y, tw.y, ai[4 * q + 1]);
+          ar[4 * q + 2] = fmaf(v.z, tw.x, ar[4 * q + 2]); ai[4 * q + 2] = fmaf(v.z, tw.y, ai[4 * q + 2]);
+          ar[4 * q + 3] = fmaf(v.w, tw.x, ar[4 * q + 3]); ai[4 * q + 3] = fmaf(v.w, tw.y, ai[4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) S[(16 * bg + j) * P + r] = make_float2(ar[j], ai[j]);
+    }
+    __syncthreads();
+    auto tw_at = [&](int m) {                                              // e^{-2 pi i m / nfft}, 0 <= m < nfft
+      const float2 a = WP[m >> 6], c = WF[m & 63];
+      return make_float2(a.x * c.x - a.y * c.y, a.x * c.y + a.y * c.x);
+    };
+    for (int kb = threadIdx.x; kb < s.n_bins; kb += blockDim.x) {
+      const int k = s.bin_lo + kb, r = k % P;
+      const float2 rot = tw_at(k % g.nfft);
+      float re = 0.f, im = 0.f;
+      for (int b0 = 0; b0 < 64; b0 += 16) {
+        float2 tw = tw_at((int)(((int64_t)k * b0) % g.nfft));
+#pragma unroll
+        for (int b = b0; b < b0 + 16; ++b) {
+          const float2 sv = S[b * P + r];
+          re = fmaf(sv.x, tw.x, re); re = fmaf(-sv.y, tw.y, re);
+          im = fmaf(sv.x, tw.y, im); im = fmaf(sv.y, tw.x, im);
+          const float t = tw.x * rot.x - tw.y * rot.y;
+          tw.y = tw.x * rot.y + tw.y * rot.x;
+          tw.x = t;
+        }
+      }
+      mag[kb] = sqrtf(re * re + im * im);
+    }
+  }
   __syncthreads();
-  // two bins per thread (kb and kb + half_bins) share every sample load
-  const int half_bins = (s.n_bins + 1) / 2;
+  // the direct loop: two bins per thread (kb and kb + half_bins) share every sample load
+  const int half_bins = split_p ? 0 : (s.n_bins + 1) / 2;
   for (int kb = threadIdx.x; kb < half_bins; kb += blockDim.x) {
     const int ka = s.bin_lo + kb, kc = min(ka + half_bins, s.bin_lo + s.n_bins - 1);
     double sd, cd;
@@ -991,10 +1056,21 @@ int sa_yaapt_shc(const sa_yaapt_params* p, const float* filtered_nl, int32_t B, 
   kaiser_kernel<<<(sg.nframe + 255) / 256, 256, 0, st>>>(d_win, sg.nframe, 0.5);
   const int half_bins = (sg.n_bins + 1) / 2;
   const int threads = half_bins >= 1024 ? 1024 : (std::max(half_bins, sg.max_shc > 256 ? 256 : sg.max_shc) + 31) / 32 * 32;
-  const size_t smem = (size_t)(sg.nframe + sg.n_bins + 32) * sizeof(float);
-  if (smem > 48 * 1024) return fail("sa_yaapt_shc: frame + spectrum do not fit in 48 KB of shared memory");
-  shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(filtered_nl, vuv, d_win, shc, cand_pitch, cand_merit,
-                                                                            lengths ? d_len : nullptr, n_max, stride, f_max, g, sg, pk);
+  size_t smem = (size_t)(sg.nframe + sg.n_bins + 32) * sizeof(float);
+  // two-level DFT (see the kernel) when nfft = 64 P and the P x 64 inner sums fit beside the frame: 76 KB for nfft = 8192
+  int split_p = 0;
+  if (g.nfft % 64 == 0 && !getenv("SATOOLS_B200_YAAPT_DIRECT_DFT")) {
+    const int P = g.nfft / 64;
+    const size_t need = (size_t)(((sg.nframe + 63) & ~63) + sg.n_bins + 32 + 2 * (64 * P + P + 64)) * sizeof(float);
+    if (need <= 100 * 1024) { split_p = P; smem = need; }
+  }
+  if (!split_p && smem > 48 * 1024) return fail("sa_yaapt_shc: frame + spectrum do not fit in 48 KB of shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t ea = cudaFuncSetAttribute(shc_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return fail(cudaGetErrorString(ea));
+  }
+  shc_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), split_p ? 512 : threads, smem, st>>>(
+      filtered_nl, vuv, d_win, shc, cand_pitch, cand_merit, lengths ? d_len : nullptr, n_max, stride, f_max, g, sg, pk, split_p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e));
   return 0;
