@@ -258,7 +258,7 @@ __global__ void kaiser_kernel(float* w, int n, double beta) {
 }
 
 // One block per (frame, item).  smem: [nframe] windowed, mean-free samples | [n_bins] magnitudes | [32] partial sums.
-__global__ void shc_frame_kernel(const float* __restrict__ filtered_nl, const uint8_t* __restrict__ vuv, const float* __restrict__ window,
+__global__ void __launch_bounds__(1024, 1) shc_frame_kernel(const float* __restrict__ filtered_nl, const uint8_t* __restrict__ vuv, const float* __restrict__ window,
                                  float* __restrict__ shc, float* __restrict__ cand_pitch, float* __restrict__ cand_merit,
                                  const int* __restrict__ lengths, int64_t n_max, int64_t stride, int f_max, Geometry g, ShcGeometry s,
                                  PeakParams pk, int split_p) {
