@@ -152,6 +152,7 @@ __global__ void nlfer_frame_kernel(const float* __restrict__ filtered, float* __
     const float wgt = (float)(0.5 - 0.5 * cospi(2.0 * (double)(n + 1) / (double)(g.frame_size + 2)));
     frame[n] = x[n] * wgt;
   }
+  for (int n = g.frame_size + threadIdx.x; n < 4 * ((g.frame_size + 3) / 4); n += blockDim.x) frame[n] = 0.f;
   __syncthreads();
   float mag = 0.f;
   const int k = g.bin_lo + (int)threadIdx.x;
@@ -159,20 +160,34 @@ __global__ void nlfer_frame_kernel(const float* __restrict__ filtered, float* __
     double sd, cd;
     sincospi(-2.0 * (double)k / (double)g.nfft, &sd, &cd);        // one-sample rotation e^{-2 pi i k / nfft}
     const float rc = (float)cd, rs = (float)sd;
-    float re = 0.f, im = 0.f;
-    for (int n0 = 0; n0 < g.frame_size; n0 += kResync) {
+    // Four quarter frames share every twiddle: X[k] = sum_j w^{k j Q} sum_{n < Q} x[n + j Q] w^{k n} -- one rotation per four
+    // samples instead of one per sample (7 -> 4 instructions per sample); the samples past the frame are zeros.
+    const int Q = (g.frame_size + 3) / 4;
+    float pr[4] = {0.f, 0.f, 0.f, 0.f}, pi[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n0 = 0; n0 < Q; n0 += kResync) {
       const int idx = (int)(((int64_t)k * n0) % g.nfft);          // exact phase of sample n0
       float ws, wc;
       sincospif(-2.0f * (float)idx / (float)g.nfft, &ws, &wc);
-      const int n1 = min(n0 + kResync, g.frame_size);
+      const int n1 = min(n0 + kResync, Q);
       for (int n = n0; n < n1; ++n) {
-        const float v = frame[n];
-        re = fmaf(v, wc, re);
-        im = fmaf(v, ws, im);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = frame[n + j * Q];
+          pr[j] = fmaf(v, wc, pr[j]);
+          pi[j] = fmaf(v, ws, pi[j]);
+        }
         const float t = wc * rc - ws * rs;
         ws = wc * rs + ws * rc;
         wc = t;
       }
+    }
+    float re = pr[0], im = pi[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      float ws, wc;
+      sincospif(-2.0f * (float)(int)(((int64_t)k * j * Q) % g.nfft) / (float)g.nfft, &ws, &wc);
+      re += pr[j] * wc - pi[j] * ws;
+      im += pr[j] * ws + pi[j] * wc;
     }
     mag = sqrtf(re * re + im * im);
   }
@@ -1072,7 +1087,7 @@ int sa_yaapt_frontend(const sa_yaapt_params* p, const float* wav, int32_t B, int
     const int bins = g.bin_hi - g.bin_lo;
     const int threads = (bins + 31) / 32 * 32;
     if (threads > 1024) return fail("sa_yaapt_frontend: more than 1024 bins in the F0 band");
-    const size_t smem = (size_t)(g.frame_size > 32 ? g.frame_size : 32) * sizeof(float);
+    const size_t smem = (size_t)(g.frame_size > 32 ? g.frame_size + 4 : 36) * sizeof(float);
     nlfer_frame_kernel<<<dim3((unsigned)f_max, (unsigned)B), threads, smem, st>>>(fa, d_fe, dl, n_max, stride, f_max, g);
     nlfer_normalize_kernel<<<B, 256, 0, st>>>(d_fe, energy, vuv, mean_energy, dl, n_max, f_max, g, (float)p->nlfer_thresh1);
   }
